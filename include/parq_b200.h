@@ -1,0 +1,139 @@
+/*
+ * parq_b200 -- C ABI of the B200-native PARQ decoder hot path (libparq_b200.so).
+ *
+ * Drop-in boundary: everything the reference computes inside
+ *   PARQDecoder.forward                      (model/parq_decoder.py:134-163)
+ *   -> Transformer.forward                   (model/transformer_parq.py:95-126)
+ *   -> TransformerDecoder.forward            (model/transformer_parq.py:283-337)
+ * is behind parq_decoder_forward().  The reference is pure Python/PyTorch and has no FFI of its
+ * own; the binding a maintainer would add is the ctypes stub shown in INTEGRATION.md (it is what
+ * parq_b200/_lib.py implements).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  All data pointers are DEVICE pointers owned by the
+ *     caller (PyTorch's allocator); the library never allocates or frees device memory and keeps no
+ *     pointer across calls.  Alignment: 16 bytes for every pointer; C % 256 == 0; Nq % 128 == 0.
+ *   - every call is asynchronous on the caller's stream (cudaStream_t passed as void*), performs no
+ *     host synchronisation (except parq_pack_weights, a one-off), and is graph-capturable.
+ *   - return 0 on success, negative on error (PARQ_ERR_*); parq_last_error() gives the message
+ *     (thread local).  No C++ exception crosses the ABI.  sm_100 devices only: there is no fallback.
+ */
+#ifndef PARQ_B200_H_
+#define PARQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PARQ_ABI_VERSION 1
+
+#define PARQ_OK 0
+#define PARQ_ERR_SHAPE (-1)       /* unsupported shape / alignment / null pointer */
+#define PARQ_ERR_ARCH (-2)        /* device is not sm_100 */
+#define PARQ_ERR_CUDA (-3)        /* CUDA runtime / driver error */
+#define PARQ_ERR_WORKSPACE (-4)   /* workspace or packed-weight buffer too small */
+
+/* Problem shape.  Nk = T*H*W image tokens per clip; head_dim = C / heads must be 256. */
+typedef struct ParqShape {
+  int32_t B, T, H, W;     /* clips, views per clip, feature-map height / width */
+  int32_t C;              /* token / model width (1024) */
+  int32_t Nq;             /* queries per clip (256) */
+  int32_t heads;          /* 4 */
+  int32_t ffn;            /* 768 */
+  int32_t iters;          /* recurrent iterations == DEC_LAYERS (8), weights shared */
+  int32_t num_cls;        /* NUM_SEMCLS + 1 (10) */
+  float scale[6];         /* [x0,x1,y0,y1,z0,z1] of TRANSFORMER.SCALE (config/eval.yaml:55) */
+} ParqShape;
+
+/* fp32 parameters exactly as stored in the reference's state dict, device pointers.
+ * Conv1d(k=1) weights (n, C, 1) are passed as (n, C). */
+typedef struct ParqWeightsF32 {
+  const float *pe0_w, *pe0_b, *pe2_w, *pe2_b;               /* decoder.position_encoder.{0,2}      */
+  const float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b;     /* layers.0.self_attn                  */
+  const float *ca_in_w, *ca_in_b, *ca_out_w, *ca_out_b;     /* layers.0.multihead_attn             */
+  const float *lin1_w, *lin1_b, *lin2_w, *lin2_b;           /* layers.0.linear1 / linear2          */
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+  const float *cls_w, *cls_b;                               /* mlp_heads.sem_cls_head.layers.0     */
+  const float *ctr0_w, *ctr1_g, *ctr1_b, *ctr4_w, *ctr5_g, *ctr5_b, *ctr8_w, *ctr8_b;   /* center_head   */
+  const float *size_w, *size_b;                             /* mlp_heads.size_head.layers.0        */
+  const float *rot0_w, *rot1_g, *rot1_b, *rot4_w, *rot5_g, *rot5_b, *rot8_w, *rot8_b;   /* rotation_head */
+  const float *mean_size;                                   /* (num_cls, 3) BoxProcessor table     */
+  const float *dim_t;                                       /* (128) pos2posemb3d denominators     */
+} ParqWeightsF32;
+
+/* Per-iteration outputs, each (iters, B, Nq, n) fp32 contiguous; the six required tensors are the
+ * keys of the reference's output dicts (transformer_parq.py:271-279).  Optional ones may be NULL. */
+typedef struct ParqOutputs {
+  float *pred_logits;          /* n = num_cls */
+  float *center_unnormalized;  /* n = 3 */
+  float *size_unnormalized;    /* n = 3 */
+  float *ortho6d;              /* n = 6 */
+  float *sem_cls_prob;         /* n = num_cls */
+  float *coord_pos;            /* n = 3 */
+  float *rotation;             /* optional (iters,B,Nq,9): compute_rotation_matrix_from_ortho6d (utils/ortho6d_transforms.py:53-66) */
+  float *center_im;            /* optional (iters,B,T,Nq,2): projected pixel coordinates (transformer_parq.project) */
+  uint8_t *center_valid;       /* optional (iters,B,T,Nq) */
+  float *features;             /* optional (iters,B,Nq,C): pixel-aligned sampled features */
+  float *decoder_out;          /* optional (iters,B,Nq,C): decoder-layer output fed to the heads */
+} ParqOutputs;
+
+#define PARQ_FLAG_SKIP_KV 1u     /* workspace already holds K / V^T of these tokens (parq_kv_project) */
+#define PARQ_FLAG_WEIGHT_LO 2u   /* parq_pack_weights returned 1: weights are not bf16-exact, use the 3-term GEMMs */
+
+int parq_version(void);
+const char *parq_last_error(void);
+
+/* Sizes of the caller-allocated buffers. */
+size_t parq_packed_bytes(const ParqShape *shape);
+size_t parq_workspace_bytes(const ParqShape *shape);
+
+/* One-off: split/convert the fp32 parameters into the packed bf16 [hi|lo] + fp32 layout the kernels
+ * read.  Synchronises the stream once.  Returns 0 when every GEMM weight is exactly representable in
+ * bf16, 1 when a low-order weight term exists (pass PARQ_FLAG_WEIGHT_LO to the calls below), < 0 on error. */
+int parq_pack_weights(const ParqShape *shape, const ParqWeightsF32 *w, void *packed, size_t packed_bytes, void *stream);
+
+/* T_camera_local = T_camera_pseudoCam o (T_world_pseudoCam^-1 o T_world_local)   (transformer_parq.py:298-300)
+ * T_cp, T_wp (B,T,12), T_wl (B,1,12) -> T_cl (B,T,12). */
+int parq_pose_chain(const float *T_cp, const float *T_wp, const float *T_wl, float *T_cl, int B, int T, void *stream);
+
+/* transformer_parq.project (:129-161) for normalised reference points `ref` (B,Nq,3):
+ * tokens bf16 (B,T*H*W,C) -> features (B,Nq,C), center_im (B,T,Nq,2), center_valid (B,T,Nq), coord_pos (B,Nq,3).
+ * Output pointers other than `features` may be NULL. */
+int parq_project_sample(const ParqShape *shape, const void *tokens_bf16, const float *ref, const float *T_cl,
+                        const float *camera, float *features, float *center_im, uint8_t *center_valid,
+                        float *coord_pos, void *stream);
+
+/* Hoisted cross-attention K / V^T projection of all image tokens into the workspace (once per clip batch). */
+int parq_kv_project(const ParqShape *shape, const void *tokens_bf16, const void *packed, void *workspace,
+                    size_t workspace_bytes, uint32_t flags, void *stream);
+
+/* The whole recurrent decoder.  ref0 (B,Nq,3): normalised initial reference points (sigmoid(refpoint.weight)
+ * repeated per clip).  forced_refs (iters,B,Nq,3) or NULL: teacher-forced reference points per iteration. */
+int parq_decoder_forward(const ParqShape *shape, const void *tokens_bf16, const float *camera, const float *T_cp,
+                         const float *T_wp, const float *T_wl, const float *ref0, const float *forced_refs,
+                         const void *packed, void *workspace, size_t workspace_bytes, const ParqOutputs *out,
+                         uint32_t flags, void *stream);
+
+/* ---- building blocks exported for unit tests and micro-benchmarks -------------------------------------- */
+
+/* D[M,N] = sum_t A[:, a_koff[t] : +K] * Bw[:, b_koff[t] : +K]^T  (bf16 K-major operands, fp32 accumulate),
+ * epilogue: + bias (per column, or per row when bias_per_row), optional ReLU, outputs fp32 and/or 16-bit. */
+int parq_gemm_bf16(const void *A, int64_t a_rows, int64_t a_cols, const void *Bw, int64_t b_rows, int64_t b_cols,
+                   int M, int N, int K, int nterms, const int32_t *a_koff, const int32_t *b_koff, const float *bias,
+                   int bias_per_row, int relu, float *out_f32, int64_t ld_f32, void *out_lp, int64_t ld_lp, int lp_fp16,
+                   int64_t lp_lo_off, void *stream);
+
+/* softmax(Q K^T) V for head_dim 256: Q (B*Nq, H*256) pre-scaled, K (B*Nk, H*256), Vt (H*256, ldv) 16-bit
+ * (bf16, or fp16 when fp16 != 0); out_split (B*Nq, 2*H*256) bf16 [hi|lo]; scratch >= parq_attention_scratch_bytes. */
+size_t parq_attention_scratch_bytes(int B, int H, int Nq, int Nk);
+int parq_attention(const void *Q, int64_t ldq, const void *K, int64_t ldk, const void *Vt, int64_t ldv, int B, int H,
+                   int Nq, int Nk, int fp16, void *scratch, size_t scratch_bytes, void *out_split, int force_nsplit,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARQ_B200_H_ */

@@ -1,0 +1,337 @@
+"""CPU oracle: a restatement of the reference's recurrent pixel-aligned query
+decoder (PARQ hot path).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference leg may import this module; the product path (parq_b200/) never
+does and fails loudly when its CUDA library is missing.
+
+Pinning: the reference has no tests or golden vectors for this path
+(SURVEY.md 4, 8c), so the oracle is pinned against outputs of the unmodified
+reference itself, run in the build container through oracle/ref_loader.py:
+tests/golden/make_golden.py wrote tests/golden/*.npz and
+tests/test_oracle_golden.py checks this file against them (bit-exact for the
+projection, <=2e-5 for everything else, teacher-forced per iteration).
+
+Arithmetic is plain fp32 torch on the CPU (the third-party arithmetic of the
+reference *is* torch: F.grid_sample, softmax, layer/group norm, matmul), except
+the pose/projection chain, which is restated with explicit per-operation fp32
+rounding in numpy so that it is machine independent:
+  * 3-term dot products inside Pose.inverse/compose round as
+    ((a0*b0 + a1*b1) + a2*b2) with no FMA,
+  * the point transform rounds as fma(p2,r2, fma(p1,r1, p0*r0)) then "+ t",
+which is what torch 2.11 (MKL) does for these shapes on the build container
+and reproduces the reference's center_im / center_valid bit for bit.
+
+Reference citations are to /root/reference/<file>:<line>.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+F32 = np.float32
+EPS_Z = F32(1e-3)          # Camera.eps, utils/wrappers.py:442
+
+# data/average_scan2cad.txt through BoxProcessor.init_mean_size (utils/parq_utils.py:45-88):
+# 8 Scan2CAD class means + "other" + "non-object" rows of ones; float64 in the reference.
+MEAN_SIZE = np.array([
+    [0.55067552, 0.84943989, 0.5786128],
+    [1.24506049, 0.66165523, 0.72455878],
+    [0.95658434, 0.99974904, 0.56246602],
+    [0.36641966, 0.45580824, 0.27876528],
+    [1.05132399, 1.3471979, 0.33744382],
+    [0.60740744, 0.4752175, 0.16435075],
+    [1.68820774, 0.76637348, 0.89351734],
+    [0.85305378, 0.43925023, 0.51612006],
+    [1.0, 1.0, 1.0],
+    [1.0, 1.0, 1.0]], dtype=np.float64)
+
+
+# --------------------------------------------------------------------------- #
+# A.2  pose algebra with explicit fp32 rounding (utils/wrappers.py:247-267)
+# --------------------------------------------------------------------------- #
+def _dot3(a0, b0, a1, b1, a2, b2):
+    """((a0*b0 + a1*b1) + a2*b2), every operation rounded to fp32, no FMA."""
+    return (a0 * b0 + a1 * b1) + a2 * b2
+
+
+def _fma(a, b, c):
+    """fp32 fused multiply-add emulated through float64 (the product of two
+    fp32 values is exact in float64; the final float64->fp32 rounding can differ
+    from a true fma only in double-rounding corner cases of probability ~2^-29)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(F32)
+
+
+def pose_inverse(P):
+    """Pose.inverse (wrappers.py:247-251): R' = R^T, t' = -(R^T t).  P: (...,12) fp32."""
+    P = np.asarray(P, dtype=F32)
+    R = P[..., :9].reshape(P.shape[:-1] + (3, 3))
+    t = P[..., 9:]
+    Rt = np.swapaxes(R, -1, -2)
+    tt = np.stack([-_dot3(Rt[..., i, 0], t[..., 0], Rt[..., i, 1], t[..., 1], Rt[..., i, 2], t[..., 2])
+                   for i in range(3)], -1)
+    return np.concatenate([Rt.reshape(P.shape[:-1] + (9,)), tt], -1).astype(F32)
+
+
+def pose_compose(A, B):
+    """Pose.compose (wrappers.py:253-257): R = RA RB, t = tA + RA tB (broadcasting)."""
+    A = np.asarray(A, dtype=F32)
+    B = np.asarray(B, dtype=F32)
+    shp = np.broadcast_shapes(A.shape, B.shape)
+    A = np.broadcast_to(A, shp)
+    B = np.broadcast_to(B, shp)
+    RA = A[..., :9].reshape(shp[:-1] + (3, 3))
+    RB = B[..., :9].reshape(shp[:-1] + (3, 3))
+    tA, tB = A[..., 9:], B[..., 9:]
+    R = np.empty(shp[:-1] + (3, 3), dtype=F32)
+    for i in range(3):
+        for j in range(3):
+            R[..., i, j] = _dot3(RA[..., i, 0], RB[..., 0, j], RA[..., i, 1], RB[..., 1, j], RA[..., i, 2], RB[..., 2, j])
+    t = np.stack([tA[..., i] + _dot3(RA[..., i, 0], tB[..., 0], RA[..., i, 1], tB[..., 1], RA[..., i, 2], tB[..., 2])
+                  for i in range(3)], -1)
+    return np.concatenate([R.reshape(shp[:-1] + (9,)), t], -1).astype(F32)
+
+
+def camera_from_local(T_camera_pseudoCam, T_world_pseudoCam, T_world_local):
+    """T_camera_local = T_cp @ (T_wp^-1 @ T_wl)  (transformer_parq.py:298-300).
+    (B,T,12), (B,T,12), (B,1,12) -> (B,T,12) fp32 numpy."""
+    return pose_compose(T_camera_pseudoCam, pose_compose(pose_inverse(T_world_pseudoCam), T_world_local))
+
+
+def transform_points(T_camera_local, pts):
+    """Pose.transform (wrappers.py:260-267): p @ R^T + t.  (B,T,12), (B,Nq,3) -> (B,T,Nq,3)."""
+    Tcl = np.asarray(T_camera_local, dtype=F32)
+    p = np.asarray(pts, dtype=F32)[:, None]                     # (B,1,Nq,3)
+    R = Tcl[..., :9].reshape(Tcl.shape[:-1] + (3, 3))[:, :, None]   # (B,T,1,3,3)
+    t = Tcl[..., 9:][:, :, None]                                # (B,T,1,3)
+    out = []
+    for i in range(3):
+        acc = p[..., 0] * R[..., i, 0]
+        acc = _fma(p[..., 1], R[..., i, 1], acc)
+        acc = _fma(p[..., 2], R[..., i, 2], acc)
+        out.append(acc + t[..., i])
+    return np.stack(out, -1).astype(F32)
+
+
+def pinhole_project(camera, pc):
+    """Camera.project + in_image (wrappers.py:502-522).  camera (B,T,6), pc (B,T,Nq,3)
+    -> center_im (B,T,Nq,2) fp32, valid (B,T,Nq) bool."""
+    cam = np.asarray(camera, dtype=F32)[:, :, None]             # (B,T,1,6)
+    z = pc[..., 2]
+    in_front = z > EPS_Z
+    zc = np.maximum(z, EPS_Z)
+    u = (pc[..., 0] / zc) * cam[..., 2] + cam[..., 4]
+    v = (pc[..., 1] / zc) * cam[..., 3] + cam[..., 5]
+    wm1 = cam[..., 0] - F32(1)
+    hm1 = cam[..., 1] - F32(1)
+    valid = in_front & (u >= 0) & (u <= wm1) & (v >= 0) & (v <= hm1)
+    return np.stack([u, v], -1).astype(F32), valid
+
+
+def denormalize(ref, scale):
+    """TransformerDecoder.denormalize (transformer_parq.py:198-209): p*(hi-lo)+lo per axis."""
+    s = [float(x) for x in scale]
+    return torch.stack([ref[..., 0] * (s[1] - s[0]) + s[0],
+                        ref[..., 1] * (s[3] - s[2]) + s[2],
+                        ref[..., 2] * (s[5] - s[4]) + s[4]], dim=-1)
+
+
+def normalize(c, scale):
+    """TransformerDecoder.normalize (transformer_parq.py:185-196): (c-lo)/(hi-lo) per axis."""
+    s = [float(x) for x in scale]
+    return torch.stack([(c[..., 0] - s[0]) / (s[1] - s[0]),
+                        (c[..., 1] - s[2]) / (s[3] - s[2]),
+                        (c[..., 2] - s[4]) / (s[5] - s[4])], dim=-1)
+
+
+def inverse_sigmoid(x, eps=1e-3):
+    """transformer_parq.py:38-42."""
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+# --------------------------------------------------------------------------- #
+# A.3/A.4  projection + bilinear multi-view gather (transformer_parq.py:129-161)
+# --------------------------------------------------------------------------- #
+def project_sample(tokens, coord_pos, T_camera_local, camera, H, W):
+    """tokens (B, T*H*W, C) fp32; coord_pos (B,Nq,3) metres in the local frame;
+    T_camera_local (B,T,12); camera (B,T,6).
+    Returns features (B,Nq,C), center_im (B,T,Nq,2), center_valid (B,T,Nq) bool."""
+    B, Nq = coord_pos.shape[:2]
+    Tv = T_camera_local.shape[1]
+    C = tokens.shape[-1]
+    pc = transform_points(np.asarray(T_camera_local), coord_pos.detach().numpy())
+    center_im_np, valid_np = pinhole_project(np.asarray(camera), pc)
+    center_im = torch.from_numpy(center_im_np)
+    center_valid = torch.from_numpy(valid_np)
+    w = np.float32(W)
+    h = np.float32(H)
+    # transformer_parq.py:148-150 (w,h are numpy float32 scalars there)
+    gx = 2 * center_im[..., 0] / float(w - 1) - 1
+    gy = 2 * center_im[..., 1] / float(h - 1) - 1
+    grid = torch.stack([gx, gy], dim=-1).view(B * Tv, 1, Nq, 2)
+    memory_hw = tokens.view(B * Tv, H, W, C).permute(0, 3, 1, 2)          # :302-303, channels-last strides
+    feat = F.grid_sample(memory_hw, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    feat = feat.view(B, Tv, C, Nq).permute(0, 1, 3, 2).contiguous()
+    feat = feat.sum(dim=1)                                               # ALL views, valid or not (:156)
+    cnt = center_valid.sum(dim=1)
+    cnt[cnt == 0] = 1
+    feat = feat / cnt.unsqueeze(-1)
+    return feat, center_im, center_valid
+
+
+# --------------------------------------------------------------------------- #
+# A.5  reference-point positional encoding (transformer_parq.py:45-64, 176-180)
+# --------------------------------------------------------------------------- #
+def pos_dim_t(num_pos_feats=128, temperature=10000):
+    d = torch.arange(num_pos_feats, dtype=torch.float32)
+    return temperature ** (2 * (d // 2) / num_pos_feats)
+
+
+def pos2posemb3d(pos, num_pos_feats=128, temperature=10000):
+    pos = pos * (2 * math.pi)
+    dim_t = pos_dim_t(num_pos_feats, temperature)
+    embs = []
+    for axis in (1, 0, 2):                                      # concat order (y, x, z), :63
+        a = pos[..., axis, None] / dim_t
+        embs.append(torch.stack((a[..., 0::2].sin(), a[..., 1::2].cos()), dim=-1).flatten(-2))
+    return torch.cat(embs, dim=-1)
+
+
+# --------------------------------------------------------------------------- #
+# A.6  decoder layer, heads, box update
+# --------------------------------------------------------------------------- #
+def _mha(q_in, k_in, v_in, w_in, b_in, w_out, b_out, heads, kv=None):
+    """nn.MultiheadAttention forward, need_weights path without the weights
+    (torch/nn/functional.py multi_head_attention_forward): inputs (L,B,E)/(S,B,E).
+    ``kv`` optionally carries cached (k, v) projections (iteration-invariant for
+    the cross attention; the reference recomputes them every iteration)."""
+    L, B, E = q_in.shape
+    dh = E // heads
+    q = F.linear(q_in, w_in[:E], b_in[:E])
+    if kv is None:
+        k = F.linear(k_in, w_in[E:2 * E], b_in[E:2 * E])
+        v = F.linear(v_in, w_in[2 * E:], b_in[2 * E:])
+    else:
+        k, v = kv
+    S = k.shape[0]
+    q = q.view(L, B * heads, dh).transpose(0, 1)
+    k = k.view(S, B * heads, dh).transpose(0, 1)
+    v = v.view(S, B * heads, dh).transpose(0, 1)
+    q = q * math.sqrt(1.0 / float(dh))
+    attn = torch.softmax(torch.bmm(q, k.transpose(-2, -1)), dim=-1)
+    out = torch.bmm(attn, v)
+    out = out.transpose(0, 1).contiguous().view(L * B, E)
+    return F.linear(out, w_out, b_out).view(L, B, E)
+
+
+def _head3(x_cn, sd, name):
+    """3-layer GenericMLP head (generic_mlp.py:94-110 with use_conv, norm 'ln' ->
+    GroupNorm(1,C), parq_decoder.py:90-98): x_cn (B,C,Nq)."""
+    p = "mlp_heads." + name + ".layers."
+    y = F.conv1d(x_cn, sd[p + "0.weight"])
+    y = F.relu(F.group_norm(y, 1, sd[p + "1.weight"], sd[p + "1.bias"], 1e-5))
+    y = F.conv1d(y, sd[p + "4.weight"])
+    y = F.relu(F.group_norm(y, 1, sd[p + "5.weight"], sd[p + "5.bias"], 1e-5))
+    return F.conv1d(y, sd[p + "8.weight"], sd[p + "8.bias"])
+
+
+def box_heads(x, ref, sd, scale):
+    """bbox3d_prediction (transformer_parq.py:211-281) + BoxProcessor
+    (utils/parq_utils.py:90-105).  x (B,Nq,C) decoder output, ref (B,Nq,3) normalised."""
+    xc = x.permute(0, 2, 1).contiguous()
+    logits = F.conv1d(xc, sd["mlp_heads.sem_cls_head.layers.0.weight"], sd["mlp_heads.sem_cls_head.layers.0.bias"]).transpose(1, 2)
+    center_off = _head3(xc, sd, "center_head").transpose(1, 2)
+    coord_pos = denormalize(ref, scale)
+    center = denormalize((center_off + inverse_sigmoid(ref)).sigmoid(), scale)
+    size_s = F.conv1d(xc, sd["mlp_heads.size_head.layers.0.weight"], sd["mlp_heads.size_head.layers.0.bias"]).transpose(1, 2)
+    ortho6d = _head3(xc, sd, "rotation_head").transpose(1, 2)
+    prob = torch.softmax(logits, dim=-1)
+    mean_size = torch.from_numpy(MEAN_SIZE)[prob.argmax(-1)]
+    size = torch.exp(size_s) * mean_size.float()
+    return {"pred_logits": logits, "center_unnormalized": center * 1, "size_unnormalized": size,
+            "ortho6d": ortho6d, "sem_cls_prob": prob, "coord_pos": coord_pos}
+
+
+def decoder_iteration(tokens, memory, ref, T_camera_local, camera, H, W, sd, heads=4, scale=None, kv=None):
+    """One pass of the hot loop body (transformer_parq.py:311-332) for normalised
+    reference points ``ref`` (B,Nq,3).  Returns (out_dict, next_ref, aux)."""
+    L = "parq_module.decoder.layers.0."
+    P = "parq_module.decoder.position_encoder."
+    pe = F.linear(F.relu(F.linear(pos2posemb3d(ref), sd[P + "0.weight"], sd[P + "0.bias"])), sd[P + "2.weight"], sd[P + "2.bias"])
+    pe = pe.permute(1, 0, 2)
+    feat, center_im, center_valid = project_sample(tokens, denormalize(ref, scale), T_camera_local, camera, H, W)
+    x = feat.permute(1, 0, 2)
+    qk = x + pe
+    x2 = _mha(qk, qk, x, sd[L + "self_attn.in_proj_weight"], sd[L + "self_attn.in_proj_bias"],
+              sd[L + "self_attn.out_proj.weight"], sd[L + "self_attn.out_proj.bias"], heads)
+    x = F.layer_norm(x + x2, (x.shape[-1],), sd[L + "norm1.weight"], sd[L + "norm1.bias"], 1e-5)
+    x2 = _mha(x + pe, memory, memory, sd[L + "multihead_attn.in_proj_weight"], sd[L + "multihead_attn.in_proj_bias"],
+              sd[L + "multihead_attn.out_proj.weight"], sd[L + "multihead_attn.out_proj.bias"], heads, kv=kv)
+    x = F.layer_norm(x + x2, (x.shape[-1],), sd[L + "norm2.weight"], sd[L + "norm2.bias"], 1e-5)
+    x2 = F.linear(F.relu(F.linear(x, sd[L + "linear1.weight"], sd[L + "linear1.bias"])), sd[L + "linear2.weight"], sd[L + "linear2.bias"])
+    x = F.layer_norm(x + x2, (x.shape[-1],), sd[L + "norm3.weight"], sd[L + "norm3.bias"], 1e-5)
+    x = x.permute(1, 0, 2)
+    out = box_heads(x, ref, sd, scale)
+    nxt = normalize(out["center_unnormalized"], scale)
+    aux = {"features": feat, "center_im": center_im, "center_valid": center_valid, "decoder_out": x}
+    return out, nxt, aux
+
+
+def decoder_forward(tokens, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local, sd,
+                    iters=8, heads=4, scale=(-3, 3, -2, 0.5, 0.25, 5.25), forced_refs=None,
+                    hoist_kv=True, return_aux=False):
+    """PARQDecoder.forward (parq_decoder.py:134-163) -> TransformerDecoder.forward
+    (transformer_parq.py:283-337).  All pose/camera arguments are raw tensors
+    ((B,T,12)/(B,1,12)/(B,T,6)).  ``forced_refs`` (iters,B,Nq,3): teacher-forced
+    normalised reference points per iteration.  ``hoist_kv=False`` recomputes the
+    cross-attention K/V projection every iteration exactly as the reference does
+    (used when this oracle is timed as the CPU baseline)."""
+    with torch.no_grad():
+        tokens = tokens.float()
+        B = tokens.shape[0]
+        cam = camera.float()
+        W = int(cam[0, 0, 0].item())
+        H = int(cam[0, 0, 1].item())
+        Tcl = camera_from_local(T_camera_pseudoCam.numpy(), T_world_pseudoCam.numpy(), T_world_local.numpy())
+        memory = tokens.permute(1, 0, 2)
+        E = tokens.shape[-1]
+        L = "parq_module.decoder.layers.0.multihead_attn."
+        kv = None
+        if hoist_kv:
+            kv = (F.linear(memory, sd[L + "in_proj_weight"][E:2 * E], sd[L + "in_proj_bias"][E:2 * E]),
+                  F.linear(memory, sd[L + "in_proj_weight"][2 * E:], sd[L + "in_proj_bias"][2 * E:]))
+        ref = sd["refpoint.weight"].unsqueeze(0).repeat(B, 1, 1).sigmoid()
+        outs, auxs = [], []
+        for it in range(iters):
+            if forced_refs is not None:
+                ref = forced_refs[it]
+            out, ref, aux = decoder_iteration(tokens, memory, ref, Tcl, cam.numpy(), H, W, sd, heads, scale, kv)
+            outs.append(out)
+            auxs.append(aux)
+        return (outs, auxs) if return_aux else outs
+
+
+def refs_from_outputs(outs, sd, scale=(-3, 3, -2, 0.5, 0.25, 5.25)):
+    """Normalised reference points consumed by every iteration of a run whose
+    per-iteration outputs are ``outs`` (teacher forcing):
+    ref_0 = sigmoid(refpoint), ref_i = normalize(center_{i-1})."""
+    B = outs[0]["center_unnormalized"].shape[0]
+    refs = [sd["refpoint.weight"].unsqueeze(0).repeat(B, 1, 1).sigmoid()]
+    for o in outs[:-1]:
+        refs.append(normalize(o["center_unnormalized"], scale))
+    return torch.stack(refs)
+
+
+# --------------------------------------------------------------------------- #
+# a13  ortho6d -> rotation (utils/ortho6d_transforms.py:23-66)
+# --------------------------------------------------------------------------- #
+def rotation_from_ortho6d(o):
+    """(N,6) -> (N,3,3), columns [x y z]; norms clamped at 1e-8."""
+    def nrm(v):
+        return v / torch.sqrt(v.pow(2).sum(1)).clamp(min=1e-8).unsqueeze(1)
+    x = nrm(o[:, 0:3])
+    z = nrm(torch.cross(x, o[:, 3:6], dim=1))
+    y = torch.cross(z, x, dim=1)
+    return torch.stack((x, y, z), dim=2)

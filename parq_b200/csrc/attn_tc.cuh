@@ -1,0 +1,320 @@
+// Flash-style attention for head_dim 256 on tcgen05/TMEM (sm_100a), split over keys.
+//
+// Replaces nn.MultiheadAttention's softmax(QK^T)V of the PARQ decoder layer
+// (reference transformer_parq.py:372-382; torch multi_head_attention_forward),
+// without ever materialising the (B*heads, Nq, Nk) score tensor:
+//   * cross-attention of the 256 queries of a clip over all T*H*W image tokens
+//     (bf16 operands; K and V^T are projected once per clip by gemm_tc.cuh),
+//   * self-attention among the queries (same kernel, fp16 operands, Nk = Nq).
+//
+// One CTA = (clip b, head h, 128-query tile, key split s).  Roles:
+//   warp 0   TMA producer   Q tile once, then K half-tiles / V^T chunks through a
+//                           5 x 32 KB ring (order K0, [K(j+1), V(j)] ...)
+//   warp 1   MMA issuer     S_j = Q K_j^T  (4x4 tcgen05.mma 128x128x16, SS) into one of two
+//                           S buffers;  O += P_j V_j (2x4 tcgen05.mma 128x256x16, A = P from TMEM)
+//   warp 2   TMEM allocator (512 columns: S0 | S1 | O)
+//   warps 4-7 softmax       thread = query row = TMEM lane: online softmax in the exp2 domain with
+//                           lazy rescaling of O (only when the running max grows by > 2^8),
+//                           P_j written back over S_j as packed 16-bit pairs.
+// S(j+1) is issued before waiting for P(j), so the tensor pipe runs QK^T of the next
+// tile while the softmax warps work on the current one.
+//
+// Layouts (all K-major for the MMA, 128B-swizzled by TMA):
+//   Q   [B*Nq , H*256]   rows = queries, pre-scaled by 1/sqrt(256)
+//   K   [B*Nk , H*256]   rows = keys
+//   V^T [H*256, ldv  ]   rows = channels, columns = keys of all clips (b*Nk + key)
+// Output: un-normalised partial O (fp32), running max m (log2 units) and sum l per
+// (clip, head, split, query); attn_combine_kernel merges the splits.
+#pragma once
+#include <cuda.h>
+
+#include "ptx.cuh"
+
+namespace parq {
+
+struct AttnParams {
+  int B, H, Nq, Nk;
+  int nsplit;            // number of key splits (grid.x); every split is non-empty
+  int tiles_per_split;   // key tiles (128 keys) per split
+  float* o_part;         // [((b*H+h)*nsplit + s)*Nq + q][256]
+  float2* ml_part;       // [((b*H+h)*nsplit + s)*Nq + q] = (m, l)
+};
+
+namespace attn {
+constexpr int DH = 256;
+constexpr int BQ = 128;
+constexpr int BKEY = 128;
+constexpr int NS = 5;                      // ring stages
+constexpr int STAGE_BYTES = 32 * 1024;
+constexpr int Q_BYTES = BQ * DH * 2;       // 64 KB
+constexpr int THREADS = 256;
+constexpr int SMEM_BYTES = Q_BYTES + NS * STAGE_BYTES + 1024 + 256;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
+}  // namespace attn
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool kFp16>
+__global__ void __launch_bounds__(attn::THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using namespace attn;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* ring = smem + Q_BYTES;
+  uint64_t* kv_full = reinterpret_cast<uint64_t*>(ring + NS * STAGE_BYTES);
+  uint64_t* kv_empty = kv_full + NS;
+  uint64_t* q_full = kv_empty + NS;
+  uint64_t* s_full = q_full + 1;     // [2]
+  uint64_t* p_full = s_full + 2;     // [2]
+  uint64_t* pv_done = p_full + 2;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int qt = blockIdx.y;
+  const int bh = blockIdx.z;
+  const int b = bh / p.H, h = bh % p.H;
+
+  const int ntiles = (p.Nk + BKEY - 1) / BKEY;
+  const int t0 = split * p.tiles_per_split;
+  const int t1 = min(ntiles, t0 + p.tiles_per_split);
+  const int n = t1 - t0;                 // >= 1 by construction of the grid
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_O = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0 && n > 0) {             // ---------------- TMA producer
+      const int ch0 = h * DH;
+      mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        tma_load_2d(sQ + c * (BQ * 128), &tmQ, q_full, ch0 + c * 64, b * p.Nq + qt * BQ);
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_k = [&](int tile) {
+        const int row = b * p.Nk + tile * BKEY;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          mbar_expect_tx(&kv_full[stage], STAGE_BYTES);
+          uint8_t* dst = ring + stage * STAGE_BYTES;
+          tma_load_2d(dst, &tmK, &kv_full[stage], ch0 + (half * 2) * 64, row);
+          tma_load_2d(dst + 16384, &tmK, &kv_full[stage], ch0 + (half * 2 + 1) * 64, row);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      };
+      auto load_v = [&](int tile) {
+        const int col = b * p.Nk + tile * BKEY;
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc) {
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          mbar_expect_tx(&kv_full[stage], STAGE_BYTES);
+          tma_load_2d(ring + stage * STAGE_BYTES, &tmV, &kv_full[stage], col + kc * 64, ch0);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      };
+      load_k(t0);
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) load_k(t0 + j + 1);
+        load_v(t0 + j);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n > 0) {             // ---------------- MMA issuer
+      constexpr uint32_t fmt = kFp16 ? 0u : 1u;
+      constexpr uint32_t idesc_s = umma_idesc(BQ, BKEY, fmt);
+      constexpr uint32_t idesc_pv = umma_idesc(BQ, DH, fmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_s = [&](int buf) {
+        const uint32_t d_tmem = tmem_base + buf * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&kv_full[stage], phase);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(ring + stage * STAGE_BYTES);
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const uint64_t qd = umma_desc_sw128(q_addr + (half * 2 + c2) * (BQ * 128));
+            const uint64_t kd = umma_desc_sw128(k_addr + c2 * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(d_tmem, qd + 2 * k, kd + 2 * k, idesc_s, (half | c2 | k) != 0);
+          }
+          umma_commit(&kv_empty[stage]);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&s_full[buf]);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) issue_s((j + 1) & 1);
+        const int buf = j & 1;
+        mbar_wait(&p_full[buf], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t p_tmem = tmem_base + buf * 128;
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc) {
+          mbar_wait(&kv_full[stage], phase);
+          tc_fence_after();
+          const uint64_t vd = umma_desc_sw128(smem_u32(ring + stage * STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ts(tmem_O, p_tmem + kc * 32 + k * 8, vd + 2 * k, idesc_pv, (j | kc | k) != 0);
+          umma_commit(&kv_empty[stage]);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(pv_done);
+      }
+    }
+  } else if (warp >= 4 && n > 0) {        // ---------------- softmax / correction / epilogue
+    const int q = warp - 4;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&s_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_tmem = tmem_base + lane_base + buf * 128;
+      uint32_t su[128];                                // raw fp32 bits of this row of S
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&su[c * 32]));
+      tmem_wait_ld();
+      const int nvalid = p.Nk - (t0 + j) * BKEY;     // keys of this tile that belong to the clip
+      if (nvalid < BKEY) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= nvalid) su[i] = 0xff800000u;        // -inf
+      }
+      float tmax = __uint_as_float(su[0]);
+#pragma unroll
+      for (int i = 1; i < 128; ++i) tmax = fmaxf(tmax, __uint_as_float(su[i]));
+      tmax *= LOG2E;
+      if (j == 0) {
+        m_run = tmax;
+      } else if (__any_sync(0xffffffffu, tmax > m_run + RESCALE_THRESHOLD)) {
+        // O must be quiescent: wait for P(j-1) V(j-1) to retire, then rescale this warp's 32 rows.
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        const float m_new = fmaxf(m_run, tmax);
+        const float alpha = fast_exp2(m_run - m_new);
+#pragma unroll 1
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_base + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tmem_O + lane_base + c * 32, o);
+        }
+        l_run *= alpha;
+        m_run = m_new;
+      }
+      float lsum = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i]), LOG2E, -m_run));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i + 1]), LOG2E, -m_run));
+          lsum += p0 + p1;
+          pk[i] = kFp16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
+        }
+        tmem_st32(s_tmem + half * 32, pk);
+      }
+      l_run += lsum;
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[buf]);
+    }
+    // epilogue: un-normalised O, m, l of this split
+    mbar_wait(pv_done, (n - 1) & 1);
+    tc_fence_after();
+    const long long part = (static_cast<long long>(bh) * p.nsplit + split) * p.Nq + qt * BQ + q * 32 + lane;
+    float* orow = p.o_part + part * DH;
+#pragma unroll 1
+    for (int c = 0; c < DH / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_base + c * 32, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(orow + c * 32)[i] =
+            make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
+                        __uint_as_float(o[4 * i + 3]));
+    }
+    p.ml_part[part] = make_float2(m_run, l_run);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// Merge the key splits: out = sum_s 2^(m_s-M) O_s / sum_s 2^(m_s-M) l_s, heads concatenated along
+// channels (the layout nn.MultiheadAttention feeds to out_proj), emitted as the exact bf16 split
+// [hi | lo] that the out-projection GEMM consumes.  One block per query row, thread = channel of a head.
+__global__ void __launch_bounds__(256)
+attn_combine_kernel(const float* __restrict__ o_part, const float2* __restrict__ ml_part, __nv_bfloat16* __restrict__ out,
+                    int H, int Nq, int nsplit) {
+  const int row = blockIdx.x;            // b*Nq + q
+  const int b = row / Nq, q = row % Nq;
+  const int d = threadIdx.x;
+  const int C = H * 256;
+  for (int h = 0; h < H; ++h) {
+    const long long base = (static_cast<long long>(b * H + h) * nsplit) * Nq + q;
+    float M = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, ml_part[base + static_cast<long long>(s) * Nq].x);
+    float acc = 0.f, L = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const long long idx = base + static_cast<long long>(s) * Nq;
+      const float2 ml = ml_part[idx];
+      const float w = exp2f(ml.x - M);
+      L += w * ml.y;
+      acc += w * o_part[idx * 256 + d];
+    }
+    const float v = acc / L;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[static_cast<long long>(row) * (2 * C) + h * 256 + d] = hi;
+    out[static_cast<long long>(row) * (2 * C) + C + h * 256 + d] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+}  // namespace parq

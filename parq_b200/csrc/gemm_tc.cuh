@@ -1,0 +1,244 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:
+//
+//   D[M,N] = sum_t  A_t[M,K] * B_t[N,K]^T          (bf16 operands, fp32 accumulate in TMEM)
+//
+// Both operands are K-major (K contiguous) and are fetched by TMA into a
+// 4-stage 128B-swizzled shared-memory ring; a single thread issues
+// tcgen05.mma (128 x 256 x 16) into a double-buffered 2 x 256-column TMEM
+// accumulator so that the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// "Terms": the residual stream of the decoder is fp32, so activations enter the
+// tensor cores as an exact two-way bf16 split  x = hi + lo  stored side by side
+// ([hi | lo] along K).  A GEMM with `nterms` > 1 walks several (A-column-offset,
+// B-column-offset) K-segments and accumulates them into the same tile:
+//   2 terms: (A_hi,W_hi) + (A_lo,W_hi)                 (weights exactly bf16)
+//   3 terms: ... + (A_hi,W_lo)                         (fp32 weights split too)
+//
+// Used for: the hoisted cross-attention K / V^T projections of all image tokens
+// (reference: nn.MultiheadAttention in-proj of `memory`, transformer_parq.py:377-380),
+// and every per-iteration linear layer of the decoder (in/out projections, FFN,
+// reference-point MLP, head hidden layers; transformer_parq.py:176-180,365-386,
+// generic_mlp.py:94-110).
+#pragma once
+#include <cuda.h>
+
+#include "ptx.cuh"
+
+namespace parq {
+
+struct GemmEpilogue {
+  const float* bias;   // nullptr: none
+  int bias_per_row;    // 0: bias[n] (Linear), 1: bias[m] (transposed product, e.g. V^T)
+  int relu;
+  float scale;         // applied after the bias (1/sqrt(dh) of the attention query)
+  float* out_f32;      // optional fp32 output, row-major, leading dimension ld_f32
+  long long ld_f32;
+  void* out_lp;        // optional 16-bit output (bf16, or fp16 when lp_fp16)
+  long long ld_lp;
+  int lp_fp16;
+  long long lp_lo_off; // > 0: also store the bf16 residual (v - hi) at column offset lp_lo_off
+};
+
+struct GemmParams {
+  int M, N, K;         // K per term, multiple of 64
+  int nterms;
+  int a_koff[3];       // element offset of each term along A's K axis
+  int b_koff[3];
+  GemmEpilogue ep;
+};
+
+namespace gemm {
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int THREADS = 256;
+constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+}  // namespace gemm
+
+__device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], long long row, int col0,
+                                                 int N) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  if (ep.bias != nullptr) {
+    if (ep.bias_per_row) {
+      const float b = __ldg(ep.bias + row);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += b;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += (col0 + i < N) ? __ldg(ep.bias + col0 + i) : 0.f;
+    }
+  }
+  if (ep.scale != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= ep.scale;
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  const bool full = (col0 + 32 <= N);
+  if (ep.out_f32 != nullptr) {
+    float* o = ep.out_f32 + row * ep.ld_f32 + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+      for (int i = 0; i < 32 && col0 + i < N; ++i) o[i] = v[i];
+    }
+  }
+  if (ep.out_lp != nullptr) {
+    uint16_t* o = reinterpret_cast<uint16_t*>(ep.out_lp) + row * ep.ld_lp + col0;
+    uint32_t w[16];
+    if (ep.lp_fp16) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    }
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(o)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    } else {
+      for (int i = 0; i < 32 && col0 + i < N; ++i) o[i] = static_cast<uint16_t>((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFF));
+    }
+    if (ep.lp_lo_off > 0) {   // residual of the bf16 split (only meaningful for bf16 outputs)
+      uint32_t l[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float h0 = __uint_as_float(w[i] << 16), h1 = __uint_as_float(w[i] & 0xFFFF0000u);
+        l[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
+      }
+      uint16_t* ol = o + ep.lp_lo_off;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(ol)[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+      } else {
+        for (int i = 0; i < 32 && col0 + i < N; ++i) ol[i] = static_cast<uint16_t>((i & 1) ? (l[i >> 1] >> 16) : (l[i >> 1] & 0xFFFF));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(gemm::THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using namespace gemm;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int num_tiles = tiles_m * tiles_n;
+  const int kb_per_term = p.K / BK;
+  const int num_kb = kb_per_term * p.nterms;
+
+  if (warp == 0) {
+    if (lane == 0) {                       // ---------------- TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int t = 0; t < p.nterms; ++t) {
+          for (int kb = 0; kb < kb_per_term; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+            tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], p.a_koff[t] + kb * BK, m0);
+            tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], p.b_koff[t] + kb * BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                       // ---------------- MMA issuer
+      constexpr uint32_t idesc = umma_idesc(BM, BN, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tempty_bar[acc], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {                  // ---------------- epilogue warps
+    const int q = warp - 4;                // TMEM lane quadrant == warp % 4
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int acc = lt & 1;
+      mbar_wait(&tfull_bar[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      const long long row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_wait_ld();
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) gemm_store_chunk(p.ep, r, row, col0, p.N);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace parq

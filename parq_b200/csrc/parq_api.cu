@@ -1,0 +1,686 @@
+// libparq_b200.so -- C ABI (include/parq_b200.h) and host-side orchestration of the PARQ decoder
+// hot path on sm_100a.  The library owns no device memory: weights, workspace and outputs are
+// caller-provided raw device pointers; every launch goes to the caller's stream.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/parq_b200.h"
+#include "attn_tc.cuh"
+#include "gemm_tc.cuh"
+#include "project_sample.cuh"
+#include "rowwise.cuh"
+
+namespace parq {
+
+// ------------------------------------------------------------------------------------ errors --
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) return fail(PARQ_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));   \
+  } while (0)
+#define TRY(expr)              \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != PARQ_OK) return _r; \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------- device info --
+struct DeviceInfo {
+  int ok = 0;     // 0 unknown, 1 sm_100, -1 other arch / error
+  int sms = 148;
+};
+static DeviceInfo& device_info() {
+  static thread_local DeviceInfo info;
+  if (info.ok == 0) {
+    int dev = 0, major = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
+      info.ok = (major == 10) ? 1 : -1;
+      info.sms = sms > 0 ? sms : 148;
+    } else {
+      cudaGetLastError();
+      info.ok = -1;
+    }
+  }
+  return info;
+}
+static int require_sm100() {
+  DeviceInfo& d = device_info();
+  if (d.ok != 1) return fail(PARQ_ERR_ARCH, "parq_b200 requires an sm_100 (B200) device; no fallback path exists");
+  return PARQ_OK;
+}
+
+// ------------------------------------------------------------------------------ TMA tensor maps --
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// 2-D map over a row-major 16-bit matrix: `cols` contiguous elements, `rows` rows of pitch ld elements;
+// box = 64 columns (128 bytes, SWIZZLE_128B) x box_rows.
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(PARQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(PARQ_ERR_SHAPE, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PARQ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return PARQ_OK;
+}
+
+// ---------------------------------------------------------------------------------- launchers --
+static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t a_cols, const void* Bw, uint64_t b_rows,
+                       uint64_t b_cols, const GemmParams& gp) {
+  if (gp.K <= 0 || gp.K % gemm::BK != 0) return fail(PARQ_ERR_SHAPE, "GEMM K=%d must be a positive multiple of 64", gp.K);
+  if (gp.nterms < 1 || gp.nterms > 3) return fail(PARQ_ERR_SHAPE, "GEMM nterms=%d out of range", gp.nterms);
+  CUtensorMap tmA, tmB;
+  TRY(make_map(&tmA, A, a_rows, a_cols, a_cols, gemm::BM));
+  TRY(make_map(&tmB, Bw, b_rows, b_cols, b_cols, gemm::BN));
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((gp.M + gemm::BM - 1) / gemm::BM) * ((gp.N + gemm::BN - 1) / gemm::BN);
+  const int grid = tiles < device_info().sms ? tiles : device_info().sms;
+  gemm_tc_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, gp);
+  CUDA_TRY(cudaGetLastError());
+  return PARQ_OK;
+}
+
+struct SplitPlan {
+  int nsplit, tiles_per_split;
+};
+// Key-split heuristic: minimise waves x (tiles per CTA + fixed per-CTA overhead) over the SM count.
+static SplitPlan plan_split(int items, int ntiles, int sms, int force) {
+  SplitPlan best{1, ntiles};
+  if (force > 0) {
+    int tps = (ntiles + force - 1) / force;
+    return SplitPlan{(ntiles + tps - 1) / tps, tps};
+  }
+  double best_cost = 1e30;
+  const int smax = ntiles < 32 ? ntiles : 32;
+  for (int s = 1; s <= smax; ++s) {
+    const int tps = (ntiles + s - 1) / s;
+    const int ns = (ntiles + tps - 1) / tps;
+    const long long ctas = static_cast<long long>(items) * ns;
+    const long long waves = (ctas + sms - 1) / sms;
+    const double cost = static_cast<double>(waves) * (tps + 3.0) + 0.02 * ns;   // small penalty per extra partial
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = SplitPlan{ns, tps};
+    }
+  }
+  return best;
+}
+
+static size_t attn_scratch_bytes(int B, int H, int Nq, int nsplit) {
+  const size_t rows = static_cast<size_t>(B) * H * nsplit * Nq;
+  return align_up(rows * 256 * sizeof(float), 256) + align_up(rows * sizeof(float2), 256);
+}
+
+static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const void* K, uint64_t ldk, const void* Vt,
+                            uint64_t ldv, int B, int H, int Nq, int Nk, bool fp16, void* scratch, size_t scratch_bytes,
+                            __nv_bfloat16* out_split, int force_nsplit) {
+  if (Nq % attn::BQ != 0) return fail(PARQ_ERR_SHAPE, "Nq=%d must be a multiple of 128", Nq);
+  const int ntiles = (Nk + attn::BKEY - 1) / attn::BKEY;
+  const SplitPlan plan = plan_split(B * H * (Nq / attn::BQ), ntiles, device_info().sms, force_nsplit);
+  if (attn_scratch_bytes(B, H, Nq, plan.nsplit) > scratch_bytes)
+    return fail(PARQ_ERR_WORKSPACE, "attention scratch too small: need %zu, have %zu", attn_scratch_bytes(B, H, Nq, plan.nsplit),
+                scratch_bytes);
+  const uint64_t C = static_cast<uint64_t>(H) * 256;
+  CUtensorMap tmQ, tmK, tmV;
+  TRY(make_map(&tmQ, Q, static_cast<uint64_t>(B) * Nq, C, ldq, attn::BQ));
+  TRY(make_map(&tmK, K, static_cast<uint64_t>(B) * Nk, C, ldk, attn::BKEY));
+  TRY(make_map(&tmV, Vt, C, static_cast<uint64_t>(B) * Nk, ldv, 256));
+  AttnParams ap;
+  ap.B = B; ap.H = H; ap.Nq = Nq; ap.Nk = Nk;
+  ap.nsplit = plan.nsplit;
+  ap.tiles_per_split = plan.tiles_per_split;
+  const size_t rows = static_cast<size_t>(B) * H * plan.nsplit * Nq;
+  ap.o_part = reinterpret_cast<float*>(scratch);
+  ap.ml_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(scratch) + align_up(rows * 256 * sizeof(float), 256));
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(plan.nsplit, Nq / attn::BQ, B * H);
+  if (fp16)
+    attn_tc_kernel<true><<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, ap);
+  else
+    attn_tc_kernel<false><<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, ap);
+  CUDA_TRY(cudaGetLastError());
+  attn_combine_kernel<<<B * Nq, 256, 0, st>>>(ap.o_part, ap.ml_part, out_split, H, Nq, plan.nsplit);
+  CUDA_TRY(cudaGetLastError());
+  return PARQ_OK;
+}
+
+// ------------------------------------------------------------------------- packed weight layout --
+struct Packed {
+  // bf16 [rows, 2K] = [hi | lo]
+  size_t pe0, pe2, sa_qk, sa_v, sa_out, ca_q, ca_k, ca_v, ca_out, lin1, lin2, hd1, ctr4, rot4;
+  // fp32 vectors / small matrices
+  size_t pe0_b, pe2_b, sa_qk_b, sa_v_b, sa_out_b, ca_q_b, ca_k_b, ca_v_b, ca_out_b, lin1_b, lin2_b;
+  size_t ln1_g, ln1_b, ln2_g, ln2_b, ln3_g, ln3_b;
+  size_t ctr1_g, ctr1_b, rot1_g, rot1_b, ctr5_g, ctr5_b, rot5_g, rot5_b;
+  size_t cls_w, cls_b, size_w, size_b, ctr8_w, ctr8_b, rot8_w, rot8_b, mean_size, dim_t;
+  size_t lo_flag;
+  size_t total;
+};
+static Packed packed_layout(const ParqShape& s) {
+  Packed p;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 256);
+    return o;
+  };
+  const size_t C = s.C, F = s.ffn, PE = 384;
+  auto mat = [&](size_t rows, size_t K) { return take(rows * 2 * K * 2); };
+  p.pe0 = mat(C, PE);  p.pe2 = mat(C, C);
+  p.sa_qk = mat(2 * C, C);  p.sa_v = mat(C, C);  p.sa_out = mat(C, C);
+  p.ca_q = mat(C, C);  p.ca_k = mat(C, C);  p.ca_v = mat(C, C);  p.ca_out = mat(C, C);
+  p.lin1 = mat(F, C);  p.lin2 = mat(C, F);
+  p.hd1 = mat(2 * C, C);  p.ctr4 = mat(C, C);  p.rot4 = mat(C, C);
+  auto vec = [&](size_t n) { return take(n * 4); };
+  p.pe0_b = vec(C);  p.pe2_b = vec(C);  p.sa_qk_b = vec(2 * C);  p.sa_v_b = vec(C);  p.sa_out_b = vec(C);
+  p.ca_q_b = vec(C);  p.ca_k_b = vec(C);  p.ca_v_b = vec(C);  p.ca_out_b = vec(C);  p.lin1_b = vec(F);  p.lin2_b = vec(C);
+  p.ln1_g = vec(C);  p.ln1_b = vec(C);  p.ln2_g = vec(C);  p.ln2_b = vec(C);  p.ln3_g = vec(C);  p.ln3_b = vec(C);
+  p.ctr1_g = vec(C);  p.ctr1_b = vec(C);  p.rot1_g = vec(C);  p.rot1_b = vec(C);
+  p.ctr5_g = vec(C);  p.ctr5_b = vec(C);  p.rot5_g = vec(C);  p.rot5_b = vec(C);
+  p.cls_w = vec(static_cast<size_t>(s.num_cls) * C);  p.cls_b = vec(s.num_cls);
+  p.size_w = vec(3 * C);  p.size_b = vec(3);  p.ctr8_w = vec(3 * C);  p.ctr8_b = vec(3);
+  p.rot8_w = vec(6 * C);  p.rot8_b = vec(6);
+  p.mean_size = vec(static_cast<size_t>(s.num_cls) * 3);  p.dim_t = vec(128);
+  p.lo_flag = take(4);
+  p.total = off;
+  return p;
+}
+
+// dst[r, k] = bf16(mul*src[r,k]), dst[r, K+k] = bf16 residual; flags a non-zero residual.
+__global__ void split_weight_kernel(const float* __restrict__ src, int rows, int K, float mul, __nv_bfloat16* __restrict__ dst,
+                                    int* __restrict__ lo_flag) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * K) return;
+  const long long r = i / K, k = i % K;
+  const float v = src[i] * mul;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  dst[r * 2 * K + k] = h;
+  dst[r * 2 * K + K + k] = l;
+  if (__bfloat162float(l) != 0.f) atomicOr(lo_flag, 1);
+}
+__global__ void copy_scale_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, float mul) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * mul;
+}
+
+// --------------------------------------------------------------------------- workspace layout --
+struct Workspace {
+  size_t Kc, Vt, T_cl, ref_cur, a_pos, a_peh, pe, x0, a_x, a_xpe, qk_s, vt_s, scratch, a_attn, y, x1, x2, x3, a_x1pe, q_c,
+      a_x2, a_ffn, a_x3, h1, a_h1, h2, gn1, gn2;
+  size_t scratch_bytes, ldv, ldvs, total;
+  SplitPlan cross, self;
+};
+static Workspace workspace_layout(const ParqShape& s, int sms) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 1024);
+    return o;
+  };
+  const size_t C = s.C, R = static_cast<size_t>(s.B) * s.Nq, Nk = static_cast<size_t>(s.T) * s.H * s.W, Nt = s.B * Nk;
+  w.ldv = align_up(Nt, 64);
+  w.ldvs = align_up(R, 64);
+  w.Kc = take(Nt * C * 2);
+  w.Vt = take(C * w.ldv * 2);
+  w.T_cl = take(static_cast<size_t>(s.B) * s.T * 12 * 4);
+  w.ref_cur = take(R * 3 * 4);
+  w.a_pos = take(R * 768 * 2);
+  w.a_peh = take(R * 2 * C * 2);
+  w.pe = take(R * C * 4);
+  w.x0 = take(R * C * 4);
+  w.a_x = take(R * 2 * C * 2);
+  w.a_xpe = take(R * 2 * C * 2);
+  w.qk_s = take(R * 2 * C * 2);
+  w.vt_s = take(C * w.ldvs * 2);
+  const int qtiles = s.Nq / attn::BQ;
+  w.cross = plan_split(s.B * s.heads * qtiles, static_cast<int>((Nk + attn::BKEY - 1) / attn::BKEY), sms, 0);
+  w.self = plan_split(s.B * s.heads * qtiles, (s.Nq + attn::BKEY - 1) / attn::BKEY, sms, 0);
+  const int smax = w.cross.nsplit > w.self.nsplit ? w.cross.nsplit : w.self.nsplit;
+  w.scratch_bytes = attn_scratch_bytes(s.B, s.heads, s.Nq, smax);
+  w.scratch = take(w.scratch_bytes);
+  w.a_attn = take(R * 2 * C * 2);
+  w.y = take(R * C * 4);
+  w.x1 = take(R * C * 4);
+  w.x2 = take(R * C * 4);
+  w.x3 = take(R * C * 4);
+  w.a_x1pe = take(R * 2 * C * 2);
+  w.q_c = take(R * C * 2);
+  w.a_x2 = take(R * 2 * C * 2);
+  w.a_ffn = take(R * 2 * static_cast<size_t>(s.ffn) * 2);
+  w.a_x3 = take(R * 2 * C * 2);
+  w.h1 = take(R * 2 * C * 4);
+  w.a_h1 = take(R * 4 * C * 2);
+  w.h2 = take(R * 2 * C * 4);
+  w.gn1 = take(static_cast<size_t>(s.B) * 2 * GN_BLOCKS * sizeof(double2));
+  w.gn2 = take(static_cast<size_t>(s.B) * 2 * GN_BLOCKS * sizeof(double2));
+  w.total = off;
+  return w;
+}
+
+static int check_shape(const ParqShape* s) {
+  if (s == nullptr) return fail(PARQ_ERR_SHAPE, "null shape");
+  if (s->B < 1 || s->T < 1 || s->H < 1 || s->W < 1 || s->iters < 1) return fail(PARQ_ERR_SHAPE, "non-positive dimension");
+  if (s->C != 1024) return fail(PARQ_ERR_SHAPE, "C=%d: this build supports the reference width C=1024 only", s->C);
+  if (s->heads * 256 != s->C) return fail(PARQ_ERR_SHAPE, "head_dim must be 256 (C=%d, heads=%d)", s->C, s->heads);
+  if (s->Nq % 128 != 0 || s->Nq < 128) return fail(PARQ_ERR_SHAPE, "Nq=%d must be a positive multiple of 128", s->Nq);
+  if (s->ffn % 64 != 0 || s->ffn < 64) return fail(PARQ_ERR_SHAPE, "ffn=%d must be a positive multiple of 64", s->ffn);
+  if (s->num_cls < 1 || s->num_cls > 16) return fail(PARQ_ERR_SHAPE, "num_cls=%d out of range [1,16]", s->num_cls);
+  const long long nt = static_cast<long long>(s->B) * s->T * s->H * s->W;
+  if (nt > 0x7fffffffLL - 512) return fail(PARQ_ERR_SHAPE, "too many image tokens for 32-bit TMA coordinates");
+  return PARQ_OK;
+}
+
+// activation x weight GEMM helper: A = [hi|lo] activations (a_base column offset selects a group),
+// W = packed [hi|lo] weights; 2 terms when the weights are bf16-exact, else 3.
+static void term_offsets(GemmParams& gp, int K, bool w_lo, int a_base) {
+  gp.K = K;
+  gp.nterms = w_lo ? 3 : 2;
+  gp.a_koff[0] = a_base;      gp.b_koff[0] = 0;
+  gp.a_koff[1] = a_base + K;  gp.b_koff[1] = 0;
+  gp.a_koff[2] = a_base;      gp.b_koff[2] = K;
+}
+static GemmEpilogue epilogue_none() {
+  GemmEpilogue e;
+  memset(&e, 0, sizeof(e));
+  e.scale = 1.0f;
+  return e;
+}
+
+static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, const uint8_t* pk, const Packed& P, bool w_lo,
+                      uint8_t* ws, const Workspace& W) {
+  const int C = s.C;
+  const long long Nt = static_cast<long long>(s.B) * s.T * s.H * s.W;
+  // K = tokens Wk^T + bk : A = tokens (single bf16 term), B = Wk [hi|lo]
+  GemmParams gk;
+  memset(&gk, 0, sizeof(gk));
+  gk.M = static_cast<int>(Nt);  gk.N = C;  gk.K = C;
+  gk.nterms = w_lo ? 2 : 1;
+  gk.a_koff[0] = 0; gk.b_koff[0] = 0; gk.a_koff[1] = 0; gk.b_koff[1] = C;
+  gk.ep = epilogue_none();
+  gk.ep.bias = reinterpret_cast<const float*>(pk + P.ca_k_b);
+  gk.ep.out_lp = ws + W.Kc;  gk.ep.ld_lp = C;
+  TRY(launch_gemm(st, tokens, Nt, C, pk + P.ca_k, C, 2 * C, gk));
+  // V^T = Wv tokens^T + bv (per row) : A = Wv [hi|lo], B = tokens
+  GemmParams gv;
+  memset(&gv, 0, sizeof(gv));
+  gv.M = C;  gv.N = static_cast<int>(Nt);  gv.K = C;
+  gv.nterms = w_lo ? 2 : 1;
+  gv.a_koff[0] = 0; gv.b_koff[0] = 0; gv.a_koff[1] = C; gv.b_koff[1] = 0;
+  gv.ep = epilogue_none();
+  gv.ep.bias = reinterpret_cast<const float*>(pk + P.ca_v_b);
+  gv.ep.bias_per_row = 1;
+  gv.ep.out_lp = ws + W.Vt;  gv.ep.ld_lp = static_cast<long long>(W.ldv);
+  TRY(launch_gemm(st, pk + P.ca_v, C, 2 * C, tokens, Nt, C, gv));
+  return PARQ_OK;
+}
+
+}  // namespace parq
+
+using namespace parq;
+
+// =============================================================================== C ABI ========
+extern "C" {
+
+int parq_version(void) { return PARQ_ABI_VERSION; }
+const char* parq_last_error(void) { return g_err; }
+
+size_t parq_packed_bytes(const ParqShape* shape) {
+  if (check_shape(shape) != PARQ_OK) return 0;
+  return packed_layout(*shape).total;
+}
+size_t parq_workspace_bytes(const ParqShape* shape) {
+  if (check_shape(shape) != PARQ_OK) return 0;
+  return workspace_layout(*shape, device_info().sms).total;
+}
+
+int parq_pack_weights(const ParqShape* shape, const ParqWeightsF32* w, void* packed, size_t packed_bytes, void* stream) {
+  TRY(check_shape(shape));
+  if (w == nullptr || packed == nullptr) return fail(PARQ_ERR_SHAPE, "null pointer");
+  const ParqShape& s = *shape;
+  const Packed P = packed_layout(s);
+  if (packed_bytes < P.total) return fail(PARQ_ERR_WORKSPACE, "packed buffer too small: need %zu, have %zu", P.total, packed_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* pk = static_cast<uint8_t*>(packed);
+  int* flag = reinterpret_cast<int*>(pk + P.lo_flag);
+  CUDA_TRY(cudaMemsetAsync(flag, 0, 4, st));
+  const int C = s.C, F = s.ffn;
+  auto split = [&](const float* src, int rows, int K, float mul, size_t dst_off, size_t row0) -> int {
+    if (src == nullptr) return fail(PARQ_ERR_SHAPE, "null weight pointer");
+    const long long n = static_cast<long long>(rows) * K;
+    split_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+        src, rows, K, mul, reinterpret_cast<__nv_bfloat16*>(pk + dst_off) + row0 * 2 * K, flag);
+    return PARQ_OK;
+  };
+  auto vec = [&](const float* src, int n, float mul, size_t dst_off, size_t el0) -> int {
+    if (src == nullptr) return fail(PARQ_ERR_SHAPE, "null weight pointer");
+    copy_scale_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, reinterpret_cast<float*>(pk + dst_off) + el0, n, mul);
+    return PARQ_OK;
+  };
+  const float qs = 0.0625f;   // 1/sqrt(head_dim 256): exact power of two, folded into Wq / bq
+  const long long CC = static_cast<long long>(C) * C;
+  TRY(split(w->pe0_w, C, 384, 1.f, P.pe0, 0));
+  TRY(split(w->pe2_w, C, C, 1.f, P.pe2, 0));
+  TRY(split(w->sa_in_w, C, C, qs, P.sa_qk, 0));
+  TRY(split(w->sa_in_w + CC, C, C, 1.f, P.sa_qk, C));
+  TRY(split(w->sa_in_w + 2 * CC, C, C, 1.f, P.sa_v, 0));
+  TRY(split(w->sa_out_w, C, C, 1.f, P.sa_out, 0));
+  TRY(split(w->ca_in_w, C, C, qs, P.ca_q, 0));
+  TRY(split(w->ca_in_w + CC, C, C, 1.f, P.ca_k, 0));
+  TRY(split(w->ca_in_w + 2 * CC, C, C, 1.f, P.ca_v, 0));
+  TRY(split(w->ca_out_w, C, C, 1.f, P.ca_out, 0));
+  TRY(split(w->lin1_w, F, C, 1.f, P.lin1, 0));
+  TRY(split(w->lin2_w, C, F, 1.f, P.lin2, 0));
+  TRY(split(w->ctr0_w, C, C, 1.f, P.hd1, 0));
+  TRY(split(w->rot0_w, C, C, 1.f, P.hd1, C));
+  TRY(split(w->ctr4_w, C, C, 1.f, P.ctr4, 0));
+  TRY(split(w->rot4_w, C, C, 1.f, P.rot4, 0));
+  TRY(vec(w->pe0_b, C, 1.f, P.pe0_b, 0));
+  TRY(vec(w->pe2_b, C, 1.f, P.pe2_b, 0));
+  TRY(vec(w->sa_in_b, C, qs, P.sa_qk_b, 0));
+  TRY(vec(w->sa_in_b + C, C, 1.f, P.sa_qk_b, C));
+  TRY(vec(w->sa_in_b + 2 * C, C, 1.f, P.sa_v_b, 0));
+  TRY(vec(w->sa_out_b, C, 1.f, P.sa_out_b, 0));
+  TRY(vec(w->ca_in_b, C, qs, P.ca_q_b, 0));
+  TRY(vec(w->ca_in_b + C, C, 1.f, P.ca_k_b, 0));
+  TRY(vec(w->ca_in_b + 2 * C, C, 1.f, P.ca_v_b, 0));
+  TRY(vec(w->ca_out_b, C, 1.f, P.ca_out_b, 0));
+  TRY(vec(w->lin1_b, F, 1.f, P.lin1_b, 0));
+  TRY(vec(w->lin2_b, C, 1.f, P.lin2_b, 0));
+  TRY(vec(w->ln1_g, C, 1.f, P.ln1_g, 0));  TRY(vec(w->ln1_b, C, 1.f, P.ln1_b, 0));
+  TRY(vec(w->ln2_g, C, 1.f, P.ln2_g, 0));  TRY(vec(w->ln2_b, C, 1.f, P.ln2_b, 0));
+  TRY(vec(w->ln3_g, C, 1.f, P.ln3_g, 0));  TRY(vec(w->ln3_b, C, 1.f, P.ln3_b, 0));
+  TRY(vec(w->ctr1_g, C, 1.f, P.ctr1_g, 0));  TRY(vec(w->ctr1_b, C, 1.f, P.ctr1_b, 0));
+  TRY(vec(w->rot1_g, C, 1.f, P.rot1_g, 0));  TRY(vec(w->rot1_b, C, 1.f, P.rot1_b, 0));
+  TRY(vec(w->ctr5_g, C, 1.f, P.ctr5_g, 0));  TRY(vec(w->ctr5_b, C, 1.f, P.ctr5_b, 0));
+  TRY(vec(w->rot5_g, C, 1.f, P.rot5_g, 0));  TRY(vec(w->rot5_b, C, 1.f, P.rot5_b, 0));
+  TRY(vec(w->cls_w, s.num_cls * C, 1.f, P.cls_w, 0));  TRY(vec(w->cls_b, s.num_cls, 1.f, P.cls_b, 0));
+  TRY(vec(w->size_w, 3 * C, 1.f, P.size_w, 0));  TRY(vec(w->size_b, 3, 1.f, P.size_b, 0));
+  TRY(vec(w->ctr8_w, 3 * C, 1.f, P.ctr8_w, 0));  TRY(vec(w->ctr8_b, 3, 1.f, P.ctr8_b, 0));
+  TRY(vec(w->rot8_w, 6 * C, 1.f, P.rot8_w, 0));  TRY(vec(w->rot8_b, 6, 1.f, P.rot8_b, 0));
+  TRY(vec(w->mean_size, s.num_cls * 3, 1.f, P.mean_size, 0));
+  TRY(vec(w->dim_t, 128, 1.f, P.dim_t, 0));
+  CUDA_TRY(cudaGetLastError());
+  int w_lo = 0;
+  CUDA_TRY(cudaMemcpyAsync(&w_lo, flag, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return w_lo != 0 ? 1 : 0;
+}
+
+int parq_pose_chain(const float* T_cp, const float* T_wp, const float* T_wl, float* T_cl, int B, int T, void* stream) {
+  TRY(require_sm100());
+  if (!T_cp || !T_wp || !T_wl || !T_cl || B < 1 || T < 1) return fail(PARQ_ERR_SHAPE, "bad pose_chain arguments");
+  pose_chain_kernel<<<(B * T + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(T_cp, T_wp, T_wl, T_cl, B, T);
+  CUDA_TRY(cudaGetLastError());
+  return PARQ_OK;
+}
+
+static void fill_sample_params(SampleParams& sp, const ParqShape& s) {
+  memset(&sp, 0, sizeof(sp));
+  sp.B = s.B; sp.T = s.T; sp.H = s.H; sp.W = s.W; sp.C = s.C; sp.Nq = s.Nq;
+  for (int i = 0; i < 3; ++i) {
+    // (hi - lo) is evaluated in double from the config floats, then enters the fp32 op as a scalar
+    sp.span[i] = static_cast<float>(static_cast<double>(s.scale[2 * i + 1]) - static_cast<double>(s.scale[2 * i]));
+    sp.lo[i] = s.scale[2 * i];
+  }
+}
+
+int parq_project_sample(const ParqShape* shape, const void* tokens_bf16, const float* ref, const float* T_cl, const float* camera,
+                        float* features, float* center_im, uint8_t* center_valid, float* coord_pos, void* stream) {
+  TRY(require_sm100());
+  TRY(check_shape(shape));
+  if (!tokens_bf16 || !ref || !T_cl || !camera || !features) return fail(PARQ_ERR_SHAPE, "null pointer");
+  SampleParams sp;
+  fill_sample_params(sp, *shape);
+  sp.tokens = static_cast<const __nv_bfloat16*>(tokens_bf16);
+  sp.ref = ref; sp.T_cl = T_cl; sp.camera = camera;
+  sp.feat = features; sp.center_im = center_im; sp.valid = center_valid; sp.coord_pos = coord_pos;
+  project_sample_kernel<<<shape->B * shape->Nq, shape->C / 8, 0, static_cast<cudaStream_t>(stream)>>>(sp);
+  CUDA_TRY(cudaGetLastError());
+  return PARQ_OK;
+}
+
+int parq_gemm_bf16(const void* A, int64_t a_rows, int64_t a_cols, const void* Bw, int64_t b_rows, int64_t b_cols, int M, int N,
+                   int K, int nterms, const int32_t* a_koff, const int32_t* b_koff, const float* bias, int bias_per_row, int relu,
+                   float* out_f32, int64_t ld_f32, void* out_lp, int64_t ld_lp, int lp_fp16, int64_t lp_lo_off, void* stream) {
+  TRY(require_sm100());
+  if (!A || !Bw || M < 1 || N < 1 || !a_koff || !b_koff) return fail(PARQ_ERR_SHAPE, "bad GEMM arguments");
+  GemmParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.M = M; gp.N = N; gp.K = K; gp.nterms = nterms;
+  for (int t = 0; t < nterms && t < 3; ++t) { gp.a_koff[t] = a_koff[t]; gp.b_koff[t] = b_koff[t]; }
+  gp.ep = epilogue_none();
+  gp.ep.bias = bias; gp.ep.bias_per_row = bias_per_row; gp.ep.relu = relu;
+  gp.ep.out_f32 = out_f32; gp.ep.ld_f32 = ld_f32;
+  gp.ep.out_lp = out_lp; gp.ep.ld_lp = ld_lp; gp.ep.lp_fp16 = lp_fp16; gp.ep.lp_lo_off = lp_lo_off;
+  return launch_gemm(static_cast<cudaStream_t>(stream), A, a_rows, a_cols, Bw, b_rows, b_cols, gp);
+}
+
+size_t parq_attention_scratch_bytes(int B, int H, int Nq, int Nk) {
+  const int ntiles = (Nk + attn::BKEY - 1) / attn::BKEY;
+  return attn_scratch_bytes(B, H, Nq, ntiles < 32 ? ntiles : 32);
+}
+
+int parq_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* Vt, int64_t ldv, int B, int H, int Nq, int Nk,
+                   int fp16, void* scratch, size_t scratch_bytes, void* out_split, int force_nsplit, void* stream) {
+  TRY(require_sm100());
+  if (!Q || !K || !Vt || !scratch || !out_split || B < 1 || H < 1 || Nk < 1) return fail(PARQ_ERR_SHAPE, "bad attention arguments");
+  return launch_attention(static_cast<cudaStream_t>(stream), Q, ldq, K, ldk, Vt, ldv, B, H, Nq, Nk, fp16 != 0, scratch, scratch_bytes,
+                          static_cast<__nv_bfloat16*>(out_split), force_nsplit);
+}
+
+int parq_kv_project(const ParqShape* shape, const void* tokens_bf16, const void* packed, void* workspace, size_t workspace_bytes,
+                    uint32_t flags, void* stream) {
+  TRY(require_sm100());
+  TRY(check_shape(shape));
+  if (!tokens_bf16 || !packed || !workspace) return fail(PARQ_ERR_SHAPE, "null pointer");
+  const Workspace W = workspace_layout(*shape, device_info().sms);
+  if (workspace_bytes < W.total) return fail(PARQ_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", W.total, workspace_bytes);
+  const Packed P = packed_layout(*shape);
+  return kv_project(*shape, static_cast<cudaStream_t>(stream), tokens_bf16, static_cast<const uint8_t*>(packed), P,
+                    (flags & PARQ_FLAG_WEIGHT_LO) != 0, static_cast<uint8_t*>(workspace), W);
+}
+
+int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const float* camera, const float* T_cp, const float* T_wp,
+                         const float* T_wl, const float* ref0, const float* forced_refs, const void* packed, void* workspace,
+                         size_t workspace_bytes, const ParqOutputs* out, uint32_t flags, void* stream) {
+  TRY(require_sm100());
+  TRY(check_shape(shape));
+  if (!tokens_bf16 || !camera || !T_cp || !T_wp || !T_wl || !packed || !workspace || !out) return fail(PARQ_ERR_SHAPE, "null pointer");
+  if (!ref0 && !forced_refs) return fail(PARQ_ERR_SHAPE, "need ref0 or forced_refs");
+  if (!out->pred_logits || !out->center_unnormalized || !out->size_unnormalized || !out->ortho6d || !out->sem_cls_prob || !out->coord_pos)
+    return fail(PARQ_ERR_SHAPE, "required output pointer is null");
+  const ParqShape& s = *shape;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Workspace W = workspace_layout(s, device_info().sms);
+  if (workspace_bytes < W.total) return fail(PARQ_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", W.total, workspace_bytes);
+  const Packed P = packed_layout(s);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const bool w_lo = (flags & PARQ_FLAG_WEIGHT_LO) != 0;
+  const int C = s.C, F = s.ffn, R = s.B * s.Nq;
+  auto F32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  auto BF = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  auto PF = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
+
+  // K0: pose chain
+  pose_chain_kernel<<<(s.B * s.T + 127) / 128, 128, 0, st>>>(T_cp, T_wp, T_wl, F32(W.T_cl), s.B, s.T);
+  CUDA_TRY(cudaGetLastError());
+  // K4: hoisted K / V^T projection of the image tokens (iteration invariant)
+  if (!(flags & PARQ_FLAG_SKIP_KV)) TRY(kv_project(s, st, tokens_bf16, pk, P, w_lo, ws, W));
+
+  SampleParams sp;
+  fill_sample_params(sp, s);
+  HeadsParams hp;
+  memset(&hp, 0, sizeof(hp));
+  for (int i = 0; i < 3; ++i) { hp.span[i] = sp.span[i]; hp.lo[i] = sp.lo[i]; }
+
+  for (int it = 0; it < s.iters; ++it) {
+    const float* ref = forced_refs ? forced_refs + static_cast<size_t>(it) * R * 3 : (it == 0 ? ref0 : F32(W.ref_cur));
+    // K2: reference-point positional feature  pe = W2 relu(W1 posemb + b1) + b2
+    posemb_kernel<<<(R * 384 + 255) / 256, 256, 0, st>>>(ref, PF(P.dim_t), BF(W.a_pos), R);
+    CUDA_TRY(cudaGetLastError());
+    {
+      GemmParams g; memset(&g, 0, sizeof(g));
+      g.M = R; g.N = C; term_offsets(g, 384, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.pe0_b); g.ep.relu = 1;
+      g.ep.out_lp = ws + W.a_peh; g.ep.ld_lp = 2 * C; g.ep.lp_lo_off = C;
+      TRY(launch_gemm(st, ws + W.a_pos, R, 768, pk + P.pe0, C, 768, g));
+      memset(&g, 0, sizeof(g));
+      g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.pe2_b);
+      g.ep.out_f32 = F32(W.pe); g.ep.ld_f32 = C;
+      TRY(launch_gemm(st, ws + W.a_peh, R, 2 * C, pk + P.pe2, C, 2 * C, g));
+    }
+    // K1: projection + multi-view bilinear gather (+pe, + operand splits)
+    sp.tokens = static_cast<const __nv_bfloat16*>(tokens_bf16);
+    sp.ref = ref; sp.T_cl = F32(W.T_cl); sp.camera = camera; sp.pe = F32(W.pe);
+    sp.feat = out->features ? out->features + static_cast<size_t>(it) * R * C : F32(W.x0);
+    sp.a_x = BF(W.a_x); sp.a_xpe = BF(W.a_xpe);
+    sp.center_im = out->center_im ? out->center_im + static_cast<size_t>(it) * s.B * s.T * s.Nq * 2 : nullptr;
+    sp.valid = out->center_valid ? out->center_valid + static_cast<size_t>(it) * s.B * s.T * s.Nq : nullptr;
+    sp.coord_pos = nullptr;
+    project_sample_kernel<<<R, C / 8, 0, st>>>(sp);
+    CUDA_TRY(cudaGetLastError());
+    const float* x0 = sp.feat;
+    // K3: self-attention among the queries (fp16 operands), out-projection, residual + LN1
+    {
+      GemmParams g; memset(&g, 0, sizeof(g));
+      g.M = R; g.N = 2 * C; term_offsets(g, C, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.sa_qk_b);
+      g.ep.out_lp = ws + W.qk_s; g.ep.ld_lp = 2 * C; g.ep.lp_fp16 = 1;
+      TRY(launch_gemm(st, ws + W.a_xpe, R, 2 * C, pk + P.sa_qk, 2 * C, 2 * C, g));
+      // V^T = Wv x^T + bv : weights are the A operand, activations the B operand
+      memset(&g, 0, sizeof(g));
+      g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : 2;
+      g.a_koff[0] = 0; g.b_koff[0] = 0; g.a_koff[1] = 0; g.b_koff[1] = C; g.a_koff[2] = C; g.b_koff[2] = 0;
+      g.ep = epilogue_none(); g.ep.bias = PF(P.sa_v_b); g.ep.bias_per_row = 1;
+      g.ep.out_lp = ws + W.vt_s; g.ep.ld_lp = static_cast<long long>(W.ldvs); g.ep.lp_fp16 = 1;
+      TRY(launch_gemm(st, pk + P.sa_v, C, 2 * C, ws + W.a_x, R, 2 * C, g));
+      TRY(launch_attention(st, ws + W.qk_s, 2 * C, ws + W.qk_s + static_cast<size_t>(C) * 2, 2 * C, ws + W.vt_s, W.ldvs, s.B, s.heads,
+                           s.Nq, s.Nq, true, ws + W.scratch, W.scratch_bytes, BF(W.a_attn), W.self.nsplit));
+      memset(&g, 0, sizeof(g));
+      g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.sa_out_b);
+      g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
+      TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.sa_out, C, 2 * C, g));
+      add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(x0, F32(W.y), PF(P.ln1_g), PF(P.ln1_b), F32(W.pe), F32(W.x1), nullptr,
+                                                      BF(W.a_x1pe), R);
+      CUDA_TRY(cudaGetLastError());
+    }
+    // K5: cross-attention over all image tokens (bf16 operands), out-projection, residual + LN2
+    {
+      GemmParams g; memset(&g, 0, sizeof(g));
+      g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.ca_q_b);
+      g.ep.out_lp = ws + W.q_c; g.ep.ld_lp = C;
+      TRY(launch_gemm(st, ws + W.a_x1pe, R, 2 * C, pk + P.ca_q, C, 2 * C, g));
+      const int Nk = s.T * s.H * s.W;
+      TRY(launch_attention(st, ws + W.q_c, C, ws + W.Kc, C, ws + W.Vt, W.ldv, s.B, s.heads, s.Nq, Nk, false, ws + W.scratch,
+                           W.scratch_bytes, BF(W.a_attn), W.cross.nsplit));
+      memset(&g, 0, sizeof(g));
+      g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.ca_out_b);
+      g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
+      TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.ca_out, C, 2 * C, g));
+      add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(F32(W.x1), F32(W.y), PF(P.ln2_g), PF(P.ln2_b), nullptr, F32(W.x2), BF(W.a_x2),
+                                                      nullptr, R);
+      CUDA_TRY(cudaGetLastError());
+    }
+    // K6: FFN, residual + LN3
+    float* x3 = out->decoder_out ? out->decoder_out + static_cast<size_t>(it) * R * C : F32(W.x3);
+    {
+      GemmParams g; memset(&g, 0, sizeof(g));
+      g.M = R; g.N = F; term_offsets(g, C, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.lin1_b); g.ep.relu = 1;
+      g.ep.out_lp = ws + W.a_ffn; g.ep.ld_lp = 2 * F; g.ep.lp_lo_off = F;
+      TRY(launch_gemm(st, ws + W.a_x2, R, 2 * C, pk + P.lin1, F, 2 * C, g));
+      memset(&g, 0, sizeof(g));
+      g.M = R; g.N = C; term_offsets(g, F, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.lin2_b);
+      g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
+      TRY(launch_gemm(st, ws + W.a_ffn, R, 2 * F, pk + P.lin2, C, 2 * F, g));
+      add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(F32(W.x2), F32(W.y), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr, R);
+      CUDA_TRY(cudaGetLastError());
+    }
+    // K7: heads (two hidden layers with per-clip GroupNorm) + box update
+    {
+      GemmParams g; memset(&g, 0, sizeof(g));
+      g.M = R; g.N = 2 * C; term_offsets(g, C, w_lo, 0);
+      g.ep = epilogue_none();
+      g.ep.out_f32 = F32(W.h1); g.ep.ld_f32 = 2 * C;
+      TRY(launch_gemm(st, ws + W.a_x3, R, 2 * C, pk + P.hd1, 2 * C, 2 * C, g));
+      gn_stats_kernel<<<dim3(GN_BLOCKS, 2, s.B), 256, 0, st>>>(F32(W.h1), 2 * C, C, s.Nq, reinterpret_cast<double2*>(ws + W.gn1));
+      gn_apply_kernel<<<R, 256, 0, st>>>(F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1), PF(P.ctr1_g),
+                                         PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1));
+      CUDA_TRY(cudaGetLastError());
+      for (int hd = 0; hd < 2; ++hd) {
+        memset(&g, 0, sizeof(g));
+        g.M = R; g.N = C; term_offsets(g, C, w_lo, hd * 2 * C);
+        g.ep = epilogue_none();
+        g.ep.out_f32 = F32(W.h2) + hd * C; g.ep.ld_f32 = 2 * C;
+        TRY(launch_gemm(st, ws + W.a_h1, R, 4 * C, pk + (hd == 0 ? P.ctr4 : P.rot4), C, 2 * C, g));
+      }
+      gn_stats_kernel<<<dim3(GN_BLOCKS, 2, s.B), 256, 0, st>>>(F32(W.h2), 2 * C, C, s.Nq, reinterpret_cast<double2*>(ws + W.gn2));
+      CUDA_TRY(cudaGetLastError());
+      hp.x = x3; hp.h2 = F32(W.h2); hp.partial = reinterpret_cast<const double2*>(ws + W.gn2);
+      hp.gamma_c = PF(P.ctr5_g); hp.beta_c = PF(P.ctr5_b); hp.gamma_r = PF(P.rot5_g); hp.beta_r = PF(P.rot5_b);
+      hp.w_cls = PF(P.cls_w); hp.b_cls = PF(P.cls_b); hp.w_size = PF(P.size_w); hp.b_size = PF(P.size_b);
+      hp.w_c3 = PF(P.ctr8_w); hp.b_c3 = PF(P.ctr8_b); hp.w_r3 = PF(P.rot8_w); hp.b_r3 = PF(P.rot8_b);
+      hp.ref = ref; hp.mean_size = PF(P.mean_size);
+      const size_t o = static_cast<size_t>(it) * R;
+      hp.logits = out->pred_logits + o * s.num_cls; hp.prob = out->sem_cls_prob + o * s.num_cls;
+      hp.center = out->center_unnormalized + o * 3; hp.size = out->size_unnormalized + o * 3;
+      hp.ortho6d = out->ortho6d + o * 6; hp.coord_pos = out->coord_pos + o * 3;
+      hp.rot = out->rotation ? out->rotation + o * 9 : nullptr;
+      hp.ref_next = F32(W.ref_cur);
+      hp.R = R; hp.Nq = s.Nq; hp.C = C; hp.num_cls = s.num_cls;
+      heads_final_kernel<1024><<<(R + 3) / 4, 128, 0, st>>>(hp);
+      CUDA_TRY(cudaGetLastError());
+    }
+  }
+  return PARQ_OK;
+}
+
+}  // extern "C"

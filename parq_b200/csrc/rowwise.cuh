@@ -1,0 +1,266 @@
+// Row-wise (per query) kernels between the tensor-core GEMMs of one decoder iteration.
+// All statistics, the residual stream and the box epilogue stay in fp32; GEMM inputs are
+// emitted as an exact two-way bf16 split [hi | lo] (see gemm_tc.cuh).
+#pragma once
+#include "ptx.cuh"
+
+namespace parq {
+
+__device__ __forceinline__ void store_split(__nv_bfloat16* hi_ptr, long long lo_off, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi_ptr[0] = h;
+  hi_ptr[lo_off] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pos2posemb3d (reference transformer_parq.py:45-64): 128 sin/cos features per axis, axes
+// concatenated in the order (y, x, z).  out: (R, 2*384) [hi|lo].
+// ---------------------------------------------------------------------------------------------
+__global__ void posemb_kernel(const float* __restrict__ ref, const float* __restrict__ dim_t, __nv_bfloat16* __restrict__ out,
+                              int R) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * 384) return;
+  const int row = idx / 384, j = idx % 384;
+  const int seg = j >> 7, i = j & 127;
+  const int axis = (seg == 0) ? 1 : (seg == 1 ? 0 : 2);
+  const float a = __fdiv_rn(__fmul_rn(ref[row * 3 + axis], 6.283185307179586f), dim_t[i]);
+  const float v = (i & 1) ? cosf(a) : sinf(a);
+  store_split(out + static_cast<long long>(row) * 768 + j, 384, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// x_out = LayerNorm(x_in + y) (post-norm residual, reference transformer_parq.py:375-376, 381-385),
+// eps 1e-5, biased variance.  One warp per row.  Also emits the bf16 split of x_out and, when pe is
+// given, of x_out + pe (the cross-attention query input, transformer_parq.py:377).
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256)
+add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y, const float* __restrict__ gamma,
+              const float* __restrict__ beta, const float* __restrict__ pe, float* __restrict__ x_out,
+              __nv_bfloat16* __restrict__ a_x, __nv_bfloat16* __restrict__ a_xpe, int R) {
+  constexpr int PER = C / 32;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const long long base = static_cast<long long>(row) * C;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(x_in + base + c);
+    const float4 bb = *reinterpret_cast<const float4*>(y + base + c);
+    v[4 * i] = a.x + bb.x; v[4 * i + 1] = a.y + bb.y; v[4 * i + 2] = a.z + bb.z; v[4 * i + 3] = a.w + bb.w;
+    s += v[4 * i] + v[4 * i + 1] + v[4 * i + 2] + v[4 * i + 3];
+  }
+  const float mean = warp_sum(s) / C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; ss += d * d; }
+  const float rstd = 1.f / sqrtf(warp_sum(ss) / C + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    float o[4];
+    o[0] = (v[4 * i] - mean) * rstd * g.x + be.x;
+    o[1] = (v[4 * i + 1] - mean) * rstd * g.y + be.y;
+    o[2] = (v[4 * i + 2] - mean) * rstd * g.z + be.z;
+    o[3] = (v[4 * i + 3] - mean) * rstd * g.w + be.w;
+    *reinterpret_cast<float4*>(x_out + base + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a_x != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) store_split(a_x + static_cast<long long>(row) * (2 * C) + c + k, C, o[k]);
+    }
+    if (a_xpe != nullptr) {
+      const float4 e = *reinterpret_cast<const float4*>(pe + base + c);
+      const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) store_split(a_xpe + static_cast<long long>(row) * (2 * C) + c + k, C, o[k] + ev[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm(1, C) of the 3-layer heads (reference generic_mlp.py:85-86): statistics over the whole
+// (C x Nq) block of one clip.  Two phases, deterministic:
+//   gn_stats_kernel : grid (GN_BLOCKS, groups, B) -> partial (sum, sumsq) in double
+//   gn_apply_kernel : reduces the partials in fixed order, applies affine + ReLU, emits bf16 split
+// h: (B*Nq, ldh) fp32, group g occupies columns [g*C, (g+1)*C).
+// ---------------------------------------------------------------------------------------------
+constexpr int GN_BLOCKS = 16;
+
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ h, int ldh, int C, int Nq, double2* __restrict__ partial) {
+  const int blk = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+  const int rows_per = (Nq + GN_BLOCKS - 1) / GN_BLOCKS;
+  const int r0 = blk * rows_per, r1 = min(Nq, r0 + rows_per);
+  float s = 0.f, ss = 0.f;
+  double ds = 0.0, dss = 0.0;
+  for (int r = r0; r < r1; ++r) {
+    const float* rowp = h + (static_cast<long long>(b) * Nq + r) * ldh + g * C;
+    s = 0.f; ss = 0.f;
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(rowp + c);
+      s += v.x + v.y + v.z + v.w;
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ds += s; dss += ss;
+  }
+  __shared__ double sh[2][256];
+  sh[0][threadIdx.x] = ds;
+  sh[1][threadIdx.x] = dss;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(static_cast<long long>(b) * gridDim.y + g) * GN_BLOCKS + blk] = make_double2(sh[0][0], sh[1][0]);
+}
+
+__device__ __forceinline__ void gn_mean_rstd(const double2* partial, int groups, int b, int g, int C, int Nq, float& mean,
+                                             float& rstd) {
+  double s = 0.0, ss = 0.0;
+  const double2* pp = partial + (static_cast<long long>(b) * groups + g) * GN_BLOCKS;
+  for (int i = 0; i < GN_BLOCKS; ++i) { s += pp[i].x; ss += pp[i].y; }
+  const double n = static_cast<double>(C) * Nq;
+  const double m = s / n;
+  const double var = fmax(ss / n - m * m, 0.0);
+  mean = static_cast<float>(m);
+  rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
+}
+
+// out: (B*Nq, groups * 2C): group g's [hi | lo] at columns [g*2C, (g+1)*2C)
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ h, int ldh, int C, int Nq, int groups, const double2* __restrict__ partial,
+                const float* __restrict__ gamma0, const float* __restrict__ beta0, const float* __restrict__ gamma1,
+                const float* __restrict__ beta1, __nv_bfloat16* __restrict__ out) {
+  const int row = blockIdx.x;           // b*Nq + q
+  const int b = row / Nq;
+  for (int g = 0; g < groups; ++g) {
+    float mean, rstd;
+    gn_mean_rstd(partial, groups, b, g, C, Nq, mean, rstd);
+    const float* gamma = g == 0 ? gamma0 : gamma1;
+    const float* beta = g == 0 ? beta0 : beta1;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float v = h[static_cast<long long>(row) * ldh + g * C + c];
+      const float o = fmaxf((v - mean) * rstd * gamma[c] + beta[c], 0.f);
+      store_split(out + static_cast<long long>(row) * (groups * 2 * C) + g * 2 * C + c, C, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final layer of the four heads + box update, one warp per query
+// (reference transformer_parq.py:236-279, utils/parq_utils.py:90-105):
+//   cls    = Wcls x + b             (10)      size_s = Wsz x + b   (3)
+//   c_off  = Wc3 relu(GN(h2c)) + b  (3)       ortho6d = Wr3 relu(GN(h2r)) + b (6)
+//   coord_pos = denorm(ref);  center = denorm(sigmoid(c_off + inverse_sigmoid(ref)))
+//   prob = softmax(cls);  size = exp(size_s) * mean_size[argmax prob];  ref_next = norm(center)
+// ---------------------------------------------------------------------------------------------
+struct HeadsParams {
+  const float* x;          // (R, C)   decoder-layer output (after LN3)
+  const float* h2;         // (R, 2C)  pre-GroupNorm hidden of layer 2: center | rotation
+  const double2* partial;  // GN partial sums of h2, groups = 2
+  const float *gamma_c, *beta_c, *gamma_r, *beta_r;
+  const float *w_cls, *b_cls, *w_size, *b_size, *w_c3, *b_c3, *w_r3, *b_r3;   // (n, C) row-major, fp32
+  const float* ref;        // (R, 3) normalised reference points of this iteration
+  const float* mean_size;  // (num_cls, 3)
+  float *logits, *center, *size, *ortho6d, *prob, *coord_pos;   // outputs of this iteration
+  float* ref_next;         // (R, 3)
+  float* rot;              // optional (R, 9): rotation matrix of ortho6d (utils/ortho6d_transforms.py:53-66)
+  int R, Nq, C, num_cls;
+  float span[3], lo[3];
+};
+
+template <int C>
+__global__ void __launch_bounds__(128)
+heads_final_kernel(const HeadsParams p) {
+  constexpr int PER = C / 32;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.R) return;
+  const int b = row / p.Nq;
+  float xv[PER], hc[PER], hr[PER];
+  float mean_c, rstd_c, mean_r, rstd_r;
+  gn_mean_rstd(p.partial, 2, b, 0, C, p.Nq, mean_c, rstd_c);
+  gn_mean_rstd(p.partial, 2, b, 1, C, p.Nq, mean_r, rstd_r);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = i * 32 + lane;
+    xv[i] = p.x[static_cast<long long>(row) * C + c];
+    const float a = p.h2[static_cast<long long>(row) * (2 * C) + c];
+    const float r = p.h2[static_cast<long long>(row) * (2 * C) + C + c];
+    hc[i] = fmaxf((a - mean_c) * rstd_c * p.gamma_c[c] + p.beta_c[c], 0.f);
+    hr[i] = fmaxf((r - mean_r) * rstd_r * p.gamma_r[c] + p.beta_r[c], 0.f);
+  }
+  auto dot = [&](const float* w, const float (&v)[PER]) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) s = fmaf(w[i * 32 + lane], v[i], s);
+    return warp_sum(s);
+  };
+  float cls[16];
+  for (int j = 0; j < p.num_cls; ++j) cls[j] = dot(p.w_cls + j * C, xv) + p.b_cls[j];
+  float sz[3], co[3], o6[6];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) sz[j] = dot(p.w_size + j * C, xv) + p.b_size[j];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) co[j] = dot(p.w_c3 + j * C, hc) + p.b_c3[j];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) o6[j] = dot(p.w_r3 + j * C, hr) + p.b_r3[j];
+  if (lane != 0) return;
+
+  // softmax + first-index argmax over the probabilities (torch.argmax tie rule)
+  float mx = cls[0];
+  for (int j = 1; j < p.num_cls; ++j) mx = fmaxf(mx, cls[j]);
+  float e[16], den = 0.f;
+  for (int j = 0; j < p.num_cls; ++j) { e[j] = expf(cls[j] - mx); den += e[j]; }
+  int arg = 0;
+  float best = -1.f;
+  for (int j = 0; j < p.num_cls; ++j) {
+    const float pr = e[j] / den;
+    p.prob[static_cast<long long>(row) * p.num_cls + j] = pr;
+    p.logits[static_cast<long long>(row) * p.num_cls + j] = cls[j];
+    if (pr > best) { best = pr; arg = j; }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float r = p.ref[row * 3 + j];
+    const float rc = fminf(fmaxf(r, 0.f), 1.f);
+    const float inv_sig = logf(fmaxf(rc, 1e-3f) / fmaxf(1.f - rc, 1e-3f));
+    const float sg = 1.f / (1.f + expf(-(co[j] + inv_sig)));
+    const float center = __fadd_rn(__fmul_rn(sg, p.span[j]), p.lo[j]);
+    p.center[row * 3 + j] = center;
+    p.coord_pos[row * 3 + j] = __fadd_rn(__fmul_rn(r, p.span[j]), p.lo[j]);
+    p.size[row * 3 + j] = expf(sz[j]) * p.mean_size[arg * 3 + j];
+    p.ref_next[row * 3 + j] = __fdiv_rn(__fadd_rn(center, -p.lo[j]), p.span[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) p.ortho6d[row * 6 + j] = o6[j];
+  if (p.rot != nullptr) {
+    // Gram-Schmidt: x = a/|a|, z = (x X b)/|x X b|, y = z X x; columns [x y z]; norms clamped at 1e-8
+    const float na = fmaxf(sqrtf(o6[0] * o6[0] + o6[1] * o6[1] + o6[2] * o6[2]), 1e-8f);
+    const float x0 = o6[0] / na, x1 = o6[1] / na, x2 = o6[2] / na;
+    float z0 = x1 * o6[5] - x2 * o6[4], z1 = x2 * o6[3] - x0 * o6[5], z2 = x0 * o6[4] - x1 * o6[3];
+    const float nz = fmaxf(sqrtf(z0 * z0 + z1 * z1 + z2 * z2), 1e-8f);
+    z0 /= nz; z1 /= nz; z2 /= nz;
+    const float y0 = z1 * x2 - z2 * x1, y1 = z2 * x0 - z0 * x2, y2 = z0 * x1 - z1 * x0;
+    float* r = p.rot + static_cast<long long>(row) * 9;
+    r[0] = x0; r[1] = y0; r[2] = z0;
+    r[3] = x1; r[4] = y1; r[5] = z1;
+    r[6] = x2; r[7] = y2; r[8] = z2;
+  }
+}
+
+}  // namespace parq

@@ -1,0 +1,329 @@
+"""Host side of the B200 PARQ decoder: a drop-in for the reference's ``PARQDecoder``.
+
+``PARQDecoderB200`` keeps the reference module's constructor, parameter names
+(the 65 state-dict keys) and ``forward`` signature/outputs
+(/root/reference/model/parq_decoder.py:30-163), so ``parq_lightning.py:58,88``
+can use it unchanged and released checkpoints load with ``strict=True``.  Its
+``forward`` does not execute any PyTorch math of the decoder: it hands raw device
+pointers to ``parq_decoder_forward`` in libparq_b200.so.  PyTorch is used for
+device memory, the current stream and (one-off) parameter storage only.
+
+No fallback: training mode, autograd, CPU tensors or a missing shared library
+raise instead of silently running something else.
+"""
+import ctypes as C
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from . import _lib
+from .inputs import POS_FEATS
+from .wrappers import raw
+
+# BoxProcessor mean sizes (reference utils/parq_utils.py:45-88 over data/average_scan2cad.txt):
+# chair, table, cabinet, trash bin, bookshelf, display, sofa, bathtub, other, non-object.
+MEAN_SIZE = (
+    (0.55067552, 0.84943989, 0.5786128), (1.24506049, 0.66165523, 0.72455878),
+    (0.95658434, 0.99974904, 0.56246602), (0.36641966, 0.45580824, 0.27876528),
+    (1.05132399, 1.3471979, 0.33744382), (0.60740744, 0.4752175, 0.16435075),
+    (1.68820774, 0.76637348, 0.89351734), (0.85305378, 0.43925023, 0.51612006),
+    (1.0, 1.0, 1.0), (1.0, 1.0, 1.0))
+
+OUTPUT_KEYS = (("pred_logits", None), ("center_unnormalized", 3), ("size_unnormalized", 3), ("ortho6d", 6),
+               ("sem_cls_prob", None), ("coord_pos", 3))
+
+
+def default_cfg(num_queries=256, dec_layers=8):
+    """MODEL.DECODER of the reference's config/eval.yaml:37-56 as an attribute namespace."""
+    return SimpleNamespace(
+        DIM_IN=1024, NUM_QUERIES=num_queries, NUM_SEMCLS=9, LOSS_WEIGHT=[5.0, 5.0, 5.0, 1.0], FOR_VIS=False,
+        TRACK_SCALE=[-1.5, 1.5, -2, 1, 0, 2], SHARE_MLP_HEADS=True, MEAN_SIZE_PATH=None, EVAL_TYPE="f1",
+        CONF_THRESH=0.8, ENABLE_NMS=True,
+        TRANSFORMER=SimpleNamespace(DEC_DIM=1024, QUERIES_DIM=1024, DEC_HEADS=4, DEC_LAYERS=dec_layers, DEC_FFN_DIM=768,
+                                    DROPOUT_RATE=0.1, SCALE=[-3, 3, -2, 0.5, 0.25, 5.25], SHARE_WEIGHTS=True))
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dim_t(device):
+    # pos2posemb3d denominators, computed with the reference's own torch expression
+    # (transformer_parq.py:49-50) so the table is bit-identical to the oracle's.
+    d = torch.arange(POS_FEATS, dtype=torch.float32)
+    return (10000 ** (2 * (d // 2) / POS_FEATS)).to(device)
+
+
+def make_shape(B, T, H, W, C_, Nq, heads, ffn, iters, num_cls, scale):
+    s = _lib.ParqShape()
+    s.B, s.T, s.H, s.W, s.C, s.Nq, s.heads, s.ffn, s.iters, s.num_cls = B, T, H, W, C_, Nq, heads, ffn, iters, num_cls
+    for i in range(6):
+        s.scale[i] = float(scale[i])
+    return s
+
+
+class DecoderEngine:
+    """Packed weights + workspace + calls into the C ABI for one device."""
+
+    def __init__(self, state_dict, device, heads=4, num_cls=10, scale=(-3, 3, -2, 0.5, 0.25, 5.25), iters=8):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise NotImplementedError("parq_b200 runs on sm_100 CUDA devices only")
+        self.heads, self.num_cls, self.scale, self.iters = heads, num_cls, tuple(float(x) for x in scale), iters
+        sd = state_dict
+        L = "parq_module.decoder.layers.0."
+        Pn = "parq_module.decoder.position_encoder."
+        Hn = "mlp_heads."
+        self.C = sd[L + "norm1.weight"].shape[0]
+        self.ffn = sd[L + "linear1.weight"].shape[0]
+        self.Nq = sd["refpoint.weight"].shape[0]
+        names = {
+            "pe0_w": Pn + "0.weight", "pe0_b": Pn + "0.bias", "pe2_w": Pn + "2.weight", "pe2_b": Pn + "2.bias",
+            "sa_in_w": L + "self_attn.in_proj_weight", "sa_in_b": L + "self_attn.in_proj_bias",
+            "sa_out_w": L + "self_attn.out_proj.weight", "sa_out_b": L + "self_attn.out_proj.bias",
+            "ca_in_w": L + "multihead_attn.in_proj_weight", "ca_in_b": L + "multihead_attn.in_proj_bias",
+            "ca_out_w": L + "multihead_attn.out_proj.weight", "ca_out_b": L + "multihead_attn.out_proj.bias",
+            "lin1_w": L + "linear1.weight", "lin1_b": L + "linear1.bias", "lin2_w": L + "linear2.weight", "lin2_b": L + "linear2.bias",
+            "ln1_g": L + "norm1.weight", "ln1_b": L + "norm1.bias", "ln2_g": L + "norm2.weight", "ln2_b": L + "norm2.bias",
+            "ln3_g": L + "norm3.weight", "ln3_b": L + "norm3.bias",
+            "cls_w": Hn + "sem_cls_head.layers.0.weight", "cls_b": Hn + "sem_cls_head.layers.0.bias",
+            "ctr0_w": Hn + "center_head.layers.0.weight", "ctr1_g": Hn + "center_head.layers.1.weight",
+            "ctr1_b": Hn + "center_head.layers.1.bias", "ctr4_w": Hn + "center_head.layers.4.weight",
+            "ctr5_g": Hn + "center_head.layers.5.weight", "ctr5_b": Hn + "center_head.layers.5.bias",
+            "ctr8_w": Hn + "center_head.layers.8.weight", "ctr8_b": Hn + "center_head.layers.8.bias",
+            "size_w": Hn + "size_head.layers.0.weight", "size_b": Hn + "size_head.layers.0.bias",
+            "rot0_w": Hn + "rotation_head.layers.0.weight", "rot1_g": Hn + "rotation_head.layers.1.weight",
+            "rot1_b": Hn + "rotation_head.layers.1.bias", "rot4_w": Hn + "rotation_head.layers.4.weight",
+            "rot5_g": Hn + "rotation_head.layers.5.weight", "rot5_b": Hn + "rotation_head.layers.5.bias",
+            "rot8_w": Hn + "rotation_head.layers.8.weight", "rot8_b": Hn + "rotation_head.layers.8.bias",
+        }
+        keep = {}
+        w = _lib.ParqWeightsF32()
+        for field, key in names.items():
+            t = sd[key].detach().to(self.device, torch.float32).contiguous()
+            keep[field] = t
+            setattr(w, field, t.data_ptr())
+        keep["mean_size"] = torch.tensor(MEAN_SIZE, dtype=torch.float64)[: num_cls].float().to(self.device).contiguous()
+        keep["dim_t"] = _dim_t(self.device).contiguous()
+        w.mean_size = keep["mean_size"].data_ptr()
+        w.dim_t = keep["dim_t"].data_ptr()
+        self.refpoint = sd["refpoint.weight"].detach().to(self.device, torch.float32).contiguous()
+        shape = self._shape(1, 1, 1, 1)
+        nbytes = self.lib.parq_packed_bytes(C.byref(shape))
+        if nbytes == 0:
+            raise _lib.ParqError("parq_packed_bytes: " + self.lib.parq_last_error().decode())
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.check(self.lib.parq_pack_weights(C.byref(shape), C.byref(w), _ptr(self.packed), nbytes, _stream()),
+                            "parq_pack_weights")
+        self.weight_lo = bool(rc)
+        self._ws = None
+        self._ws_key = None
+        del keep
+
+    def _shape(self, B, T, H, W):
+        return make_shape(B, T, H, W, self.C, self.Nq, self.heads, self.ffn, self.iters, self.num_cls, self.scale)
+
+    def _workspace(self, shape, key):
+        if self._ws_key != key:
+            nbytes = self.lib.parq_workspace_bytes(C.byref(shape))
+            if nbytes == 0:
+                raise _lib.ParqError("parq_workspace_bytes: " + self.lib.parq_last_error().decode())
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_key = key
+        return self._ws
+
+    @property
+    def flags(self):
+        return _lib.PARQ_FLAG_WEIGHT_LO if self.weight_lo else 0
+
+    def forward(self, tokens, camera, T_cp, T_wp, T_wl, H, W, forced_refs=None, ref0=None, debug=False, skip_kv=False):
+        """tokens (B, T*H*W, C) bf16 (fp32 is rounded to bf16); camera (B,T,6); poses (B,T,12)/(B,1,12) fp32.
+        Returns a dict of stacked per-iteration tensors (iters, B, Nq, n)."""
+        if tokens.device != self.device:
+            raise NotImplementedError("tokens must live on %s (no host or cross-device fallback)" % self.device)
+        B, T = T_cp.shape[0], T_cp.shape[1]
+        if tokens.dim() != 3 or tokens.shape[0] != B or tokens.shape[1] != T * H * W or tokens.shape[2] != self.C:
+            raise ValueError("tokens must be (B=%d, T*H*W=%d, C=%d), got %s" % (B, T * H * W, self.C, tuple(tokens.shape)))
+        if tokens.dtype != torch.bfloat16:
+            tokens = tokens.to(torch.bfloat16)
+        tokens = tokens.contiguous()
+        f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+        camera, T_cp, T_wp, T_wl = f32(camera), f32(T_cp), f32(T_wp), f32(T_wl)
+        if T_wl.shape[1] != 1:
+            raise ValueError("T_world_local must have shape (B, 1, 12)")
+        shape = self._shape(B, T, H, W)
+        ws = self._workspace(shape, (B, T, H, W))
+        it, Nq, dev = self.iters, self.Nq, self.device
+        outs = {k: torch.empty(it, B, Nq, n if n else self.num_cls, dtype=torch.float32, device=dev) for k, n in OUTPUT_KEYS}
+        po = _lib.ParqOutputs()
+        for k in outs:
+            setattr(po, k, outs[k].data_ptr())
+        if debug:
+            outs["rotation"] = torch.empty(it, B, Nq, 3, 3, dtype=torch.float32, device=dev)
+            outs["center_im"] = torch.empty(it, B, T, Nq, 2, dtype=torch.float32, device=dev)
+            outs["center_valid"] = torch.empty(it, B, T, Nq, dtype=torch.uint8, device=dev)
+            outs["features"] = torch.empty(it, B, Nq, self.C, dtype=torch.float32, device=dev)
+            outs["decoder_out"] = torch.empty(it, B, Nq, self.C, dtype=torch.float32, device=dev)
+            for k in ("rotation", "center_im", "center_valid", "features", "decoder_out"):
+                setattr(po, k, outs[k].data_ptr())
+        if ref0 is None:
+            ref0 = self.refpoint.sigmoid().unsqueeze(0).repeat(B, 1, 1)
+        ref0 = f32(ref0)
+        fr = f32(forced_refs) if forced_refs is not None else None
+        if fr is not None and tuple(fr.shape) != (it, B, Nq, 3):
+            raise ValueError("forced_refs must be (iters, B, Nq, 3)")
+        flags = self.flags | (_lib.PARQ_FLAG_SKIP_KV if skip_kv else 0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.parq_decoder_forward(C.byref(shape), _ptr(tokens), _ptr(camera), _ptr(T_cp), _ptr(T_wp), _ptr(T_wl),
+                                                     _ptr(ref0), _ptr(fr), _ptr(self.packed), _ptr(ws), ws.numel(), C.byref(po),
+                                                     flags, _stream()), "parq_decoder_forward")
+        # keep inputs alive until the stream has consumed them
+        for t in (tokens, camera, T_cp, T_wp, T_wl, ref0, fr):
+            if t is not None:
+                t.record_stream(torch.cuda.current_stream())
+        if "center_valid" in outs:
+            outs["center_valid"] = outs["center_valid"].bool()
+        return outs
+
+    def kv_project(self, tokens, B, T, H, W):
+        shape = self._shape(B, T, H, W)
+        ws = self._workspace(shape, (B, T, H, W))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.parq_kv_project(C.byref(shape), _ptr(tokens), _ptr(self.packed), _ptr(ws), ws.numel(), self.flags,
+                                                _stream()), "parq_kv_project")
+
+
+def pose_chain(T_cp, T_wp, T_wl):
+    """T_camera_local (B,T,12) on the GPU with the oracle's rounding (reference transformer_parq.py:298-300)."""
+    lib = _lib.load()
+    T_cp, T_wp, T_wl = (raw(t).float().contiguous() for t in (T_cp, T_wp, T_wl))
+    B, T = T_cp.shape[:2]
+    out = torch.empty_like(T_cp)
+    with torch.cuda.device(T_cp.device):
+        _lib.check(lib.parq_pose_chain(_ptr(T_cp), _ptr(T_wp), _ptr(T_wl), _ptr(out), B, T, _stream()), "parq_pose_chain")
+    return out
+
+
+def project(tokens, query_pos, T_camera_local, camera, H, W):
+    """Drop-in for ``model.transformer_parq.project`` (:129-161) on bf16 tokens (B, T*H*W, C):
+    ``query_pos`` (B,Nq,3) are metric points in the local frame.  Returns
+    (features (B,Nq,C), center_im (B,T,Nq,2), center_valid (B,T,Nq) bool)."""
+    lib = _lib.load()
+    T_cl = raw(T_camera_local).float().contiguous()
+    cam = raw(camera).float().contiguous()
+    B, T = T_cl.shape[:2]
+    Nq, Cc = query_pos.shape[1], tokens.shape[-1]
+    if tokens.dtype != torch.bfloat16:
+        tokens = tokens.to(torch.bfloat16)
+    tokens = tokens.contiguous()
+    q = query_pos.float().contiguous()
+    # identity "denormalisation": p*1 + 0 is exact, so metric points pass through unchanged
+    shape = make_shape(B, T, H, W, Cc, Nq, Cc // 256, 768, 1, 10, (0, 1, 0, 1, 0, 1))
+    dev = tokens.device
+    feat = torch.empty(B, Nq, Cc, dtype=torch.float32, device=dev)
+    cim = torch.empty(B, T, Nq, 2, dtype=torch.float32, device=dev)
+    val = torch.empty(B, T, Nq, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.parq_project_sample(C.byref(shape), _ptr(tokens), _ptr(q), _ptr(T_cl), _ptr(cam), _ptr(feat), _ptr(cim),
+                                           _ptr(val), None, _stream()), "parq_project_sample")
+    return feat, cim, val.bool()
+
+
+class _Params(nn.Module):
+    """Parameter container; never called."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container")
+
+
+def _head(dim, out, hidden, dropout):
+    """Same layer sequence as the reference's GenericMLP with use_conv / norm 'ln'
+    (generic_mlp.py:94-110): indices 0,1,4,5,8 carry the parameters."""
+    layers, prev = [], dim
+    for h in hidden:
+        layers += [nn.Conv1d(prev, h, 1, bias=False), nn.GroupNorm(1, h), nn.ReLU(), nn.Dropout(p=dropout)]
+        prev = h
+    layers.append(nn.Conv1d(prev, out, 1, bias=True))
+    m = _Params()
+    m.layers = nn.Sequential(*layers)
+    return m
+
+
+class PARQDecoderB200(nn.Module):
+    """B200 drop-in for the reference ``PARQDecoder`` (inference only)."""
+
+    def __init__(self, cfg=None):
+        super().__init__()
+        cfg = cfg or default_cfg()
+        tr = cfg.TRANSFORMER
+        self.dim_in, self.num_queries, self.num_semcls = cfg.DIM_IN, cfg.NUM_QUERIES, cfg.NUM_SEMCLS
+        self.for_vis, self.track_scale, self.enable_nms = cfg.FOR_VIS, cfg.TRACK_SCALE, cfg.ENABLE_NMS
+        if not cfg.SHARE_MLP_HEADS or not tr.SHARE_WEIGHTS:
+            raise NotImplementedError("only SHARE_MLP_HEADS=True / SHARE_WEIGHTS=True (the shipped configs) are supported")
+        if tr.DEC_DIM != cfg.DIM_IN or tr.QUERIES_DIM != tr.DEC_DIM:
+            raise NotImplementedError("DEC_DIM, QUERIES_DIM and DIM_IN must agree")
+        D = tr.DEC_DIM
+        self.heads, self.iters, self.scale = tr.DEC_HEADS, tr.DEC_LAYERS, list(tr.SCALE)
+        self.mlp_heads = nn.ModuleDict([
+            ("sem_cls_head", _head(D, cfg.NUM_SEMCLS + 1, [], 0.3)),
+            ("center_head", _head(D, 3, [D, D], 0.0)),
+            ("size_head", _head(D, 3, [], 0.3)),
+            ("rotation_head", _head(D, 6, [D, D], 0.0)),
+        ])
+        layer = _Params()
+        layer.self_attn = nn.MultiheadAttention(D, tr.DEC_HEADS, dropout=tr.DROPOUT_RATE)
+        layer.multihead_attn = nn.MultiheadAttention(D, tr.DEC_HEADS, dropout=tr.DROPOUT_RATE)
+        layer.linear1 = nn.Linear(D, tr.DEC_FFN_DIM)
+        layer.linear2 = nn.Linear(tr.DEC_FFN_DIM, D)
+        layer.norm1, layer.norm2, layer.norm3 = nn.LayerNorm(D), nn.LayerNorm(D), nn.LayerNorm(D)
+        dec = _Params()
+        dec.layers = nn.ModuleList([layer])
+        dec.norm = nn.LayerNorm(D)        # present in checkpoints, never applied (transformer_parq.py:174)
+        dec.position_encoder = nn.Sequential(nn.Linear(3 * POS_FEATS, D), nn.ReLU(), nn.Linear(D, D))
+        self.parq_module = _Params()
+        self.parq_module.decoder = dec
+        for p in self.parq_module.parameters():          # Transformer._reset_parameters, :89-92
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        dec.mlp_heads = self.mlp_heads                    # alias -> duplicate state-dict keys (parq_decoder.py:66)
+        self.refpoint = nn.Embedding(cfg.NUM_QUERIES, 3)
+        self.feature_hw = None       # optional (H, W) hint: avoids the camera D2H read of transformer_parq.py:301
+        self._engine = None
+        self._engine_key = None
+
+    def _get_engine(self, device):
+        params = list(self.parameters())
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._engine is None or self._engine_key != key:
+            self._engine = DecoderEngine(self.state_dict(), device, heads=self.heads, num_cls=self.num_semcls + 1,
+                                         scale=self.scale, iters=self.iters)
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, intput_tokens, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local):
+        if self.training:
+            raise NotImplementedError("PARQDecoderB200 is inference-only: call .eval() (no training fallback exists)")
+        if torch.is_grad_enabled() and (intput_tokens.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # inference library: gradients cannot flow through the C ABI
+            if intput_tokens.requires_grad:
+                raise NotImplementedError("autograd through PARQDecoderB200 is not supported; wrap the call in torch.no_grad()")
+        if intput_tokens.device.type != "cuda":
+            raise NotImplementedError("PARQDecoderB200 needs CUDA tensors on an sm_100 device (no CPU fallback)")
+        cam = raw(camera)
+        if self.feature_hw is not None:
+            H, W = self.feature_hw
+        else:
+            wh = cam[0, 0, :2].tolist()       # same device->host read as the reference (transformer_parq.py:301)
+            W, H = int(wh[0]), int(wh[1])
+        eng = self._get_engine(intput_tokens.device)
+        with torch.no_grad():
+            outs = eng.forward(intput_tokens, cam, raw(T_camera_pseudoCam), raw(T_world_pseudoCam), raw(T_world_local), H, W)
+        return [{k: outs[k][i] for k, _ in OUTPUT_KEYS} for i in range(self.iters)]

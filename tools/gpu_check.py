@@ -1,0 +1,190 @@
+"""Stage-by-stage numerical bring-up of the CUDA kernels on a B200 (developer tool).
+
+    python tools/gpu_check.py <stage> [...]     stages: gemm attn sample forward
+
+Each stage prints PASS/FAIL lines with the measured error; run every stage in its own
+process (tools/gpu_check.sh) under `timeout`, so that a deadlocked kernel cannot hang the box.
+The formal parity tests live in tests/ (pytest -m gpu); this tool checks the same things with more
+diagnostics.  It uses oracle/ only as the checker.
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+
+from parq_b200 import _lib, inputs as I
+from parq_b200.decoder import DecoderEngine, _ptr, _stream, pose_chain, project
+
+dev = torch.device("cuda:0")
+ok_all = True
+
+
+def report(name, err, tol):
+    global ok_all
+    good = bool(err <= tol)
+    ok_all &= good
+    print("%s  %-60s err=%.3e tol=%.1e" % ("PASS" if good else "FAIL", name, err, tol), flush=True)
+
+
+def relerr(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp(min=1e-30)).item()
+
+
+def gemm(A, Bw, M, N, K, nterms=1, a_koff=(0, 0, 0), b_koff=(0, 0, 0), bias=None, bias_per_row=0, relu=0,
+         want_f32=True, lp=None, lp_ld=None, lp_fp16=0, lo_off=0):
+    lib = _lib.load()
+    out = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev) if want_f32 else None
+    ak = (C.c_int32 * 3)(*a_koff)
+    bk = (C.c_int32 * 3)(*b_koff)
+    _lib.check(lib.parq_gemm_bf16(_ptr(A), A.shape[0], A.shape[1], _ptr(Bw), Bw.shape[0], Bw.shape[1], M, N, K, nterms, ak, bk,
+                                  _ptr(bias), bias_per_row, relu, _ptr(out), N, _ptr(lp), lp_ld or 0, lp_fp16, lo_off, _stream()),
+               "parq_gemm_bf16")
+    torch.cuda.synchronize()
+    return out
+
+
+def stage_gemm():
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for (M, N, K) in ((128, 256, 64), (256, 512, 128), (300, 768, 1024), (4096, 1024, 1024)):
+        A = torch.randn(M, K, generator=g).to(dev).bfloat16()
+        Bw = torch.randn(N, K, generator=g).to(dev).bfloat16()
+        out = gemm(A, Bw, M, N, K)
+        ref = A.float() @ Bw.float().t()
+        report("gemm %dx%dx%d plain" % (M, N, K), relerr(out, ref), 1e-5)
+    # two-term split + bias + relu + fp32 and split-bf16 outputs
+    M, N, K = 384, 1024, 384
+    x = torch.randn(M, K, generator=g).to(dev)
+    W = I.bf16_round(torch.randn(N, K, generator=g) * 0.05).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    A = torch.cat([hi, lo], 1).contiguous()
+    Bw = torch.cat([W.bfloat16(), torch.zeros_like(W).bfloat16()], 1).contiguous()
+    lp = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device=dev)
+    out = gemm(A, Bw, M, N, K, nterms=2, a_koff=(0, K, 0), b_koff=(0, 0, K), bias=bias, relu=1, lp=lp, lp_ld=2 * N, lo_off=N)
+    ref = torch.relu((x.double() @ W.double().t()).float() + bias)
+    report("gemm 2-term split + bias + relu (fp32 out)", relerr(out, ref), 3e-5)
+    report("gemm split-bf16 output hi+lo", relerr(lp[:, :N].float() + lp[:, N:].float(), ref), 3e-5)
+    # transposed product with per-row bias, fp16 output, ragged N and padded ld
+    M, N, K = 1024, 1000, 1024
+    Wv = I.bf16_round(torch.randn(M, K, generator=g) * 0.05).to(dev).bfloat16()
+    X = torch.randn(N, K, generator=g).to(dev).bfloat16()
+    bias = torch.randn(M, generator=g).to(dev)
+    ld = 1024
+    lp = torch.zeros(M, ld, dtype=torch.float16, device=dev)
+    gemm(Wv, X, M, N, K, bias=bias, bias_per_row=1, want_f32=False, lp=lp, lp_ld=ld, lp_fp16=1)
+    ref = Wv.float() @ X.float().t() + bias[:, None]
+    report("gemm V^T form: row bias, fp16 out, ragged N", relerr(lp[:, :N].float(), ref), 1e-3)
+    report("gemm V^T form: padding untouched", lp[:, N:].abs().max().item(), 0.0)
+
+
+def attention_ref(Q, K, V):
+    # Q (B,H,Nq,dh) pre-scaled, K/V (B,H,Nk,dh): fp32 softmax attention
+    s = torch.einsum("bhqd,bhkd->bhqk", Q.double(), K.double())
+    p = torch.softmax(s, -1)
+    return torch.einsum("bhqk,bhkd->bhqd", p, V.double()).float()
+
+
+def run_attention(B, H, Nq, Nk, fp16, nsplit, g, scale=1.0, spike=False):
+    lib = _lib.load()
+    dt = torch.float16 if fp16 else torch.bfloat16
+    Cc = H * 256
+    Q = (torch.randn(B * Nq, Cc, generator=g) * scale / 16).to(dev).to(dt)
+    K = torch.randn(B * Nk, Cc, generator=g).to(dev).to(dt)
+    V = torch.randn(B * Nk, Cc, generator=g).to(dev).to(dt)
+    if spike:   # a few huge keys late in the sequence force the lazy-rescale path
+        K[Nk - 3::Nk] *= 12
+    ldv = (B * Nk + 63) // 64 * 64
+    Vt = torch.zeros(Cc, ldv, dtype=dt, device=dev)
+    Vt[:, : B * Nk] = V.t()
+    nb = lib.parq_attention_scratch_bytes(B, H, Nq, Nk)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+    out = torch.zeros(B * Nq, 2 * Cc, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.parq_attention(_ptr(Q), Cc, _ptr(K), Cc, _ptr(Vt), ldv, B, H, Nq, Nk, int(fp16), _ptr(scratch), nb, _ptr(out),
+                                  nsplit, _stream()), "parq_attention")
+    torch.cuda.synchronize()
+    got = (out[:, :Cc].float() + out[:, Cc:].float()).view(B, Nq, H, 256).permute(0, 2, 1, 3)
+    ref = attention_ref(Q.float().view(B, Nq, H, 256).permute(0, 2, 1, 3), K.float().view(B, Nk, H, 256).permute(0, 2, 1, 3),
+                        V.float().view(B, Nk, H, 256).permute(0, 2, 1, 3))
+    return relerr(got, ref)
+
+
+def stage_attn():
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for (B, H, Nq, Nk, fp16, ns) in ((1, 1, 128, 128, False, 1), (1, 1, 128, 256, False, 1), (1, 1, 128, 384, False, 1),
+                                     (1, 1, 128, 384, False, 3), (1, 2, 256, 420, False, 2), (2, 4, 256, 1000, False, 0),
+                                     (2, 4, 256, 256, True, 1), (1, 4, 128, 128, True, 1)):
+        e = run_attention(B, H, Nq, Nk, fp16, ns, g)
+        report("attn B%d H%d Nq%d Nk%d %s nsplit=%d" % (B, H, Nq, Nk, "fp16" if fp16 else "bf16", ns), e, 2e-3 if fp16 else 1e-2)
+    e = run_attention(1, 2, 128, 1024, False, 1, g, scale=4.0, spike=True)
+    report("attn peaked scores + spikes (lazy rescale path)", e, 1e-2)
+
+
+def stage_sample():
+    from oracle import parq_oracle as O
+    for (B, T, H, W, Nq, seed, wild) in ((2, 3, 12, 16, 256, 0, False), (1, 2, 10, 14, 128, 1, True), (1, 8, 60, 80, 256, 2, False),
+                                         (2, 33, 6, 8, 128, 3, True)):
+        tokens = I.make_tokens(B, T, H, W, seed=seed)
+        cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed, wild=wild)
+        Tcl_ref = O.camera_from_local(Tcp._data.numpy(), Twp._data.numpy(), Twl._data.numpy())
+        Tcl = pose_chain(Tcp._data.to(dev), Twp._data.to(dev), Twl._data.to(dev))
+        same = np.array_equal(Tcl.cpu().numpy().view(np.uint32), Tcl_ref.view(np.uint32))
+        report("pose_chain bit-exact B%d T%d" % (B, T), 0.0 if same else 1.0, 0.0)
+        gq = torch.Generator().manual_seed(seed)
+        lo = torch.tensor([-3.0, -2.0, 0.25])
+        span = torch.tensor([6.0, 2.5, 5.0])
+        pts = torch.rand(B, Nq, 3, generator=gq) * span + lo
+        f_ref, ci_ref, cv_ref = O.project_sample(tokens, pts, Tcl_ref, cam._data.numpy(), H, W)
+        feat, cim, val = project(tokens.to(dev), pts.to(dev), Tcl, cam._data.to(dev), H, W)
+        torch.cuda.synchronize()
+        same = np.array_equal(cim.cpu().numpy().view(np.uint32), ci_ref.numpy().view(np.uint32))
+        nbad = int((cim.cpu() != ci_ref).sum())
+        report("center_im bit-exact B%d T%d %dx%d (%d mismatches)" % (B, T, H, W, nbad), 0.0 if same else 1.0, 0.0)
+        report("center_valid equal (valid frac %.2f)" % cv_ref.float().mean().item(), float((val.cpu() != cv_ref).sum()), 0.0)
+        report("sampled features", relerr(feat.cpu(), f_ref), 1e-5)
+
+
+def stage_forward():
+    from oracle import parq_oracle as O
+    for (B, T, H, W, Nq, seed, wild) in ((2, 3, 12, 16, 256, 0, False), (1, 2, 10, 14, 128, 1, True)):
+        sd = I.make_weights(seed, Nq)
+        tokens = I.make_tokens(B, T, H, W, seed=seed)
+        cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed, wild=wild)
+        outs, auxs = O.decoder_forward(tokens, cam._data, Tcp._data, Twp._data, Twl._data, sd, return_aux=True)
+        refs = O.refs_from_outputs(outs, sd)
+        eng = DecoderEngine(sd, dev)
+        t0 = time.time()
+        got = eng.forward(tokens.to(dev), cam._data.to(dev), Tcp._data.to(dev), Twp._data.to(dev), Twl._data.to(dev), H, W,
+                          forced_refs=refs.to(dev), debug=True)
+        torch.cuda.synchronize()
+        print("forward call %.1f ms (weight_lo=%s)" % ((time.time() - t0) * 1e3, eng.weight_lo))
+        for it in (0, 1, 7):
+            tag = "B%d it%d " % (B, it)
+            cim = got["center_im"][it].cpu()
+            report(tag + "center_im bit-exact", float((cim != auxs[it]["center_im"]).sum()), 0.0)
+            report(tag + "center_valid", float((got["center_valid"][it].cpu() != auxs[it]["center_valid"]).sum()), 0.0)
+            report(tag + "features", relerr(got["features"][it].cpu(), auxs[it]["features"]), 1e-5)
+            report(tag + "decoder_out", relerr(got["decoder_out"][it].cpu(), auxs[it]["decoder_out"]), 1e-3)
+            for k in ("pred_logits", "center_unnormalized", "size_unnormalized", "ortho6d", "sem_cls_prob", "coord_pos"):
+                report(tag + k, relerr(got[k][it].cpu(), outs[it][k]), 0.0 if k == "coord_pos" else 1e-3)
+            Rm = O.rotation_from_ortho6d(outs[it]["ortho6d"].reshape(-1, 6)).view(B, Nq, 3, 3)
+            report(tag + "rotation", relerr(got["rotation"][it].cpu(), Rm), 2e-3)
+        free = eng.forward(tokens.to(dev), cam._data.to(dev), Tcp._data.to(dev), Twp._data.to(dev), Twl._data.to(dev), H, W)
+        outs_free = O.decoder_forward(tokens, cam._data, Tcp._data, Twp._data, Twl._data, sd)
+        for it in (0, 3, 7):
+            print("free-running it%d center relerr %.2e" % (it, relerr(free["center_unnormalized"][it].cpu(),
+                                                                        outs_free[it]["center_unnormalized"])))
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0), flush=True)
+    for st in sys.argv[1:]:
+        print("==== stage", st, flush=True)
+        globals()["stage_" + st]()
+    print("ALL PASS" if ok_all else "SOME FAILED")
+    sys.exit(0 if ok_all else 1)
