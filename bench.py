@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the PARQ decoder hot path (BASELINE.json config 2) -- see DESIGN.md "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the whole decoder (hoisted K/V projection + 8 recurrent iterations) over one batch of
+16 synthetic clips per GPU (8 views of 60x80 tokens x 1024 channels, 256 queries).  Prints ONE JSON line.
+`--impl reference` times the CPU port of the reference's own decoder (oracle/parq_oracle.py, reference op
+order incl. the per-iteration K/V re-projection) on the host cores for a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "decoder clips/sec"
+UNIT = "clips/s"
+CFG = dict(clips_per_gpu=16, views=8, H=60, W=80, C=1024, queries=256, iterations=8, heads=4, ffn=768)
+
+
+def workload_config(n_gpus):
+    c = dict(CFG)
+    c["workload"] = ("PARQ decoder-only bf16: batch 16 clips x 8 views per GPU, 256 queries, 8 iterations, "
+                     "precomputed synthetic FPN features (BASELINE.json configs[1])")
+    c["global_clips"] = CFG["clips_per_gpu"] * n_gpus
+    c["parallelism"] = "clips sharded over %d GPU(s), no collective on the hot path" % n_gpus
+    c["l2"] = "inputs larger than L2: 1.26 GB tokens + 2.5 GB K/V streamed every step (L2 = 126 MB); no explicit flush"
+    return c
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ reference arm --
+def oracle_clip_inputs(seed=100):
+    from parq_b200 import inputs as I
+    sd = I.make_weights(0, CFG["queries"])
+    tokens = I.make_tokens(1, CFG["views"], CFG["H"], CFG["W"], seed=seed)
+    cam, Tcp, Twp, Twl = I.make_geometry(1, CFG["views"], CFG["H"], CFG["W"], seed=seed)
+    return sd, tokens, cam._data, Tcp._data, Twp._data, Twl._data
+
+
+def time_oracle(iters, reps, threads):
+    """Seconds per clip of the reference-order CPU decoder on `threads` host threads; `iters` of the 8
+    iterations are executed (every iteration is identical work) and the time is scaled to a full clip."""
+    from oracle import parq_oracle as O
+    torch.set_num_threads(threads)
+    sd, tokens, cam, Tcp, Twp, Twl = oracle_clip_inputs()
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.decoder_forward(tokens, cam, Tcp, Twp, Twl, sd, iters=iters, hoist_kv=False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best * CFG["iterations"] / iters
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import parq_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd, tokens, cam, Tcp, Twp, Twl = oracle_clip_inputs()
+    # size the per-step sample so that (steps + warmup) steps end within ~4 minutes
+    t0 = time.perf_counter()
+    O.decoder_forward(tokens, cam, Tcp, Twp, Twl, sd, iters=1, hoist_kv=False)
+    t_it = time.perf_counter() - t0
+    total = args.steps + args.warmup
+    iters = max(1, min(CFG["iterations"], int(240.0 / max(total * t_it, 1e-6))))
+    for _ in range(args.warmup):
+        O.decoder_forward(tokens, cam, Tcp, Twp, Twl, sd, iters=iters, hoist_kv=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.decoder_forward(tokens, cam, Tcp, Twp, Twl, sd, iters=iters, hoist_kv=False)
+    dt = (time.perf_counter() - t0) / args.steps
+    sec_per_clip = dt * CFG["iterations"] / iters
+    value = 1.0 / sec_per_clip
+    sample = ("1 clip per step (8 views x 4800 tokens x 1024 ch, 256 queries), %d of 8 recurrent iterations executed and scaled to 8; "
+              "reference op order (K/V projection repeated every iteration), fp32, torch CPU" % iters)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------- our arm --
+def run_ours(args):
+    import torch.distributed as dist
+    from parq_b200 import _lib, inputs as I
+    from parq_b200.decoder import PARQDecoderB200, default_cfg
+    from parq_b200.wrappers import Camera, Pose
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch N>1 with torch.distributed.run" % (args.gpus, world))
+    if args.warmup < 3:
+        raise SystemExit("--warmup must be >= 3")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, T, H, W, Nq, IT = CFG["clips_per_gpu"], CFG["views"], CFG["H"], CFG["W"], CFG["queries"], CFG["iterations"]
+    Nk, Cc = T * H * W, CFG["C"]
+    model = PARQDecoderB200(default_cfg(Nq, IT)).eval()
+    model.load_state_dict(I.make_weights(0, Nq), strict=True)
+    model = model.to(dev)
+    model.feature_hw = (H, W)
+    # this rank's clips: global clip ids rank*B .. rank*B+B-1 (block partition, parq_b200.shard.clip_range)
+    tok_host = torch.empty(B, Nk, Cc, dtype=torch.bfloat16).pin_memory()
+    for b in range(B):
+        tok_host[b] = I.make_tokens(1, T, H, W, seed=1000 + rank * B + b)[0].to(torch.bfloat16)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=2000 + rank)
+    geo_host = [t._data.pin_memory() for t in (cam, Tcp, Twp, Twl)]
+    tokens = tok_host.to(dev)
+    geo = [Camera(geo_host[0].to(dev)), Pose(geo_host[1].to(dev)), Pose(geo_host[2].to(dev)), Pose(geo_host[3].to(dev))]
+    lib = _lib.load()
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for _ in range(args.warmup):
+        model(tokens, *geo)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.parq_kernel_launches()
+    _lib.profile_enable(["cross_attn", "project_sample", "kv_proj"], 64 * args.steps + 64)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = model(tokens, *geo)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.parq_kernel_launches() - n0
+    prof = _lib.profile_collect()
+    clocks = sampler.stop() if rank == 0 else None
+    _lib.profile_enable([], 0)
+
+    # ---- full per-kernel-class breakdown (separate pass: events around every launch) ------------
+    _lib.profile_enable(list(_lib.PROFILE_TAGS), 512)
+    model(tokens, *geo)
+    torch.cuda.synchronize()
+    breakdown = _lib.profile_collect()
+    _lib.profile_enable([], 0)
+
+    # ---- end to end through the public module API with host buffers -----------------------------
+    copy_stream = torch.cuda.Stream()
+    tok_dev = [torch.empty_like(tokens), torch.empty_like(tokens)]
+    geo_dev = [[torch.empty_like(g._data) for g in geo] for _ in range(2)]
+    keys = ("pred_logits", "center_unnormalized", "size_unnormalized", "ortho6d", "sem_cls_prob")
+    res_host = {k: torch.empty_like(out[-1][k], device="cpu").pin_memory() for k in keys}
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    main = torch.cuda.current_stream()
+
+    def e2e_steps(n):
+        for i in range(n):
+            s = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[s])                       # buffer s free again
+                tok_dev[s].copy_(tok_host, non_blocking=True)             # H2D of this step's inputs
+                for d, h in zip(geo_dev[s], geo_host):
+                    d.copy_(h, non_blocking=True)
+                copied[s].record(copy_stream)
+            main.wait_event(copied[s])
+            o = model(tok_dev[s], Camera(geo_dev[s][0]), Pose(geo_dev[s][1]), Pose(geo_dev[s][2]), Pose(geo_dev[s][3]))
+            consumed[s].record(main)
+            for k in keys:
+                res_host[k].copy_(o[-1][k], non_blocking=True)            # D2H of the step's detections
+        torch.cuda.synchronize()
+
+    for s in range(2):
+        consumed[s].record(main)
+    e2e_steps(args.warmup)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_steps(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    h2d = tok_host.numel() * 2 + sum(g.numel() * 4 for g in geo_host)
+    d2h = sum(v.numel() * 4 for v in res_host.values())
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    if rank == 0:
+        pk = peaks()
+        step_ms = ms / args.steps
+        value = world * B / (step_ms * 1e-3)
+        ca_ms, ca_n = prof["cross_attn"]
+        flops = 4.0 * B * Nq * Nk * Cc                                    # QK^T + PV over all heads, per launch
+        ach = flops / (ca_ms / max(ca_n, 1) * 1e-3) / 1e12 if ca_n else None
+        ps_ms, ps_n = prof["project_sample"]
+        samp_bytes = 4.0 * B * T * Nq * Cc * 2 + B * Nq * Cc * (4 + 2 * 4) + B * T * Nq * 9.0     # upper bound: all corners in bounds
+        kv_ms, kv_n = prof["kv_proj"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("cross_attn_dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": world * B / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "note": "PARQDecoderB200.forward on pinned host tokens (bf16) + poses, double-buffered H2D on a copy stream, D2H of the last-iteration detections"},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "attn_tc_kernel<bf16> (cross-attention over %d image tokens)" % Nk, "bound": "tensor",
+                         "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sustained"]) if ach else None,
+                         "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                         "flops_per_launch": flops, "ms_per_launch": ca_ms / max(ca_n, 1), "launches_timed": ca_n, "traffic": traffic},
+            "roofline_sampling": {"kernel": "project_sample_kernel", "bound": "hbm",
+                                  "achieved": samp_bytes / (ps_ms / max(ps_n, 1) * 1e-3) / 1e9 if ps_n else None, "peak": pk["hbm"], "unit": "GB/s",
+                                  "frac": samp_bytes / (ps_ms / max(ps_n, 1) * 1e-3) / 1e9 / pk["hbm"] if ps_n else None,
+                                  "bytes_per_launch_upper_bound": samp_bytes, "ms_per_launch": ps_ms / max(ps_n, 1)},
+            "roofline_kv_proj": {"kernel": "gemm_tc_kernel (K and V^T projection, 2 launches/step)", "bound": "tensor",
+                                 "achieved": (4.0 * B * Nk * Cc * Cc) / (kv_ms / max(kv_n // 2, 1) * 1e-3) / 1e12 if kv_n else None,
+                                 "peak": pk["tf_sustained"], "unit": "TFLOP/s"},
+            "breakdown_ms_per_step": {k: round(v[0], 4) for k, v in breakdown.items() if k != "_dropped"},
+            "breakdown_launches": {k: v[1] for k, v in breakdown.items() if k != "_dropped"},
+        }
+        if world == 1:
+            threads = os.cpu_count() or 1
+            sec = time_oracle(iters=2, reps=1, threads=threads)
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "1 clip (8 views x 4800 tokens x 1024 ch, 256 queries), 2 of 8 iterations timed and scaled to 8; "
+                                              "oracle port in the reference's op order (K/V re-projected every iteration), fp32 torch CPU"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,19 @@ int parq_attention(const void *Q, int64_t ldq, const void *K, int64_t ldk, const
                    int Nq, int Nk, int fp16, void *scratch, size_t scratch_bytes, void *out_split, int force_nsplit,
                    void *stream);
 
+/* ---- instrumentation ------------------------------------------------------------------------------------ */
+
+/* Number of kernels this library has launched from the calling thread since load. */
+unsigned long long parq_kernel_launches(void);
+
+/* Event profiling of the launches inside the calls above.  tag bits: 0 K/V projection GEMMs, 1 project_sample,
+ * 2 per-iteration GEMMs, 3 self-attention, 4 cross-attention, 5 split combine, 6 row-wise kernels.
+ * parq_profile_enable(mask, max_records) arms it (mask 0 disarms); parq_profile_collect waits for the recorded
+ * events and returns, per tag (arrays of 8), the summed device milliseconds and the number of launches; its
+ * return value is 1 if records were dropped because max_records was reached. */
+int parq_profile_enable(uint32_t tag_mask, int max_records);
+int parq_profile_collect(float *ms_per_tag, int *launches_per_tag);
+
 #ifdef __cplusplus
 }
 #endif

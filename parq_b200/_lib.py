@@ -17,7 +17,9 @@ EXPORTS = [
     "parq_version", "parq_last_error", "parq_packed_bytes", "parq_workspace_bytes", "parq_pack_weights",
     "parq_pose_chain", "parq_project_sample", "parq_kv_project", "parq_decoder_forward",
     "parq_gemm_bf16", "parq_attention_scratch_bytes", "parq_attention",
+    "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect",
 ]
+PROFILE_TAGS = ("kv_proj", "project_sample", "gemm", "self_attn", "cross_attn", "combine", "rowwise")
 
 
 class ParqShape(C.Structure):
@@ -92,8 +94,31 @@ def load():
     lib.parq_attention_scratch_bytes.argtypes = [i32, i32, i32, i32]
     lib.parq_attention.restype = C.c_int
     lib.parq_attention.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp, sz, vp, i32, vp]
+    lib.parq_kernel_launches.restype = C.c_ulonglong
+    lib.parq_profile_enable.restype = C.c_int
+    lib.parq_profile_enable.argtypes = [u32, i32]
+    lib.parq_profile_collect.restype = C.c_int
+    lib.parq_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     _lib = lib
     return lib
+
+
+def profile_enable(tags, max_records=4096):
+    """Arm event profiling for the named tags (see PROFILE_TAGS); empty disarms."""
+    mask = 0
+    for t in tags:
+        mask |= 1 << PROFILE_TAGS.index(t)
+    check(load().parq_profile_enable(mask, max_records), "parq_profile_enable")
+
+
+def profile_collect():
+    """{tag: (total_ms, launches)} for the launches recorded since the last call."""
+    ms = (C.c_float * 8)()
+    n = (C.c_int * 8)()
+    dropped = check(load().parq_profile_collect(ms, n), "parq_profile_collect")
+    out = {t: (float(ms[i]), int(n[i])) for i, t in enumerate(PROFILE_TAGS)}
+    out["_dropped"] = bool(dropped)
+    return out
 
 
 def check(rc, what):

@@ -37,6 +37,36 @@ static int fail(int code, const char* fmt, ...) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ------------------------------------------------------- launch accounting / event profiling --
+// Every kernel launch is counted (parq_kernel_launches).  When enabled with parq_profile_enable, launches
+// whose tag is in the mask are bracketed by CUDA events on the launching stream; parq_profile_collect
+// returns the summed device time and launch count per tag.
+enum ProfTag { TAG_KV_PROJ = 0, TAG_SAMPLE = 1, TAG_GEMM = 2, TAG_SELF_ATTN = 3, TAG_CROSS_ATTN = 4, TAG_COMBINE = 5, TAG_ROWWISE = 6, TAG_COUNT = 8 };
+struct Profiler {
+  bool on = false;
+  uint32_t mask = 0;
+  int cap = 0, n = 0;
+  cudaEvent_t* ev = nullptr;   // 2 per record
+  int* tag = nullptr;
+};
+static thread_local Profiler g_prof;
+static thread_local unsigned long long g_launches = 0;
+struct ProfScope {
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(int tag, cudaStream_t s, int nlaunch = 1) : st(s) {
+    g_launches += nlaunch;
+    if (g_prof.on && (g_prof.mask >> tag & 1u) && g_prof.n < g_prof.cap) {
+      idx = g_prof.n++;
+      g_prof.tag[idx] = tag;
+      cudaEventRecord(g_prof.ev[2 * idx], st);
+    }
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof.ev[2 * idx + 1], st);
+  }
+};
+
 // ------------------------------------------------------------------------------- device info --
 struct DeviceInfo {
   int ok = 0;     // 0 unknown, 1 sm_100, -1 other arch / error
@@ -97,7 +127,7 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
 
 // ---------------------------------------------------------------------------------- launchers --
 static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t a_cols, const void* Bw, uint64_t b_rows,
-                       uint64_t b_cols, const GemmParams& gp) {
+                       uint64_t b_cols, const GemmParams& gp, int tag = TAG_GEMM) {
   if (gp.K <= 0 || gp.K % gemm::BK != 0) return fail(PARQ_ERR_SHAPE, "GEMM K=%d must be a positive multiple of 64", gp.K);
   if (gp.nterms < 1 || gp.nterms > 3) return fail(PARQ_ERR_SHAPE, "GEMM nterms=%d out of range", gp.nterms);
   CUtensorMap tmA, tmB;
@@ -110,7 +140,10 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
   }
   const int tiles = ((gp.M + gemm::BM - 1) / gemm::BM) * ((gp.N + gemm::BN - 1) / gemm::BN);
   const int grid = tiles < device_info().sms ? tiles : device_info().sms;
-  gemm_tc_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, gp);
+  {
+    ProfScope ps(tag, st);
+    gemm_tc_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, gp);
+  }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
 }
@@ -174,12 +207,18 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
     attr_set = true;
   }
   dim3 grid(plan.nsplit, Nq / attn::BQ, B * H);
-  if (fp16)
-    attn_tc_kernel<true><<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, ap);
-  else
-    attn_tc_kernel<false><<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, ap);
+  {
+    ProfScope ps(fp16 ? TAG_SELF_ATTN : TAG_CROSS_ATTN, st);
+    if (fp16)
+      attn_tc_kernel<true><<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, ap);
+    else
+      attn_tc_kernel<false><<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, ap);
+  }
   CUDA_TRY(cudaGetLastError());
-  attn_combine_kernel<<<B * Nq, 256, 0, st>>>(ap.o_part, ap.ml_part, out_split, H, Nq, plan.nsplit);
+  {
+    ProfScope ps(TAG_COMBINE, st);
+    attn_combine_kernel<<<B * Nq, 256, 0, st>>>(ap.o_part, ap.ml_part, out_split, H, Nq, plan.nsplit);
+  }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
 }
@@ -341,7 +380,7 @@ static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, c
   gk.ep = epilogue_none();
   gk.ep.bias = reinterpret_cast<const float*>(pk + P.ca_k_b);
   gk.ep.out_lp = ws + W.Kc;  gk.ep.ld_lp = C;
-  TRY(launch_gemm(st, tokens, Nt, C, pk + P.ca_k, C, 2 * C, gk));
+  TRY(launch_gemm(st, tokens, Nt, C, pk + P.ca_k, C, 2 * C, gk, TAG_KV_PROJ));
   // V^T = Wv tokens^T + bv (per row) : A = Wv [hi|lo], B = tokens
   GemmParams gv;
   memset(&gv, 0, sizeof(gv));
@@ -352,7 +391,7 @@ static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, c
   gv.ep.bias = reinterpret_cast<const float*>(pk + P.ca_v_b);
   gv.ep.bias_per_row = 1;
   gv.ep.out_lp = ws + W.Vt;  gv.ep.ld_lp = static_cast<long long>(W.ldv);
-  TRY(launch_gemm(st, pk + P.ca_v, C, 2 * C, tokens, Nt, C, gv));
+  TRY(launch_gemm(st, pk + P.ca_v, C, 2 * C, tokens, Nt, C, gv, TAG_KV_PROJ));
   return PARQ_OK;
 }
 
@@ -365,6 +404,40 @@ extern "C" {
 
 int parq_version(void) { return PARQ_ABI_VERSION; }
 const char* parq_last_error(void) { return g_err; }
+
+unsigned long long parq_kernel_launches(void) { return g_launches; }
+
+int parq_profile_enable(uint32_t tag_mask, int max_records) {
+  Profiler& p = g_prof;
+  if (max_records > p.cap) {
+    for (int i = 0; i < 2 * p.cap; ++i) cudaEventDestroy(p.ev[i]);
+    delete[] p.ev;
+    delete[] p.tag;
+    p.ev = new cudaEvent_t[2 * max_records];
+    p.tag = new int[max_records];
+    for (int i = 0; i < 2 * max_records; ++i) CUDA_TRY(cudaEventCreate(&p.ev[i]));
+    p.cap = max_records;
+  }
+  p.n = 0;
+  p.mask = tag_mask;
+  p.on = tag_mask != 0 && max_records > 0;
+  return PARQ_OK;
+}
+
+int parq_profile_collect(float* ms_per_tag, int* launches_per_tag) {
+  Profiler& p = g_prof;
+  for (int t = 0; t < TAG_COUNT; ++t) { ms_per_tag[t] = 0.f; launches_per_tag[t] = 0; }
+  for (int i = 0; i < p.n; ++i) {
+    CUDA_TRY(cudaEventSynchronize(p.ev[2 * i + 1]));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, p.ev[2 * i], p.ev[2 * i + 1]));
+    ms_per_tag[p.tag[i]] += ms;
+    launches_per_tag[p.tag[i]] += 1;
+  }
+  const int dropped = (p.n >= p.cap) ? 1 : 0;
+  p.n = 0;
+  return dropped;
+}
 
 size_t parq_packed_bytes(const ParqShape* shape) {
   if (check_shape(shape) != PARQ_OK) return 0;
@@ -451,7 +524,10 @@ int parq_pack_weights(const ParqShape* shape, const ParqWeightsF32* w, void* pac
 int parq_pose_chain(const float* T_cp, const float* T_wp, const float* T_wl, float* T_cl, int B, int T, void* stream) {
   TRY(require_sm100());
   if (!T_cp || !T_wp || !T_wl || !T_cl || B < 1 || T < 1) return fail(PARQ_ERR_SHAPE, "bad pose_chain arguments");
-  pose_chain_kernel<<<(B * T + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(T_cp, T_wp, T_wl, T_cl, B, T);
+  {
+    ProfScope ps(TAG_ROWWISE, static_cast<cudaStream_t>(stream));
+    pose_chain_kernel<<<(B * T + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(T_cp, T_wp, T_wl, T_cl, B, T);
+  }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
 }
@@ -476,7 +552,10 @@ int parq_project_sample(const ParqShape* shape, const void* tokens_bf16, const f
   sp.tokens = static_cast<const __nv_bfloat16*>(tokens_bf16);
   sp.ref = ref; sp.T_cl = T_cl; sp.camera = camera;
   sp.feat = features; sp.center_im = center_im; sp.valid = center_valid; sp.coord_pos = coord_pos;
-  project_sample_kernel<<<shape->B * shape->Nq, shape->C / 8, 0, static_cast<cudaStream_t>(stream)>>>(sp);
+  {
+    ProfScope ps(TAG_SAMPLE, static_cast<cudaStream_t>(stream));
+    project_sample_kernel<<<shape->B * shape->Nq, shape->C / 8, 0, static_cast<cudaStream_t>(stream)>>>(sp);
+  }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
 }
@@ -545,7 +624,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   auto PF = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
 
   // K0: pose chain
-  pose_chain_kernel<<<(s.B * s.T + 127) / 128, 128, 0, st>>>(T_cp, T_wp, T_wl, F32(W.T_cl), s.B, s.T);
+  { ProfScope ps(TAG_ROWWISE, st); pose_chain_kernel<<<(s.B * s.T + 127) / 128, 128, 0, st>>>(T_cp, T_wp, T_wl, F32(W.T_cl), s.B, s.T); }
   CUDA_TRY(cudaGetLastError());
   // K4: hoisted K / V^T projection of the image tokens (iteration invariant)
   if (!(flags & PARQ_FLAG_SKIP_KV)) TRY(kv_project(s, st, tokens_bf16, pk, P, w_lo, ws, W));
@@ -559,7 +638,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   for (int it = 0; it < s.iters; ++it) {
     const float* ref = forced_refs ? forced_refs + static_cast<size_t>(it) * R * 3 : (it == 0 ? ref0 : F32(W.ref_cur));
     // K2: reference-point positional feature  pe = W2 relu(W1 posemb + b1) + b2
-    posemb_kernel<<<(R * 384 + 255) / 256, 256, 0, st>>>(ref, PF(P.dim_t), BF(W.a_pos), R);
+    { ProfScope ps(TAG_ROWWISE, st); posemb_kernel<<<(R * 384 + 255) / 256, 256, 0, st>>>(ref, PF(P.dim_t), BF(W.a_pos), R); }
     CUDA_TRY(cudaGetLastError());
     {
       GemmParams g; memset(&g, 0, sizeof(g));
@@ -581,7 +660,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     sp.center_im = out->center_im ? out->center_im + static_cast<size_t>(it) * s.B * s.T * s.Nq * 2 : nullptr;
     sp.valid = out->center_valid ? out->center_valid + static_cast<size_t>(it) * s.B * s.T * s.Nq : nullptr;
     sp.coord_pos = nullptr;
-    project_sample_kernel<<<R, C / 8, 0, st>>>(sp);
+    { ProfScope ps(TAG_SAMPLE, st); project_sample_kernel<<<R, C / 8, 0, st>>>(sp); }
     CUDA_TRY(cudaGetLastError());
     const float* x0 = sp.feat;
     // K3: self-attention among the queries (fp16 operands), out-projection, residual + LN1
@@ -605,8 +684,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.sa_out_b);
       g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
       TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.sa_out, C, 2 * C, g));
-      add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(x0, F32(W.y), PF(P.ln1_g), PF(P.ln1_b), F32(W.pe), F32(W.x1), nullptr,
-                                                      BF(W.a_x1pe), R);
+      { ProfScope ps(TAG_ROWWISE, st); add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(x0, F32(W.y), PF(P.ln1_g), PF(P.ln1_b), F32(W.pe), F32(W.x1), nullptr,
+                                                      BF(W.a_x1pe), R); }
       CUDA_TRY(cudaGetLastError());
     }
     // K5: cross-attention over all image tokens (bf16 operands), out-projection, residual + LN2
@@ -624,8 +703,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.ca_out_b);
       g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
       TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.ca_out, C, 2 * C, g));
-      add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(F32(W.x1), F32(W.y), PF(P.ln2_g), PF(P.ln2_b), nullptr, F32(W.x2), BF(W.a_x2),
-                                                      nullptr, R);
+      { ProfScope ps(TAG_ROWWISE, st); add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(F32(W.x1), F32(W.y), PF(P.ln2_g), PF(P.ln2_b), nullptr, F32(W.x2), BF(W.a_x2),
+                                                      nullptr, R); }
       CUDA_TRY(cudaGetLastError());
     }
     // K6: FFN, residual + LN3
@@ -641,7 +720,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.lin2_b);
       g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
       TRY(launch_gemm(st, ws + W.a_ffn, R, 2 * F, pk + P.lin2, C, 2 * F, g));
-      add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(F32(W.x2), F32(W.y), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr, R);
+      { ProfScope ps(TAG_ROWWISE, st); add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(F32(W.x2), F32(W.y), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr, R); }
       CUDA_TRY(cudaGetLastError());
     }
     // K7: heads (two hidden layers with per-clip GroupNorm) + box update
@@ -651,9 +730,9 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none();
       g.ep.out_f32 = F32(W.h1); g.ep.ld_f32 = 2 * C;
       TRY(launch_gemm(st, ws + W.a_x3, R, 2 * C, pk + P.hd1, 2 * C, 2 * C, g));
-      gn_stats_kernel<<<dim3(GN_BLOCKS, 2, s.B), 256, 0, st>>>(F32(W.h1), 2 * C, C, s.Nq, reinterpret_cast<double2*>(ws + W.gn1));
-      gn_apply_kernel<<<R, 256, 0, st>>>(F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1), PF(P.ctr1_g),
-                                         PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1));
+      { ProfScope ps(TAG_ROWWISE, st); gn_stats_kernel<<<dim3(GN_BLOCKS, 2, s.B), 256, 0, st>>>(F32(W.h1), 2 * C, C, s.Nq, reinterpret_cast<double2*>(ws + W.gn1)); }
+      { ProfScope ps(TAG_ROWWISE, st); gn_apply_kernel<<<R, 256, 0, st>>>(F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1), PF(P.ctr1_g),
+                                         PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1)); }
       CUDA_TRY(cudaGetLastError());
       for (int hd = 0; hd < 2; ++hd) {
         memset(&g, 0, sizeof(g));
@@ -662,7 +741,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
         g.ep.out_f32 = F32(W.h2) + hd * C; g.ep.ld_f32 = 2 * C;
         TRY(launch_gemm(st, ws + W.a_h1, R, 4 * C, pk + (hd == 0 ? P.ctr4 : P.rot4), C, 2 * C, g));
       }
-      gn_stats_kernel<<<dim3(GN_BLOCKS, 2, s.B), 256, 0, st>>>(F32(W.h2), 2 * C, C, s.Nq, reinterpret_cast<double2*>(ws + W.gn2));
+      { ProfScope ps(TAG_ROWWISE, st); gn_stats_kernel<<<dim3(GN_BLOCKS, 2, s.B), 256, 0, st>>>(F32(W.h2), 2 * C, C, s.Nq, reinterpret_cast<double2*>(ws + W.gn2)); }
       CUDA_TRY(cudaGetLastError());
       hp.x = x3; hp.h2 = F32(W.h2); hp.partial = reinterpret_cast<const double2*>(ws + W.gn2);
       hp.gamma_c = PF(P.ctr5_g); hp.beta_c = PF(P.ctr5_b); hp.gamma_r = PF(P.rot5_g); hp.beta_r = PF(P.rot5_b);
@@ -676,7 +755,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       hp.rot = out->rotation ? out->rotation + o * 9 : nullptr;
       hp.ref_next = F32(W.ref_cur);
       hp.R = R; hp.Nq = s.Nq; hp.C = C; hp.num_cls = s.num_cls;
-      heads_final_kernel<1024><<<(R + 3) / 4, 128, 0, st>>>(hp);
+      { ProfScope ps(TAG_ROWWISE, st); heads_final_kernel<1024><<<(R + 3) / 4, 128, 0, st>>>(hp); }
       CUDA_TRY(cudaGetLastError());
     }
   }

@@ -1,0 +1,87 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference decoder
+(/root/reference, imported through oracle/ref_loader.py) on the deterministic synthetic
+inputs of parq_b200.inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The fixtures pin oracle/parq_oracle.py (tests/test_oracle_golden.py) and the CUDA path
+(tests/test_gpu_parity.py).  Inputs/weights are NOT stored: they are regenerated from the
+seeds and verified against the checksums recorded here.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_loader import decoder_cfg, load_reference  # noqa: E402
+from parq_b200 import inputs as I  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FEAT_STRIDE = 16     # sampled features are stored for every 16th channel
+
+CASES = {
+    # name: (B, T, H, W, Nq, seed, wild, smooth)
+    "small": (2, 3, 12, 16, 256, 0, False, True),
+    "ragged_wild": (1, 2, 10, 14, 128, 1, True, True),
+    "white_noise": (1, 4, 15, 20, 256, 2, False, False),
+}
+PROJ_CASES = {
+    # projection-only cases at benchmark geometry: (B, T, H, W, Nq, seed, wild)
+    "proj_c1": (1, 8, 60, 80, 256, 3, False),
+    "proj_c4_views": (1, 32, 30, 40, 512, 4, False),
+    "proj_wild": (2, 5, 24, 32, 128, 5, True),
+}
+
+
+def main():
+    ns = load_reference()
+    torch.manual_seed(0)
+    for name, (B, T, H, W, Nq, seed, wild, smooth) in CASES.items():
+        sd = I.make_weights(seed, Nq)
+        ref = ns.PARQDecoder(decoder_cfg(Nq)).eval()
+        ref.load_state_dict(sd, strict=True)
+        tokens = I.make_tokens(B, T, H, W, seed=seed, smooth=smooth)
+        cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed, wild=wild)
+        rc, rp = ns.Camera(cam._data), ns.Pose
+        with torch.no_grad():
+            outs = ref(tokens, rc, rp(Tcp._data), rp(Twp._data), rp(Twl._data))
+            Tcl = rp(Tcp._data) @ (rp(Twp._data).inverse() @ rp(Twl._data))
+            memory_hw = tokens.view(B * T, H, W, -1).permute(0, 3, 1, 2)
+            feats, cims, vals = [], [], []
+            for o in outs:
+                f, ci, cv = ns.project(memory_hw, o["coord_pos"], Tcl, rc)
+                feats.append(f[..., ::FEAT_STRIDE].numpy())
+                cims.append(ci.numpy())
+                vals.append(cv.numpy())
+        data = {"shape": np.array([B, T, H, W, Nq, seed, int(wild), int(smooth)]),
+                "weights_sum": np.array(I.tensor_checksum(*[sd[k] for k in sorted(sd)])),
+                "inputs_sum": np.array(I.tensor_checksum(tokens, cam._data, Tcp._data, Twp._data, Twl._data)),
+                "T_camera_local": Tcl._data.numpy(),
+                "features": np.stack(feats), "center_im": np.stack(cims), "center_valid": np.stack(vals)}
+        for k in outs[0]:
+            data[k] = np.stack([o[k].numpy() for o in outs])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
+        print(name, {k: v.shape for k, v in data.items() if hasattr(v, "shape")})
+    for name, (B, T, H, W, Nq, seed, wild) in PROJ_CASES.items():
+        tokens = I.make_tokens(B, T, H, W, seed=seed)
+        cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed, wild=wild)
+        g = torch.Generator().manual_seed(seed)
+        pts = torch.rand(B, Nq, 3, generator=g) * torch.tensor([6.0, 2.5, 5.0]) + torch.tensor([-3.0, -2.0, 0.25])
+        rc, rp = ns.Camera(cam._data), ns.Pose
+        with torch.no_grad():
+            Tcl = rp(Tcp._data) @ (rp(Twp._data).inverse() @ rp(Twl._data))
+            f, ci, cv = ns.project(tokens.view(B * T, H, W, -1).permute(0, 3, 1, 2), pts, Tcl, rc)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"),
+                            shape=np.array([B, T, H, W, Nq, seed, int(wild), 1]),
+                            inputs_sum=np.array(I.tensor_checksum(tokens, cam._data, Tcp._data, Twp._data, Twl._data, pts)),
+                            points=pts.numpy(), T_camera_local=Tcl._data.numpy(), features=f[..., ::FEAT_STRIDE].numpy(),
+                            center_im=ci.numpy(), center_valid=cv.numpy())
+        print(name, "valid fraction %.3f" % cv.float().mean().item())
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,234 @@
+"""Parity of the CUDA path (through the C ABI) against the golden fixtures of the unmodified
+reference, against the CPU oracle on seeded inputs, and -- at benchmark sizes -- through
+size-independent properties.  Run on a B200: `pytest -m gpu`.
+
+Bars: center_im / center_valid / coord_pos bit-exact in fp32; sampled features,
+box parameters, logits and probabilities max|d|/max|ref| <= 1e-3, teacher-forced per iteration.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import OUT_KEYS, bit_equal, load_golden, regenerate_case, relerr
+from oracle import parq_oracle as O
+from parq_b200 import _lib, inputs as I
+from parq_b200.decoder import DecoderEngine, PARQDecoderB200, _ptr, _stream, default_cfg, pose_chain, project
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3          # north_star: "within 1e-3 relative (bf16 attention)"
+FEAT_TOL = 1e-5     # the gather itself is fp32 on identical bf16 token values
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available() and torch.cuda.get_device_capability(0)[0] == 10, "needs an sm_100 device"
+    return torch.device("cuda:0")
+
+
+def _engine_forward(eng, c, dev, **kw):
+    out = eng.forward(c["tokens"].to(dev), c["camera"].to(dev), c["T_cp"].to(dev), c["T_wp"].to(dev), c["T_wl"].to(dev),
+                      c["H"], c["W"], **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+# ---------------------------------------------------------------- projection: bit-exact ----
+@pytest.mark.parametrize("name", ["proj_c1", "proj_c4_views", "proj_wild"])
+def test_projection_against_reference_golden(dev, name):
+    gold = load_golden(name)
+    c = regenerate_case(gold)
+    Tcl = pose_chain(c["T_cp"].to(dev), c["T_wp"].to(dev), c["T_wl"].to(dev))
+    assert bit_equal(Tcl, gold["T_camera_local"]), "T_camera_local differs from the reference"
+    feat, cim, val = project(c["tokens"].to(dev), c["points"].to(dev), Tcl, c["camera"].to(dev), c["H"], c["W"])
+    assert bit_equal(cim, gold["center_im"]), "%d coordinates differ" % int((cim.cpu().numpy() != gold["center_im"]).sum())
+    assert np.array_equal(val.cpu().numpy(), gold["center_valid"])
+    assert relerr(feat.cpu()[..., ::16], gold["features"]) <= FEAT_TOL
+
+
+def test_projection_edge_cases(dev):
+    # points exactly on the image border, behind the camera, at the clamp depth, and far outside
+    B, T, H, W, Nq = 1, 2, 6, 8, 128
+    tokens = I.make_tokens(B, T, H, W, seed=11)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=11)
+    eye = torch.tensor([1., 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]).expand(B, T, 12).contiguous()
+    pts = torch.zeros(B, Nq, 3)
+    pts[0, :, 2] = 1.0
+    f, cx, cy = cam._data[0, 0, 2].item(), cam._data[0, 0, 4].item(), cam._data[0, 0, 5].item()
+    special = [((0 - cx) / f, (0 - cy) / f, 1.0), ((W - 1 - cx) / f, (H - 1 - cy) / f, 1.0), (0, 0, -1.0), (0, 0, 1e-3),
+               (0, 0, 9.9e-4), (50.0, 50.0, 1.0), (-50.0, 0.0, 1.0), ((W - 1.5 - cx) / f, (H - 0.5 - cy) / f, 1.0)]
+    for i, p in enumerate(special):
+        pts[0, i] = torch.tensor(p)
+    f_ref, ci_ref, cv_ref = O.project_sample(tokens, pts, eye.numpy(), cam._data.numpy(), H, W)
+    feat, cim, val = project(tokens.to(dev), pts.to(dev), eye.to(dev), cam._data.to(dev), H, W)
+    assert bit_equal(cim, ci_ref) and torch.equal(val.cpu(), cv_ref)
+    assert relerr(feat.cpu(), f_ref) <= FEAT_TOL
+
+
+# ------------------------------------------------------- full decoder: teacher-forced ----
+@pytest.mark.parametrize("name", ["small", "ragged_wild", "white_noise"])
+def test_decoder_against_reference_golden(dev, name):
+    gold = load_golden(name)
+    c = regenerate_case(gold)
+    sd = c["sd"]
+    iters = gold["coord_pos"].shape[0]
+    gold_outs = [{k: torch.from_numpy(gold[k][i]) for k in OUT_KEYS} for i in range(iters)]
+    refs = O.refs_from_outputs(gold_outs, sd)
+    eng = DecoderEngine(sd, dev)
+    got = _engine_forward(eng, c, dev, forced_refs=refs.to(dev), debug=True)
+    flips = 0
+    for i in range(iters):
+        assert bit_equal(got["coord_pos"][i], gold["coord_pos"][i]), "iteration %d" % i
+        assert bit_equal(got["center_im"][i], gold["center_im"][i]), "iteration %d" % i
+        assert np.array_equal(got["center_valid"][i].cpu().numpy(), gold["center_valid"][i])
+        assert relerr(got["features"][i].cpu()[..., ::16], gold["features"][i]) <= FEAT_TOL
+        same_cls = got["sem_cls_prob"][i].cpu().argmax(-1) == torch.from_numpy(gold["sem_cls_prob"][i]).argmax(-1)
+        flips += int((~same_cls).sum())
+        for k in ("pred_logits", "center_unnormalized", "ortho6d", "sem_cls_prob"):
+            assert relerr(got[k][i].cpu(), gold[k][i]) <= TOL, (k, i)
+        # size = exp(s) * mean_size[argmax]: compare where the arg-max class agrees (a flip changes the
+        # looked-up mean size discontinuously; flips are counted and bounded below)
+        sz, gz = got["size_unnormalized"][i].cpu()[same_cls], torch.from_numpy(gold["size_unnormalized"][i])[same_cls]
+        assert relerr(sz, gz) <= TOL, ("size_unnormalized", i)
+    assert flips <= 2, "%d arg-max class flips" % flips
+
+
+def test_decoder_c1_shape_against_oracle(dev):
+    # BASELINE config 1 geometry: 1 clip, 8 views of 60x80 tokens, 256 queries, 8 iterations
+    B, T, H, W, Nq, seed = 1, 8, 60, 80, 256, 21
+    sd = I.make_weights(seed, Nq)
+    tokens = I.make_tokens(B, T, H, W, seed=seed)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+    c = dict(tokens=tokens, camera=cam._data, T_cp=Tcp._data, T_wp=Twp._data, T_wl=Twl._data, H=H, W=W)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    outs, auxs = O.decoder_forward(tokens, cam._data, Tcp._data, Twp._data, Twl._data, sd, return_aux=True)
+    refs = O.refs_from_outputs(outs, sd)
+    eng = DecoderEngine(sd, dev)
+    got = _engine_forward(eng, c, dev, forced_refs=refs.to(dev), debug=True)
+    for i in range(8):
+        assert bit_equal(got["center_im"][i], auxs[i]["center_im"]) and torch.equal(got["center_valid"][i].cpu(), auxs[i]["center_valid"])
+        assert relerr(got["features"][i].cpu(), auxs[i]["features"]) <= FEAT_TOL
+        assert relerr(got["decoder_out"][i].cpu(), auxs[i]["decoder_out"]) <= TOL
+        for k in ("pred_logits", "center_unnormalized", "ortho6d", "sem_cls_prob"):
+            assert relerr(got[k][i].cpu(), outs[i][k]) <= TOL, (k, i)
+    # rotation epilogue = compute_rotation_matrix_from_ortho6d of the emitted ortho6d
+    R = O.rotation_from_ortho6d(got["ortho6d"][7].cpu().reshape(-1, 6)).view(B, Nq, 3, 3)
+    assert relerr(got["rotation"][7].cpu(), R) <= 1e-5
+    # free-running (no teacher forcing) stays close for the first iterations; later ones are reported only
+    free = _engine_forward(eng, c, dev)
+    assert relerr(free["center_unnormalized"][0].cpu(), outs[0]["center_unnormalized"]) <= TOL
+    assert relerr(free["center_unnormalized"][1].cpu(), outs[1]["center_unnormalized"]) <= 5 * TOL
+
+
+def test_module_forward_matches_engine_and_reference_api(dev):
+    gold = load_golden("small")
+    c = regenerate_case(gold)
+    m = PARQDecoderB200(default_cfg(c["Nq"])).eval()
+    m.load_state_dict(c["sd"], strict=True)
+    m = m.to(dev)
+    cam, Tcp, Twp, Twl = I.make_geometry(c["B"], c["T"], c["H"], c["W"], seed=c["seed"])
+    out = m(c["tokens"].to(dev), cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
+    torch.cuda.synchronize()
+    assert isinstance(out, list) and len(out) == 8 and set(out[0].keys()) == set(OUT_KEYS)
+    assert out[0]["pred_logits"].shape == (c["B"], c["Nq"], 10) and out[0]["ortho6d"].shape == (c["B"], c["Nq"], 6)
+    for k in OUT_KEYS:   # iteration 0 consumes sigmoid(refpoint) computed on the device
+        assert relerr(out[0][k].cpu(), gold[k][0]) <= TOL, k
+    with pytest.raises(NotImplementedError):
+        m.train()(c["tokens"].to(dev), cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
+
+
+# ------------------------------------------------------------------ kernel unit tests ----
+def _gemm(dev, A, Bw, M, N, K, **kw):
+    lib = _lib.load()
+    out = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
+    ak, bk = (C.c_int32 * 3)(*kw.get("a_koff", (0, 0, 0))), (C.c_int32 * 3)(*kw.get("b_koff", (0, 0, 0)))
+    _lib.check(lib.parq_gemm_bf16(_ptr(A), A.shape[0], A.shape[1], _ptr(Bw), Bw.shape[0], Bw.shape[1], M, N, K, kw.get("nterms", 1),
+                                  ak, bk, _ptr(kw.get("bias")), 0, kw.get("relu", 0), _ptr(out), N, None, 0, 0, 0, _stream()), "gemm")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 768, 1024), (4096, 1024, 384), (1, 16, 64)])
+def test_gemm_against_fp32(dev, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    Bw = torch.randn(N, K, generator=g).to(dev).bfloat16()
+    assert relerr(_gemm(dev, A, Bw, M, N, K), A.float() @ Bw.float().t()) <= 1e-5
+
+
+def test_gemm_three_term_split_recovers_fp32_product(dev):
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 256, 512, 256
+    x, W = torch.randn(M, K, generator=g).to(dev), (torch.randn(N, K, generator=g) * 0.05).to(dev)
+    sp = lambda t: torch.cat([t.bfloat16(), (t - t.bfloat16().float()).bfloat16()], 1).contiguous()
+    bias = torch.randn(N, generator=g).to(dev)
+    out = _gemm(dev, sp(x), sp(W), M, N, K, nterms=3, a_koff=(0, K, 0), b_koff=(0, 0, K), bias=bias, relu=1)
+    ref = torch.relu((x.double() @ W.double().t()).float() + bias)
+    assert relerr(out, ref) <= 3e-5
+
+
+def _attention(dev, B, H, Nq, Nk, fp16, nsplit, seed, scale=1.0, spike=False):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(seed)
+    dt, Cc = (torch.float16 if fp16 else torch.bfloat16), H * 256
+    Q = (torch.randn(B * Nq, Cc, generator=g) * scale / 16).to(dev).to(dt)
+    K = torch.randn(B * Nk, Cc, generator=g).to(dev).to(dt)
+    V = torch.randn(B * Nk, Cc, generator=g).to(dev).to(dt)
+    if spike:
+        K[Nk - 3::Nk] *= 12
+    ldv = (B * Nk + 63) // 64 * 64
+    Vt = torch.zeros(Cc, ldv, dtype=dt, device=dev)
+    Vt[:, : B * Nk] = V.t()
+    nb = lib.parq_attention_scratch_bytes(B, H, Nq, Nk)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+    out = torch.zeros(B * Nq, 2 * Cc, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.parq_attention(_ptr(Q), Cc, _ptr(K), Cc, _ptr(Vt), ldv, B, H, Nq, Nk, int(fp16), _ptr(scratch), nb, _ptr(out),
+                                  nsplit, _stream()), "attention")
+    torch.cuda.synchronize()
+    got = (out[:, :Cc].float() + out[:, Cc:].float()).view(B, Nq, H, 256).permute(0, 2, 1, 3)
+    hv = lambda t, n: t.float().view(B, n, H, 256).permute(0, 2, 1, 3).double()
+    p = torch.softmax(torch.einsum("bhqd,bhkd->bhqk", hv(Q, Nq), hv(K, Nk)), -1)
+    return relerr(got, torch.einsum("bhqk,bhkd->bhqd", p, hv(V, Nk)).float())
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,fp16,nsplit", [(1, 1, 128, 128, False, 1), (1, 1, 128, 384, False, 3), (1, 2, 256, 420, False, 2),
+                                                   (2, 4, 256, 1000, False, 0), (2, 4, 256, 256, True, 1), (1, 1, 128, 1, False, 1)])
+def test_attention_against_fp32_softmax(dev, B, H, Nq, Nk, fp16, nsplit):
+    assert _attention(dev, B, H, Nq, Nk, fp16, nsplit, seed=Nk) <= (2e-3 if fp16 else 1e-2)
+
+
+def test_attention_lazy_rescale_path(dev):
+    assert _attention(dev, 1, 2, 128, 1024, False, 1, seed=3, scale=4.0, spike=True) <= 1e-2
+
+
+# ------------------------------------------------ benchmark-size properties (config 2) ----
+def test_config2_properties(dev):
+    B, T, H, W, Nq, seed = 16, 8, 60, 80, 256, 31
+    sd = I.make_weights(seed, Nq)
+    eng = DecoderEngine(sd, dev)
+    tokens = I.make_tokens(B, T, H, W, seed=seed).to(dev).bfloat16()
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    refs = torch.rand(8, B, Nq, 3, generator=g).to(dev)          # fixed reference points: no recurrence
+    args = lambda sl: (tokens[sl], cam._data[sl].to(dev), Tcp._data[sl].to(dev), Twp._data[sl].to(dev), Twl._data[sl].to(dev), H, W)
+    full = eng.forward(*args(slice(0, B)), forced_refs=refs, debug=True)
+    torch.cuda.synchronize()
+    for k in OUT_KEYS:
+        assert torch.isfinite(full[k]).all(), k
+    assert (full["sem_cls_prob"].sum(-1) - 1).abs().max() <= 1e-5
+    R = full["rotation"][-1].reshape(-1, 3, 3)
+    assert (R.transpose(1, 2) @ R - torch.eye(3, device=dev)).abs().max() <= 1e-4
+    # coord_pos is the exact denormalisation of the forced reference points
+    lo, span = torch.tensor([-3.0, -2.0, 0.25], device=dev), torch.tensor([6.0, 2.5, 5.0], device=dev)
+    assert torch.equal(full["coord_pos"], refs * span + lo)
+    # clip independence: a clip decoded alone equals the same clip decoded inside the batch
+    # (different key-split plans => only the split-combine order changes)
+    full = {k: v.clone() for k, v in full.items()}
+    for b in (0, 9):
+        one = eng.forward(*args(slice(b, b + 1)), forced_refs=refs[:, b:b + 1].contiguous(), debug=True)
+        torch.cuda.synchronize()
+        assert torch.equal(one["center_im"][:, 0], full["center_im"][:, b])
+        assert torch.equal(one["features"][:, 0], full["features"][:, b])
+        for k in ("pred_logits", "center_unnormalized", "ortho6d"):
+            assert relerr(one[k][:, 0], full[k][:, b]) <= 1e-4, (k, b)

@@ -1,0 +1,120 @@
+"""Host-side logic that needs no GPU: module/state-dict compatibility with the reference,
+wrapper algebra, argument validation, ABI surface."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, bit_equal
+from oracle import parq_oracle as O
+from parq_b200 import _lib, inputs as I
+from parq_b200.decoder import PARQDecoderB200, default_cfg, make_shape
+from parq_b200.wrappers import Camera, Pose, raw
+
+
+def test_state_dict_matches_reference_layout():
+    m = PARQDecoderB200(default_cfg()).eval()
+    sd = m.state_dict()
+    spec = I.state_dict_spec(256)
+    assert list(sd.keys()) == [k for k, _ in spec] and len(sd) == 65
+    assert all(tuple(sd[k].shape) == s for k, s in spec)
+    # aliases share storage (reference parq_decoder.py:66)
+    assert sd["mlp_heads.center_head.layers.0.weight"].data_ptr() == sd["parq_module.decoder.mlp_heads.center_head.layers.0.weight"].data_ptr()
+    m.load_state_dict(I.make_weights(3), strict=True)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference tree not present")
+def test_state_dict_against_live_reference():
+    from oracle.ref_loader import decoder_cfg, load_reference
+    ref = load_reference().PARQDecoder(decoder_cfg(256))
+    ours = PARQDecoderB200(default_cfg(256))
+    assert list(ref.state_dict().keys()) == list(ours.state_dict().keys())
+    ours.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_wrappers_follow_reference_semantics():
+    cam, Tcp, Twp, Twl = I.make_geometry(2, 3, 12, 16, seed=0)
+    assert tuple(Tcp.shape) == (2, 3) and tuple(cam.shape) == (2, 3) and tuple(Twl.shape) == (2, 1)
+    T = Tcp @ (Twp.inverse() @ Twl)
+    ref = O.camera_from_local(Tcp._data.numpy(), Twp._data.numpy(), Twl._data.numpy())
+    assert np.allclose(T._data.numpy(), ref, atol=1e-6)
+    ident = Twp @ Twp.inverse()
+    assert torch.allclose(ident.R, torch.eye(3).expand(2, 3, 3, 3), atol=1e-5) and ident.t.abs().max() < 1e-5
+    s = Camera(torch.tensor([[320., 240., 288.8, 288.8, 159.5, 119.5]])).scale(0.25)
+    assert torch.allclose(s._data, torch.tensor([[80., 60., 72.2, 72.2, 39.5, 29.5]]))
+    p2d, valid = cam.project(torch.tensor([0.1, 0.05, 2.0]).expand(2, 3, 4, 3))
+    assert p2d.shape == (2, 3, 4, 2) and valid.dtype == torch.bool
+    assert raw(cam) is cam._data and raw(cam._data) is cam._data
+    with pytest.raises(ValueError):
+        Pose(torch.zeros(3, 11))
+    with pytest.raises(TypeError):
+        raw(object())
+
+
+def test_decoder_refuses_unsupported_use():
+    m = PARQDecoderB200(default_cfg())
+    tok = torch.zeros(1, 12, 1024)
+    with pytest.raises(NotImplementedError):
+        m(tok, None, None, None, None)                 # training mode
+    m.eval()
+    with pytest.raises(NotImplementedError):
+        m(tok, None, None, None, None)                 # CPU tensors: no fallback
+    cfg = default_cfg()
+    cfg.SHARE_MLP_HEADS = False
+    with pytest.raises(NotImplementedError):
+        PARQDecoderB200(cfg)
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "parq_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(parq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_functions()
+    assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), "libparq_b200.so does not export " + n
+    assert lib.parq_version() == 1
+
+
+def test_shape_validation_without_gpu():
+    lib = _lib.load()
+    good = make_shape(16, 8, 60, 80, 1024, 256, 4, 768, 8, 10, I.SCALE)
+    assert lib.parq_packed_bytes(C.byref(good)) > 60e6
+    # K (1.26 GB) + V^T (1.26 GB) + per-iteration scratch at config 2
+    assert 2.5e9 < lib.parq_workspace_bytes(C.byref(good)) < 4e9
+    for bad in (make_shape(1, 1, 4, 4, 1024, 100, 4, 768, 8, 10, I.SCALE),      # Nq not a multiple of 128
+                make_shape(1, 1, 4, 4, 512, 256, 4, 768, 8, 10, I.SCALE),       # unsupported width
+                make_shape(1, 1, 4, 4, 1024, 256, 8, 768, 8, 10, I.SCALE)):     # head_dim != 256
+        assert lib.parq_workspace_bytes(C.byref(bad)) == 0
+        assert len(lib.parq_last_error()) > 0
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.ParqShape) == 10 * 4 + 6 * 4
+    assert C.sizeof(_lib.ParqWeightsF32) == 8 * len(_lib.WEIGHT_FIELDS) == 8 * 44
+    assert C.sizeof(_lib.ParqOutputs) == 8 * 11
+    hdr = open(os.path.join(ROOT, "include", "parq_b200.h")).read()
+    body = hdr[hdr.index("typedef struct ParqWeightsF32"):hdr.index("} ParqWeightsF32;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\*\s*([a-z0-9_]+)\s*[,;]", body)
+    assert fields == _lib.WEIGHT_FIELDS
+    body = hdr[hdr.index("typedef struct ParqOutputs"):hdr.index("} ParqOutputs;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    assert re.findall(r"\*\s*([a-z0-9_]+)\s*;", body) == _lib.OUTPUT_FIELDS
+
+
+def test_synthetic_inputs_are_deterministic_and_bf16_exact():
+    a = I.make_tokens(1, 2, 6, 8, seed=5)
+    b = I.make_tokens(1, 2, 6, 8, seed=5)
+    assert bit_equal(a, b) and bit_equal(a, I.bf16_round(a))
+    sd = I.make_weights(1)
+    for k, v in sd.items():
+        if v.dim() >= 2 and k != "refpoint.weight":
+            assert bit_equal(v, I.bf16_round(v)), k

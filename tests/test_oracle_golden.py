@@ -1,0 +1,74 @@
+"""The oracle (oracle/parq_oracle.py) against outputs of the unmodified reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import OUT_KEYS, bit_equal, load_golden, regenerate_case, relerr
+from oracle import parq_oracle as O
+
+FULL = ["small", "ragged_wild", "white_noise"]
+PROJ = ["proj_c1", "proj_c4_views", "proj_wild"]
+
+
+@pytest.mark.parametrize("name", FULL + PROJ)
+def test_pose_chain_bit_exact(name):
+    gold = load_golden(name)
+    c = regenerate_case(gold)
+    Tcl = O.camera_from_local(c["T_cp"].numpy(), c["T_wp"].numpy(), c["T_wl"].numpy())
+    assert bit_equal(Tcl, gold["T_camera_local"])
+
+
+@pytest.mark.parametrize("name", PROJ)
+def test_projection_bit_exact(name):
+    gold = load_golden(name)
+    c = regenerate_case(gold)
+    feat, cim, val = O.project_sample(c["tokens"], c["points"], gold["T_camera_local"], c["camera"].numpy(), c["H"], c["W"])
+    assert bit_equal(cim, gold["center_im"])
+    assert np.array_equal(val.numpy(), gold["center_valid"])
+    assert relerr(feat[..., ::16], gold["features"]) <= 1e-6
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_decoder_teacher_forced(name):
+    gold = load_golden(name)
+    c = regenerate_case(gold)
+    sd = c["sd"]
+    gold_outs = [{k: torch.from_numpy(gold[k][i]) for k in OUT_KEYS} for i in range(gold["coord_pos"].shape[0])]
+    refs = O.refs_from_outputs(gold_outs, sd)
+    outs, auxs = O.decoder_forward(c["tokens"], c["camera"], c["T_cp"], c["T_wp"], c["T_wl"], sd, forced_refs=refs, return_aux=True)
+    for i, (o, a) in enumerate(zip(outs, auxs)):
+        assert bit_equal(o["coord_pos"], gold["coord_pos"][i]), "teacher-forced reference points differ at iteration %d" % i
+        assert bit_equal(a["center_im"], gold["center_im"][i])
+        assert np.array_equal(a["center_valid"].numpy(), gold["center_valid"][i])
+        assert relerr(a["features"][..., ::16], gold["features"][i]) <= 1e-6
+        for k in OUT_KEYS:
+            assert relerr(o[k], gold[k][i]) <= 2e-5, (k, i)
+
+
+def test_decoder_free_running_first_iterations():
+    # the recurrence amplifies rounding noise: gate the first two iterations only
+    gold = load_golden("small")
+    c = regenerate_case(gold)
+    outs = O.decoder_forward(c["tokens"], c["camera"], c["T_cp"], c["T_wp"], c["T_wl"], c["sd"], iters=2)
+    for i in range(2):
+        for k in OUT_KEYS:
+            assert relerr(outs[i][k], gold[k][i]) <= 1e-4, (k, i)
+
+
+def test_unhoisted_kv_matches_hoisted():
+    gold = load_golden("ragged_wild")
+    c = regenerate_case(gold)
+    a = O.decoder_forward(c["tokens"], c["camera"], c["T_cp"], c["T_wp"], c["T_wl"], c["sd"], iters=1, hoist_kv=True)
+    b = O.decoder_forward(c["tokens"], c["camera"], c["T_cp"], c["T_wp"], c["T_wl"], c["sd"], iters=1, hoist_kv=False)
+    for k in OUT_KEYS:
+        assert relerr(a[0][k], b[0][k]) <= 1e-5
+
+
+def test_mean_size_table_and_rotation():
+    assert O.MEAN_SIZE.shape == (10, 3) and np.all(O.MEAN_SIZE[8:] == 1.0)
+    g = torch.Generator().manual_seed(0)
+    R = O.rotation_from_ortho6d(torch.randn(64, 6, generator=g))
+    eye = torch.eye(3).expand(64, 3, 3)
+    assert torch.allclose(R.transpose(1, 2) @ R, eye, atol=1e-5)
+    assert torch.allclose(torch.linalg.det(R), torch.ones(64), atol=1e-5)
