@@ -133,6 +133,10 @@ int parq_attention(const void *Q, int64_t ldq, const void *K, int64_t ldk, const
                    int Nq, int Nk, int fp16, void *scratch, size_t scratch_bytes, void *out_split, int force_nsplit,
                    void *stream);
 
+/* Byte offset of a named intermediate inside the workspace (tests / debugging): "pe","x0","x1","x2","x3","y","h1","h2",
+ * "q_c","qk_s","vt_s","a_attn","Kc","Vt","T_cl"; "ldv","ldvs","cross_nsplit","self_nsplit" return those values. -1 if unknown. */
+long long parq_workspace_offset(const ParqShape *shape, const char *name);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
 
 /* Number of kernels this library has launched from the calling thread since load. */

@@ -266,16 +266,22 @@ def decoder_iteration(tokens, memory, ref, T_camera_local, camera, H, W, sd, hea
     qk = x + pe
     x2 = _mha(qk, qk, x, sd[L + "self_attn.in_proj_weight"], sd[L + "self_attn.in_proj_bias"],
               sd[L + "self_attn.out_proj.weight"], sd[L + "self_attn.out_proj.bias"], heads)
+    sa_out = x2
     x = F.layer_norm(x + x2, (x.shape[-1],), sd[L + "norm1.weight"], sd[L + "norm1.bias"], 1e-5)
+    x1 = x
     x2 = _mha(x + pe, memory, memory, sd[L + "multihead_attn.in_proj_weight"], sd[L + "multihead_attn.in_proj_bias"],
               sd[L + "multihead_attn.out_proj.weight"], sd[L + "multihead_attn.out_proj.bias"], heads, kv=kv)
+    ca_out = x2
     x = F.layer_norm(x + x2, (x.shape[-1],), sd[L + "norm2.weight"], sd[L + "norm2.bias"], 1e-5)
+    x2_ln = x
     x2 = F.linear(F.relu(F.linear(x, sd[L + "linear1.weight"], sd[L + "linear1.bias"])), sd[L + "linear2.weight"], sd[L + "linear2.bias"])
     x = F.layer_norm(x + x2, (x.shape[-1],), sd[L + "norm3.weight"], sd[L + "norm3.bias"], 1e-5)
     x = x.permute(1, 0, 2)
     out = box_heads(x, ref, sd, scale)
     nxt = normalize(out["center_unnormalized"], scale)
-    aux = {"features": feat, "center_im": center_im, "center_valid": center_valid, "decoder_out": x}
+    aux = {"features": feat, "center_im": center_im, "center_valid": center_valid, "decoder_out": x,
+           "pe": pe.permute(1, 0, 2), "self_attn_out": sa_out.permute(1, 0, 2), "x1": x1.permute(1, 0, 2),
+           "cross_attn_out": ca_out.permute(1, 0, 2), "x2": x2_ln.permute(1, 0, 2)}
     return out, nxt, aux
 
 

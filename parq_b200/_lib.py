@@ -17,7 +17,7 @@ EXPORTS = [
     "parq_version", "parq_last_error", "parq_packed_bytes", "parq_workspace_bytes", "parq_pack_weights",
     "parq_pose_chain", "parq_project_sample", "parq_kv_project", "parq_decoder_forward",
     "parq_gemm_bf16", "parq_attention_scratch_bytes", "parq_attention",
-    "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect",
+    "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect", "parq_workspace_offset",
 ]
 PROFILE_TAGS = ("kv_proj", "project_sample", "gemm", "self_attn", "cross_attn", "combine", "rowwise")
 
@@ -94,6 +94,8 @@ def load():
     lib.parq_attention_scratch_bytes.argtypes = [i32, i32, i32, i32]
     lib.parq_attention.restype = C.c_int
     lib.parq_attention.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp, sz, vp, i32, vp]
+    lib.parq_workspace_offset.restype = C.c_longlong
+    lib.parq_workspace_offset.argtypes = [C.POINTER(ParqShape), C.c_char_p]
     lib.parq_kernel_launches.restype = C.c_ulonglong
     lib.parq_profile_enable.restype = C.c_int
     lib.parq_profile_enable.argtypes = [u32, i32]

@@ -223,11 +223,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
       for (int i = 1; i < 128; ++i) tmax = fmaxf(tmax, __uint_as_float(su[i]));
       tmax *= LOG2E;
+      // mbarrier waits are by phase parity, so every completion of pv_done has to be observed exactly
+      // once and in order (skipping one lets a later wait alias an older phase): tile j consumes the
+      // completion of P(j-1)V(j-1) either here, before touching O, or at the end of the iteration.
+      bool pv_seen = (j == 0);
       if (j == 0) {
         m_run = tmax;
       } else if (__any_sync(0xffffffffu, tmax > m_run + RESCALE_THRESHOLD)) {
         // O must be quiescent: wait for P(j-1) V(j-1) to retire, then rescale this warp's 32 rows.
         mbar_wait(pv_done, (j - 1) & 1);
+        pv_seen = true;
         tc_fence_after();
         const float m_new = fmaxf(m_run, tmax);
         const float alpha = fast_exp2(m_run - m_new);
@@ -260,6 +265,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[buf]);
+      if (!pv_seen) mbar_wait(pv_done, (j - 1) & 1);
     }
     // epilogue: un-normalised O, m, l of this split
     mbar_wait(pv_done, (n - 1) & 1);

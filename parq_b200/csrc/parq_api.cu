@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/parq_b200.h"
@@ -437,6 +438,20 @@ int parq_profile_collect(float* ms_per_tag, int* launches_per_tag) {
   const int dropped = (p.n >= p.cap) ? 1 : 0;
   p.n = 0;
   return dropped;
+}
+
+long long parq_workspace_offset(const ParqShape* shape, const char* name) {
+  if (check_shape(shape) != PARQ_OK || name == nullptr) return -1;
+  const Workspace W = workspace_layout(*shape, device_info().sms);
+  const struct { const char* n; size_t off; } tab[] = {
+      {"Kc", W.Kc}, {"Vt", W.Vt}, {"T_cl", W.T_cl}, {"pe", W.pe}, {"x0", W.x0}, {"qk_s", W.qk_s}, {"vt_s", W.vt_s},
+      {"a_attn", W.a_attn}, {"y", W.y}, {"x1", W.x1}, {"x2", W.x2}, {"x3", W.x3}, {"q_c", W.q_c}, {"h1", W.h1}, {"h2", W.h2},
+      {"ldv", W.ldv}, {"ldvs", W.ldvs}, {"cross_nsplit", static_cast<size_t>(W.cross.nsplit)},
+      {"self_nsplit", static_cast<size_t>(W.self.nsplit)}};
+  for (const auto& e : tab)
+    if (strcmp(e.n, name) == 0) return static_cast<long long>(e.off);
+  fail(PARQ_ERR_SHAPE, "unknown workspace region '%s'", name);
+  return -1;
 }
 
 size_t parq_packed_bytes(const ParqShape* shape) {

@@ -193,6 +193,18 @@ class DecoderEngine:
             outs["center_valid"] = outs["center_valid"].bool()
         return outs
 
+    def workspace_view(self, name, B, T, H, W, dtype, shape):
+        """A typed view of a named intermediate of the last forward (tests / debugging)."""
+        sh = self._shape(B, T, H, W)
+        off = self.lib.parq_workspace_offset(C.byref(sh), name.encode())
+        if off < 0:
+            raise _lib.ParqError(self.lib.parq_last_error().decode())
+        n = int(torch.tensor(shape).prod().item()) * torch.empty(0, dtype=dtype).element_size()
+        return self._ws[off: off + n].view(dtype).view(*shape)
+
+    def workspace_value(self, name, B, T, H, W):
+        return int(self.lib.parq_workspace_offset(C.byref(self._shape(B, T, H, W)), name.encode()))
+
     def kv_project(self, tokens, B, T, H, W):
         shape = self._shape(B, T, H, W)
         ws = self._workspace(shape, (B, T, H, W))

@@ -181,6 +181,102 @@ def stage_forward():
                                                                         outs_free[it]["center_unnormalized"])))
 
 
+def stage_interm():
+    """Where does the error enter?  Compares the workspace intermediates of a 1-iteration forward with the oracle's."""
+    from oracle import parq_oracle as O
+    import torch.nn.functional as F
+    for (B, T, H, W, Nq, seed) in ((1, 8, 60, 80, 256, 21), (2, 3, 12, 16, 256, 0)):
+        sd = I.make_weights(seed, Nq)
+        tokens = I.make_tokens(B, T, H, W, seed=seed)
+        cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+        outs, auxs = O.decoder_forward(tokens, cam._data, Tcp._data, Twp._data, Twl._data, sd, iters=1, return_aux=True)
+        eng = DecoderEngine(sd, dev, iters=1)
+        got = eng.forward(tokens.to(dev), cam._data.to(dev), Tcp._data.to(dev), Twp._data.to(dev), Twl._data.to(dev), H, W, debug=True)
+        torch.cuda.synchronize()
+        R, Cc, Nk = B * Nq, 1024, T * H * W
+        a = auxs[0]
+        view = lambda n, dt, sh: eng.workspace_view(n, B, T, H, W, dt, sh).cpu()
+        print("---- B%d T%d %dx%d  (cross nsplit %d)" % (B, T, H, W, eng.workspace_value("cross_nsplit", B, T, H, W)))
+        print("pe        %.2e" % relerr(view("pe", torch.float32, (B, Nq, Cc)), a["pe"]))
+        print("x1 (LN1)  %.2e" % relerr(view("x1", torch.float32, (B, Nq, Cc)), a["x1"]))
+        print("x2 (LN2)  %.2e" % relerr(view("x2", torch.float32, (B, Nq, Cc)), a["x2"]))
+        print("dec out   %.2e" % relerr(got["decoder_out"][0].cpu(), a["decoder_out"]))
+        # K / V^T of the image tokens vs fp32 projections
+        Lm = "parq_module.decoder.layers.0.multihead_attn."
+        Kf = F.linear(tokens, sd[Lm + "in_proj_weight"][Cc:2 * Cc], sd[Lm + "in_proj_bias"][Cc:2 * Cc]).view(B * Nk, Cc)
+        Vf = F.linear(tokens, sd[Lm + "in_proj_weight"][2 * Cc:], sd[Lm + "in_proj_bias"][2 * Cc:]).view(B * Nk, Cc)
+        ldv = eng.workspace_value("ldv", B, T, H, W)
+        print("K  bf16   %.2e" % relerr(view("Kc", torch.bfloat16, (B * Nk, Cc)).float(), Kf))
+        print("V^T bf16  %.2e" % relerr(view("Vt", torch.bfloat16, (Cc, ldv))[:, : B * Nk].float(), Vf.t()))
+        # attention outputs (pre out-proj): a_attn holds the LAST attention (cross) as [hi|lo]
+        at = view("a_attn", torch.bfloat16, (R, 2 * Cc)).float()
+        at = at[:, :Cc] + at[:, Cc:]
+        L = "parq_module.decoder.layers.0."
+        q = F.linear(a["x1"] + a["pe"], sd[Lm + "in_proj_weight"][:Cc], sd[Lm + "in_proj_bias"][:Cc]) / 16
+        qh = q.view(B, Nq, 4, 256).permute(0, 2, 1, 3).double()
+        kh = Kf.view(B, Nk, 4, 256).permute(0, 2, 1, 3).double()
+        vh = Vf.view(B, Nk, 4, 256).permute(0, 2, 1, 3).double()
+        p = torch.softmax(qh @ kh.transpose(-1, -2), -1)
+        ref_attn = (p @ vh).permute(0, 2, 1, 3).reshape(R, Cc).float()
+        print("cross attn (pre out-proj) %.2e   |max| %.3f" % (relerr(at, ref_attn), ref_attn.abs().max()))
+        print("q_c bf16  %.2e" % relerr(view("q_c", torch.bfloat16, (R, Cc)).float(), q.reshape(R, Cc)))
+        print("score stats: max |s| %.2f, row max-mean %.2f" % ((qh @ kh.transpose(-1, -2)).abs().max(), ((qh @ kh.transpose(-1, -2)).max(-1).values - (qh @ kh.transpose(-1, -2)).mean(-1)).mean()))
+
+
+def stage_attnbig():
+    """Scale-dependent attention check: many key tiles per CTA."""
+    g = torch.Generator(device="cpu").manual_seed(7)
+    for (B, H, Nq, Nk, ns) in ((1, 1, 128, 2048, 1), (1, 1, 128, 4096, 1), (1, 1, 128, 8192, 1), (1, 1, 128, 8192, 4),
+                               (1, 4, 256, 38400, 18), (1, 4, 256, 38400, 1), (1, 4, 256, 38400, 0)):
+        e = run_attention(B, H, Nq, Nk, False, ns, g)
+        report("attn B%d H%d Nq%d Nk%d bf16 nsplit=%d" % (B, H, Nq, Nk, ns), e, 1e-2)
+
+
+def stage_attnsplit():
+    """Per-split diagnosis: compares every CTA's partial (O/l, lse) against torch over its own key range."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(7)
+    B, H, Nq, Nk, ns = 1, 4, 256, 38400, 18
+    Cc = H * 256
+    Q = (torch.randn(B * Nq, Cc, generator=g) / 16).to(dev).bfloat16()
+    K = torch.randn(B * Nk, Cc, generator=g).to(dev).bfloat16()
+    V = torch.randn(B * Nk, Cc, generator=g).to(dev).bfloat16()
+    ldv = (B * Nk + 63) // 64 * 64
+    Vt = torch.zeros(Cc, ldv, dtype=torch.bfloat16, device=dev)
+    Vt[:, : B * Nk] = V.t()
+    nb = lib.parq_attention_scratch_bytes(B, H, Nq, Nk)
+    scratch = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    out = torch.zeros(B * Nq, 2 * Cc, dtype=torch.bfloat16, device=dev)
+    for trial in range(3):
+        scratch.zero_()
+        _lib.check(lib.parq_attention(_ptr(Q), Cc, _ptr(K), Cc, _ptr(Vt), ldv, B, H, Nq, Nk, 0, _ptr(scratch), nb, _ptr(out), ns, _stream()), "attn")
+        torch.cuda.synchronize()
+        rows = B * H * ns * Nq
+        o_part = scratch[: rows * 256 * 4].view(torch.float32).view(B * H, ns, Nq, 256)
+        off = (rows * 256 * 4 + 255) // 256 * 256
+        ml = scratch[off: off + rows * 8].view(torch.float32).view(B * H, ns, Nq, 2)
+        tps = (300 + ns - 1) // ns
+        bad = []
+        for h in range(H):
+            q = Q[:, h * 256:(h + 1) * 256].double()
+            for sidx in range(ns):
+                k0, k1 = sidx * tps * 128, min(Nk, (sidx + 1) * tps * 128)
+                sc = (q @ K[k0:k1, h * 256:(h + 1) * 256].double().t()) * 1.4426950408889634
+                mx = sc.max(-1, keepdim=True).values
+                pr = torch.exp2(sc - mx)
+                ref_o = (pr @ V[k0:k1, h * 256:(h + 1) * 256].double()) / pr.sum(-1, keepdim=True)
+                ref_lse = mx[:, 0] + torch.log2(pr.sum(-1))
+                got_o = o_part[h, sidx].double() / ml[h, sidx, :, 1:2].double()
+                got_lse = ml[h, sidx, :, 0].double() + torch.log2(ml[h, sidx, :, 1].double())
+                for qt in range(2):
+                    sl = slice(qt * 128, qt * 128 + 128)
+                    eo = ((got_o[sl] - ref_o[sl]).abs().max() / ref_o[sl].abs().max()).item()
+                    el = (got_lse[sl] - ref_lse[sl]).abs().max().item()
+                    if eo > 5e-3 or el > 5e-3 or eo != eo:
+                        bad.append((h, sidx, qt, round(eo, 4), round(el, 4)))
+        print("trial %d: %d bad CTAs of %d: %s" % (trial, len(bad), H * ns * 2, bad[:24]), flush=True)
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0), flush=True)
     for st in sys.argv[1:]:
