@@ -211,6 +211,17 @@ def run_ours(args):
     breakdown = _lib.profile_collect()
     _lib.profile_enable([], 0)
 
+    # ---- algorithmic bytes of the gather: count the in-bounds bilinear corners of this very run ----
+    dbg = model._engine.forward(tokens, geo[0]._data, geo[1]._data, geo[2]._data, geo[3]._data, H, W, debug=True)
+    torch.cuda.synchronize()
+    cu, cv = dbg["center_im"][..., 0], dbg["center_im"][..., 1]
+    x0, y0 = torch.floor(cu), torch.floor(cv)
+    nx = ((x0 >= 0) & (x0 <= W - 1)).int() + ((x0 + 1 >= 0) & (x0 + 1 <= W - 1)).int()
+    ny = ((y0 >= 0) & (y0 <= H - 1)).int() + ((y0 + 1 >= 0) & (y0 + 1 <= H - 1)).int()
+    n_inb = float((nx * ny).sum().item()) / IT          # in-bounds corner texels per launch (mean over the 8 iterations)
+    valid_frac = float(dbg["center_valid"].float().mean().item())
+    del dbg
+
     # ---- end to end through the public module API with host buffers -----------------------------
     copy_stream = torch.cuda.Stream()
     tok_dev = [torch.empty_like(tokens), torch.empty_like(tokens)]
@@ -266,7 +277,8 @@ def run_ours(args):
         flops = 4.0 * B * Nq * Nk * Cc                                    # QK^T + PV over all heads, per launch
         ach = flops / (ca_ms / max(ca_n, 1) * 1e-3) / 1e12 if ca_n else None
         ps_ms, ps_n = prof["project_sample"]
-        samp_bytes = 4.0 * B * T * Nq * Cc * 2 + B * Nq * Cc * (4 + 2 * 4) + B * T * Nq * 9.0     # upper bound: all corners in bounds
+        # texels actually fetched (bf16) + pe read + features fp32 + the two [hi|lo] operand splits + center_im/valid
+        samp_bytes = n_inb * Cc * 2 + B * Nq * Cc * (4 + 4 + 2 * 4) + B * T * Nq * 9.0
         kv_ms, kv_n = prof["kv_proj"]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -287,7 +299,8 @@ def run_ours(args):
             "roofline_sampling": {"kernel": "project_sample_kernel", "bound": "hbm",
                                   "achieved": samp_bytes / (ps_ms / max(ps_n, 1) * 1e-3) / 1e9 if ps_n else None, "peak": pk["hbm"], "unit": "GB/s",
                                   "frac": samp_bytes / (ps_ms / max(ps_n, 1) * 1e-3) / 1e9 / pk["hbm"] if ps_n else None,
-                                  "bytes_per_launch_upper_bound": samp_bytes, "ms_per_launch": ps_ms / max(ps_n, 1)},
+                                  "bytes_per_launch": samp_bytes, "in_bounds_corners_per_launch": n_inb, "valid_view_fraction": valid_frac,
+                                  "ms_per_launch": ps_ms / max(ps_n, 1)},
             "roofline_kv_proj": {"kernel": "gemm_tc_kernel (K and V^T projection, 2 launches/step)", "bound": "tensor",
                                  "achieved": (4.0 * B * Nk * Cc * Cc) / (kv_ms / max(kv_n // 2, 1) * 1e-3) / 1e12 if kv_n else None,
                                  "peak": pk["tf_sustained"], "unit": "TFLOP/s"},

@@ -296,30 +296,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
 // Merge the key splits: out = sum_s 2^(m_s-M) O_s / sum_s 2^(m_s-M) l_s, heads concatenated along
 // channels (the layout nn.MultiheadAttention feeds to out_proj), emitted as the exact bf16 split
-// [hi | lo] that the out-projection GEMM consumes.  One block per query row, thread = channel of a head.
+// [hi | lo] that the out-projection GEMM consumes.  One block per query row; 64 threads per head, a
+// thread owns 4 consecutive channels (float4 loads, independent over the splits).
 __global__ void __launch_bounds__(256)
 attn_combine_kernel(const float* __restrict__ o_part, const float2* __restrict__ ml_part, __nv_bfloat16* __restrict__ out,
                     int H, int Nq, int nsplit) {
   const int row = blockIdx.x;            // b*Nq + q
   const int b = row / Nq, q = row % Nq;
-  const int d = threadIdx.x;
   const int C = H * 256;
-  for (int h = 0; h < H; ++h) {
+  for (int item = threadIdx.x; item < H * 64; item += blockDim.x) {
+    const int h = item >> 6, d = (item & 63) * 4;
     const long long base = (static_cast<long long>(b * H + h) * nsplit) * Nq + q;
     float M = -INFINITY;
-    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, ml_part[base + static_cast<long long>(s) * Nq].x);
-    float acc = 0.f, L = 0.f;
+    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldg(&ml_part[base + static_cast<long long>(s) * Nq].x));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float L = 0.f;
+#pragma unroll 4
     for (int s = 0; s < nsplit; ++s) {
       const long long idx = base + static_cast<long long>(s) * Nq;
-      const float2 ml = ml_part[idx];
+      const float2 ml = __ldg(&ml_part[idx]);
+      const float4 o = __ldg(reinterpret_cast<const float4*>(o_part + idx * 256 + d));
       const float w = exp2f(ml.x - M);
       L += w * ml.y;
-      acc += w * o_part[idx * 256 + d];
+      acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
     }
-    const float v = acc / L;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    out[static_cast<long long>(row) * (2 * C) + h * 256 + d] = hi;
-    out[static_cast<long long>(row) * (2 * C) + C + h * 256 + d] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const float inv = 1.f / L;
+    const float v[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+    const uint32_t h0 = pack_bf16x2(v[0], v[1]), h1 = pack_bf16x2(v[2], v[3]);
+    const uint32_t l0 = pack_bf16x2(v[0] - __uint_as_float(h0 << 16), v[1] - __uint_as_float(h0 & 0xFFFF0000u));
+    const uint32_t l1 = pack_bf16x2(v[2] - __uint_as_float(h1 << 16), v[3] - __uint_as_float(h1 & 0xFFFF0000u));
+    __nv_bfloat16* dst = out + static_cast<long long>(row) * (2 * C) + h * 256 + d;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(dst + C) = make_uint2(l0, l1);
   }
 }
 

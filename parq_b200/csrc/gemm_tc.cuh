@@ -30,7 +30,6 @@ struct GemmEpilogue {
   const float* bias;   // nullptr: none
   int bias_per_row;    // 0: bias[n] (Linear), 1: bias[m] (transposed product, e.g. V^T)
   int relu;
-  float scale;         // applied after the bias (1/sqrt(dh) of the attention query)
   float* out_f32;      // optional fp32 output, row-major, leading dimension ld_f32
   long long ld_f32;
   void* out_lp;        // optional 16-bit output (bf16, or fp16 when lp_fp16)
@@ -55,27 +54,23 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_BYTES = BN * BK * 2;   // 32 KB
 constexpr int THREADS = 256;
-constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
 }  // namespace gemm
 
-__device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], long long row, int col0,
-                                                 int N) {
+// Epilogue for one row x 32 accumulator columns: bias / ReLU, then fp32 and/or 16-bit stores
+// (bf16 or fp16; optionally the bf16 residual "lo" for the split layout).  Everything is
+// statically indexed so the values stay in registers; `full` = all 32 columns are in range.
+__device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], const float* sbias, float row_bias,
+                                                 long long row, int col0, int N) {
   float v[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-  if (ep.bias != nullptr) {
-    if (ep.bias_per_row) {
-      const float b = __ldg(ep.bias + row);
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + row_bias;
+  if (sbias != nullptr) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += b;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += (col0 + i < N) ? __ldg(ep.bias + col0 + i) : 0.f;
+    for (int i = 0; i < 8; ++i) {
+      const float4 b4 = reinterpret_cast<const float4*>(sbias)[i];
+      v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
     }
-  }
-  if (ep.scale != 1.0f) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= ep.scale;
   }
   if (ep.relu) {
 #pragma unroll
@@ -88,7 +83,9 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
 #pragma unroll
       for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     } else {
-      for (int i = 0; i < 32 && col0 + i < N; ++i) o[i] = v[i];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < N) o[i] = v[i];
     }
   }
   if (ep.out_lp != nullptr) {
@@ -105,7 +102,9 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
 #pragma unroll
       for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(o)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
     } else {
-      for (int i = 0; i < 32 && col0 + i < N; ++i) o[i] = static_cast<uint16_t>((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFF));
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < N) o[i] = static_cast<uint16_t>((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu));
     }
     if (ep.lp_lo_off > 0) {   // residual of the bf16 split (only meaningful for bf16 outputs)
       uint32_t l[16];
@@ -119,7 +118,9 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
 #pragma unroll
         for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(ol)[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
       } else {
-        for (int i = 0; i < 32 && col0 + i < N; ++i) ol[i] = static_cast<uint16_t>((i & 1) ? (l[i >> 1] >> 16) : (l[i >> 1] & 0xFFFF));
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < N) ol[i] = static_cast<uint16_t>((i & 1) ? (l[i >> 1] >> 16) : (l[i >> 1] & 0xFFFFu));
       }
     }
   }
@@ -137,6 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -165,6 +167,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = (p.M + BM - 1) / BM;
   const int num_tiles = tiles_m * tiles_n;
+  // Tile order: the dimension with FEWER tiles varies fastest, so that the CTAs running at the same
+  // time share the tile of the large (streamed) operand through L2 and it is read from HBM once.
+  const bool m_fastest = tiles_m <= tiles_n;
+  auto tile_origin = [&](int tile, int& m0, int& n0) {
+    if (m_fastest) { m0 = (tile % tiles_m) * BM; n0 = (tile / tiles_m) * BN; }
+    else           { m0 = (tile / tiles_n) * BM; n0 = (tile % tiles_n) * BN; }
+  };
   const int kb_per_term = p.K / BK;
   const int num_kb = kb_per_term * p.nterms;
 
@@ -173,13 +182,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        int m0, n0;
+        tile_origin(tile, m0, n0);
         for (int t = 0; t < p.nterms; ++t) {
+          // static selects (not p.a_koff[t]): a dynamically indexed parameter array would force the whole
+          // parameter block into local memory
+          const int ak = t == 0 ? p.a_koff[0] : (t == 1 ? p.a_koff[1] : p.a_koff[2]);
+          const int bk = t == 0 ? p.b_koff[0] : (t == 1 ? p.b_koff[1] : p.b_koff[2]);
           for (int kb = 0; kb < kb_per_term; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-            tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], p.a_koff[t] + kb * BK, m0);
-            tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], p.b_koff[t] + kb * BK, n0);
+            tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], ak + kb * BK, m0);
+            tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], bk + kb * BK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -212,21 +226,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {                  // ---------------- epilogue warps
     const int q = warp - 4;                // TMEM lane quadrant == warp % 4
+    const int et = threadIdx.x - 128;      // 0..127
+    const bool col_bias = (p.ep.bias != nullptr) && !p.ep.bias_per_row;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      int m0, n0;
+      tile_origin(tile, m0, n0);
       const int acc = lt & 1;
+      const long long row = m0 + q * 32 + lane;
+      // stage this tile's bias while the MMA of the tile is still running
+      float row_bias = 0.f;
+      if (col_bias) {
+        float* sb = sbias + acc * BN;
+        sb[et] = (n0 + et < p.N) ? __ldg(p.ep.bias + n0 + et) : 0.f;
+        sb[et + 128] = (n0 + et + 128 < p.N) ? __ldg(p.ep.bias + n0 + et + 128) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      } else if (p.ep.bias != nullptr && row < p.M) {
+        row_bias = __ldg(p.ep.bias + row);
+      }
       mbar_wait(&tfull_bar[acc], (lt >> 1) & 1);
       tc_fence_after();
-      const long long row = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr, r0);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
+      for (int c = 0; c < BN / 32; c += 2) {
         tmem_wait_ld();
-        const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) gemm_store_chunk(p.ep, r, row, col0, p.N);
+        tmem_ld32(taddr + (c + 1) * 32, r1);                 // next chunk in flight while this one is stored
+        int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) gemm_store_chunk(p.ep, r0, col_bias ? sbias + acc * BN + c * 32 : nullptr, row_bias, row, col0, p.N);
+        tmem_wait_ld();
+        if (c + 2 < BN / 32) tmem_ld32(taddr + (c + 2) * 32, r0);
+        col0 += 32;
+        if (row < p.M && col0 < p.N) gemm_store_chunk(p.ep, r1, col_bias ? sbias + acc * BN + (c + 1) * 32 : nullptr, row_bias, row, col0, p.N);
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);

@@ -364,7 +364,6 @@ static void term_offsets(GemmParams& gp, int K, bool w_lo, int a_base) {
 static GemmEpilogue epilogue_none() {
   GemmEpilogue e;
   memset(&e, 0, sizeof(e));
-  e.scale = 1.0f;
   return e;
 }
 
@@ -770,7 +769,16 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       hp.rot = out->rotation ? out->rotation + o * 9 : nullptr;
       hp.ref_next = F32(W.ref_cur);
       hp.R = R; hp.Nq = s.Nq; hp.C = C; hp.num_cls = s.num_cls;
-      { ProfScope ps(TAG_ROWWISE, st); heads_final_kernel<1024><<<(R + 3) / 4, 128, 0, st>>>(hp); }
+      { ProfScope ps(TAG_ROWWISE, st); {
+        const int rpb = (R + device_info().sms - 1) / device_info().sms;     // rows per block: one block per SM
+        const size_t hsm = static_cast<size_t>(s.num_cls + 12) * C * sizeof(float);
+        static thread_local bool hattr = false;
+        if (!hattr) {
+          cudaFuncSetAttribute(heads_final_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(HEADS_MAX_OUT * 1024 * sizeof(float)));
+          hattr = true;
+        }
+        heads_final_kernel<1024><<<(R + rpb - 1) / rpb, 256, hsm, st>>>(hp, rpb);
+      } }
       CUDA_TRY(cudaGetLastError());
     }
   }

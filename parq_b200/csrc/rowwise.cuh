@@ -12,6 +12,18 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* hi_ptr, long long lo_
   hi_ptr[lo_off] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// 8 consecutive values -> 8 bf16 "hi" (16 bytes) at dst and 8 bf16 residuals at dst + lo_off
+__device__ __forceinline__ void store_split8(__nv_bfloat16* dst, long long lo_off, const float (&v)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    lo[i] = pack_bf16x2(v[2 * i] - __uint_as_float(hi[i] << 16), v[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u));
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -44,46 +56,47 @@ __global__ void __launch_bounds__(256)
 add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y, const float* __restrict__ gamma,
               const float* __restrict__ beta, const float* __restrict__ pe, float* __restrict__ x_out,
               __nv_bfloat16* __restrict__ a_x, __nv_bfloat16* __restrict__ a_xpe, int R) {
-  constexpr int PER = C / 32;
+  constexpr int PASSES = C / 256;          // a lane owns 8 consecutive channels per pass
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
   const long long base = static_cast<long long>(row) * C;
-  float v[PER];
+  float v[PASSES][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < PER / 4; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    const float4 a = *reinterpret_cast<const float4*>(x_in + base + c);
-    const float4 bb = *reinterpret_cast<const float4*>(y + base + c);
-    v[4 * i] = a.x + bb.x; v[4 * i + 1] = a.y + bb.y; v[4 * i + 2] = a.z + bb.z; v[4 * i + 3] = a.w + bb.w;
-    s += v[4 * i] + v[4 * i + 1] + v[4 * i + 2] + v[4 * i + 3];
+  for (int i = 0; i < PASSES; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(x_in + base + c), a1 = *reinterpret_cast<const float4*>(x_in + base + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(y + base + c), b1 = *reinterpret_cast<const float4*>(y + base + c + 4);
+    v[i][0] = a0.x + b0.x; v[i][1] = a0.y + b0.y; v[i][2] = a0.z + b0.z; v[i][3] = a0.w + b0.w;
+    v[i][4] = a1.x + b1.x; v[i][5] = a1.y + b1.y; v[i][6] = a1.z + b1.z; v[i][7] = a1.w + b1.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[i][k];
   }
   const float mean = warp_sum(s) / C;
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; ss += d * d; }
+  for (int i = 0; i < PASSES; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; ss += d * d; }
   const float rstd = 1.f / sqrtf(warp_sum(ss) / C + 1e-5f);
 #pragma unroll
-  for (int i = 0; i < PER / 4; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
-    const float4 be = *reinterpret_cast<const float4*>(beta + c);
-    float o[4];
-    o[0] = (v[4 * i] - mean) * rstd * g.x + be.x;
-    o[1] = (v[4 * i + 1] - mean) * rstd * g.y + be.y;
-    o[2] = (v[4 * i + 2] - mean) * rstd * g.z + be.z;
-    o[3] = (v[4 * i + 3] - mean) * rstd * g.w + be.w;
+  for (int i = 0; i < PASSES; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 e0 = *reinterpret_cast<const float4*>(beta + c), e1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * g[k] + be[k];
     *reinterpret_cast<float4*>(x_out + base + c) = make_float4(o[0], o[1], o[2], o[3]);
-    if (a_x != nullptr) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) store_split(a_x + static_cast<long long>(row) * (2 * C) + c + k, C, o[k]);
-    }
+    *reinterpret_cast<float4*>(x_out + base + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    if (a_x != nullptr) store_split8(a_x + static_cast<long long>(row) * (2 * C) + c, C, o);
     if (a_xpe != nullptr) {
-      const float4 e = *reinterpret_cast<const float4*>(pe + base + c);
-      const float ev[4] = {e.x, e.y, e.z, e.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) store_split(a_xpe + static_cast<long long>(row) * (2 * C) + c + k, C, o[k] + ev[k]);
+      const float4 p0 = *reinterpret_cast<const float4*>(pe + base + c), p1 = *reinterpret_cast<const float4*>(pe + base + c + 4);
+      const float op[8] = {o[0] + p0.x, o[1] + p0.y, o[2] + p0.z, o[3] + p0.w, o[4] + p1.x, o[5] + p1.y, o[6] + p1.z, o[7] + p1.w};
+      store_split8(a_xpe + static_cast<long long>(row) * (2 * C) + c, C, op);
     }
   }
 }
@@ -140,23 +153,32 @@ __device__ __forceinline__ void gn_mean_rstd(const double2* partial, int groups,
   rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
 }
 
-// out: (B*Nq, groups * 2C): group g's [hi | lo] at columns [g*2C, (g+1)*2C)
+// out: (B*Nq, groups * 2C): group g's [hi | lo] at columns [g*2C, (g+1)*2C).  One block per row;
+// a thread owns 8 consecutive channels (C/8 threads per group).
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ h, int ldh, int C, int Nq, int groups, const double2* __restrict__ partial,
                 const float* __restrict__ gamma0, const float* __restrict__ beta0, const float* __restrict__ gamma1,
                 const float* __restrict__ beta1, __nv_bfloat16* __restrict__ out) {
   const int row = blockIdx.x;           // b*Nq + q
   const int b = row / Nq;
-  for (int g = 0; g < groups; ++g) {
+  const int per_group = C / 8;
+  for (int item = threadIdx.x; item < groups * per_group; item += blockDim.x) {
+    const int g = item / per_group, c = (item % per_group) * 8;
     float mean, rstd;
     gn_mean_rstd(partial, groups, b, g, C, Nq, mean, rstd);
     const float* gamma = g == 0 ? gamma0 : gamma1;
     const float* beta = g == 0 ? beta0 : beta1;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const float v = h[static_cast<long long>(row) * ldh + g * C + c];
-      const float o = fmaxf((v - mean) * rstd * gamma[c] + beta[c], 0.f);
-      store_split(out + static_cast<long long>(row) * (groups * 2 * C) + g * 2 * C + c, C, o);
-    }
+    const float* src = h + static_cast<long long>(row) * ldh + g * C + c;
+    const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 e0 = *reinterpret_cast<const float4*>(beta + c), e1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaxf((v[k] - mean) * rstd * gg[k] + be[k], 0.f);
+    store_split8(out + static_cast<long long>(row) * (groups * 2 * C) + g * 2 * C + c, C, o);
   }
 }
 
@@ -183,13 +205,30 @@ struct HeadsParams {
   float span[3], lo[3];
 };
 
+constexpr int HEADS_MAX_OUT = 16 + 3 + 3 + 6;   // cls (<=16) + size + center + rotation rows of weights
+
+// Block = 8 warps; the (num_cls + 12) x C final-layer weights are staged once per block in shared memory
+// and every warp then walks rows (queries) blockIdx.x*rows_per_block ...; one warp per row.
 template <int C>
-__global__ void __launch_bounds__(128)
-heads_final_kernel(const HeadsParams p) {
+__global__ void __launch_bounds__(256)
+heads_final_kernel(const HeadsParams p, int rows_per_block) {
   constexpr int PER = C / 32;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  extern __shared__ float sw[];           // [(num_cls + 12)][C]
+  const int nw = p.num_cls + 12;
+  for (int i = threadIdx.x * 4; i < nw * C; i += blockDim.x * 4) {
+    const int j = i / C, c = i % C;
+    const float* src = j < p.num_cls ? p.w_cls + j * C : (j < p.num_cls + 3 ? p.w_size + (j - p.num_cls) * C
+                       : (j < p.num_cls + 6 ? p.w_c3 + (j - p.num_cls - 3) * C : p.w_r3 + (j - p.num_cls - 6) * C));
+    *reinterpret_cast<float4*>(sw + i) = *reinterpret_cast<const float4*>(src + c);
+  }
+  __syncthreads();
+  const float* s_cls = sw;
+  const float* s_size = sw + p.num_cls * C;
+  const float* s_c3 = s_size + 3 * C;
+  const float* s_r3 = s_c3 + 3 * C;
   const int lane = threadIdx.x & 31;
-  if (row >= p.R) return;
+  const int row_end = min(p.R, (blockIdx.x + 1) * rows_per_block);
+  for (int row = blockIdx.x * rows_per_block + (threadIdx.x >> 5); row < row_end; row += (blockDim.x >> 5)) {
   const int b = row / p.Nq;
   float xv[PER], hc[PER], hr[PER];
   float mean_c, rstd_c, mean_r, rstd_r;
@@ -211,15 +250,15 @@ heads_final_kernel(const HeadsParams p) {
     return warp_sum(s);
   };
   float cls[16];
-  for (int j = 0; j < p.num_cls; ++j) cls[j] = dot(p.w_cls + j * C, xv) + p.b_cls[j];
+  for (int j = 0; j < p.num_cls; ++j) cls[j] = dot(s_cls + j * C, xv) + p.b_cls[j];
   float sz[3], co[3], o6[6];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) sz[j] = dot(p.w_size + j * C, xv) + p.b_size[j];
+  for (int j = 0; j < 3; ++j) sz[j] = dot(s_size + j * C, xv) + p.b_size[j];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) co[j] = dot(p.w_c3 + j * C, hc) + p.b_c3[j];
+  for (int j = 0; j < 3; ++j) co[j] = dot(s_c3 + j * C, hc) + p.b_c3[j];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) o6[j] = dot(p.w_r3 + j * C, hr) + p.b_r3[j];
-  if (lane != 0) return;
+  for (int j = 0; j < 6; ++j) o6[j] = dot(s_r3 + j * C, hr) + p.b_r3[j];
+  if (lane != 0) continue;
 
   // softmax + first-index argmax over the probabilities (torch.argmax tie rule)
   float mx = cls[0];
@@ -261,6 +300,7 @@ heads_final_kernel(const HeadsParams p) {
     r[3] = x1; r[4] = y1; r[5] = z1;
     r[6] = x2; r[7] = y2; r[8] = z2;
   }
+  }   // row loop
 }
 
 }  // namespace parq
