@@ -38,6 +38,7 @@ struct AttnParams {
   int tiles_per_split;   // key tiles (128 keys) per split
   float* o_part;         // [((b*H+h)*nsplit + s)*Nq + q][256]
   float2* ml_part;       // [((b*H+h)*nsplit + s)*Nq + q] = (m, l)
+  __nv_bfloat16* out_direct;   // nsplit == 1 only: normalised output (B*Nq, 2*H*256) [hi|lo], no combine pass
 };
 
 namespace attn {
@@ -267,23 +268,49 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_arrive(&p_full[buf]);
       if (!pv_seen) mbar_wait(pv_done, (j - 1) & 1);
     }
-    // epilogue: un-normalised O, m, l of this split
+    // epilogue
     mbar_wait(pv_done, (n - 1) & 1);
     tc_fence_after();
-    const long long part = (static_cast<long long>(bh) * p.nsplit + split) * p.Nq + qt * BQ + q * 32 + lane;
-    float* orow = p.o_part + part * DH;
+    if (p.out_direct != nullptr) {
+      // single split: normalise here and emit the [hi|lo] operand of the out-projection directly
+      const float inv = 1.f / l_run;
+      const int C = p.H * DH;
+      __nv_bfloat16* dst = p.out_direct + (static_cast<long long>(b) * p.Nq + qt * BQ + q * 32 + lane) * (2 * C) + h * DH;
 #pragma unroll 1
-    for (int c = 0; c < DH / 32; ++c) {
-      uint32_t o[32];
-      tmem_ld32(tmem_O + lane_base + c * 32, o);
-      tmem_wait_ld();
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tmem_O + lane_base + c * 32, o);
+        tmem_wait_ld();
+        uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        reinterpret_cast<float4*>(orow + c * 32)[i] =
-            make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
-                        __uint_as_float(o[4 * i + 3]));
+        for (int i = 0; i < 16; ++i) {
+          const float v0 = __uint_as_float(o[2 * i]) * inv, v1 = __uint_as_float(o[2 * i + 1]) * inv;
+          hi[i] = pack_bf16x2(v0, v1);
+          lo[i] = pack_bf16x2(v0 - __uint_as_float(hi[i] << 16), v1 - __uint_as_float(hi[i] & 0xFFFF0000u));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          reinterpret_cast<uint4*>(dst + c * 32)[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+          reinterpret_cast<uint4*>(dst + C + c * 32)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+        }
+      }
+    } else {
+      // un-normalised O, m, l of this split for attn_combine_kernel
+      const long long part = (static_cast<long long>(bh) * p.nsplit + split) * p.Nq + qt * BQ + q * 32 + lane;
+      float* orow = p.o_part + part * DH;
+#pragma unroll 1
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tmem_O + lane_base + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<float4*>(orow + c * 32)[i] =
+              make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
+                          __uint_as_float(o[4 * i + 3]));
+      }
+      p.ml_part[part] = make_float2(m_run, l_run);
     }
-    p.ml_part[part] = make_float2(m_run, l_run);
   }
 
   tc_fence_before();

@@ -36,6 +36,8 @@ struct GemmEpilogue {
   long long ld_lp;
   int lp_fp16;
   long long lp_lo_off; // > 0: also store the bf16 residual (v - hi) at column offset lp_lo_off
+  double2* gn_out;     // optional: per-tile (sum, sum of squares) of the outputs, slot m_tile*gn_stride + n_tile
+  int gn_stride;
 };
 
 struct GemmParams {
@@ -54,14 +56,38 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_BYTES = BN * BK * 2;   // 32 KB
 constexpr int THREADS = 256;
-constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
+constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/ + 64 /*GroupNorm tile sums*/ +
+                           4 * 32 * 33 * 4 /*per-warp store staging*/;
 }  // namespace gemm
 
-// Epilogue for one row x 32 accumulator columns: bias / ReLU, then fp32 and/or 16-bit stores
-// (bf16 or fp16; optionally the bf16 residual "lo" for the split layout).  Everything is
-// statically indexed so the values stay in registers; `full` = all 32 columns are in range.
+// Coalesced write of a warp's 32x32 block of 32-bit words (fp32 values, or packed 16-bit pairs when
+// words_per_row == 16) that was staged in shared memory as stage[row][word] with row stride 33:
+// eight (four) consecutive lanes cover one output row, so every store instruction writes whole 128-byte
+// (64-byte) row segments instead of 32 scattered 16-byte pieces.
+template <int kWordsPerRow, typename T>
+__device__ __forceinline__ void gemm_flush_stage(const uint32_t* stage, T* out, long long ld_elems, long long row0, int lane, int M) {
+  constexpr int LANES_PER_ROW = kWordsPerRow / 4;
+  constexpr int ROWS_PER_IT = 32 / LANES_PER_ROW;
+  constexpr int ELEMS_PER_WORD = 4 / sizeof(T);
+#pragma unroll
+  for (int it = 0; it < 32 / ROWS_PER_IT; ++it) {
+    const int r = it * ROWS_PER_IT + lane / LANES_PER_ROW;
+    const int w = (lane % LANES_PER_ROW) * 4;
+    const uint32_t* sp = stage + r * 33 + w;
+    const uint4 v = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+    if (row0 + r < M) *reinterpret_cast<uint4*>(out + (row0 + r) * ld_elems + w * ELEMS_PER_WORD) = v;
+  }
+}
+
+// Epilogue for a warp's 32 rows x 32 accumulator columns (thread = row): bias / ReLU, GroupNorm tile sums,
+// then fp32 and/or 16-bit outputs (bf16 or fp16; optionally the bf16 residual "lo" of the split layout).
+// Full chunks go through the per-warp shared-memory stage for coalesced stores; a ragged last chunk
+// (N not a multiple of 32) is written directly with per-element guards.
 __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], const float* sbias, float row_bias,
-                                                 long long row, int col0, int N) {
+                                                 long long row0, int lane, int col0, int M, int N, uint32_t* stage, float& gsum,
+                                                 float& gsq) {
+  const long long row = row0 + lane;
+  const bool row_ok = row < M;
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + row_bias;
@@ -77,19 +103,27 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   }
   const bool full = (col0 + 32 <= N);
+  if (ep.gn_out != nullptr && row_ok) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (full || col0 + i < N) { gsum += v[i]; gsq = fmaf(v[i], v[i], gsq); }
+  }
   if (ep.out_f32 != nullptr) {
-    float* o = ep.out_f32 + row * ep.ld_f32 + col0;
     if (full) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else {
+      for (int i = 0; i < 32; ++i) stage[lane * 33 + i] = __float_as_uint(v[i]);
+      __syncwarp();
+      gemm_flush_stage<32>(stage, ep.out_f32 + col0, ep.ld_f32, row0, lane, M);
+      __syncwarp();
+    } else if (row_ok) {
+      float* o = ep.out_f32 + row * ep.ld_f32 + col0;
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (col0 + i < N) o[i] = v[i];
     }
   }
   if (ep.out_lp != nullptr) {
-    uint16_t* o = reinterpret_cast<uint16_t*>(ep.out_lp) + row * ep.ld_lp + col0;
+    uint16_t* obase = reinterpret_cast<uint16_t*>(ep.out_lp) + col0;
     uint32_t w[16];
     if (ep.lp_fp16) {
 #pragma unroll
@@ -100,8 +134,12 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
     }
     if (full) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(o)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-    } else {
+      for (int i = 0; i < 16; ++i) stage[lane * 33 + i] = w[i];
+      __syncwarp();
+      gemm_flush_stage<16>(stage, obase, ep.ld_lp, row0, lane, M);
+      __syncwarp();
+    } else if (row_ok) {
+      uint16_t* o = obase + row * ep.ld_lp;
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (col0 + i < N) o[i] = static_cast<uint16_t>((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu));
@@ -113,11 +151,14 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
         const float h0 = __uint_as_float(w[i] << 16), h1 = __uint_as_float(w[i] & 0xFFFF0000u);
         l[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
       }
-      uint16_t* ol = o + ep.lp_lo_off;
       if (full) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(ol)[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
-      } else {
+        for (int i = 0; i < 16; ++i) stage[lane * 33 + i] = l[i];
+        __syncwarp();
+        gemm_flush_stage<16>(stage, obase + ep.lp_lo_off, ep.ld_lp, row0, lane, M);
+        __syncwarp();
+      } else if (row_ok) {
+        uint16_t* ol = obase + row * ep.ld_lp + ep.lp_lo_off;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (col0 + i < N) ol[i] = static_cast<uint16_t>((i & 1) ? (l[i >> 1] >> 16) : (l[i >> 1] & 0xFFFFu));
@@ -139,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [2][BN]
+  uint32_t* sstage = reinterpret_cast<uint32_t*>(sbias + 2 * BN) + 16;                   // [4 warps][32][33], after the GN sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -233,7 +275,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int m0, n0;
       tile_origin(tile, m0, n0);
       const int acc = lt & 1;
-      const long long row = m0 + q * 32 + lane;
+      const long long row0 = m0 + q * 32;
+      const long long row = row0 + lane;
+      uint32_t* stage = sstage + q * (32 * 33);
       // stage this tile's bias while the MMA of the tile is still running
       float row_bias = 0.f;
       if (col_bias) {
@@ -248,20 +292,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       uint32_t r0[32], r1[32];
+      float gsum = 0.f, gsq = 0.f;
       tmem_ld32(taddr, r0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c += 2) {
         tmem_wait_ld();
         tmem_ld32(taddr + (c + 1) * 32, r1);                 // next chunk in flight while this one is stored
         int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) gemm_store_chunk(p.ep, r0, col_bias ? sbias + acc * BN + c * 32 : nullptr, row_bias, row, col0, p.N);
+        if (col0 < p.N) gemm_store_chunk(p.ep, r0, col_bias ? sbias + acc * BN + c * 32 : nullptr, row_bias, row0, lane, col0, p.M, p.N, stage, gsum, gsq);
         tmem_wait_ld();
         if (c + 2 < BN / 32) tmem_ld32(taddr + (c + 2) * 32, r0);
         col0 += 32;
-        if (row < p.M && col0 < p.N) gemm_store_chunk(p.ep, r1, col_bias ? sbias + acc * BN + (c + 1) * 32 : nullptr, row_bias, row, col0, p.N);
+        if (col0 < p.N) gemm_store_chunk(p.ep, r1, col_bias ? sbias + acc * BN + (c + 1) * 32 : nullptr, row_bias, row0, lane, col0, p.M, p.N, stage, gsum, gsq);
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
+      if (p.ep.gn_out != nullptr) {
+        // deterministic tile statistics for the following GroupNorm: lanes -> warp (shuffles, double) -> 4 warps (smem)
+        double ds = gsum, dq = gsq;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          ds += __shfl_xor_sync(0xffffffffu, ds, o);
+          dq += __shfl_xor_sync(0xffffffffu, dq, o);
+        }
+        double* sg = reinterpret_cast<double*>(sbias + 2 * BN);      // [4][2]
+        if (lane == 0) { sg[2 * q] = ds; sg[2 * q + 1] = dq; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0)
+          p.ep.gn_out[static_cast<long long>(m0 / BM) * p.ep.gn_stride + n0 / BN] =
+              make_double2((sg[0] + sg[2]) + (sg[4] + sg[6]), (sg[1] + sg[3]) + (sg[5] + sg[7]));
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
     }
   }
 

@@ -198,6 +198,7 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
   ap.B = B; ap.H = H; ap.Nq = Nq; ap.Nk = Nk;
   ap.nsplit = plan.nsplit;
   ap.tiles_per_split = plan.tiles_per_split;
+  ap.out_direct = plan.nsplit == 1 ? out_split : nullptr;
   const size_t rows = static_cast<size_t>(B) * H * plan.nsplit * Nq;
   ap.o_part = reinterpret_cast<float*>(scratch);
   ap.ml_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(scratch) + align_up(rows * 256 * sizeof(float), 256));
@@ -216,7 +217,7 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
       attn_tc_kernel<false><<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, ap);
   }
   CUDA_TRY(cudaGetLastError());
-  {
+  if (plan.nsplit > 1) {
     ProfScope ps(TAG_COMBINE, st);
     attn_combine_kernel<<<B * Nq, 256, 0, st>>>(ap.o_part, ap.ml_part, out_split, H, Nq, plan.nsplit);
   }
@@ -333,8 +334,8 @@ static Workspace workspace_layout(const ParqShape& s, int sms) {
   w.h1 = take(R * 2 * C * 4);
   w.a_h1 = take(R * 4 * C * 2);
   w.h2 = take(R * 2 * C * 4);
-  w.gn1 = take(static_cast<size_t>(s.B) * 2 * GN_BLOCKS * sizeof(double2));
-  w.gn2 = take(static_cast<size_t>(s.B) * 2 * GN_BLOCKS * sizeof(double2));
+  w.gn1 = take(R / 128 * GN_SLOTS_PER_MTILE * sizeof(double2));
+  w.gn2 = take(R / 128 * GN_SLOTS_PER_MTILE * sizeof(double2));
   w.total = off;
   return w;
 }
@@ -743,8 +744,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.M = R; g.N = 2 * C; term_offsets(g, C, w_lo, 0);
       g.ep = epilogue_none();
       g.ep.out_f32 = F32(W.h1); g.ep.ld_f32 = 2 * C;
+      g.ep.gn_out = reinterpret_cast<double2*>(ws + W.gn1); g.ep.gn_stride = GN_SLOTS_PER_MTILE;
       TRY(launch_gemm(st, ws + W.a_x3, R, 2 * C, pk + P.hd1, 2 * C, 2 * C, g));
-      { ProfScope ps(TAG_ROWWISE, st); gn_stats_kernel<<<dim3(GN_BLOCKS, 2, s.B), 256, 0, st>>>(F32(W.h1), 2 * C, C, s.Nq, reinterpret_cast<double2*>(ws + W.gn1)); }
       { ProfScope ps(TAG_ROWWISE, st); gn_apply_kernel<<<R, 256, 0, st>>>(F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1), PF(P.ctr1_g),
                                          PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1)); }
       CUDA_TRY(cudaGetLastError());
@@ -753,10 +754,9 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
         g.M = R; g.N = C; term_offsets(g, C, w_lo, hd * 2 * C);
         g.ep = epilogue_none();
         g.ep.out_f32 = F32(W.h2) + hd * C; g.ep.ld_f32 = 2 * C;
+        g.ep.gn_out = reinterpret_cast<double2*>(ws + W.gn2) + hd * (C / 256); g.ep.gn_stride = GN_SLOTS_PER_MTILE;
         TRY(launch_gemm(st, ws + W.a_h1, R, 4 * C, pk + (hd == 0 ? P.ctr4 : P.rot4), C, 2 * C, g));
       }
-      { ProfScope ps(TAG_ROWWISE, st); gn_stats_kernel<<<dim3(GN_BLOCKS, 2, s.B), 256, 0, st>>>(F32(W.h2), 2 * C, C, s.Nq, reinterpret_cast<double2*>(ws + W.gn2)); }
-      CUDA_TRY(cudaGetLastError());
       hp.x = x3; hp.h2 = F32(W.h2); hp.partial = reinterpret_cast<const double2*>(ws + W.gn2);
       hp.gamma_c = PF(P.ctr5_g); hp.beta_c = PF(P.ctr5_b); hp.gamma_r = PF(P.rot5_g); hp.beta_r = PF(P.rot5_b);
       hp.w_cls = PF(P.cls_w); hp.b_cls = PF(P.cls_b); hp.w_size = PF(P.size_w); hp.b_size = PF(P.size_b);
@@ -771,10 +771,10 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       hp.R = R; hp.Nq = s.Nq; hp.C = C; hp.num_cls = s.num_cls;
       { ProfScope ps(TAG_ROWWISE, st); {
         const int rpb = (R + device_info().sms - 1) / device_info().sms;     // rows per block: one block per SM
-        const size_t hsm = static_cast<size_t>(s.num_cls + 12) * C * sizeof(float);
+        const size_t hsm = static_cast<size_t>(s.num_cls + 12 + 4) * C * sizeof(float);
         static thread_local bool hattr = false;
         if (!hattr) {
-          cudaFuncSetAttribute(heads_final_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(HEADS_MAX_OUT * 1024 * sizeof(float)));
+          cudaFuncSetAttribute(heads_final_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>((HEADS_MAX_OUT + 4) * 1024 * sizeof(float)));
           hattr = true;
         }
         heads_final_kernel<1024><<<(R + rpb - 1) / rpb, 256, hsm, st>>>(hp, rpb);

@@ -182,26 +182,29 @@ project_sample_kernel(const SampleParams p) {
     }
     nvalid += __popc(__ballot_sync(0xffffffffu, is_valid));
 
-    // ---- all lanes gather, four views in flight
-    const int nv = min(32, p.T - tb);
-    for (int v0 = 0; v0 < nv; v0 += 4) {
+    // ---- all lanes gather.  Only views with at least one in-bounds corner contribute (zero padding):
+    // their lane ids are compacted from a ballot, four of them (16 independent 16-byte loads) in flight.
+    unsigned live = __ballot_sync(0xffffffffu, tap.inb != 0);
+    while (live != 0u) {
       uint4 tex[4][4];
       float wgt[4][4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int src = min(v0 + k, nv - 1);
+        const bool have = live != 0u;
+        const int src = have ? (__ffs(live) - 1) : 0;
+        if (have) live &= live - 1;
         const int x0 = __shfl_sync(0xffffffffu, tap.x0, src);
         const int y0 = __shfl_sync(0xffffffffu, tap.y0, src);
         const float fx = __shfl_sync(0xffffffffu, tap.fx, src);
         const float fy = __shfl_sync(0xffffffffu, tap.fy, src);
         int inb = __shfl_sync(0xffffffffu, tap.inb, src);
-        if (v0 + k >= nv) inb = 0;
+        if (!have) inb = 0;
         const float ex = 1.f - fx, sy_ = 1.f - fy;       // distances to east / south (ATen CPU form)
         wgt[k][0] = sy_ * ex;   // nw
         wgt[k][1] = sy_ * fx;   // ne
         wgt[k][2] = fy * ex;    // sw
         wgt[k][3] = fy * fx;    // se
-        const long long view = static_cast<long long>(b) * p.T + tb + v0 + k;
+        const long long view = static_cast<long long>(b) * p.T + tb + src;
         const __nv_bfloat16* base = p.tokens + ((view * p.H + y0) * p.W + x0) * static_cast<long long>(p.C) + ch;
         const long long rowpitch = static_cast<long long>(p.W) * p.C;
 #pragma unroll

@@ -104,51 +104,26 @@ add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y, const
 // ---------------------------------------------------------------------------------------------
 // GroupNorm(1, C) of the 3-layer heads (reference generic_mlp.py:85-86): statistics over the whole
 // (C x Nq) block of one clip.  Two phases, deterministic:
-//   gn_stats_kernel : grid (GN_BLOCKS, groups, B) -> partial (sum, sumsq) in double
+//   GEMM epilogue   : per-tile (sum, sumsq) partials in double (fixed slots -> deterministic)
 //   gn_apply_kernel : reduces the partials in fixed order, applies affine + ReLU, emits bf16 split
 // h: (B*Nq, ldh) fp32, group g occupies columns [g*C, (g+1)*C).
 // ---------------------------------------------------------------------------------------------
-constexpr int GN_BLOCKS = 16;
+// Statistics come from the GEMM epilogue (gemm_tc.cuh): one (sum, sumsq) double2 per 128x256 output tile in
+// slot m_tile*8 + n_tile, where n_tile = g*(C/256) + tile-in-group.  A clip owns Nq/128 consecutive m-tiles.
+constexpr int GN_SLOTS_PER_MTILE = 8;
 
-__global__ void __launch_bounds__(256)
-gn_stats_kernel(const float* __restrict__ h, int ldh, int C, int Nq, double2* __restrict__ partial) {
-  const int blk = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
-  const int rows_per = (Nq + GN_BLOCKS - 1) / GN_BLOCKS;
-  const int r0 = blk * rows_per, r1 = min(Nq, r0 + rows_per);
-  float s = 0.f, ss = 0.f;
-  double ds = 0.0, dss = 0.0;
-  for (int r = r0; r < r1; ++r) {
-    const float* rowp = h + (static_cast<long long>(b) * Nq + r) * ldh + g * C;
-    s = 0.f; ss = 0.f;
-    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
-      const float4 v = *reinterpret_cast<const float4*>(rowp + c);
-      s += v.x + v.y + v.z + v.w;
-      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    }
-    ds += s; dss += ss;
-  }
-  __shared__ double sh[2][256];
-  sh[0][threadIdx.x] = ds;
-  sh[1][threadIdx.x] = dss;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
-      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) partial[(static_cast<long long>(b) * gridDim.y + g) * GN_BLOCKS + blk] = make_double2(sh[0][0], sh[1][0]);
-}
-
-__device__ __forceinline__ void gn_mean_rstd(const double2* partial, int groups, int b, int g, int C, int Nq, float& mean,
-                                             float& rstd) {
+__device__ __forceinline__ void gn_mean_rstd(const double2* partial, int b, int g, int C, int Nq, float& mean, float& rstd) {
   double s = 0.0, ss = 0.0;
-  const double2* pp = partial + (static_cast<long long>(b) * groups + g) * GN_BLOCKS;
-  for (int i = 0; i < GN_BLOCKS; ++i) { s += pp[i].x; ss += pp[i].y; }
-  const double n = static_cast<double>(C) * Nq;
-  const double m = s / n;
-  const double var = fmax(ss / n - m * m, 0.0);
+  const int mt = Nq / 128, nt = C / 256;
+  for (int m = 0; m < mt; ++m)
+    for (int n = 0; n < nt; ++n) {
+      const double2 v = partial[static_cast<long long>(b * mt + m) * GN_SLOTS_PER_MTILE + g * nt + n];
+      s += v.x;
+      ss += v.y;
+    }
+  const double cnt = static_cast<double>(C) * Nq;
+  const double m = s / cnt;
+  const double var = fmax(ss / cnt - m * m, 0.0);
   mean = static_cast<float>(m);
   rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
 }
@@ -162,10 +137,12 @@ gn_apply_kernel(const float* __restrict__ h, int ldh, int C, int Nq, int groups,
   const int row = blockIdx.x;           // b*Nq + q
   const int b = row / Nq;
   const int per_group = C / 8;
+  __shared__ float s_stat[2][2];
+  if (threadIdx.x < groups) gn_mean_rstd(partial, b, threadIdx.x, C, Nq, s_stat[threadIdx.x][0], s_stat[threadIdx.x][1]);
+  __syncthreads();
   for (int item = threadIdx.x; item < groups * per_group; item += blockDim.x) {
     const int g = item / per_group, c = (item % per_group) * 8;
-    float mean, rstd;
-    gn_mean_rstd(partial, groups, b, g, C, Nq, mean, rstd);
+    const float mean = s_stat[g][0], rstd = s_stat[g][1];
     const float* gamma = g == 0 ? gamma0 : gamma1;
     const float* beta = g == 0 ? beta0 : beta1;
     const float* src = h + static_cast<long long>(row) * ldh + g * C + c;
@@ -193,7 +170,7 @@ gn_apply_kernel(const float* __restrict__ h, int ldh, int C, int Nq, int groups,
 struct HeadsParams {
   const float* x;          // (R, C)   decoder-layer output (after LN3)
   const float* h2;         // (R, 2C)  pre-GroupNorm hidden of layer 2: center | rotation
-  const double2* partial;  // GN partial sums of h2, groups = 2
+  const double2* partial;  // GroupNorm tile sums of h2 written by the GEMM epilogue
   const float *gamma_c, *beta_c, *gamma_r, *beta_r;
   const float *w_cls, *b_cls, *w_size, *b_size, *w_c3, *b_c3, *w_r3, *b_r3;   // (n, C) row-major, fp32
   const float* ref;        // (R, 3) normalised reference points of this iteration
@@ -213,8 +190,12 @@ template <int C>
 __global__ void __launch_bounds__(256)
 heads_final_kernel(const HeadsParams p, int rows_per_block) {
   constexpr int PER = C / 32;
-  extern __shared__ float sw[];           // [(num_cls + 12)][C]
+  extern __shared__ float sw[];           // [(num_cls + 12)][C] weights, then gamma_c | beta_c | gamma_r | beta_r
   const int nw = p.num_cls + 12;
+  float* s_aff = sw + nw * C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_aff[i] = p.gamma_c[i]; s_aff[C + i] = p.beta_c[i]; s_aff[2 * C + i] = p.gamma_r[i]; s_aff[3 * C + i] = p.beta_r[i];
+  }
   for (int i = threadIdx.x * 4; i < nw * C; i += blockDim.x * 4) {
     const int j = i / C, c = i % C;
     const float* src = j < p.num_cls ? p.w_cls + j * C : (j < p.num_cls + 3 ? p.w_size + (j - p.num_cls) * C
@@ -231,17 +212,18 @@ heads_final_kernel(const HeadsParams p, int rows_per_block) {
   for (int row = blockIdx.x * rows_per_block + (threadIdx.x >> 5); row < row_end; row += (blockDim.x >> 5)) {
   const int b = row / p.Nq;
   float xv[PER], hc[PER], hr[PER];
-  float mean_c, rstd_c, mean_r, rstd_r;
-  gn_mean_rstd(p.partial, 2, b, 0, C, p.Nq, mean_c, rstd_c);
-  gn_mean_rstd(p.partial, 2, b, 1, C, p.Nq, mean_r, rstd_r);
+  float mean_l = 0.f, rstd_l = 0.f;
+  if (lane < 2) gn_mean_rstd(p.partial, b, lane, C, p.Nq, mean_l, rstd_l);
+  const float mean_c = __shfl_sync(0xffffffffu, mean_l, 0), rstd_c = __shfl_sync(0xffffffffu, rstd_l, 0);
+  const float mean_r = __shfl_sync(0xffffffffu, mean_l, 1), rstd_r = __shfl_sync(0xffffffffu, rstd_l, 1);
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int c = i * 32 + lane;
     xv[i] = p.x[static_cast<long long>(row) * C + c];
     const float a = p.h2[static_cast<long long>(row) * (2 * C) + c];
     const float r = p.h2[static_cast<long long>(row) * (2 * C) + C + c];
-    hc[i] = fmaxf((a - mean_c) * rstd_c * p.gamma_c[c] + p.beta_c[c], 0.f);
-    hr[i] = fmaxf((r - mean_r) * rstd_r * p.gamma_r[c] + p.beta_r[c], 0.f);
+    hc[i] = fmaxf((a - mean_c) * rstd_c * s_aff[c] + s_aff[C + c], 0.f);
+    hr[i] = fmaxf((r - mean_r) * rstd_r * s_aff[2 * C + c] + s_aff[3 * C + c], 0.f);
   }
   auto dot = [&](const float* w, const float (&v)[PER]) {
     float s = 0.f;

@@ -125,6 +125,8 @@ class DecoderEngine:
         self.weight_lo = bool(rc)
         self._ws = None
         self._ws_key = None
+        self._graphs = {}
+        self._ref0_cache = None
         del keep
 
     def _shape(self, B, T, H, W):
@@ -136,6 +138,7 @@ class DecoderEngine:
             if nbytes == 0:
                 raise _lib.ParqError("parq_workspace_bytes: " + self.lib.parq_last_error().decode())
             self._ws = None
+            self._graphs.clear()          # captured graphs point into the old workspace
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._ws_key = key
         return self._ws
@@ -144,9 +147,40 @@ class DecoderEngine:
     def flags(self):
         return _lib.PARQ_FLAG_WEIGHT_LO if self.weight_lo else 0
 
-    def forward(self, tokens, camera, T_cp, T_wp, T_wl, H, W, forced_refs=None, ref0=None, debug=False, skip_kv=False):
+    def _alloc_outputs(self, B, T, debug):
+        it, Nq, dev = self.iters, self.Nq, self.device
+        outs = {k: torch.empty(it, B, Nq, n if n else self.num_cls, dtype=torch.float32, device=dev) for k, n in OUTPUT_KEYS}
+        if debug:
+            outs["rotation"] = torch.empty(it, B, Nq, 3, 3, dtype=torch.float32, device=dev)
+            outs["center_im"] = torch.empty(it, B, T, Nq, 2, dtype=torch.float32, device=dev)
+            outs["center_valid"] = torch.empty(it, B, T, Nq, dtype=torch.uint8, device=dev)
+            outs["features"] = torch.empty(it, B, Nq, self.C, dtype=torch.float32, device=dev)
+            outs["decoder_out"] = torch.empty(it, B, Nq, self.C, dtype=torch.float32, device=dev)
+        po = _lib.ParqOutputs()
+        for k in outs:
+            setattr(po, k, outs[k].data_ptr())
+        return outs, po
+
+    def _launch(self, shape, tokens, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.parq_decoder_forward(C.byref(shape), _ptr(tokens), _ptr(camera), _ptr(T_cp), _ptr(T_wp), _ptr(T_wl),
+                                                     _ptr(ref0), _ptr(fr), _ptr(self.packed), _ptr(ws), ws.numel(), C.byref(po),
+                                                     flags, _stream()), "parq_decoder_forward")
+
+    def _ref0(self, B):
+        # sigmoid(refpoint.weight) repeated per clip (reference transformer_parq.py:121,309); cached per batch size
+        if self._ref0_cache is None or self._ref0_cache.shape[0] != B:
+            self._ref0_cache = self.refpoint.sigmoid().unsqueeze(0).repeat(B, 1, 1).contiguous()
+        return self._ref0_cache
+
+    def forward(self, tokens, camera, T_cp, T_wp, T_wl, H, W, forced_refs=None, ref0=None, debug=False, skip_kv=False,
+                graph=False):
         """tokens (B, T*H*W, C) bf16 (fp32 is rounded to bf16); camera (B,T,6); poses (B,T,12)/(B,1,12) fp32.
-        Returns a dict of stacked per-iteration tensors (iters, B, Nq, n)."""
+        Returns a dict of stacked per-iteration tensors (iters, B, Nq, n).
+
+        ``graph=True`` replays the whole forward (~180 kernel launches) as ONE CUDA graph captured on first
+        use for this exact set of input buffers; the returned tensors are then static buffers that the next
+        replay overwrites."""
         if tokens.device != self.device:
             raise NotImplementedError("tokens must live on %s (no host or cross-device fallback)" % self.device)
         B, T = T_cp.shape[0], T_cp.shape[1]
@@ -161,34 +195,35 @@ class DecoderEngine:
             raise ValueError("T_world_local must have shape (B, 1, 12)")
         shape = self._shape(B, T, H, W)
         ws = self._workspace(shape, (B, T, H, W))
-        it, Nq, dev = self.iters, self.Nq, self.device
-        outs = {k: torch.empty(it, B, Nq, n if n else self.num_cls, dtype=torch.float32, device=dev) for k, n in OUTPUT_KEYS}
-        po = _lib.ParqOutputs()
-        for k in outs:
-            setattr(po, k, outs[k].data_ptr())
-        if debug:
-            outs["rotation"] = torch.empty(it, B, Nq, 3, 3, dtype=torch.float32, device=dev)
-            outs["center_im"] = torch.empty(it, B, T, Nq, 2, dtype=torch.float32, device=dev)
-            outs["center_valid"] = torch.empty(it, B, T, Nq, dtype=torch.uint8, device=dev)
-            outs["features"] = torch.empty(it, B, Nq, self.C, dtype=torch.float32, device=dev)
-            outs["decoder_out"] = torch.empty(it, B, Nq, self.C, dtype=torch.float32, device=dev)
-            for k in ("rotation", "center_im", "center_valid", "features", "decoder_out"):
-                setattr(po, k, outs[k].data_ptr())
-        if ref0 is None:
-            ref0 = self.refpoint.sigmoid().unsqueeze(0).repeat(B, 1, 1)
-        ref0 = f32(ref0)
+        ref0 = self._ref0(B) if ref0 is None else f32(ref0)
         fr = f32(forced_refs) if forced_refs is not None else None
-        if fr is not None and tuple(fr.shape) != (it, B, Nq, 3):
+        if fr is not None and tuple(fr.shape) != (self.iters, B, self.Nq, 3):
             raise ValueError("forced_refs must be (iters, B, Nq, 3)")
         flags = self.flags | (_lib.PARQ_FLAG_SKIP_KV if skip_kv else 0)
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.parq_decoder_forward(C.byref(shape), _ptr(tokens), _ptr(camera), _ptr(T_cp), _ptr(T_wp), _ptr(T_wl),
-                                                     _ptr(ref0), _ptr(fr), _ptr(self.packed), _ptr(ws), ws.numel(), C.byref(po),
-                                                     flags, _stream()), "parq_decoder_forward")
-        # keep inputs alive until the stream has consumed them
-        for t in (tokens, camera, T_cp, T_wp, T_wl, ref0, fr):
-            if t is not None:
-                t.record_stream(torch.cuda.current_stream())
+        if graph:
+            key = (tokens.data_ptr(), camera.data_ptr(), T_cp.data_ptr(), T_wp.data_ptr(), T_wl.data_ptr(), ref0.data_ptr(),
+                   fr.data_ptr() if fr is not None else 0, B, T, H, W, flags, bool(debug), ws.data_ptr())
+            entry = self._graphs.get(key)
+            if entry is None:
+                outs, po = self._alloc_outputs(B, T, debug)
+                self._launch(shape, tokens, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags)   # lazy one-off setup outside capture
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch(shape, tokens, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags)
+                if len(self._graphs) >= 8:
+                    self._graphs.pop(next(iter(self._graphs)))
+                entry = (g, outs, (tokens, camera, T_cp, T_wp, T_wl, ref0, fr))     # keep the captured buffers alive
+                self._graphs[key] = entry
+            entry[0].replay()
+            outs = dict(entry[1])
+        else:
+            outs, po = self._alloc_outputs(B, T, debug)
+            self._launch(shape, tokens, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags)
+            # keep inputs alive until the stream has consumed them
+            for t in (tokens, camera, T_cp, T_wp, T_wl, ref0, fr):
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream())
         if "center_valid" in outs:
             outs["center_valid"] = outs["center_valid"].bool()
         return outs
@@ -308,6 +343,7 @@ class PARQDecoderB200(nn.Module):
         dec.mlp_heads = self.mlp_heads                    # alias -> duplicate state-dict keys (parq_decoder.py:66)
         self.refpoint = nn.Embedding(cfg.NUM_QUERIES, 3)
         self.feature_hw = None       # optional (H, W) hint: avoids the camera D2H read of transformer_parq.py:301
+        self.use_cuda_graph = False  # replay the forward as one CUDA graph per distinct set of input buffers
         self._engine = None
         self._engine_key = None
 
@@ -337,5 +373,6 @@ class PARQDecoderB200(nn.Module):
             W, H = int(wh[0]), int(wh[1])
         eng = self._get_engine(intput_tokens.device)
         with torch.no_grad():
-            outs = eng.forward(intput_tokens, cam, raw(T_camera_pseudoCam), raw(T_world_pseudoCam), raw(T_world_local), H, W)
+            outs = eng.forward(intput_tokens, cam, raw(T_camera_pseudoCam), raw(T_world_pseudoCam), raw(T_world_local), H, W,
+                               graph=self.use_cuda_graph)
         return [{k: outs[k][i] for k, _ in OUTPUT_KEYS} for i in range(self.iters)]

@@ -232,3 +232,20 @@ def test_config2_properties(dev):
         assert torch.equal(one["features"][:, 0], full["features"][:, b])
         for k in ("pred_logits", "center_unnormalized", "ortho6d"):
             assert relerr(one[k][:, 0], full[k][:, b]) <= 1e-4, (k, b)
+
+
+def test_cuda_graph_replay_matches_eager(dev):
+    gold = load_golden("small")
+    c = regenerate_case(gold)
+    eng = DecoderEngine(c["sd"], dev)
+    args = [c[k].to(dev) for k in ("tokens", "camera", "T_cp", "T_wp", "T_wl")]
+    args[0] = args[0].bfloat16()
+    eager = eng.forward(*args, c["H"], c["W"])
+    torch.cuda.synchronize()
+    eager = {k: v.clone() for k, v in eager.items()}
+    for _ in range(3):                       # capture on first use, then pure replays
+        replay = eng.forward(*args, c["H"], c["W"], graph=True)
+    torch.cuda.synchronize()
+    for k in OUT_KEYS:
+        assert torch.equal(replay[k], eager[k]), k
+    assert len(eng._graphs) == 1
