@@ -771,13 +771,13 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       hp.R = R; hp.Nq = s.Nq; hp.C = C; hp.num_cls = s.num_cls;
       { ProfScope ps(TAG_ROWWISE, st); {
         const int rpb = (R + device_info().sms - 1) / device_info().sms;     // rows per block: one block per SM
-        const size_t hsm = static_cast<size_t>(s.num_cls + 12 + 4) * C * sizeof(float);
+        const size_t hsm = static_cast<size_t>(HEADS_SLOTS + 4) * C * sizeof(float);
         static thread_local bool hattr = false;
         if (!hattr) {
-          cudaFuncSetAttribute(heads_final_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>((HEADS_MAX_OUT + 4) * 1024 * sizeof(float)));
+          cudaFuncSetAttribute(heads_final_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hsm));
           hattr = true;
         }
-        heads_final_kernel<1024><<<(R + rpb - 1) / rpb, 256, hsm, st>>>(hp, rpb);
+        heads_final_kernel<1024><<<(R + rpb - 1) / rpb, 512, hsm, st>>>(hp, rpb);
       } }
       CUDA_TRY(cudaGetLastError());
     }

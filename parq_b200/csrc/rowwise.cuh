@@ -182,107 +182,128 @@ struct HeadsParams {
   float span[3], lo[3];
 };
 
-constexpr int HEADS_MAX_OUT = 16 + 3 + 3 + 6;   // cls (<=16) + size + center + rotation rows of weights
+constexpr int HEADS_CLS_SLOTS = 16;                              // class logits padded to 16 output slots
+constexpr int HEADS_SLOTS = HEADS_CLS_SLOTS + 3 + 3 + 6;         // + size, centre offset, ortho6d = 28 (<= 32 lanes)
 
-// Block = 8 warps; the (num_cls + 12) x C final-layer weights are staged once per block in shared memory
-// and every warp then walks rows (queries) blockIdx.x*rows_per_block ...; one warp per row.
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block = 16 warps.  The 28 x C final-layer weights (zero rows for unused class slots) and the GroupNorm
+// affine parameters are staged once per block in shared memory; each warp then walks rows (queries), one
+// row at a time: 28 independent dot-product chains per lane, a butterfly reduction of all 28, and an
+// epilogue in which lane j owns output slot j (softmax/arg-max through warp shuffles).
 template <int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 heads_final_kernel(const HeadsParams p, int rows_per_block) {
   constexpr int PER = C / 32;
-  extern __shared__ float sw[];           // [(num_cls + 12)][C] weights, then gamma_c | beta_c | gamma_r | beta_r
-  const int nw = p.num_cls + 12;
-  float* s_aff = sw + nw * C;
+  extern __shared__ float sw[];           // [HEADS_SLOTS][C] weights, then gamma_c | beta_c | gamma_r | beta_r
+  float* s_aff = sw + HEADS_SLOTS * C;
+  for (int i = threadIdx.x * 4; i < HEADS_SLOTS * C; i += blockDim.x * 4) {
+    const int j = i / C, c = i % C;
+    const float* src = nullptr;
+    if (j < HEADS_CLS_SLOTS) src = j < p.num_cls ? p.w_cls + j * C : nullptr;
+    else if (j < HEADS_CLS_SLOTS + 3) src = p.w_size + (j - HEADS_CLS_SLOTS) * C;
+    else if (j < HEADS_CLS_SLOTS + 6) src = p.w_c3 + (j - HEADS_CLS_SLOTS - 3) * C;
+    else src = p.w_r3 + (j - HEADS_CLS_SLOTS - 6) * C;
+    *reinterpret_cast<float4*>(sw + i) = src ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     s_aff[i] = p.gamma_c[i]; s_aff[C + i] = p.beta_c[i]; s_aff[2 * C + i] = p.gamma_r[i]; s_aff[3 * C + i] = p.beta_r[i];
   }
-  for (int i = threadIdx.x * 4; i < nw * C; i += blockDim.x * 4) {
-    const int j = i / C, c = i % C;
-    const float* src = j < p.num_cls ? p.w_cls + j * C : (j < p.num_cls + 3 ? p.w_size + (j - p.num_cls) * C
-                       : (j < p.num_cls + 6 ? p.w_c3 + (j - p.num_cls - 3) * C : p.w_r3 + (j - p.num_cls - 6) * C));
-    *reinterpret_cast<float4*>(sw + i) = *reinterpret_cast<const float4*>(src + c);
-  }
   __syncthreads();
-  const float* s_cls = sw;
-  const float* s_size = sw + p.num_cls * C;
-  const float* s_c3 = s_size + 3 * C;
-  const float* s_r3 = s_c3 + 3 * C;
   const int lane = threadIdx.x & 31;
   const int row_end = min(p.R, (blockIdx.x + 1) * rows_per_block);
   for (int row = blockIdx.x * rows_per_block + (threadIdx.x >> 5); row < row_end; row += (blockDim.x >> 5)) {
-  const int b = row / p.Nq;
-  float xv[PER], hc[PER], hr[PER];
-  float mean_l = 0.f, rstd_l = 0.f;
-  if (lane < 2) gn_mean_rstd(p.partial, b, lane, C, p.Nq, mean_l, rstd_l);
-  const float mean_c = __shfl_sync(0xffffffffu, mean_l, 0), rstd_c = __shfl_sync(0xffffffffu, rstd_l, 0);
-  const float mean_r = __shfl_sync(0xffffffffu, mean_l, 1), rstd_r = __shfl_sync(0xffffffffu, rstd_l, 1);
+    const int b = row / p.Nq;
+    float mean_l = 0.f, rstd_l = 0.f;
+    if (lane < 2) gn_mean_rstd(p.partial, b, lane, C, p.Nq, mean_l, rstd_l);
+    const float mean_c = __shfl_sync(0xffffffffu, mean_l, 0), rstd_c = __shfl_sync(0xffffffffu, rstd_l, 0);
+    const float mean_r = __shfl_sync(0xffffffffu, mean_l, 1), rstd_r = __shfl_sync(0xffffffffu, rstd_l, 1);
+    float acc[HEADS_SLOTS];
 #pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int c = i * 32 + lane;
-    xv[i] = p.x[static_cast<long long>(row) * C + c];
-    const float a = p.h2[static_cast<long long>(row) * (2 * C) + c];
-    const float r = p.h2[static_cast<long long>(row) * (2 * C) + C + c];
-    hc[i] = fmaxf((a - mean_c) * rstd_c * s_aff[c] + s_aff[C + c], 0.f);
-    hr[i] = fmaxf((r - mean_r) * rstd_r * s_aff[2 * C + c] + s_aff[3 * C + c], 0.f);
+    for (int j = 0; j < HEADS_SLOTS; ++j) acc[j] = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < PER; ++i) {
+      const int c = i * 32 + lane;
+      const float xv = p.x[static_cast<long long>(row) * C + c];
+      const float a = p.h2[static_cast<long long>(row) * (2 * C) + c];
+      const float r = p.h2[static_cast<long long>(row) * (2 * C) + C + c];
+      const float hc = fmaxf((a - mean_c) * rstd_c * s_aff[c] + s_aff[C + c], 0.f);
+      const float hr = fmaxf((r - mean_r) * rstd_r * s_aff[2 * C + c] + s_aff[3 * C + c], 0.f);
+#pragma unroll
+      for (int j = 0; j < HEADS_SLOTS; ++j) {
+        const float v = j < HEADS_CLS_SLOTS + 3 ? xv : (j < HEADS_CLS_SLOTS + 6 ? hc : hr);
+        acc[j] = fmaf(sw[j * C + c], v, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < HEADS_SLOTS; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    // lane j keeps output slot j
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < HEADS_SLOTS; ++j)
+      if (lane == j) mine = acc[j];
+    const bool is_cls = lane < p.num_cls;
+    const int k3 = lane >= HEADS_CLS_SLOTS + 3 ? lane - HEADS_CLS_SLOTS - 3 : lane - HEADS_CLS_SLOTS;   // axis for size / centre lanes
+    if (is_cls) mine += p.b_cls[lane];
+    else if (lane >= HEADS_CLS_SLOTS && lane < HEADS_CLS_SLOTS + 3) mine += p.b_size[lane - HEADS_CLS_SLOTS];
+    else if (lane >= HEADS_CLS_SLOTS + 3 && lane < HEADS_CLS_SLOTS + 6) mine += p.b_c3[lane - HEADS_CLS_SLOTS - 3];
+    else if (lane >= HEADS_CLS_SLOTS + 6 && lane < HEADS_SLOTS) mine += p.b_r3[lane - HEADS_CLS_SLOTS - 6];
+    // softmax over the class lanes; arg-max of the probabilities with torch's first-index tie rule
+    const float mx = warp_max(is_cls ? mine : -INFINITY);
+    const float e = is_cls ? expf(mine - mx) : 0.f;
+    const float den = warp_sum(e);
+    const float pr = e / den;
+    float best = is_cls ? pr : -1.f;
+    int arg = is_cls ? lane : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (is_cls) {
+      p.prob[static_cast<long long>(row) * p.num_cls + lane] = pr;
+      p.logits[static_cast<long long>(row) * p.num_cls + lane] = mine;
+    }
+    if (lane >= HEADS_CLS_SLOTS && lane < HEADS_CLS_SLOTS + 3) {
+      p.size[row * 3 + k3] = expf(mine) * p.mean_size[arg * 3 + k3];
+    } else if (lane >= HEADS_CLS_SLOTS + 3 && lane < HEADS_CLS_SLOTS + 6) {
+      const float rr = p.ref[row * 3 + k3];
+      const float rc = fminf(fmaxf(rr, 0.f), 1.f);
+      const float inv_sig = logf(fmaxf(rc, 1e-3f) / fmaxf(1.f - rc, 1e-3f));
+      const float sg = 1.f / (1.f + expf(-(mine + inv_sig)));
+      const float center = __fadd_rn(__fmul_rn(sg, p.span[k3]), p.lo[k3]);
+      p.center[row * 3 + k3] = center;
+      p.coord_pos[row * 3 + k3] = __fadd_rn(__fmul_rn(rr, p.span[k3]), p.lo[k3]);
+      p.ref_next[row * 3 + k3] = __fdiv_rn(__fadd_rn(center, -p.lo[k3]), p.span[k3]);
+    } else if (lane >= HEADS_CLS_SLOTS + 6 && lane < HEADS_SLOTS) {
+      p.ortho6d[row * 6 + lane - HEADS_CLS_SLOTS - 6] = mine;
+    }
+    if (p.rot != nullptr) {
+      // Gram-Schmidt: x = a/|a|, z = (x X b)/|x X b|, y = z X x; columns [x y z]; norms clamped at 1e-8
+      float o6[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) o6[k] = __shfl_sync(0xffffffffu, mine, HEADS_CLS_SLOTS + 6 + k);
+      if (lane == 0) {
+        const float na = fmaxf(sqrtf(o6[0] * o6[0] + o6[1] * o6[1] + o6[2] * o6[2]), 1e-8f);
+        const float x0 = o6[0] / na, x1 = o6[1] / na, x2 = o6[2] / na;
+        float z0 = x1 * o6[5] - x2 * o6[4], z1 = x2 * o6[3] - x0 * o6[5], z2 = x0 * o6[4] - x1 * o6[3];
+        const float nz = fmaxf(sqrtf(z0 * z0 + z1 * z1 + z2 * z2), 1e-8f);
+        z0 /= nz; z1 /= nz; z2 /= nz;
+        const float y0 = z1 * x2 - z2 * x1, y1 = z2 * x0 - z0 * x2, y2 = z0 * x1 - z1 * x0;
+        float* r = p.rot + static_cast<long long>(row) * 9;
+        r[0] = x0; r[1] = y0; r[2] = z0;
+        r[3] = x1; r[4] = y1; r[5] = z1;
+        r[6] = x2; r[7] = y2; r[8] = z2;
+      }
+    }
   }
-  auto dot = [&](const float* w, const float (&v)[PER]) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) s = fmaf(w[i * 32 + lane], v[i], s);
-    return warp_sum(s);
-  };
-  float cls[16];
-  for (int j = 0; j < p.num_cls; ++j) cls[j] = dot(s_cls + j * C, xv) + p.b_cls[j];
-  float sz[3], co[3], o6[6];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) sz[j] = dot(s_size + j * C, xv) + p.b_size[j];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) co[j] = dot(s_c3 + j * C, hc) + p.b_c3[j];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) o6[j] = dot(s_r3 + j * C, hr) + p.b_r3[j];
-  if (lane != 0) continue;
-
-  // softmax + first-index argmax over the probabilities (torch.argmax tie rule)
-  float mx = cls[0];
-  for (int j = 1; j < p.num_cls; ++j) mx = fmaxf(mx, cls[j]);
-  float e[16], den = 0.f;
-  for (int j = 0; j < p.num_cls; ++j) { e[j] = expf(cls[j] - mx); den += e[j]; }
-  int arg = 0;
-  float best = -1.f;
-  for (int j = 0; j < p.num_cls; ++j) {
-    const float pr = e[j] / den;
-    p.prob[static_cast<long long>(row) * p.num_cls + j] = pr;
-    p.logits[static_cast<long long>(row) * p.num_cls + j] = cls[j];
-    if (pr > best) { best = pr; arg = j; }
-  }
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const float r = p.ref[row * 3 + j];
-    const float rc = fminf(fmaxf(r, 0.f), 1.f);
-    const float inv_sig = logf(fmaxf(rc, 1e-3f) / fmaxf(1.f - rc, 1e-3f));
-    const float sg = 1.f / (1.f + expf(-(co[j] + inv_sig)));
-    const float center = __fadd_rn(__fmul_rn(sg, p.span[j]), p.lo[j]);
-    p.center[row * 3 + j] = center;
-    p.coord_pos[row * 3 + j] = __fadd_rn(__fmul_rn(r, p.span[j]), p.lo[j]);
-    p.size[row * 3 + j] = expf(sz[j]) * p.mean_size[arg * 3 + j];
-    p.ref_next[row * 3 + j] = __fdiv_rn(__fadd_rn(center, -p.lo[j]), p.span[j]);
-  }
-#pragma unroll
-  for (int j = 0; j < 6; ++j) p.ortho6d[row * 6 + j] = o6[j];
-  if (p.rot != nullptr) {
-    // Gram-Schmidt: x = a/|a|, z = (x X b)/|x X b|, y = z X x; columns [x y z]; norms clamped at 1e-8
-    const float na = fmaxf(sqrtf(o6[0] * o6[0] + o6[1] * o6[1] + o6[2] * o6[2]), 1e-8f);
-    const float x0 = o6[0] / na, x1 = o6[1] / na, x2 = o6[2] / na;
-    float z0 = x1 * o6[5] - x2 * o6[4], z1 = x2 * o6[3] - x0 * o6[5], z2 = x0 * o6[4] - x1 * o6[3];
-    const float nz = fmaxf(sqrtf(z0 * z0 + z1 * z1 + z2 * z2), 1e-8f);
-    z0 /= nz; z1 /= nz; z2 /= nz;
-    const float y0 = z1 * x2 - z2 * x1, y1 = z2 * x0 - z0 * x2, y2 = z0 * x1 - z1 * x0;
-    float* r = p.rot + static_cast<long long>(row) * 9;
-    r[0] = x0; r[1] = y0; r[2] = z0;
-    r[3] = x1; r[4] = y1; r[5] = z1;
-    r[6] = x2; r[7] = y2; r[8] = z2;
-  }
-  }   // row loop
 }
 
 }  // namespace parq

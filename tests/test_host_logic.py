@@ -118,3 +118,19 @@ def test_synthetic_inputs_are_deterministic_and_bf16_exact():
     for k, v in sd.items():
         if v.dim() >= 2 and k != "refpoint.weight":
             assert bit_equal(v, I.bf16_round(v)), k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference tree not present")
+def test_accelerate_patches_the_reference_module_in_place():
+    from oracle.ref_loader import decoder_cfg, load_reference
+    from parq_b200.decoder import accelerate
+    ref = load_reference().PARQDecoder(decoder_cfg(256)).eval()
+    keys = list(ref.state_dict().keys())
+    acc = accelerate(ref, feature_hw=(12, 16))
+    assert acc is ref and list(ref.state_dict().keys()) == keys          # same object, same checkpoint layout
+    assert hasattr(ref, "loss") and hasattr(ref, "parse_pred")            # the reference's other methods are untouched
+    cam, Tcp, Twp, Twl = I.make_geometry(1, 2, 12, 16, seed=0)
+    with pytest.raises(NotImplementedError):                              # CPU tensors: refuse, never fall back
+        ref(torch.zeros(1, 2 * 12 * 16, 1024), cam, Tcp, Twp, Twl)
+    with pytest.raises(NotImplementedError):
+        ref.train()(torch.zeros(1, 2 * 12 * 16, 1024), cam, Tcp, Twp, Twl)
