@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libparq_b200.so")
 
 PARQ_FLAG_SKIP_KV = 1
 PARQ_FLAG_WEIGHT_LO = 2
+PARQ_FLAG_NO_PDL = 4
 
 EXPORTS = [
     "parq_version", "parq_last_error", "parq_packed_bytes", "parq_workspace_bytes", "parq_pack_weights",

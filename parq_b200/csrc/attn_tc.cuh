@@ -39,6 +39,7 @@ struct AttnParams {
   float* o_part;         // [((b*H+h)*nsplit + s)*Nq + q][256]
   float2* ml_part;       // [((b*H+h)*nsplit + s)*Nq + q] = (m, l)
   __nv_bfloat16* out_direct;   // nsplit == 1 only: normalised output (B*Nq, 2*H*256) [hi|lo], no combine pass
+  int kv_const;                // K / V^T were written >= 2 launches ago: their first tiles are fetched before the PDL wait
 };
 
 namespace attn {
@@ -117,10 +118,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0 && n > 0) {             // ---------------- TMA producer
       const int ch0 = h * DH;
-      mbar_expect_tx(q_full, Q_BYTES);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        tma_load_2d(sQ + c * (BQ * 128), &tmQ, q_full, ch0 + c * 64, b * p.Nq + qt * BQ);
       int stage = 0;
       uint32_t phase = 0;
       auto load_k = [&](int tile) {
@@ -145,13 +142,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       };
-      load_k(t0);
+      // ring order: K(0), [K(j+1), V(j)] ...  With an old (cached) K the first two key tiles are requested
+      // before the programmatic-dependency wait; Q comes from the previous kernel and follows the wait.
+      const bool early = p.kv_const != 0;
+      if (early) {
+        load_k(t0);
+        if (n > 1) load_k(t0 + 1);
+      }
+      pdl_wait();
+      pdl_launch_dependents();
+      mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        tma_load_2d(sQ + c * (BQ * 128), &tmQ, q_full, ch0 + c * 64, b * p.Nq + qt * BQ);
+      if (!early) load_k(t0);
       for (int j = 0; j < n; ++j) {
-        if (j + 1 < n) load_k(t0 + j + 1);
+        if (j + 1 < n && !(early && j == 0)) load_k(t0 + j + 1);
         load_v(t0 + j);
       }
+    } else {
+      pdl_wait();
+      pdl_launch_dependents();
     }
   } else if (warp == 1) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (lane == 0 && n > 0) {             // ---------------- MMA issuer
       constexpr uint32_t fmt = kFp16 ? 0u : 1u;
       constexpr uint32_t idesc_s = umma_idesc(BQ, BKEY, fmt);
@@ -202,6 +217,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     }
   } else if (warp >= 4 && n > 0) {        // ---------------- softmax / correction / epilogue
+    pdl_wait();
+    pdl_launch_dependents();
     const int q = warp - 4;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
@@ -313,6 +330,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   }
 
+  if (warp == 2 || warp == 3 || n <= 0) {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -328,6 +349,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 __global__ void __launch_bounds__(256)
 attn_combine_kernel(const float* __restrict__ o_part, const float2* __restrict__ ml_part, __nv_bfloat16* __restrict__ out,
                     int H, int Nq, int nsplit) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x;            // b*Nq + q
   const int b = row / Nq, q = row % Nq;
   const int C = H * 256;

@@ -45,6 +45,7 @@ struct GemmParams {
   int nterms;
   int a_koff[3];       // element offset of each term along A's K axis
   int b_koff[3];
+  int const_operand;   // 1: A holds constants (weights), 2: B does -- its first tiles are fetched before the PDL wait
   GemmEpilogue ep;
 };
 
@@ -221,27 +222,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {                       // ---------------- TMA producer
+      // static selects (not p.a_koff[t]): a dynamically indexed parameter array would force the whole
+      // parameter block into local memory
+      auto a_off = [&](int t) { return t == 0 ? p.a_koff[0] : (t == 1 ? p.a_koff[1] : p.a_koff[2]); };
+      auto b_off = [&](int t) { return t == 0 ? p.b_koff[0] : (t == 1 ? p.b_koff[1] : p.b_koff[2]); };
+      // The operand that holds weights does not depend on the previous kernel: its first ring stages are
+      // requested before the programmatic-dependency wait, so the fetch overlaps the predecessor's tail.
+      int pre = 0;
+      if (p.const_operand != 0 && static_cast<int>(blockIdx.x) < num_tiles) {
+        int m0, n0;
+        tile_origin(blockIdx.x, m0, n0);
+        pre = num_kb < STAGES ? num_kb : STAGES;
+        for (int i = 0; i < pre; ++i) {
+          const int t = i / kb_per_term, kb = i % kb_per_term;
+          mbar_expect_tx(&full_bar[i], A_BYTES + B_BYTES);
+          if (p.const_operand == 1) tma_load_2d(sA + i * A_BYTES, &tmA, &full_bar[i], a_off(t) + kb * BK, m0);
+          else                      tma_load_2d(sB + i * B_BYTES, &tmB, &full_bar[i], b_off(t) + kb * BK, n0);
+        }
+      }
+      pdl_wait();
+      pdl_launch_dependents();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m0, n0;
         tile_origin(tile, m0, n0);
         for (int t = 0; t < p.nterms; ++t) {
-          // static selects (not p.a_koff[t]): a dynamically indexed parameter array would force the whole
-          // parameter block into local memory
-          const int ak = t == 0 ? p.a_koff[0] : (t == 1 ? p.a_koff[1] : p.a_koff[2]);
-          const int bk = t == 0 ? p.b_koff[0] : (t == 1 ? p.b_koff[1] : p.b_koff[2]);
+          const int ak = a_off(t), bk = b_off(t);
           for (int kb = 0; kb < kb_per_term; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-            tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], ak + kb * BK, m0);
-            tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], bk + kb * BK, n0);
+            const bool prefetched = pre > 0;       // first k-blocks of this CTA's first tile
+            if (!prefetched) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+            } else {
+              --pre;
+            }
+            if (!(prefetched && p.const_operand == 1)) tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], ak + kb * BK, m0);
+            if (!(prefetched && p.const_operand == 2)) tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], bk + kb * BK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
+    } else {
+      pdl_wait();
+      pdl_launch_dependents();
     }
   } else if (warp == 1) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (lane == 0) {                       // ---------------- MMA issuer
       constexpr uint32_t idesc = umma_idesc(BM, BN, 1);
       int stage = 0;
@@ -267,6 +295,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {                  // ---------------- epilogue warps
+    pdl_wait();
+    pdl_launch_dependents();
     const int q = warp - 4;                // TMEM lane quadrant == warp % 4
     const int et = threadIdx.x - 128;      // 0..127
     const bool col_bias = (p.ep.bias != nullptr) && !p.ep.bias_per_row;
@@ -326,6 +356,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (warp == 2 || warp == 3) {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {

@@ -94,6 +94,32 @@ static int require_sm100() {
   return PARQ_OK;
 }
 
+// ------------------------------------------------------------------------------------ launch --
+// Inside parq_decoder_forward every kernel is launched with programmatic stream serialisation (PDL, see
+// ptx.cuh): the next kernel's prologue overlaps the tail of the current one, also inside a captured graph.
+// The stand-alone entry points launch plainly (their inputs may come from the caller's previous kernel).
+static thread_local bool g_pdl = false;
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(g_pdl) { g_pdl = on; }
+  ~PdlScope() { g_pdl = prev; }
+};
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------ TMA tensor maps --
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -143,7 +169,7 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
   const int grid = tiles < device_info().sms ? tiles : device_info().sms;
   {
     ProfScope ps(tag, st);
-    gemm_tc_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, gp);
+    launch_k(gemm_tc_kernel, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, gp);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
@@ -182,7 +208,7 @@ static size_t attn_scratch_bytes(int B, int H, int Nq, int nsplit) {
 
 static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const void* K, uint64_t ldk, const void* Vt,
                             uint64_t ldv, int B, int H, int Nq, int Nk, bool fp16, void* scratch, size_t scratch_bytes,
-                            __nv_bfloat16* out_split, int force_nsplit) {
+                            __nv_bfloat16* out_split, int force_nsplit, bool kv_const = false) {
   if (Nq % attn::BQ != 0) return fail(PARQ_ERR_SHAPE, "Nq=%d must be a multiple of 128", Nq);
   const int ntiles = (Nk + attn::BKEY - 1) / attn::BKEY;
   const SplitPlan plan = plan_split(B * H * (Nq / attn::BQ), ntiles, device_info().sms, force_nsplit);
@@ -199,6 +225,7 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
   ap.nsplit = plan.nsplit;
   ap.tiles_per_split = plan.tiles_per_split;
   ap.out_direct = plan.nsplit == 1 ? out_split : nullptr;
+  ap.kv_const = kv_const ? 1 : 0;
   const size_t rows = static_cast<size_t>(B) * H * plan.nsplit * Nq;
   ap.o_part = reinterpret_cast<float*>(scratch);
   ap.ml_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(scratch) + align_up(rows * 256 * sizeof(float), 256));
@@ -212,14 +239,14 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
   {
     ProfScope ps(fp16 ? TAG_SELF_ATTN : TAG_CROSS_ATTN, st);
     if (fp16)
-      attn_tc_kernel<true><<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, ap);
+      launch_k(attn_tc_kernel<true>, grid, dim3(attn::THREADS), attn::SMEM_BYTES, st, tmQ, tmK, tmV, ap);
     else
-      attn_tc_kernel<false><<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tmQ, tmK, tmV, ap);
+      launch_k(attn_tc_kernel<false>, grid, dim3(attn::THREADS), attn::SMEM_BYTES, st, tmQ, tmK, tmV, ap);
   }
   CUDA_TRY(cudaGetLastError());
   if (plan.nsplit > 1) {
     ProfScope ps(TAG_COMBINE, st);
-    attn_combine_kernel<<<B * Nq, 256, 0, st>>>(ap.o_part, ap.ml_part, out_split, H, Nq, plan.nsplit);
+    launch_k(attn_combine_kernel, dim3(B * Nq), dim3(256), 0, st, ap.o_part, ap.ml_part, out_split, H, Nq, plan.nsplit);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
@@ -357,6 +384,7 @@ static int check_shape(const ParqShape* s) {
 // W = packed [hi|lo] weights; 2 terms when the weights are bf16-exact, else 3.
 static void term_offsets(GemmParams& gp, int K, bool w_lo, int a_base) {
   gp.K = K;
+  gp.const_operand = 2;          // activations x weights: the B operand holds constants
   gp.nterms = w_lo ? 3 : 2;
   gp.a_koff[0] = a_base;      gp.b_koff[0] = 0;
   gp.a_koff[1] = a_base + K;  gp.b_koff[1] = 0;
@@ -377,6 +405,7 @@ static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, c
   memset(&gk, 0, sizeof(gk));
   gk.M = static_cast<int>(Nt);  gk.N = C;  gk.K = C;
   gk.nterms = w_lo ? 2 : 1;
+  gk.const_operand = 2;
   gk.a_koff[0] = 0; gk.b_koff[0] = 0; gk.a_koff[1] = 0; gk.b_koff[1] = C;
   gk.ep = epilogue_none();
   gk.ep.bias = reinterpret_cast<const float*>(pk + P.ca_k_b);
@@ -387,6 +416,7 @@ static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, c
   memset(&gv, 0, sizeof(gv));
   gv.M = C;  gv.N = static_cast<int>(Nt);  gv.K = C;
   gv.nterms = w_lo ? 2 : 1;
+  gv.const_operand = 1;
   gv.a_koff[0] = 0; gv.b_koff[0] = 0; gv.a_koff[1] = C; gv.b_koff[1] = 0;
   gv.ep = epilogue_none();
   gv.ep.bias = reinterpret_cast<const float*>(pk + P.ca_v_b);
@@ -547,6 +577,8 @@ int parq_pose_chain(const float* T_cp, const float* T_wp, const float* T_wl, flo
   return PARQ_OK;
 }
 
+static size_t sample_smem(int T) { return static_cast<size_t>(SAMPLE_QPB) * T * sizeof(ViewTap); }
+
 static void fill_sample_params(SampleParams& sp, const ParqShape& s) {
   memset(&sp, 0, sizeof(sp));
   sp.B = s.B; sp.T = s.T; sp.H = s.H; sp.W = s.W; sp.C = s.C; sp.Nq = s.Nq;
@@ -569,7 +601,7 @@ int parq_project_sample(const ParqShape* shape, const void* tokens_bf16, const f
   sp.feat = features; sp.center_im = center_im; sp.valid = center_valid; sp.coord_pos = coord_pos;
   {
     ProfScope ps(TAG_SAMPLE, static_cast<cudaStream_t>(stream));
-    project_sample_kernel<<<shape->B * shape->Nq, shape->C / 8, 0, static_cast<cudaStream_t>(stream)>>>(sp);
+    project_sample_kernel<<<shape->B * shape->Nq / SAMPLE_QPB, shape->C / 8, sample_smem(shape->T), static_cast<cudaStream_t>(stream)>>>(sp);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
@@ -633,13 +665,14 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const bool w_lo = (flags & PARQ_FLAG_WEIGHT_LO) != 0;
+  const PdlScope pdl((flags & PARQ_FLAG_NO_PDL) == 0);
   const int C = s.C, F = s.ffn, R = s.B * s.Nq;
   auto F32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto BF = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
   auto PF = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
 
   // K0: pose chain
-  { ProfScope ps(TAG_ROWWISE, st); pose_chain_kernel<<<(s.B * s.T + 127) / 128, 128, 0, st>>>(T_cp, T_wp, T_wl, F32(W.T_cl), s.B, s.T); }
+  { ProfScope ps(TAG_ROWWISE, st); launch_k(pose_chain_kernel, dim3((s.B * s.T + 127) / 128), dim3(128), 0, st, T_cp, T_wp, T_wl, F32(W.T_cl), s.B, s.T); }
   CUDA_TRY(cudaGetLastError());
   // K4: hoisted K / V^T projection of the image tokens (iteration invariant)
   if (!(flags & PARQ_FLAG_SKIP_KV)) TRY(kv_project(s, st, tokens_bf16, pk, P, w_lo, ws, W));
@@ -653,7 +686,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   for (int it = 0; it < s.iters; ++it) {
     const float* ref = forced_refs ? forced_refs + static_cast<size_t>(it) * R * 3 : (it == 0 ? ref0 : F32(W.ref_cur));
     // K2: reference-point positional feature  pe = W2 relu(W1 posemb + b1) + b2
-    { ProfScope ps(TAG_ROWWISE, st); posemb_kernel<<<(R * 384 + 255) / 256, 256, 0, st>>>(ref, PF(P.dim_t), BF(W.a_pos), R); }
+    { ProfScope ps(TAG_ROWWISE, st); launch_k(posemb_kernel, dim3((R * 384 + 255) / 256), dim3(256), 0, st, ref, PF(P.dim_t), BF(W.a_pos), R); }
     CUDA_TRY(cudaGetLastError());
     {
       GemmParams g; memset(&g, 0, sizeof(g));
@@ -675,7 +708,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     sp.center_im = out->center_im ? out->center_im + static_cast<size_t>(it) * s.B * s.T * s.Nq * 2 : nullptr;
     sp.valid = out->center_valid ? out->center_valid + static_cast<size_t>(it) * s.B * s.T * s.Nq : nullptr;
     sp.coord_pos = nullptr;
-    { ProfScope ps(TAG_SAMPLE, st); project_sample_kernel<<<R, C / 8, 0, st>>>(sp); }
+    { ProfScope ps(TAG_SAMPLE, st); launch_k(project_sample_kernel, dim3(R / SAMPLE_QPB), dim3(C / 8), sample_smem(s.T), st, sp); }
     CUDA_TRY(cudaGetLastError());
     const float* x0 = sp.feat;
     // K3: self-attention among the queries (fp16 operands), out-projection, residual + LN1
@@ -687,7 +720,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       TRY(launch_gemm(st, ws + W.a_xpe, R, 2 * C, pk + P.sa_qk, 2 * C, 2 * C, g));
       // V^T = Wv x^T + bv : weights are the A operand, activations the B operand
       memset(&g, 0, sizeof(g));
-      g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : 2;
+      g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : 2; g.const_operand = 1;
       g.a_koff[0] = 0; g.b_koff[0] = 0; g.a_koff[1] = 0; g.b_koff[1] = C; g.a_koff[2] = C; g.b_koff[2] = 0;
       g.ep = epilogue_none(); g.ep.bias = PF(P.sa_v_b); g.ep.bias_per_row = 1;
       g.ep.out_lp = ws + W.vt_s; g.ep.ld_lp = static_cast<long long>(W.ldvs); g.ep.lp_fp16 = 1;
@@ -699,8 +732,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.sa_out_b);
       g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
       TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.sa_out, C, 2 * C, g));
-      { ProfScope ps(TAG_ROWWISE, st); add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(x0, F32(W.y), PF(P.ln1_g), PF(P.ln1_b), F32(W.pe), F32(W.x1), nullptr,
-                                                      BF(W.a_x1pe), R); }
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, x0, F32(W.y), PF(P.ln1_g), PF(P.ln1_b), F32(W.pe), F32(W.x1),
+                                               nullptr, BF(W.a_x1pe), R); }
       CUDA_TRY(cudaGetLastError());
     }
     // K5: cross-attention over all image tokens (bf16 operands), out-projection, residual + LN2
@@ -712,14 +745,14 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       TRY(launch_gemm(st, ws + W.a_x1pe, R, 2 * C, pk + P.ca_q, C, 2 * C, g));
       const int Nk = s.T * s.H * s.W;
       TRY(launch_attention(st, ws + W.q_c, C, ws + W.Kc, C, ws + W.Vt, W.ldv, s.B, s.heads, s.Nq, Nk, false, ws + W.scratch,
-                           W.scratch_bytes, BF(W.a_attn), W.cross.nsplit));
+                           W.scratch_bytes, BF(W.a_attn), W.cross.nsplit, /*kv_const=*/true));
       memset(&g, 0, sizeof(g));
       g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
       g.ep = epilogue_none(); g.ep.bias = PF(P.ca_out_b);
       g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
       TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.ca_out, C, 2 * C, g));
-      { ProfScope ps(TAG_ROWWISE, st); add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(F32(W.x1), F32(W.y), PF(P.ln2_g), PF(P.ln2_b), nullptr, F32(W.x2), BF(W.a_x2),
-                                                      nullptr, R); }
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x1), F32(W.y), PF(P.ln2_g), PF(P.ln2_b), nullptr, F32(W.x2),
+                                               BF(W.a_x2), nullptr, R); }
       CUDA_TRY(cudaGetLastError());
     }
     // K6: FFN, residual + LN3
@@ -735,7 +768,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.lin2_b);
       g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
       TRY(launch_gemm(st, ws + W.a_ffn, R, 2 * F, pk + P.lin2, C, 2 * F, g));
-      { ProfScope ps(TAG_ROWWISE, st); add_ln_kernel<1024><<<(R + 7) / 8, 256, 0, st>>>(F32(W.x2), F32(W.y), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr, R); }
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x2), F32(W.y), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr, R); }
       CUDA_TRY(cudaGetLastError());
     }
     // K7: heads (two hidden layers with per-clip GroupNorm) + box update
@@ -746,8 +779,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep.out_f32 = F32(W.h1); g.ep.ld_f32 = 2 * C;
       g.ep.gn_out = reinterpret_cast<double2*>(ws + W.gn1); g.ep.gn_stride = GN_SLOTS_PER_MTILE;
       TRY(launch_gemm(st, ws + W.a_x3, R, 2 * C, pk + P.hd1, 2 * C, 2 * C, g));
-      { ProfScope ps(TAG_ROWWISE, st); gn_apply_kernel<<<R, 256, 0, st>>>(F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1), PF(P.ctr1_g),
-                                         PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1)); }
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(gn_apply_kernel, dim3(R), dim3(256), 0, st, F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1),
+                                               PF(P.ctr1_g), PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1)); }
       CUDA_TRY(cudaGetLastError());
       for (int hd = 0; hd < 2; ++hd) {
         memset(&g, 0, sizeof(g));
@@ -777,7 +810,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
           cudaFuncSetAttribute(heads_final_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hsm));
           hattr = true;
         }
-        heads_final_kernel<1024><<<(R + rpb - 1) / rpb, 512, hsm, st>>>(hp, rpb);
+        launch_k(heads_final_kernel<1024>, dim3((R + rpb - 1) / rpb), dim3(512), hsm, st, hp, rpb);
       } }
       CUDA_TRY(cudaGetLastError());
     }

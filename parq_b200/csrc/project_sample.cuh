@@ -49,6 +49,8 @@ __device__ __forceinline__ void pose_inverse(const float* A, float* out) {
 
 __global__ void pose_chain_kernel(const float* __restrict__ T_cp, const float* __restrict__ T_wp,
                                   const float* __restrict__ T_wl, float* __restrict__ T_cl, int B, int T) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * T) return;
   const int b = i / T;
@@ -82,10 +84,11 @@ struct SampleParams {
   float span[3], lo[3];          // denormalisation: p*span + lo
 };
 
-struct ViewTap {                 // one view's bilinear footprint
+struct ViewTap {                 // one (query, view) bilinear footprint
   int x0, y0;                    // floor of the sample position (may be out of range)
   float fx, fy;                  // fractional parts
-  int inb;                       // bit0 nw, bit1 ne, bit2 sw, bit3 se in bounds
+  int inb;                       // bit0 nw, bit1 ne, bit2 sw, bit3 se in bounds; bit4: the view is VALID for the average
+  float u, v;                    // projected pixel coordinates (center_im), parked here until they may be written
 };
 
 __device__ __forceinline__ uint4 ldg_nc_16(const void* p) {
@@ -103,163 +106,223 @@ __device__ __forceinline__ void fma_bf16x8(float (&acc)[8], const uint4& v, floa
   }
 }
 
-// grid = B*Nq blocks, block = (C/256) warps; warp w owns channels [256w, 256w+256).
-__global__ void __launch_bounds__(128)
+constexpr int SAMPLE_QPB = 4;                  // queries per block (Nq % 4 == 0, so a block never straddles clips)
+constexpr int SAMPLE_VIEWS_IN_FLIGHT = 2;      // views gathered per round: 8 independent 16-byte loads per lane
+
+// grid = B*Nq/4 blocks of 4 warps.
+// Phase 1: one THREAD per (query, view) pair of the block's 4 queries projects the reference point and leaves the
+//          bilinear footprint in shared memory (the IEEE-exact projection is instruction-heavy: doing it once per
+//          pair instead of once per warp is what makes the kernel memory- rather than issue-bound).
+// Phase 2: warp w owns channels [256w, 256w+256) of every query: per query the views with at least one in-bounds
+//          corner are compacted from a ballot and gathered with 16-byte loads, two views (8 loads) in flight.
+// Programmatic dependent launch: reference points, poses and tokens are inputs or were produced at least two
+// launches earlier, so phase 1 and the first round of texel loads are issued BEFORE the dependency wait (they
+// overlap the tail of the previous kernel); `pe` (previous kernel) is read and all outputs are written after it.
+__global__ void __launch_bounds__(128, 7)
 project_sample_kernel(const SampleParams p) {
-  const int bq = blockIdx.x;
-  const int b = bq / p.Nq, q = bq % p.Nq;
+  constexpr int V = SAMPLE_VIEWS_IN_FLIGHT;
+  extern __shared__ ViewTap s_tap[];             // [SAMPLE_QPB][T]
+  const int row0 = blockIdx.x * SAMPLE_QPB;      // first (b*Nq + q) row of this block
+  const int b = row0 / p.Nq;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = warp * 256 + lane * 8;
-
-  // reference point -> metres in the local frame: p*span + lo (separately rounded mul, add)
-  const float rx = p.ref[bq * 3 + 0], ry = p.ref[bq * 3 + 1], rz = p.ref[bq * 3 + 2];
-  const float px = __fadd_rn(__fmul_rn(rx, p.span[0]), p.lo[0]);
-  const float py = __fadd_rn(__fmul_rn(ry, p.span[1]), p.lo[1]);
-  const float pz = __fadd_rn(__fmul_rn(rz, p.span[2]), p.lo[2]);
-  if (threadIdx.x == 0 && p.coord_pos != nullptr) {
-    p.coord_pos[bq * 3 + 0] = px;
-    p.coord_pos[bq * 3 + 1] = py;
-    p.coord_pos[bq * 3 + 2] = pz;
-  }
-
-  float tot[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) tot[i] = 0.f;
-  int nvalid = 0;
   const float Wm1 = static_cast<float>(p.W - 1), Hm1 = static_cast<float>(p.H - 1);
   const float sx = Wm1 / 2.f, sy = Hm1 / 2.f;          // ATen CPU grid_sampler: scaling = (size-1)/2
+  const int npairs = SAMPLE_QPB * p.T;
+  const bool early = npairs <= static_cast<int>(blockDim.x);   // one pair per thread: its outputs can wait in registers
+  if (!early) {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
 
-  for (int tb = 0; tb < p.T; tb += 32) {
-    // ---- lane t projects view tb+t
-    const int t = tb + lane;
+  // ---------------------------------------------------------------- phase 1: projection
+  for (int pair = threadIdx.x; pair < npairs; pair += blockDim.x) {
+    const int qi = pair / p.T, t = pair - qi * p.T;
+    const int row = row0 + qi;
+    // reference point -> metres in the local frame: p*span + lo (separately rounded mul, add)
+    const float px = __fadd_rn(__fmul_rn(p.ref[row * 3 + 0], p.span[0]), p.lo[0]);
+    const float py = __fadd_rn(__fmul_rn(p.ref[row * 3 + 1], p.span[1]), p.lo[1]);
+    const float pz = __fadd_rn(__fmul_rn(p.ref[row * 3 + 2], p.span[2]), p.lo[2]);
+    if (t == 0 && p.coord_pos != nullptr && !early) {
+      p.coord_pos[row * 3 + 0] = px; p.coord_pos[row * 3 + 1] = py; p.coord_pos[row * 3 + 2] = pz;
+    }
+    const float* Tc = p.T_cl + (static_cast<long long>(b) * p.T + t) * 12;
+    const float* cam = p.camera + (static_cast<long long>(b) * p.T + t) * 6;
+    float pc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float a = __fmul_rn(px, Tc[3 * i]);
+      a = __fmaf_rn(py, Tc[3 * i + 1], a);
+      a = __fmaf_rn(pz, Tc[3 * i + 2], a);
+      pc[i] = __fadd_rn(a, Tc[9 + i]);
+    }
+    const float eps = 1e-3f;
+    const bool in_front = pc[2] > eps;
+    const float zc = fmaxf(pc[2], eps);
+    const float u = __fadd_rn(__fmul_rn(__fdiv_rn(pc[0], zc), cam[2]), cam[4]);
+    const float v = __fadd_rn(__fmul_rn(__fdiv_rn(pc[1], zc), cam[3]), cam[5]);
+    const float wm1 = __fadd_rn(cam[0], -1.f), hm1 = __fadd_rn(cam[1], -1.f);
+    const int is_valid = in_front && (u >= 0.f) && (u <= wm1) && (v >= 0.f) && (v <= hm1);
+    // normalised grid and back (transformer_parq.py:148-150 then grid_sampler unnormalize)
+    const float gx = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, u), Wm1), -1.f);
+    const float gy = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, v), Hm1), -1.f);
+    const float ix = __fmul_rn(__fadd_rn(gx, 1.f), sx);
+    const float iy = __fmul_rn(__fadd_rn(gy, 1.f), sy);
+    const float x0f = floorf(ix), y0f = floorf(iy);
     ViewTap tap;
-    tap.x0 = tap.y0 = 0;
-    tap.fx = tap.fy = 0.f;
-    tap.inb = 0;
-    int is_valid = 0;
-    if (t < p.T) {
-      const float* Tc = p.T_cl + (static_cast<long long>(b) * p.T + t) * 12;
-      const float* cam = p.camera + (static_cast<long long>(b) * p.T + t) * 6;
-      float pc[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        float a = __fmul_rn(px, Tc[3 * i]);
-        a = __fmaf_rn(py, Tc[3 * i + 1], a);
-        a = __fmaf_rn(pz, Tc[3 * i + 2], a);
-        pc[i] = __fadd_rn(a, Tc[9 + i]);
-      }
-      const float eps = 1e-3f;
-      const bool in_front = pc[2] > eps;
-      const float zc = fmaxf(pc[2], eps);
-      const float u = __fadd_rn(__fmul_rn(__fdiv_rn(pc[0], zc), cam[2]), cam[4]);
-      const float v = __fadd_rn(__fmul_rn(__fdiv_rn(pc[1], zc), cam[3]), cam[5]);
-      const float wm1 = __fadd_rn(cam[0], -1.f), hm1 = __fadd_rn(cam[1], -1.f);
-      is_valid = in_front && (u >= 0.f) && (u <= wm1) && (v >= 0.f) && (v <= hm1);
-      if (warp == 0) {
-        const long long o = (static_cast<long long>(b) * p.T + t) * p.Nq + q;
-        if (p.center_im != nullptr) {
-          p.center_im[o * 2] = u;
-          p.center_im[o * 2 + 1] = v;
-        }
-        if (p.valid != nullptr) p.valid[o] = static_cast<uint8_t>(is_valid);
-      }
-      // normalised grid and back (transformer_parq.py:148-150 then grid_sampler unnormalize)
-      const float gx = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, u), Wm1), -1.f);
-      const float gy = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, v), Hm1), -1.f);
-      const float ix = __fmul_rn(__fadd_rn(gx, 1.f), sx);
-      const float iy = __fmul_rn(__fadd_rn(gy, 1.f), sy);
-      const float x0f = floorf(ix), y0f = floorf(iy);
-      tap.fx = ix - x0f;
-      tap.fy = iy - y0f;
-      // in-bounds tests in float (ix may be huge or NaN), then a safe int conversion
-      const bool xw = (x0f >= 0.f) && (x0f <= Wm1), xe = (x0f >= -1.f) && (x0f <= Wm1 - 1.f);
-      const bool yn = (y0f >= 0.f) && (y0f <= Hm1), ys = (y0f >= -1.f) && (y0f <= Hm1 - 1.f);
-      tap.inb = (xw && yn ? 1 : 0) | (xe && yn ? 2 : 0) | (xw && ys ? 4 : 0) | (xe && ys ? 8 : 0);
-      if (tap.inb) {
-        tap.x0 = static_cast<int>(x0f);
-        tap.y0 = static_cast<int>(y0f);
-      }
+    tap.fx = ix - x0f;
+    tap.fy = iy - y0f;
+    // in-bounds tests in float (ix may be huge or NaN), then a safe int conversion
+    const bool xw = (x0f >= 0.f) && (x0f <= Wm1), xe = (x0f >= -1.f) && (x0f <= Wm1 - 1.f);
+    const bool yn = (y0f >= 0.f) && (y0f <= Hm1), ys = (y0f >= -1.f) && (y0f <= Hm1 - 1.f);
+    tap.inb = (xw && yn ? 1 : 0) | (xe && yn ? 2 : 0) | (xw && ys ? 4 : 0) | (xe && ys ? 8 : 0);
+    tap.x0 = tap.inb ? static_cast<int>(x0f) : 0;
+    tap.y0 = tap.inb ? static_cast<int>(y0f) : 0;
+    tap.inb |= is_valid ? 16 : 0;
+    tap.u = u;
+    tap.v = v;
+    s_tap[pair] = tap;
+    if (!early) {
+      const long long oc = (static_cast<long long>(b) * p.T + t) * p.Nq + (row - b * p.Nq);
+      if (p.center_im != nullptr) { p.center_im[oc * 2] = u; p.center_im[oc * 2 + 1] = v; }
+      if (p.valid != nullptr) p.valid[oc] = static_cast<uint8_t>(is_valid);
     }
-    nvalid += __popc(__ballot_sync(0xffffffffu, is_valid));
+  }
+  __syncthreads();
 
-    // ---- all lanes gather.  Only views with at least one in-bounds corner contribute (zero padding):
-    // their lane ids are compacted from a ballot, four of them (16 independent 16-byte loads) in flight.
-    unsigned live = __ballot_sync(0xffffffffu, tap.inb != 0);
-    while (live != 0u) {
-      uint4 tex[4][4];
-      float wgt[4][4];
+  // ---------------------------------------------------------------- phase 2: gather
+  // All control flow below is warp-uniform (`live` is a ballot, taps are shared-memory broadcasts): absent views
+  // and out-of-bounds corners cost no instructions.  The first round of loads of query j+1 is issued before the
+  // epilogue of query j, so a warp always has texel loads in flight.
+  const long long rowpitch = static_cast<long long>(p.W) * p.C;
+  const ViewTap* taps = s_tap;     // taps of the query whose views are being issued
+  int tb = 0, nvalid = 0;          // 32-view chunk cursor and valid-view count of that query
+  unsigned live = 0u;              // views of the chunk with at least one in-bounds corner, not yet issued
+  uint4 tex[V][4];
+  float wgt[V][4];
+  int inb[V];
+  auto load_chunk = [&]() {
+    const int inb_l = (tb + lane < p.T) ? taps[tb + lane].inb : 0;
+    nvalid += __popc(__ballot_sync(0xffffffffu, inb_l & 16));
+    live = __ballot_sync(0xffffffffu, (inb_l & 15) != 0);
+  };
+  auto begin_query = [&](int qi) {
+    taps = s_tap + qi * p.T;
+    tb = 0;
+    nvalid = 0;
+    load_chunk();
+    while (live == 0u && tb + 32 < p.T) { tb += 32; load_chunk(); }
+  };
+  auto issue_round = [&]() {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool have = live != 0u;
-        const int src = have ? (__ffs(live) - 1) : 0;
-        if (have) live &= live - 1;
-        const int x0 = __shfl_sync(0xffffffffu, tap.x0, src);
-        const int y0 = __shfl_sync(0xffffffffu, tap.y0, src);
-        const float fx = __shfl_sync(0xffffffffu, tap.fx, src);
-        const float fy = __shfl_sync(0xffffffffu, tap.fy, src);
-        int inb = __shfl_sync(0xffffffffu, tap.inb, src);
-        if (!have) inb = 0;
-        const float ex = 1.f - fx, sy_ = 1.f - fy;       // distances to east / south (ATen CPU form)
-        wgt[k][0] = sy_ * ex;   // nw
-        wgt[k][1] = sy_ * fx;   // ne
-        wgt[k][2] = fy * ex;    // sw
-        wgt[k][3] = fy * fx;    // se
+    for (int k = 0; k < V; ++k) {
+      inb[k] = 0;
+      if (live != 0u) {
+        const int src = __ffs(live) - 1;
+        live &= live - 1;
+        const ViewTap tp = taps[tb + src];               // shared-memory broadcast
+        inb[k] = tp.inb & 15;
+        const float ex = 1.f - tp.fx, sy_ = 1.f - tp.fy;   // distances to east / south (ATen CPU form)
+        wgt[k][0] = sy_ * ex;      // nw
+        wgt[k][1] = sy_ * tp.fx;   // ne
+        wgt[k][2] = tp.fy * ex;    // sw
+        wgt[k][3] = tp.fy * tp.fx; // se
         const long long view = static_cast<long long>(b) * p.T + tb + src;
-        const __nv_bfloat16* base = p.tokens + ((view * p.H + y0) * p.W + x0) * static_cast<long long>(p.C) + ch;
-        const long long rowpitch = static_cast<long long>(p.W) * p.C;
+        const __nv_bfloat16* base = p.tokens + ((view * p.H + tp.y0) * p.W + tp.x0) * static_cast<long long>(p.C) + ch;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (inb & (1 << c)) {
-            tex[k][c] = ldg_nc_16(base + (c >> 1) * rowpitch + (c & 1) * p.C);
-          } else {
-            tex[k][c] = make_uint4(0, 0, 0, 0);
-            wgt[k][c] = 0.f;
-          }
+        for (int c = 0; c < 4; ++c)
+          if (inb[k] & (1 << c)) tex[k][c] = ldg_nc_16(base + (c >> 1) * rowpitch + (c & 1) * p.C);
+        while (live == 0u && tb + 32 < p.T) { tb += 32; load_chunk(); }
+      }
+    }
+  };
+
+  begin_query(0);
+  issue_round();
+  if (early) {
+    pdl_wait();
+    pdl_launch_dependents();
+    if (static_cast<int>(threadIdx.x) < npairs && (p.center_im != nullptr || p.valid != nullptr)) {
+      const int pqi = threadIdx.x / p.T, pt = threadIdx.x - pqi * p.T;      // pair index == thread index in phase 1
+      const long long oc = (static_cast<long long>(b) * p.T + pt) * p.Nq + (row0 + pqi - b * p.Nq);
+      const ViewTap tp = s_tap[threadIdx.x];
+      if (p.center_im != nullptr) { p.center_im[oc * 2] = tp.u; p.center_im[oc * 2 + 1] = tp.v; }
+      if (p.valid != nullptr) p.valid[oc] = static_cast<uint8_t>((tp.inb >> 4) & 1);
+    }
+    if (p.coord_pos != nullptr && threadIdx.x < SAMPLE_QPB * 3) {
+      const int r = row0 + threadIdx.x / 3, a = threadIdx.x % 3;
+      p.coord_pos[r * 3 + a] = __fadd_rn(__fmul_rn(p.ref[r * 3 + a], p.span[a]), p.lo[a]);
+    }
+  }
+#pragma unroll 1
+  for (int qi = 0; qi < SAMPLE_QPB; ++qi) {
+    const int row = row0 + qi;
+    const long long o = static_cast<long long>(row) * p.C + ch;
+    float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+    if (p.a_xpe != nullptr) {                                // in flight while the texels arrive
+      e0 = reinterpret_cast<const float4*>(p.pe + o)[0];
+      e1 = reinterpret_cast<const float4*>(p.pe + o)[1];
+    }
+    float tot[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot[i] = 0.f;
+    while (inb[0] != 0) {                                    // the first slot is empty only when no view is left
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        if (inb[k] != 0) {
+          float acc[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)                        // corner order nw, ne, sw, se as in ATen
+            if (inb[k] & (1 << c)) fma_bf16x8(acc, tex[k][c], wgt[k][c]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) tot[i] += acc[i];
         }
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) fma_bf16x8(acc, tex[k][c], wgt[k][c]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tot[i] += acc[i];
-      }
+      issue_round();
     }
-  }
+    const int nv = nvalid;                                   // every chunk of this query has been visited
+    if (qi + 1 < SAMPLE_QPB) {
+      begin_query(qi + 1);
+      issue_round();
+    }
 
-  const float cnt = static_cast<float>(max(nvalid, 1));
-  float f[8];
+    // sum over ALL views / max(#valid views, 1): x / n through one reciprocal and a Newton correction
+    // (q = x*r; q += (x - n*q)*r), which reproduces the correctly rounded quotient of the reference's true division
+    const float cnt = static_cast<float>(max(nv, 1));
+    const float rc = __frcp_rn(cnt);
+    float f[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f[i] = tot[i] / cnt;
-  const long long o = static_cast<long long>(bq) * p.C + ch;
-  reinterpret_cast<float4*>(p.feat + o)[0] = make_float4(f[0], f[1], f[2], f[3]);
-  reinterpret_cast<float4*>(p.feat + o)[1] = make_float4(f[4], f[5], f[6], f[7]);
-  if (p.a_x != nullptr) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      hi[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-      lo[i] = pack_bf16x2(f[2 * i] - __uint_as_float(hi[i] << 16), f[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u));
+    for (int i = 0; i < 8; ++i) {
+      const float q0 = tot[i] * rc;
+      f[i] = nv <= 1 ? tot[i] : __fmaf_rn(__fmaf_rn(-cnt, q0, tot[i]), rc, q0);
     }
-    __nv_bfloat16* dst = p.a_x + static_cast<long long>(bq) * (2 * p.C) + ch;
-    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(dst + p.C) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  }
-  if (p.a_xpe != nullptr) {
-    const float4 e0 = reinterpret_cast<const float4*>(p.pe + o)[0], e1 = reinterpret_cast<const float4*>(p.pe + o)[1];
-    const float g[8] = {f[0] + e0.x, f[1] + e0.y, f[2] + e0.z, f[3] + e0.w, f[4] + e1.x, f[5] + e1.y, f[6] + e1.z, f[7] + e1.w};
-    uint32_t hi[4], lo[4];
+    reinterpret_cast<float4*>(p.feat + o)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(p.feat + o)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    if (p.a_x != nullptr) {
+      uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      hi[i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
-      lo[i] = pack_bf16x2(g[2 * i] - __uint_as_float(hi[i] << 16), g[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u));
+      for (int i = 0; i < 4; ++i) {
+        hi[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+        lo[i] = pack_bf16x2(f[2 * i] - __uint_as_float(hi[i] << 16), f[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u));
+      }
+      __nv_bfloat16* dst = p.a_x + static_cast<long long>(row) * (2 * p.C) + ch;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(dst + p.C) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    __nv_bfloat16* dst = p.a_xpe + static_cast<long long>(bq) * (2 * p.C) + ch;
-    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(dst + p.C) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (p.a_xpe != nullptr) {
+      const float g[8] = {f[0] + e0.x, f[1] + e0.y, f[2] + e0.z, f[3] + e0.w, f[4] + e1.x, f[5] + e1.y, f[6] + e1.z, f[7] + e1.w};
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        hi[i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
+        lo[i] = pack_bf16x2(g[2 * i] - __uint_as_float(hi[i] << 16), g[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u));
+      }
+      __nv_bfloat16* dst = p.a_xpe + static_cast<long long>(row) * (2 * p.C) + ch;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(dst + p.C) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 

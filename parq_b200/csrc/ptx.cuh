@@ -25,6 +25,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------- programmatic dependent launch --
+// Every kernel of the forward is launched with programmatic stream serialisation: its CTAs may become
+// resident while the previous kernel is still draining.  Contract used throughout this library:
+//   prologue (barrier init, TMEM alloc, loads of CONSTANTS or of data produced >= 2 launches earlier)
+//   pdl_wait()               -- previous kernel complete, its writes visible; nothing is written before this
+//   pdl_launch_dependents()  -- only now may the NEXT kernel start its own prologue
+// Because a kernel releases its dependents only after its own wait, at most one successor overlaps it, so
+// "produced >= 2 launches earlier" is complete by the time any prologue runs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier --
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -36,6 +36,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 __global__ void posemb_kernel(const float* __restrict__ ref, const float* __restrict__ dim_t, __nv_bfloat16* __restrict__ out,
                               int R) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * 384) return;
   const int row = idx / 384, j = idx % 384;
@@ -57,6 +59,8 @@ add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y, const
               const float* __restrict__ beta, const float* __restrict__ pe, float* __restrict__ x_out,
               __nv_bfloat16* __restrict__ a_x, __nv_bfloat16* __restrict__ a_xpe, int R) {
   constexpr int PASSES = C / 256;          // a lane owns 8 consecutive channels per pass
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -134,6 +138,8 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ h, int ldh, int C, int Nq, int groups, const double2* __restrict__ partial,
                 const float* __restrict__ gamma0, const float* __restrict__ beta0, const float* __restrict__ gamma1,
                 const float* __restrict__ beta1, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x;           // b*Nq + q
   const int b = row / Nq;
   const int per_group = C / 8;
@@ -191,14 +197,74 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Epilogue of one row: lane j holds output slot j (bias not yet added).
+__device__ __forceinline__ void heads_row_epilogue(const HeadsParams& p, int row, int lane, float mine) {
+  const bool is_cls = lane < p.num_cls;
+  const int k3 = lane >= HEADS_CLS_SLOTS + 3 ? lane - HEADS_CLS_SLOTS - 3 : lane - HEADS_CLS_SLOTS;   // axis for size / centre lanes
+  if (is_cls) mine += p.b_cls[lane];
+  else if (lane >= HEADS_CLS_SLOTS && lane < HEADS_CLS_SLOTS + 3) mine += p.b_size[lane - HEADS_CLS_SLOTS];
+  else if (lane >= HEADS_CLS_SLOTS + 3 && lane < HEADS_CLS_SLOTS + 6) mine += p.b_c3[lane - HEADS_CLS_SLOTS - 3];
+  else if (lane >= HEADS_CLS_SLOTS + 6 && lane < HEADS_SLOTS) mine += p.b_r3[lane - HEADS_CLS_SLOTS - 6];
+  // softmax over the class lanes; arg-max of the probabilities with torch's first-index tie rule
+  const float mx = warp_max(is_cls ? mine : -INFINITY);
+  const float e = is_cls ? expf(mine - mx) : 0.f;
+  const float den = warp_sum(e);
+  const float pr = e / den;
+  float best = is_cls ? pr : -1.f;
+  int arg = is_cls ? lane : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  if (is_cls) {
+    p.prob[static_cast<long long>(row) * p.num_cls + lane] = pr;
+    p.logits[static_cast<long long>(row) * p.num_cls + lane] = mine;
+  }
+  if (lane >= HEADS_CLS_SLOTS && lane < HEADS_CLS_SLOTS + 3) {
+    p.size[row * 3 + k3] = expf(mine) * p.mean_size[arg * 3 + k3];
+  } else if (lane >= HEADS_CLS_SLOTS + 3 && lane < HEADS_CLS_SLOTS + 6) {
+    const float rr = p.ref[row * 3 + k3];
+    const float rc = fminf(fmaxf(rr, 0.f), 1.f);
+    const float inv_sig = logf(fmaxf(rc, 1e-3f) / fmaxf(1.f - rc, 1e-3f));
+    const float sg = 1.f / (1.f + expf(-(mine + inv_sig)));
+    const float center = __fadd_rn(__fmul_rn(sg, p.span[k3]), p.lo[k3]);
+    p.center[row * 3 + k3] = center;
+    p.coord_pos[row * 3 + k3] = __fadd_rn(__fmul_rn(rr, p.span[k3]), p.lo[k3]);
+    p.ref_next[row * 3 + k3] = __fdiv_rn(__fadd_rn(center, -p.lo[k3]), p.span[k3]);
+  } else if (lane >= HEADS_CLS_SLOTS + 6 && lane < HEADS_SLOTS) {
+    p.ortho6d[row * 6 + lane - HEADS_CLS_SLOTS - 6] = mine;
+  }
+  if (p.rot != nullptr) {
+    // Gram-Schmidt: x = a/|a|, z = (x X b)/|x X b|, y = z X x; columns [x y z]; norms clamped at 1e-8
+    float o6[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o6[k] = __shfl_sync(0xffffffffu, mine, HEADS_CLS_SLOTS + 6 + k);
+    if (lane == 0) {
+      const float na = fmaxf(sqrtf(o6[0] * o6[0] + o6[1] * o6[1] + o6[2] * o6[2]), 1e-8f);
+      const float x0 = o6[0] / na, x1 = o6[1] / na, x2 = o6[2] / na;
+      float z0 = x1 * o6[5] - x2 * o6[4], z1 = x2 * o6[3] - x0 * o6[5], z2 = x0 * o6[4] - x1 * o6[3];
+      const float nz = fmaxf(sqrtf(z0 * z0 + z1 * z1 + z2 * z2), 1e-8f);
+      z0 /= nz; z1 /= nz; z2 /= nz;
+      const float y0 = z1 * x2 - z2 * x1, y1 = z2 * x0 - z0 * x2, y2 = z0 * x1 - z1 * x0;
+      float* r = p.rot + static_cast<long long>(row) * 9;
+      r[0] = x0; r[1] = y0; r[2] = z0;
+      r[3] = x1; r[4] = y1; r[5] = z1;
+      r[6] = x2; r[7] = y2; r[8] = z2;
+    }
+  }
+}
+
 // Block = 16 warps.  The 28 x C final-layer weights (zero rows for unused class slots) and the GroupNorm
-// affine parameters are staged once per block in shared memory; each warp then walks rows (queries), one
-// row at a time: 28 independent dot-product chains per lane, a butterfly reduction of all 28, and an
-// epilogue in which lane j owns output slot j (softmax/arg-max through warp shuffles).
+// affine parameters are staged once per block in shared memory (before the dependency wait: they are
+// constants); each warp then walks PAIRS of rows (queries) so that every weight read from shared memory
+// feeds two rows: 2 x 28 independent dot-product chains per lane, a butterfly reduction, and an epilogue
+// in which lane j owns output slot j (softmax/arg-max through warp shuffles).
 template <int C>
 __global__ void __launch_bounds__(512)
 heads_final_kernel(const HeadsParams p, int rows_per_block) {
-  constexpr int PER = C / 32;
+  constexpr int NR = 2;
   extern __shared__ float sw[];           // [HEADS_SLOTS][C] weights, then gamma_c | beta_c | gamma_r | beta_r
   float* s_aff = sw + HEADS_SLOTS * C;
   for (int i = threadIdx.x * 4; i < HEADS_SLOTS * C; i += blockDim.x * 4) {
@@ -213,95 +279,93 @@ heads_final_kernel(const HeadsParams p, int rows_per_block) {
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     s_aff[i] = p.gamma_c[i]; s_aff[C + i] = p.beta_c[i]; s_aff[2 * C + i] = p.gamma_r[i]; s_aff[3 * C + i] = p.beta_r[i];
   }
+  // everything above is constant weights: staged while the previous kernel drains
+  pdl_wait();
+  pdl_launch_dependents();
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int row_end = min(p.R, (blockIdx.x + 1) * rows_per_block);
-  for (int row = blockIdx.x * rows_per_block + (threadIdx.x >> 5); row < row_end; row += (blockDim.x >> 5)) {
-    const int b = row / p.Nq;
-    float mean_l = 0.f, rstd_l = 0.f;
-    if (lane < 2) gn_mean_rstd(p.partial, b, lane, C, p.Nq, mean_l, rstd_l);
-    const float mean_c = __shfl_sync(0xffffffffu, mean_l, 0), rstd_c = __shfl_sync(0xffffffffu, rstd_l, 0);
-    const float mean_r = __shfl_sync(0xffffffffu, mean_l, 1), rstd_r = __shfl_sync(0xffffffffu, rstd_l, 1);
-    float acc[HEADS_SLOTS];
+  for (int row0 = blockIdx.x * rows_per_block + NR * (threadIdx.x >> 5); row0 < row_end; row0 += NR * (blockDim.x >> 5)) {
+    float mean_c[NR], rstd_c[NR], mean_r[NR], rstd_r[NR];
+    long long xoff[NR];
 #pragma unroll
-    for (int j = 0; j < HEADS_SLOTS; ++j) acc[j] = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < PER; ++i) {
-      const int c = i * 32 + lane;
-      const float xv = p.x[static_cast<long long>(row) * C + c];
-      const float a = p.h2[static_cast<long long>(row) * (2 * C) + c];
-      const float r = p.h2[static_cast<long long>(row) * (2 * C) + C + c];
-      const float hc = fmaxf((a - mean_c) * rstd_c * s_aff[c] + s_aff[C + c], 0.f);
-      const float hr = fmaxf((r - mean_r) * rstd_r * s_aff[2 * C + c] + s_aff[3 * C + c], 0.f);
+    for (int r = 0; r < NR; ++r) {
+      const int row = min(row0 + r, row_end - 1);          // a missing second row repeats the first (result discarded)
+      xoff[r] = static_cast<long long>(row) * C;
+      float mean_l = 0.f, rstd_l = 0.f;
+      if (lane < 2) gn_mean_rstd(p.partial, row / p.Nq, lane, C, p.Nq, mean_l, rstd_l);
+      mean_c[r] = __shfl_sync(0xffffffffu, mean_l, 0); rstd_c[r] = __shfl_sync(0xffffffffu, rstd_l, 0);
+      mean_r[r] = __shfl_sync(0xffffffffu, mean_l, 1); rstd_r[r] = __shfl_sync(0xffffffffu, rstd_l, 1);
+    }
+    float acc[NR][HEADS_SLOTS];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int j = 0; j < HEADS_SLOTS; ++j) acc[r][j] = 0.f;
+    // a lane owns 4 consecutive channels per step (16-byte global and shared loads); the loads of step i+1 are
+    // issued before the arithmetic of step i
+    constexpr int STEPS = C / 128;
+    float4 nx[NR], na[NR], nq[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      nx[r] = *reinterpret_cast<const float4*>(p.x + xoff[r] + lane * 4);
+      na[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xoff[r] + lane * 4);
+      nq[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xoff[r] + C + lane * 4);
+    }
+#pragma unroll 1
+    for (int i = 0; i < STEPS; ++i) {
+      const int c = i * 128 + lane * 4;
+      float4 cx[NR], ca[NR], cq[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) { cx[r] = nx[r]; ca[r] = na[r]; cq[r] = nq[r]; }
+      if (i + 1 < STEPS) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          nx[r] = *reinterpret_cast<const float4*>(p.x + xoff[r] + c + 128);
+          na[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xoff[r] + c + 128);
+          nq[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xoff[r] + C + c + 128);
+        }
+      }
+      const float4 gc = *reinterpret_cast<const float4*>(s_aff + c), bc = *reinterpret_cast<const float4*>(s_aff + C + c);
+      const float4 gr = *reinterpret_cast<const float4*>(s_aff + 2 * C + c), br = *reinterpret_cast<const float4*>(s_aff + 3 * C + c);
+      float xv[NR][4], hc[NR][4], hr[NR][4];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        xv[r][0] = cx[r].x; xv[r][1] = cx[r].y; xv[r][2] = cx[r].z; xv[r][3] = cx[r].w;
+        hc[r][0] = fmaxf((ca[r].x - mean_c[r]) * rstd_c[r] * gc.x + bc.x, 0.f);
+        hc[r][1] = fmaxf((ca[r].y - mean_c[r]) * rstd_c[r] * gc.y + bc.y, 0.f);
+        hc[r][2] = fmaxf((ca[r].z - mean_c[r]) * rstd_c[r] * gc.z + bc.z, 0.f);
+        hc[r][3] = fmaxf((ca[r].w - mean_c[r]) * rstd_c[r] * gc.w + bc.w, 0.f);
+        hr[r][0] = fmaxf((cq[r].x - mean_r[r]) * rstd_r[r] * gr.x + br.x, 0.f);
+        hr[r][1] = fmaxf((cq[r].y - mean_r[r]) * rstd_r[r] * gr.y + br.y, 0.f);
+        hr[r][2] = fmaxf((cq[r].z - mean_r[r]) * rstd_r[r] * gr.z + br.z, 0.f);
+        hr[r][3] = fmaxf((cq[r].w - mean_r[r]) * rstd_r[r] * gr.w + br.w, 0.f);
+      }
 #pragma unroll
       for (int j = 0; j < HEADS_SLOTS; ++j) {
-        const float v = j < HEADS_CLS_SLOTS + 3 ? xv : (j < HEADS_CLS_SLOTS + 6 ? hc : hr);
-        acc[j] = fmaf(sw[j * C + c], v, acc[j]);
+        const float4 w = *reinterpret_cast<const float4*>(sw + j * C + c);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const float* v = j < HEADS_CLS_SLOTS + 3 ? xv[r] : (j < HEADS_CLS_SLOTS + 6 ? hc[r] : hr[r]);
+          acc[r][j] = fmaf(w.x, v[0], acc[r][j]);
+          acc[r][j] = fmaf(w.y, v[1], acc[r][j]);
+          acc[r][j] = fmaf(w.z, v[2], acc[r][j]);
+          acc[r][j] = fmaf(w.w, v[3], acc[r][j]);
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int r = 0; r < NR; ++r) {
 #pragma unroll
-      for (int j = 0; j < HEADS_SLOTS; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-    // lane j keeps output slot j
-    float mine = 0.f;
+      for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-    for (int j = 0; j < HEADS_SLOTS; ++j)
-      if (lane == j) mine = acc[j];
-    const bool is_cls = lane < p.num_cls;
-    const int k3 = lane >= HEADS_CLS_SLOTS + 3 ? lane - HEADS_CLS_SLOTS - 3 : lane - HEADS_CLS_SLOTS;   // axis for size / centre lanes
-    if (is_cls) mine += p.b_cls[lane];
-    else if (lane >= HEADS_CLS_SLOTS && lane < HEADS_CLS_SLOTS + 3) mine += p.b_size[lane - HEADS_CLS_SLOTS];
-    else if (lane >= HEADS_CLS_SLOTS + 3 && lane < HEADS_CLS_SLOTS + 6) mine += p.b_c3[lane - HEADS_CLS_SLOTS - 3];
-    else if (lane >= HEADS_CLS_SLOTS + 6 && lane < HEADS_SLOTS) mine += p.b_r3[lane - HEADS_CLS_SLOTS - 6];
-    // softmax over the class lanes; arg-max of the probabilities with torch's first-index tie rule
-    const float mx = warp_max(is_cls ? mine : -INFINITY);
-    const float e = is_cls ? expf(mine - mx) : 0.f;
-    const float den = warp_sum(e);
-    const float pr = e / den;
-    float best = is_cls ? pr : -1.f;
-    int arg = is_cls ? lane : 0x7fffffff;
+        for (int j = 0; j < HEADS_SLOTS; ++j) acc[r][j] += __shfl_xor_sync(0xffffffffu, acc[r][j], o);
+      // lane j keeps output slot j
+      float mine = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-    }
-    if (is_cls) {
-      p.prob[static_cast<long long>(row) * p.num_cls + lane] = pr;
-      p.logits[static_cast<long long>(row) * p.num_cls + lane] = mine;
-    }
-    if (lane >= HEADS_CLS_SLOTS && lane < HEADS_CLS_SLOTS + 3) {
-      p.size[row * 3 + k3] = expf(mine) * p.mean_size[arg * 3 + k3];
-    } else if (lane >= HEADS_CLS_SLOTS + 3 && lane < HEADS_CLS_SLOTS + 6) {
-      const float rr = p.ref[row * 3 + k3];
-      const float rc = fminf(fmaxf(rr, 0.f), 1.f);
-      const float inv_sig = logf(fmaxf(rc, 1e-3f) / fmaxf(1.f - rc, 1e-3f));
-      const float sg = 1.f / (1.f + expf(-(mine + inv_sig)));
-      const float center = __fadd_rn(__fmul_rn(sg, p.span[k3]), p.lo[k3]);
-      p.center[row * 3 + k3] = center;
-      p.coord_pos[row * 3 + k3] = __fadd_rn(__fmul_rn(rr, p.span[k3]), p.lo[k3]);
-      p.ref_next[row * 3 + k3] = __fdiv_rn(__fadd_rn(center, -p.lo[k3]), p.span[k3]);
-    } else if (lane >= HEADS_CLS_SLOTS + 6 && lane < HEADS_SLOTS) {
-      p.ortho6d[row * 6 + lane - HEADS_CLS_SLOTS - 6] = mine;
-    }
-    if (p.rot != nullptr) {
-      // Gram-Schmidt: x = a/|a|, z = (x X b)/|x X b|, y = z X x; columns [x y z]; norms clamped at 1e-8
-      float o6[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) o6[k] = __shfl_sync(0xffffffffu, mine, HEADS_CLS_SLOTS + 6 + k);
-      if (lane == 0) {
-        const float na = fmaxf(sqrtf(o6[0] * o6[0] + o6[1] * o6[1] + o6[2] * o6[2]), 1e-8f);
-        const float x0 = o6[0] / na, x1 = o6[1] / na, x2 = o6[2] / na;
-        float z0 = x1 * o6[5] - x2 * o6[4], z1 = x2 * o6[3] - x0 * o6[5], z2 = x0 * o6[4] - x1 * o6[3];
-        const float nz = fmaxf(sqrtf(z0 * z0 + z1 * z1 + z2 * z2), 1e-8f);
-        z0 /= nz; z1 /= nz; z2 /= nz;
-        const float y0 = z1 * x2 - z2 * x1, y1 = z2 * x0 - z0 * x2, y2 = z0 * x1 - z1 * x0;
-        float* r = p.rot + static_cast<long long>(row) * 9;
-        r[0] = x0; r[1] = y0; r[2] = z0;
-        r[3] = x1; r[4] = y1; r[5] = z1;
-        r[6] = x2; r[7] = y2; r[8] = z2;
-      }
+      for (int j = 0; j < HEADS_SLOTS; ++j)
+        if (lane == j) mine = acc[r][j];
+      if (row0 + r < row_end) heads_row_epilogue(p, row0 + r, lane, mine);
     }
   }
 }

@@ -249,3 +249,8 @@ def test_cuda_graph_replay_matches_eager(dev):
     for k in OUT_KEYS:
         assert torch.equal(replay[k], eager[k]), k
     assert len(eng._graphs) == 1
+    # programmatic dependent launch only reorders prologues: results are bit-identical with it switched off
+    plain = eng.forward(*args, c["H"], c["W"], pdl=False)
+    torch.cuda.synchronize()
+    for k in OUT_KEYS:
+        assert torch.equal(plain[k], eager[k]), k
