@@ -118,6 +118,20 @@ int parq_decoder_forward(const ParqShape *shape, const void *tokens_bf16, const 
                          const void *packed, void *workspace, size_t workspace_bytes, const ParqOutputs *out,
                          uint32_t flags, void *stream);
 
+/* "Next" row f-2: PARQDecoder.parse_pred (model/parq_decoder.py:372-424) + nms / nms_3d_faster[_samecls]
+ * (utils/nms.py:20-70, 141-224) on the device, one CTA per clip, K <= 1024 boxes per clip.  Inputs are the LAST
+ * iteration's center_unnormalized, size_unnormalized (B,K,3), ortho6d (B,K,6) and sem_cls_prob (B,K,num_cls); the
+ * background label is num_cls-1.  track_scale is a HOST array of 6 floats (cfg TRACK_SCALE); mode 0 is the eval
+ * configuration (class-agnostic NMS, IoU threshold 0.1, track-scale filter), PARQ_NMS_SAME_CLASS |
+ * PARQ_NMS_NO_TRACK_SCALE with threshold 0.2 is the FOR_VIS branch.  Outputs: pred_mask (B,K) = nms & in-scope;
+ * optional nms_mask (B,K), scores (B,K), labels (B,K) int32, obbs (B,K,19) in the reference's Obb3D layout
+ * [xmin,xmax,ymin,ymax,zmin,zmax | T_local_object: R row-major, t | sem_id]  (utils/wrappers.py:297-321). */
+#define PARQ_NMS_SAME_CLASS 1u
+#define PARQ_NMS_NO_TRACK_SCALE 2u
+int parq_parse_pred(const float *center, const float *size, const float *ortho6d, const float *prob, int B, int K,
+                    int num_cls, const float *track_scale, double overlap_threshold, uint32_t mode, uint8_t *pred_mask,
+                    uint8_t *nms_mask, float *scores, int32_t *labels, float *obbs, void *stream);
+
 /* ---- building blocks exported for unit tests and micro-benchmarks -------------------------------------- */
 
 /* D[M,N] = sum_t A[:, a_koff[t] : +K] * Bw[:, b_koff[t] : +K]^T  (bf16 K-major operands, fp32 accumulate),

@@ -341,3 +341,64 @@ def rotation_from_ortho6d(o):
     z = nrm(torch.cross(x, o[:, 3:6], dim=1))
     y = torch.cross(z, x, dim=1)
     return torch.stack((x, y, z), dim=2)
+
+
+# --------------------------------------------------------------------------- #
+# f-2  parse_pred + NMS (model/parq_decoder.py:372-424, utils/nms.py:20-70,141-179)
+# --------------------------------------------------------------------------- #
+def box_corners_local(center, size, ortho6d):
+    """8 corners of every predicted box in the snippet-local frame, fp32 torch, in the reference's
+    operation order: R = compute_rotation_matrix_from_ortho6d (parq_decoder.py:383-386), object-frame
+    corners from +-size/2 in the order of Obb3D.bb3corners_object (utils/wrappers.py:355-392), then
+    Pose.transform = p @ R^T + t (utils/nms.py:24, wrappers.py:260-267).  (B,K,3),(B,K,3),(B,K,6) -> (B,K,8,3)."""
+    B, K = center.shape[:2]
+    R = rotation_from_ortho6d(ortho6d.contiguous().view(-1, 6)).view(B, K, 3, 3)
+    lo, hi = -size / 2, size / 2
+    xs = torch.stack([lo[..., 0], hi[..., 0], hi[..., 0], lo[..., 0], lo[..., 0], hi[..., 0], hi[..., 0], lo[..., 0]], -1)
+    ys = torch.stack([lo[..., 1], lo[..., 1], hi[..., 1], hi[..., 1], lo[..., 1], lo[..., 1], hi[..., 1], hi[..., 1]], -1)
+    zs = torch.stack([lo[..., 2], lo[..., 2], lo[..., 2], lo[..., 2], hi[..., 2], hi[..., 2], hi[..., 2], hi[..., 2]], -1)
+    c = torch.stack([xs, ys, zs], -1)                                   # (B,K,8,3)
+    return c @ R.transpose(-1, -2) + center.unsqueeze(-2)
+
+
+def nms_3d_faster(boxes, overlap_threshold):
+    """utils/nms.py:141-179 (class-agnostic greedy NMS on AABBs, float64).  boxes (n, >=7): x1,y1,z1,x2,y2,z2,score."""
+    x1, y1, z1, x2, y2, z2, score = (boxes[:, i] for i in range(7))
+    area = (x2 - x1) * (y2 - y1) * (z2 - z1)
+    order = np.argsort(score)
+    pick = []
+    while order.size != 0:
+        last = order.size
+        i = order[-1]
+        pick.append(i)
+        rest = order[: last - 1]
+        l = np.maximum(0, np.minimum(x2[i], x2[rest]) - np.maximum(x1[i], x1[rest]))
+        w = np.maximum(0, np.minimum(y2[i], y2[rest]) - np.maximum(y1[i], y1[rest]))
+        h = np.maximum(0, np.minimum(z2[i], z2[rest]) - np.maximum(z1[i], z1[rest]))
+        inter = l * w * h
+        o = inter / (area[i] + area[rest] - inter)
+        order = np.delete(order, np.concatenate(([last - 1], np.where(o > overlap_threshold)[0])))
+    return pick
+
+
+def parse_pred(last, track_scale=(-1.5, 1.5, -2, 1, 0, 2), num_semcls=9, overlap_threshold=0.1):
+    """PARQDecoder.parse_pred (parq_decoder.py:372-424) with FOR_VIS False / ENABLE_NMS True (config/eval.yaml):
+    scores, labels = max over ALL classes; AABB of the rotated corners; class-agnostic NMS over the
+    non-background boxes; pred_mask = nms & (x in (ts0,ts1)) & (z in (ts4,ts5)).
+    Returns dict(pred_mask (B,K) bool, scores (B,K), labels (B,K), aabb (B,K,6) float64)."""
+    center, size, o6, prob = (last[k].detach().float().cpu() for k in
+                              ("center_unnormalized", "size_unnormalized", "ortho6d", "sem_cls_prob"))
+    scores, labels = torch.max(prob, -1)
+    corners = box_corners_local(center, size, o6).numpy()
+    B, K = scores.shape
+    aabb = np.concatenate([corners.min(axis=2), corners.max(axis=2)], -1).astype(np.float64)     # (B,K,6)
+    mask = np.zeros((B, K), dtype=bool)
+    for b in range(B):
+        fg = np.where(labels[b].numpy() != num_semcls)[0]
+        boxes = np.concatenate([aabb[b, fg], scores[b, fg].numpy().astype(np.float64)[:, None]], 1)
+        pick = nms_3d_faster(boxes, overlap_threshold)
+        mask[b, fg[pick]] = True
+    ts = track_scale
+    valid = (center[..., 0] > ts[0]) & (center[..., 0] < ts[1]) & (center[..., 2] > ts[4]) & (center[..., 2] < ts[5])
+    return {"pred_mask": torch.from_numpy(mask) & valid, "nms_mask": torch.from_numpy(mask), "scores": scores, "labels": labels,
+            "aabb": torch.from_numpy(aabb)}

@@ -75,6 +75,6 @@ def load_reference():
     dec = _load("model.parq_decoder", os.path.join(REFERENCE_ROOT, "model", "parq_decoder.py"))
     tp = sys.modules["model.transformer_parq"]
     ns = types.SimpleNamespace(PARQDecoder=dec.PARQDecoder, project=tp.project, transformer_parq=tp,
-                               Pose=ref_utils.Pose, Camera=ref_utils.Camera, decoder_module=dec)
+                               Pose=ref_utils.Pose, Camera=ref_utils.Camera, Obb3D=ref_utils.Obb3D, decoder_module=dec)
     _loaded["ns"] = ns
     return ns

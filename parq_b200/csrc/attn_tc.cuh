@@ -40,6 +40,8 @@ struct AttnParams {
   float2* ml_part;       // [((b*H+h)*nsplit + s)*Nq + q] = (m, l)
   __nv_bfloat16* out_direct;   // nsplit == 1 only: normalised output (B*Nq, 2*H*256) [hi|lo], no combine pass
   int kv_const;                // K / V^T were written >= 2 launches ago: their first tiles are fetched before the PDL wait
+  int kv_tiled;                // K / V^T are tile-contiguous caches (gemm_tc.cuh GemmEpilogue::kv_tiled); else plain matrices
+  int ntile;                   // key tiles per clip in the tiled cache
 };
 
 namespace attn {
@@ -120,25 +122,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int ch0 = h * DH;
       int stage = 0;
       uint32_t phase = 0;
+      // plain matrices: K rows = keys of all clips, V^T columns = keys of all clips; tiled caches: one contiguous
+      // [128 keys][256 ch] (K) / [256 ch][128 keys] (V^T) block per (key tile, head)
       auto load_k = [&](int tile) {
-        const int row = b * p.Nk + tile * BKEY;
+        const int row = p.kv_tiled ? ((b * p.ntile + tile) * p.H + h) * BKEY : b * p.Nk + tile * BKEY;
+        const int col = p.kv_tiled ? 0 : ch0;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           mbar_wait(&kv_empty[stage], phase ^ 1);
           mbar_expect_tx(&kv_full[stage], STAGE_BYTES);
           uint8_t* dst = ring + stage * STAGE_BYTES;
-          tma_load_2d(dst, &tmK, &kv_full[stage], ch0 + (half * 2) * 64, row);
-          tma_load_2d(dst + 16384, &tmK, &kv_full[stage], ch0 + (half * 2 + 1) * 64, row);
+          tma_load_2d(dst, &tmK, &kv_full[stage], col + (half * 2) * 64, row);
+          tma_load_2d(dst + 16384, &tmK, &kv_full[stage], col + (half * 2 + 1) * 64, row);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       };
       auto load_v = [&](int tile) {
-        const int col = b * p.Nk + tile * BKEY;
+        const int col = p.kv_tiled ? 0 : b * p.Nk + tile * BKEY;
+        const int row = p.kv_tiled ? ((b * p.ntile + tile) * p.H + h) * DH : ch0;
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc) {
           mbar_wait(&kv_empty[stage], phase ^ 1);
           mbar_expect_tx(&kv_full[stage], STAGE_BYTES);
-          tma_load_2d(ring + stage * STAGE_BYTES, &tmV, &kv_full[stage], col + kc * 64, ch0);
+          tma_load_2d(ring + stage * STAGE_BYTES, &tmV, &kv_full[stage], col + kc * 64, row);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       };

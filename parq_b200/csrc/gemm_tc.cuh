@@ -38,7 +38,30 @@ struct GemmEpilogue {
   long long lp_lo_off; // > 0: also store the bf16 residual (v - hi) at column offset lp_lo_off
   double2* gn_out;     // optional: per-tile (sum, sum of squares) of the outputs, slot m_tile*gn_stride + n_tile
   int gn_stride;
+  // Tile-contiguous K / V^T cache for the cross-attention (16-bit output only; requires Nk % 32 == 0):
+  //   1: rows are tokens (K = tokens Wk^T):   out[((tile*H + h)*128 + key%128)*256 + ch]
+  //   2: columns are tokens (V^T = Wv tokens^T): out[((tile*H + h)*256 + ch)*128 + key%128]
+  // with token = b*Nk + key, tile = b*ntile + key/128, channel = h*256 + ch: every (key tile, head) block the attention
+  // kernel streams is one contiguous 64 KB piece of HBM.
+  int kv_tiled;
+  int kv_Nk, kv_ntile, kv_H;
 };
+
+// element offset of the 32x32 chunk whose first row / column are (row0, col0) in a tiled K / V^T cache, and its row pitch
+__device__ __forceinline__ long long kv_tiled_base(const GemmEpilogue& ep, long long row0, int col0, int& ld) {
+  const long long tok = ep.kv_tiled == 1 ? row0 : col0;
+  const int chan = ep.kv_tiled == 1 ? col0 : static_cast<int>(row0);
+  const long long b = tok / ep.kv_Nk;
+  const int key = static_cast<int>(tok - b * ep.kv_Nk);
+  const long long tile = b * ep.kv_ntile + (key >> 7);
+  const int h = chan >> 8, ch = chan & 255, kin = key & 127;
+  if (ep.kv_tiled == 1) {
+    ld = 256;
+    return ((tile * ep.kv_H + h) * 128 + kin) * 256 + ch;
+  }
+  ld = 128;
+  return ((tile * ep.kv_H + h) * 256 + ch) * 128 + kin;
+}
 
 struct GemmParams {
   int M, N, K;         // K per term, multiple of 64
@@ -66,7 +89,7 @@ constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ +
 // eight (four) consecutive lanes cover one output row, so every store instruction writes whole 128-byte
 // (64-byte) row segments instead of 32 scattered 16-byte pieces.
 template <int kWordsPerRow, typename T>
-__device__ __forceinline__ void gemm_flush_stage(const uint32_t* stage, T* out, long long ld_elems, long long row0, int lane, int M) {
+__device__ __forceinline__ void gemm_flush_stage(const uint32_t* stage, T* out, long long ld_elems, int rows_valid, int lane) {
   constexpr int LANES_PER_ROW = kWordsPerRow / 4;
   constexpr int ROWS_PER_IT = 32 / LANES_PER_ROW;
   constexpr int ELEMS_PER_WORD = 4 / sizeof(T);
@@ -76,7 +99,7 @@ __device__ __forceinline__ void gemm_flush_stage(const uint32_t* stage, T* out, 
     const int w = (lane % LANES_PER_ROW) * 4;
     const uint32_t* sp = stage + r * 33 + w;
     const uint4 v = make_uint4(sp[0], sp[1], sp[2], sp[3]);
-    if (row0 + r < M) *reinterpret_cast<uint4*>(out + (row0 + r) * ld_elems + w * ELEMS_PER_WORD) = v;
+    if (r < rows_valid) *reinterpret_cast<uint4*>(out + r * ld_elems + w * ELEMS_PER_WORD) = v;
   }
 }
 
@@ -89,6 +112,7 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
                                                  float& gsq) {
   const long long row = row0 + lane;
   const bool row_ok = row < M;
+  const int rows_valid = M - row0 < 32 ? static_cast<int>(M - row0) : 32;
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + row_bias;
@@ -114,7 +138,7 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
 #pragma unroll
       for (int i = 0; i < 32; ++i) stage[lane * 33 + i] = __float_as_uint(v[i]);
       __syncwarp();
-      gemm_flush_stage<32>(stage, ep.out_f32 + col0, ep.ld_f32, row0, lane, M);
+      gemm_flush_stage<32>(stage, ep.out_f32 + row0 * ep.ld_f32 + col0, ep.ld_f32, rows_valid, lane);
       __syncwarp();
     } else if (row_ok) {
       float* o = ep.out_f32 + row * ep.ld_f32 + col0;
@@ -123,8 +147,18 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
         if (col0 + i < N) o[i] = v[i];
     }
   }
-  if (ep.out_lp != nullptr) {
-    uint16_t* obase = reinterpret_cast<uint16_t*>(ep.out_lp) + col0;
+  if (ep.out_lp != nullptr && ep.kv_tiled != 0) {
+    // tile-contiguous K / V^T cache: the chunk is a dense 32 x 32 block with its own origin and pitch
+    // (host guarantees Nk % 32 == 0 and N % 32 == 0, so chunks are full and never straddle a key tile)
+    int ld;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(ep.out_lp) + kv_tiled_base(ep, row0, col0, ld);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) stage[lane * 33 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    __syncwarp();
+    gemm_flush_stage<16>(stage, dst, ld, rows_valid, lane);
+    __syncwarp();
+  } else if (ep.out_lp != nullptr) {
+    uint16_t* obase = reinterpret_cast<uint16_t*>(ep.out_lp) + row0 * ep.ld_lp + col0;
     uint32_t w[16];
     if (ep.lp_fp16) {
 #pragma unroll
@@ -137,10 +171,10 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
 #pragma unroll
       for (int i = 0; i < 16; ++i) stage[lane * 33 + i] = w[i];
       __syncwarp();
-      gemm_flush_stage<16>(stage, obase, ep.ld_lp, row0, lane, M);
+      gemm_flush_stage<16>(stage, obase, ep.ld_lp, rows_valid, lane);
       __syncwarp();
     } else if (row_ok) {
-      uint16_t* o = obase + row * ep.ld_lp;
+      uint16_t* o = obase + lane * ep.ld_lp;
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (col0 + i < N) o[i] = static_cast<uint16_t>((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu));
@@ -156,10 +190,10 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
 #pragma unroll
         for (int i = 0; i < 16; ++i) stage[lane * 33 + i] = l[i];
         __syncwarp();
-        gemm_flush_stage<16>(stage, obase + ep.lp_lo_off, ep.ld_lp, row0, lane, M);
+        gemm_flush_stage<16>(stage, obase + ep.lp_lo_off, ep.ld_lp, rows_valid, lane);
         __syncwarp();
       } else if (row_ok) {
-        uint16_t* ol = obase + row * ep.ld_lp + ep.lp_lo_off;
+        uint16_t* ol = obase + lane * ep.ld_lp + ep.lp_lo_off;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (col0 + i < N) ol[i] = static_cast<uint16_t>((i & 1) ? (l[i >> 1] >> 16) : (l[i >> 1] & 0xFFFFu));

@@ -11,6 +11,7 @@
 #include "../../include/parq_b200.h"
 #include "attn_tc.cuh"
 #include "gemm_tc.cuh"
+#include "parse_pred.cuh"
 #include "project_sample.cuh"
 #include "rowwise.cuh"
 
@@ -208,7 +209,7 @@ static size_t attn_scratch_bytes(int B, int H, int Nq, int nsplit) {
 
 static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const void* K, uint64_t ldk, const void* Vt,
                             uint64_t ldv, int B, int H, int Nq, int Nk, bool fp16, void* scratch, size_t scratch_bytes,
-                            __nv_bfloat16* out_split, int force_nsplit, bool kv_const = false) {
+                            __nv_bfloat16* out_split, int force_nsplit, bool kv_const = false, bool kv_tiled = false) {
   if (Nq % attn::BQ != 0) return fail(PARQ_ERR_SHAPE, "Nq=%d must be a multiple of 128", Nq);
   const int ntiles = (Nk + attn::BKEY - 1) / attn::BKEY;
   const SplitPlan plan = plan_split(B * H * (Nq / attn::BQ), ntiles, device_info().sms, force_nsplit);
@@ -218,14 +219,23 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
   const uint64_t C = static_cast<uint64_t>(H) * 256;
   CUtensorMap tmQ, tmK, tmV;
   TRY(make_map(&tmQ, Q, static_cast<uint64_t>(B) * Nq, C, ldq, attn::BQ));
-  TRY(make_map(&tmK, K, static_cast<uint64_t>(B) * Nk, C, ldk, attn::BKEY));
-  TRY(make_map(&tmV, Vt, C, static_cast<uint64_t>(B) * Nk, ldv, 256));
+  if (kv_tiled) {
+    // tile-contiguous caches written by the K / V^T projection GEMMs (GemmEpilogue::kv_tiled)
+    const uint64_t blocks = static_cast<uint64_t>(B) * ntiles * H;
+    TRY(make_map(&tmK, K, blocks * attn::BKEY, 256, 256, attn::BKEY));
+    TRY(make_map(&tmV, Vt, blocks * 256, attn::BKEY, attn::BKEY, 256));
+  } else {
+    TRY(make_map(&tmK, K, static_cast<uint64_t>(B) * Nk, C, ldk, attn::BKEY));
+    TRY(make_map(&tmV, Vt, C, static_cast<uint64_t>(B) * Nk, ldv, 256));
+  }
   AttnParams ap;
   ap.B = B; ap.H = H; ap.Nq = Nq; ap.Nk = Nk;
   ap.nsplit = plan.nsplit;
   ap.tiles_per_split = plan.tiles_per_split;
   ap.out_direct = plan.nsplit == 1 ? out_split : nullptr;
   ap.kv_const = kv_const ? 1 : 0;
+  ap.kv_tiled = kv_tiled ? 1 : 0;
+  ap.ntile = ntiles;
   const size_t rows = static_cast<size_t>(B) * H * plan.nsplit * Nq;
   ap.o_part = reinterpret_cast<float*>(scratch);
   ap.ml_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(scratch) + align_up(rows * 256 * sizeof(float), 256));
@@ -317,6 +327,7 @@ struct Workspace {
   size_t Kc, Vt, T_cl, ref_cur, a_pos, a_peh, pe, x0, a_x, a_xpe, qk_s, vt_s, scratch, a_attn, y, x1, x2, x3, a_x1pe, q_c,
       a_x2, a_ffn, a_x3, h1, a_h1, h2, gn1, gn2;
   size_t scratch_bytes, ldv, ldvs, total;
+  int kv_tiled, ntile;      // tile-contiguous K / V^T caches (needs Nk % 32 == 0), key tiles per clip
   SplitPlan cross, self;
 };
 static Workspace workspace_layout(const ParqShape& s, int sms) {
@@ -330,8 +341,11 @@ static Workspace workspace_layout(const ParqShape& s, int sms) {
   const size_t C = s.C, R = static_cast<size_t>(s.B) * s.Nq, Nk = static_cast<size_t>(s.T) * s.H * s.W, Nt = s.B * Nk;
   w.ldv = align_up(Nt, 64);
   w.ldvs = align_up(R, 64);
-  w.Kc = take(Nt * C * 2);
-  w.Vt = take(C * w.ldv * 2);
+  w.ntile = static_cast<int>((Nk + attn::BKEY - 1) / attn::BKEY);
+  w.kv_tiled = (Nk % 32 == 0) ? 1 : 0;
+  const size_t cache = w.kv_tiled ? static_cast<size_t>(s.B) * w.ntile * attn::BKEY * C * 2 : 0;
+  w.Kc = take(w.kv_tiled ? cache : Nt * C * 2);
+  w.Vt = take(w.kv_tiled ? cache : C * w.ldv * 2);
   w.T_cl = take(static_cast<size_t>(s.B) * s.T * 12 * 4);
   w.ref_cur = take(R * 3 * 4);
   w.a_pos = take(R * 768 * 2);
@@ -410,6 +424,12 @@ static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, c
   gk.ep = epilogue_none();
   gk.ep.bias = reinterpret_cast<const float*>(pk + P.ca_k_b);
   gk.ep.out_lp = ws + W.Kc;  gk.ep.ld_lp = C;
+  const int Nk = s.T * s.H * s.W;
+  if (W.kv_tiled) {
+    gk.ep.kv_tiled = 1; gk.ep.kv_Nk = Nk; gk.ep.kv_ntile = W.ntile; gk.ep.kv_H = s.heads;
+    // keys beyond Nk in a clip's last tile are never written: P is exactly 0 there, but 0 x garbage could be NaN
+    if (Nk % attn::BKEY != 0) CUDA_TRY(cudaMemsetAsync(ws + W.Vt, 0, static_cast<size_t>(s.B) * W.ntile * attn::BKEY * C * 2, st));
+  }
   TRY(launch_gemm(st, tokens, Nt, C, pk + P.ca_k, C, 2 * C, gk, TAG_KV_PROJ));
   // V^T = Wv tokens^T + bv (per row) : A = Wv [hi|lo], B = tokens
   GemmParams gv;
@@ -422,6 +442,7 @@ static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, c
   gv.ep.bias = reinterpret_cast<const float*>(pk + P.ca_v_b);
   gv.ep.bias_per_row = 1;
   gv.ep.out_lp = ws + W.Vt;  gv.ep.ld_lp = static_cast<long long>(W.ldv);
+  if (W.kv_tiled) { gv.ep.kv_tiled = 2; gv.ep.kv_Nk = Nk; gv.ep.kv_ntile = W.ntile; gv.ep.kv_H = s.heads; }
   TRY(launch_gemm(st, pk + P.ca_v, C, 2 * C, tokens, Nt, C, gv, TAG_KV_PROJ));
   return PARQ_OK;
 }
@@ -476,7 +497,7 @@ long long parq_workspace_offset(const ParqShape* shape, const char* name) {
   const struct { const char* n; size_t off; } tab[] = {
       {"Kc", W.Kc}, {"Vt", W.Vt}, {"T_cl", W.T_cl}, {"pe", W.pe}, {"x0", W.x0}, {"qk_s", W.qk_s}, {"vt_s", W.vt_s},
       {"a_attn", W.a_attn}, {"y", W.y}, {"x1", W.x1}, {"x2", W.x2}, {"x3", W.x3}, {"q_c", W.q_c}, {"h1", W.h1}, {"h2", W.h2},
-      {"ldv", W.ldv}, {"ldvs", W.ldvs}, {"cross_nsplit", static_cast<size_t>(W.cross.nsplit)},
+      {"ldv", W.ldv}, {"ldvs", W.ldvs}, {"kv_tiled", static_cast<size_t>(W.kv_tiled)}, {"ntile", static_cast<size_t>(W.ntile)}, {"cross_nsplit", static_cast<size_t>(W.cross.nsplit)},
       {"self_nsplit", static_cast<size_t>(W.self.nsplit)}};
   for (const auto& e : tab)
     if (strcmp(e.n, name) == 0) return static_cast<long long>(e.off);
@@ -602,6 +623,38 @@ int parq_project_sample(const ParqShape* shape, const void* tokens_bf16, const f
   {
     ProfScope ps(TAG_SAMPLE, static_cast<cudaStream_t>(stream));
     project_sample_kernel<<<shape->B * shape->Nq / SAMPLE_QPB, shape->C / 8, sample_smem(shape->T), static_cast<cudaStream_t>(stream)>>>(sp);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PARQ_OK;
+}
+
+int parq_parse_pred(const float* center, const float* size, const float* ortho6d, const float* prob, int B, int K, int num_cls,
+                    const float* track_scale, double overlap_threshold, uint32_t mode, uint8_t* pred_mask, uint8_t* nms_mask,
+                    float* scores, int32_t* labels, float* obbs, void* stream) {
+  TRY(require_sm100());
+  if (!center || !size || !ortho6d || !prob || !pred_mask || !track_scale) return fail(PARQ_ERR_SHAPE, "null pointer");
+  if (B < 1 || K < 1 || K > 1024 || num_cls < 2 || num_cls > 64) return fail(PARQ_ERR_SHAPE, "parse_pred supports 1..1024 boxes per clip");
+  ParsePredParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.center = center; pp.size = size; pp.ortho6d = ortho6d; pp.prob = prob;
+  pp.B = B; pp.K = K; pp.num_cls = num_cls;
+  pp.background = num_cls - 1;
+  pp.same_class = (mode & PARQ_NMS_SAME_CLASS) ? 1 : 0;
+  pp.apply_track_scale = (mode & PARQ_NMS_NO_TRACK_SCALE) ? 0 : 1;
+  for (int i = 0; i < 6; ++i) pp.track_scale[i] = track_scale[i];
+  pp.threshold = overlap_threshold;
+  pp.pred_mask = pred_mask; pp.nms_mask = nms_mask; pp.scores = scores; pp.labels = labels; pp.obbs = obbs;
+  int P = 32;
+  while (P < K) P <<= 1;
+  const size_t smem = parse_pred_smem(P);
+  static thread_local size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    CUDA_TRY(cudaFuncSetAttribute(parse_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  {
+    ProfScope ps(TAG_ROWWISE, static_cast<cudaStream_t>(stream));
+    launch_k(parse_pred_kernel, dim3(B), dim3((K + 31) / 32 * 32), smem, static_cast<cudaStream_t>(stream), pp, P);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
@@ -745,7 +798,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       TRY(launch_gemm(st, ws + W.a_x1pe, R, 2 * C, pk + P.ca_q, C, 2 * C, g));
       const int Nk = s.T * s.H * s.W;
       TRY(launch_attention(st, ws + W.q_c, C, ws + W.Kc, C, ws + W.Vt, W.ldv, s.B, s.heads, s.Nq, Nk, false, ws + W.scratch,
-                           W.scratch_bytes, BF(W.a_attn), W.cross.nsplit, /*kv_const=*/true));
+                           W.scratch_bytes, BF(W.a_attn), W.cross.nsplit, /*kv_const=*/true, W.kv_tiled != 0));
       memset(&g, 0, sizeof(g));
       g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
       g.ep = epilogue_none(); g.ep.bias = PF(P.ca_out_b);

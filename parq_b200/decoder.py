@@ -19,7 +19,7 @@ from torch import nn
 
 from . import _lib
 from .inputs import POS_FEATS
-from .wrappers import raw
+from .wrappers import Obb3D, raw
 
 # BoxProcessor mean sizes (reference utils/parq_utils.py:45-88 over data/average_scan2cad.txt):
 # chair, table, cabinet, trash bin, bookshelf, display, sofa, bathtub, other, non-object.
@@ -285,6 +285,35 @@ def project(tokens, query_pos, T_camera_local, camera, H, W):
     return feat, cim, val.bool()
 
 
+def parse_pred(out_dict, track_scale=(-1.5, 1.5, -2, 1, 0, 2), num_semcls=9, for_vis=False):
+    """Device-side ``PARQDecoder.parse_pred`` (reference model/parq_decoder.py:372-424, NMS of utils/nms.py):
+    takes the list of per-iteration dicts (or the last dict), uses the last iteration, and returns that dict with
+    ``obbs_pred`` (Obb3D (B,Nq)), ``pred_mask`` (B,Nq) bool added -- plus ``scores``, ``labels``, ``nms_mask``.
+    No host round trip: one kernel launch, one CTA per clip."""
+    last = dict(out_dict[-1] if isinstance(out_dict, (list, tuple)) else out_dict)
+    lib = _lib.load()
+    f32 = lambda t: t.detach().float().contiguous()
+    center, size, o6, prob = (f32(last[k]) for k in ("center_unnormalized", "size_unnormalized", "ortho6d", "sem_cls_prob"))
+    if center.device.type != "cuda":
+        raise NotImplementedError("parse_pred needs CUDA tensors on an sm_100 device (no CPU fallback)")
+    B, K, ncls = prob.shape
+    if ncls != num_semcls + 1:
+        raise ValueError("sem_cls_prob has %d classes, expected num_semcls + 1 = %d" % (ncls, num_semcls + 1))
+    dev = center.device
+    pred = torch.empty(B, K, dtype=torch.uint8, device=dev)
+    nmsm = torch.empty(B, K, dtype=torch.uint8, device=dev)
+    scores = torch.empty(B, K, dtype=torch.float32, device=dev)
+    labels = torch.empty(B, K, dtype=torch.int32, device=dev)
+    obbs = torch.empty(B, K, 19, dtype=torch.float32, device=dev)
+    ts = (C.c_float * 6)(*[float(x) for x in track_scale])
+    mode = (_lib.PARQ_NMS_SAME_CLASS | _lib.PARQ_NMS_NO_TRACK_SCALE) if for_vis else 0
+    with torch.cuda.device(dev):
+        _lib.check(lib.parq_parse_pred(_ptr(center), _ptr(size), _ptr(o6), _ptr(prob), B, K, ncls, ts, 0.2 if for_vis else 0.1, mode,
+                                       _ptr(pred), _ptr(nmsm), _ptr(scores), _ptr(labels), _ptr(obbs), _stream()), "parq_parse_pred")
+    last.update(obbs_pred=Obb3D(obbs), pred_mask=pred.bool(), nms_mask=nmsm.bool(), scores=scores, labels=labels.long())
+    return last
+
+
 def accelerate(decoder, feature_hw=None, use_cuda_graph=False):
     """Patch an instance of the REFERENCE's own ``PARQDecoder`` (model/parq_decoder.py:30) in place so that its
     ``forward`` (:134-163) runs on libparq_b200.so; parameters, state-dict keys and every other method
@@ -423,3 +452,7 @@ class PARQDecoderB200(nn.Module):
             outs = eng.forward(intput_tokens, cam, raw(T_camera_pseudoCam), raw(T_world_pseudoCam), raw(T_world_local), H, W,
                                graph=self.use_cuda_graph)
         return [{k: outs[k][i] for k, _ in OUTPUT_KEYS} for i in range(self.iters)]
+
+    def parse_pred(self, out_dict):
+        """Same contract as the reference's ``parse_pred`` (parq_decoder.py:372-424), computed on the device."""
+        return parse_pred(out_dict, self.track_scale, self.num_semcls, self.for_vis)

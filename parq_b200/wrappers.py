@@ -143,6 +143,28 @@ class Camera(_Wrapped):
         return p2d, valid
 
 
+class Obb3D(_Wrapped):
+    """Oriented 3D boxes, (..., 19) = bb3_object [xmin,xmax,ymin,ymax,zmin,zmax] | T_world_object (12) | sem_id
+    (reference wrappers.py:297-392); produced on the device by ``parq_parse_pred``."""
+    _width = 19
+
+    @property
+    def bb3_object(self) -> torch.Tensor:
+        return self._data[..., :6]
+
+    @property
+    def T_world_object(self) -> Pose:
+        return Pose(self._data[..., 6:18])
+
+    @property
+    def sem_id(self) -> torch.Tensor:
+        return self._data[..., 18].unsqueeze(-1)
+
+    @property
+    def bb3_size(self) -> torch.Tensor:
+        return self._data[..., 1:6:2] - self._data[..., 0:6:2]
+
+
 def raw(x) -> torch.Tensor:
     """The underlying tensor of a wrapper (ours or the reference's) or a tensor."""
     if isinstance(x, torch.Tensor):

@@ -64,6 +64,16 @@ def main():
                 "features": np.stack(feats), "center_im": np.stack(cims), "center_valid": np.stack(vals)}
         for k in outs[0]:
             data[k] = np.stack([o[k].numpy() for o in outs])
+        # post-NMS detection set of the reference's own parse_pred (parq_decoder.py:372-424).  Its only CUDA
+        # dependency is `obbs_pred.cuda()` (:403, a device move of the result); it is made a no-op here so the
+        # unmodified method runs on the CPU of the build container.
+        ns.Obb3D.cuda = lambda self: self
+        parsed = ref.parse_pred([dict(o) for o in outs])
+        data["pred_mask"] = parsed["pred_mask"].numpy()
+        data["obbs_pred"] = parsed["obbs_pred"]._data.numpy()
+        # the NMS decision alone (before the track-scale filter), from the reference's own nms() (utils/nms.py:20-32)
+        scores = torch.max(outs[-1]["sem_cls_prob"], -1)[0]
+        data["nms_mask"] = np.asarray(ns.decoder_module.nms(parsed["obbs_pred"], scores, 9, 0.1, "nms_3d_faster"))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
         print(name, {k: v.shape for k, v in data.items() if hasattr(v, "shape")})
     for name, (B, T, H, W, Nq, seed, wild) in PROJ_CASES.items():

@@ -254,3 +254,86 @@ def test_cuda_graph_replay_matches_eager(dev):
     torch.cuda.synchronize()
     for k in OUT_KEYS:
         assert torch.equal(plain[k], eager[k]), k
+
+
+# ------------------------------------------------- f-2: parse_pred + NMS on the device ----
+@pytest.mark.parametrize("name", ["small", "ragged_wild", "white_noise"])
+def test_parse_pred_kernel_against_reference_golden(dev, name):
+    # the reference's own last-iteration tensors through the device kernel: detection set, NMS decision, boxes
+    from parq_b200.decoder import parse_pred
+    gold = load_golden(name)
+    last = {k: torch.from_numpy(gold[k][-1]).to(dev) for k in ("center_unnormalized", "size_unnormalized", "ortho6d", "sem_cls_prob")}
+    got = parse_pred(last)
+    torch.cuda.synchronize()
+    assert np.array_equal(got["pred_mask"].cpu().numpy(), gold["pred_mask"])
+    assert np.array_equal(got["nms_mask"].cpu().numpy(), gold["nms_mask"])
+    obb = got["obbs_pred"]._data.cpu().numpy()
+    assert np.array_equal(obb[..., 18], gold["obbs_pred"][..., 18])                 # labels
+    assert np.abs(obb - gold["obbs_pred"]).max() <= 1e-6 * max(1.0, np.abs(gold["obbs_pred"]).max())
+
+
+@pytest.mark.parametrize("name", ["small", "ragged_wild", "white_noise"])
+def test_post_nms_detection_sets_identical(dev, name):
+    # north_star acceptance: teacher-forced decoder on the GPU -> device parse_pred == the reference's detection set
+    gold = load_golden(name)
+    c = regenerate_case(gold)
+    gold_outs = [{k: torch.from_numpy(gold[k][i]) for k in OUT_KEYS} for i in range(8)]
+    refs = O.refs_from_outputs(gold_outs, c["sd"])
+    m = PARQDecoderB200(default_cfg(c["Nq"])).eval()
+    m.load_state_dict(c["sd"], strict=True)
+    eng = DecoderEngine(c["sd"], dev)
+    got = _engine_forward(eng, c, dev, forced_refs=refs.to(dev))
+    parsed = m.parse_pred([{k: got[k][i] for k in OUT_KEYS} for i in range(8)])
+    torch.cuda.synchronize()
+    assert np.array_equal(parsed["pred_mask"].cpu().numpy(), gold["pred_mask"]), "post-NMS detection set differs from the reference"
+    # The NMS decision BEFORE the scope filter (not an output of the reference) is reported, not gated at zero: greedy
+    # NMS cascades, so one rank swap between two boxes whose scores differ by less than the 1e-3 parity tolerance
+    # (bf16 attention) can flip a chain of out-of-scope boxes.  It stays a small fraction of the boxes.
+    flips = int((parsed["nms_mask"].cpu().numpy() != gold["nms_mask"]).sum())
+    print("nms_mask flips before the scope filter: %d of %d boxes" % (flips, gold["nms_mask"].size))
+    assert flips <= 0.08 * gold["nms_mask"].size
+
+
+def test_parse_pred_random_boxes_against_oracle(dev):
+    from parq_b200.decoder import parse_pred
+    g = torch.Generator().manual_seed(77)
+    for B, K, for_vis in ((16, 256, False), (3, 512, False), (2, 100, False)):
+        last = {"center_unnormalized": (torch.rand(B, K, 3, generator=g) - 0.5) * torch.tensor([4.0, 2.0, 3.0]) + torch.tensor([0.0, 0.0, 1.2]),
+                "size_unnormalized": torch.rand(B, K, 3, generator=g) * 1.2 + 0.2,
+                "ortho6d": torch.randn(B, K, 6, generator=g),
+                "sem_cls_prob": torch.softmax(3 * torch.randn(B, K, 10, generator=g), -1)}
+        want = O.parse_pred(last)
+        got = parse_pred({k: v.to(dev) for k, v in last.items()})
+        torch.cuda.synchronize()
+        assert torch.equal(got["labels"].cpu(), want["labels"]) and torch.equal(got["scores"].cpu(), want["scores"])
+        assert torch.equal(got["nms_mask"].cpu(), want["nms_mask"]), (B, K)
+        assert torch.equal(got["pred_mask"].cpu(), want["pred_mask"]), (B, K)
+        assert 0 < int(want["nms_mask"].sum()) < B * K
+
+
+def test_kv_cache_tile_contiguous_layout(dev):
+    # hoisted K / V^T projection into the tile-contiguous caches the cross-attention streams; Nk = 576 leaves the
+    # last key tile of every clip half empty (its V^T entries must be zero, its K entries are masked by the kernel)
+    B, T, H, W, Nq, seed = 2, 3, 12, 16, 128, 4
+    sd = I.make_weights(seed, Nq)
+    eng = DecoderEngine(sd, dev)
+    tokens = I.make_tokens(B, T, H, W, seed=seed)
+    eng.kv_project(tokens.to(dev).bfloat16(), B, T, H, W)
+    torch.cuda.synchronize()
+    Nk, heads = T * H * W, 4
+    assert eng.workspace_value("kv_tiled", B, T, H, W) == 1
+    ntile = eng.workspace_value("ntile", B, T, H, W)
+    assert ntile == (Nk + 127) // 128
+    Kc = eng.workspace_view("Kc", B, T, H, W, torch.bfloat16, (B, ntile, heads, 128, 256)).float().cpu()
+    Vt = eng.workspace_view("Vt", B, T, H, W, torch.bfloat16, (B, ntile, heads, 256, 128)).float().cpu()
+    L = "parq_module.decoder.layers.0.multihead_attn."
+    Wi, bi = sd[L + "in_proj_weight"], sd[L + "in_proj_bias"]
+    Kref = tokens @ Wi[1024:2048].t() + bi[1024:2048]            # (B, Nk, C)
+    Vref = tokens @ Wi[2048:].t() + bi[2048:]
+    pad = ntile * 128 - Nk
+    Kp = torch.nn.functional.pad(Kref, (0, 0, 0, pad)).view(B, ntile, 128, heads, 256).permute(0, 1, 3, 2, 4)
+    Vp = torch.nn.functional.pad(Vref, (0, 0, 0, pad)).view(B, ntile, 128, heads, 256).permute(0, 1, 3, 4, 2)
+    keys_ok = (torch.arange(ntile * 128) < Nk).view(1, ntile, 1, 128, 1)
+    assert relerr(torch.where(keys_ok, Kc, torch.zeros(())), Kp) <= 5e-3        # bf16 storage
+    assert relerr(Vt, Vp) <= 5e-3
+    assert Vt.permute(0, 1, 2, 4, 3)[~keys_ok.expand(B, ntile, heads, 128, 1).squeeze(-1)].abs().max() == 0

@@ -72,3 +72,18 @@ def test_mean_size_table_and_rotation():
     eye = torch.eye(3).expand(64, 3, 3)
     assert torch.allclose(R.transpose(1, 2) @ R, eye, atol=1e-5)
     assert torch.allclose(torch.linalg.det(R), torch.ones(64), atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["small", "ragged_wild", "white_noise"])
+def test_oracle_parse_pred_matches_reference_detection_sets(name):
+    # post-NMS detection set and the NMS decision alone, from the reference's own parse_pred / nms (make_golden.py)
+    gold = load_golden(name)
+    last = {k: torch.from_numpy(gold[k][-1]) for k in ("center_unnormalized", "size_unnormalized", "ortho6d", "sem_cls_prob")}
+    r = O.parse_pred(last)
+    assert np.array_equal(r["pred_mask"].numpy(), gold["pred_mask"])
+    assert np.array_equal(r["nms_mask"].numpy(), gold["nms_mask"])
+    assert gold["nms_mask"].sum() >= 5                       # the fixture exercises real suppression
+    obb = gold["obbs_pred"]
+    assert np.array_equal(obb[..., 18], r["labels"].numpy().astype(np.float32))
+    aabb = O.box_corners_local(last["center_unnormalized"], last["size_unnormalized"], last["ortho6d"])
+    assert np.allclose(np.concatenate([aabb.min(2)[0].numpy(), aabb.max(2)[0].numpy()], -1), r["aabb"].numpy(), atol=0)
