@@ -69,6 +69,8 @@ struct GemmParams {
   int a_koff[3];       // element offset of each term along A's K axis
   int b_koff[3];
   int const_operand;   // 1: A holds constants (weights), 2: B does -- its first tiles are fetched before the PDL wait
+  int dual_a;          // nterms == 2 with the SAME B segment (A_hi W + A_lo W): a ring stage holds both A tiles and one B
+                       // tile, so W is fetched from L2 once per k-block instead of twice (3 stages of 64 KB)
   GemmEpilogue ep;
 };
 
@@ -207,9 +209,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using namespace gemm;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  // ring layouts: plain = 4 stages, A tiles then B tiles; dual-A = 3 stages of [A_hi | A_lo | B] (same 192 KB)
+  const bool dual = p.dual_a != 0;
+  const int nst = dual ? 3 : STAGES;
+  const uint32_t stage_tx = dual ? 2 * A_BYTES + B_BYTES : A_BYTES + B_BYTES;
+  auto a_ptr = [&](int st, int which) { return dual ? smem + st * (2 * A_BYTES + B_BYTES) + which * A_BYTES : smem + st * A_BYTES; };
+  auto b_ptr = [&](int st) { return dual ? smem + st * (2 * A_BYTES + B_BYTES) + 2 * A_BYTES : smem + STAGES * A_BYTES + st * B_BYTES; };
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -252,7 +258,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else           { m0 = (tile / tiles_n) * BM; n0 = (tile % tiles_n) * BN; }
   };
   const int kb_per_term = p.K / BK;
-  const int num_kb = kb_per_term * p.nterms;
+  const int nterm_loops = dual ? 1 : p.nterms;
+  const int num_kb = kb_per_term * nterm_loops;     // ring stages consumed per tile
 
   if (warp == 0) {
     if (lane == 0) {                       // ---------------- TMA producer
@@ -266,12 +273,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.const_operand != 0 && static_cast<int>(blockIdx.x) < num_tiles) {
         int m0, n0;
         tile_origin(blockIdx.x, m0, n0);
-        pre = num_kb < STAGES ? num_kb : STAGES;
+        pre = num_kb < nst ? num_kb : nst;
         for (int i = 0; i < pre; ++i) {
           const int t = i / kb_per_term, kb = i % kb_per_term;
-          mbar_expect_tx(&full_bar[i], A_BYTES + B_BYTES);
-          if (p.const_operand == 1) tma_load_2d(sA + i * A_BYTES, &tmA, &full_bar[i], a_off(t) + kb * BK, m0);
-          else                      tma_load_2d(sB + i * B_BYTES, &tmB, &full_bar[i], b_off(t) + kb * BK, n0);
+          mbar_expect_tx(&full_bar[i], stage_tx);
+          if (p.const_operand == 1) {
+            tma_load_2d(a_ptr(i, 0), &tmA, &full_bar[i], a_off(t) + kb * BK, m0);
+            if (dual) tma_load_2d(a_ptr(i, 1), &tmA, &full_bar[i], a_off(1) + kb * BK, m0);
+          } else {
+            tma_load_2d(b_ptr(i), &tmB, &full_bar[i], b_off(t) + kb * BK, n0);
+          }
         }
       }
       pdl_wait();
@@ -281,19 +292,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m0, n0;
         tile_origin(tile, m0, n0);
-        for (int t = 0; t < p.nterms; ++t) {
+        for (int t = 0; t < nterm_loops; ++t) {
           const int ak = a_off(t), bk = b_off(t);
           for (int kb = 0; kb < kb_per_term; ++kb) {
             const bool prefetched = pre > 0;       // first k-blocks of this CTA's first tile
             if (!prefetched) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+              mbar_expect_tx(&full_bar[stage], stage_tx);
             } else {
               --pre;
             }
-            if (!(prefetched && p.const_operand == 1)) tma_load_2d(sA + stage * A_BYTES, &tmA, &full_bar[stage], ak + kb * BK, m0);
-            if (!(prefetched && p.const_operand == 2)) tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], bk + kb * BK, n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (!(prefetched && p.const_operand == 1)) {
+              tma_load_2d(a_ptr(stage, 0), &tmA, &full_bar[stage], ak + kb * BK, m0);
+              if (dual) tma_load_2d(a_ptr(stage, 1), &tmA, &full_bar[stage], a_off(1) + kb * BK, m0);
+            }
+            if (!(prefetched && p.const_operand == 2)) tma_load_2d(b_ptr(stage), &tmB, &full_bar[stage], bk + kb * BK, n0);
+            if (++stage == nst) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -317,13 +331,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * A_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * B_BYTES));
+          const uint64_t adesc = umma_desc_sw128(smem_u32(a_ptr(stage, 0)));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(b_ptr(stage)));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          if (dual) {
+            const uint64_t adesc1 = umma_desc_sw128(smem_u32(a_ptr(stage, 1)));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ss(d_tmem, adesc1 + 2 * k, bdesc + 2 * k, idesc, 1u);
+          }
           umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);
       }

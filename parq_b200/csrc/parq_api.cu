@@ -100,6 +100,7 @@ static int require_sm100() {
 // ptx.cuh): the next kernel's prologue overlaps the tail of the current one, also inside a captured graph.
 // The stand-alone entry points launch plainly (their inputs may come from the caller's previous kernel).
 static thread_local bool g_pdl = false;
+static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;   // A/B switch for the shared-B ring layout
 struct PdlScope {
   bool prev;
   explicit PdlScope(bool on) : prev(g_pdl) { g_pdl = on; }
@@ -166,11 +167,13 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
     CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
     attr_set = true;
   }
+  GemmParams gpl = gp;
+  gpl.dual_a = (gp.nterms == 2 && gp.b_koff[0] == gp.b_koff[1] && gp.a_koff[0] != gp.a_koff[1] && !g_no_dual) ? 1 : 0;
   const int tiles = ((gp.M + gemm::BM - 1) / gemm::BM) * ((gp.N + gemm::BN - 1) / gemm::BN);
   const int grid = tiles < device_info().sms ? tiles : device_info().sms;
   {
     ProfScope ps(tag, st);
-    launch_k(gemm_tc_kernel, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, gp);
+    launch_k(gemm_tc_kernel, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, gpl);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
