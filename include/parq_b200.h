@@ -118,6 +118,25 @@ int parq_decoder_forward(const ParqShape *shape, const void *tokens_bf16, const 
                          const void *packed, void *workspace, size_t workspace_bytes, const ParqOutputs *out,
                          uint32_t flags, void *stream);
 
+/* "Next" row f-1: AddRayPE.forward (model/ray_positional_encoding.py:61-139; utils/encoding_utils.py:15-100) fused with
+ * the tokeniser of PARQ.forward (model/parq_lightning.py:75-85).  feat_nchw (B,T,C,H,W) fp32 backbone features (may be
+ * NULL when only the encoding is wanted), depth_planes (num_samples) device floats (exp(log(min)+log(max/min)*linspace)),
+ * ray_points_scale HOST array of 6 floats.  Outputs (either may be NULL): tokens_bf16 (B, T*H*W, C) = features + encoding,
+ * channels-last, the decoder's input; encoding_nchw (B,T,C,H,W) fp32, AddRayPE's own return value.
+ * parq_raype_pack_weights takes encoder.0.weight (C, 3n), encoder.0.bias, encoder.2.weight (C, C), encoder.2.bias and
+ * returns 1 when a weight is not bf16-exact (pass PARQ_FLAG_WEIGHT_LO).  PARQ_RAYPE_SPLIT_HIDDEN keeps the hidden layer as an
+ * exact [hi|lo] bf16 split (fp32-grade encoding, 2x the second GEMM); without it the hidden layer is plain bf16, which is
+ * below the bf16 rounding of the tokens themselves. */
+#define PARQ_RAYPE_SPLIT_HIDDEN 8u
+size_t parq_raype_packed_bytes(int C, int num_samples);
+size_t parq_raype_workspace_bytes(int B, int T, int H, int W, int C, int num_samples);
+int parq_raype_pack_weights(int C, int num_samples, const float *w0, const float *b0, const float *w2, const float *b2,
+                            void *packed, size_t packed_bytes, void *stream);
+int parq_raype_forward(int B, int T, int H, int W, int C, int num_samples, const float *feat_nchw, const float *camera,
+                       const float *T_cp, const float *T_wp, const float *T_wl, const float *depth_planes,
+                       const float *ray_points_scale, const void *packed, void *workspace, size_t workspace_bytes,
+                       void *tokens_bf16, float *encoding_nchw, uint32_t flags, void *stream);
+
 /* "Next" row f-2: PARQDecoder.parse_pred (model/parq_decoder.py:372-424) + nms / nms_3d_faster[_samecls]
  * (utils/nms.py:20-70, 141-224) on the device, one CTA per clip, K <= 1024 boxes per clip.  Inputs are the LAST
  * iteration's center_unnormalized, size_unnormalized (B,K,3), ortho6d (B,K,6) and sem_cls_prob (B,K,num_cls); the

@@ -402,3 +402,72 @@ def parse_pred(last, track_scale=(-1.5, 1.5, -2, 1, 0, 2), num_semcls=9, overlap
     valid = (center[..., 0] > ts[0]) & (center[..., 0] < ts[1]) & (center[..., 2] > ts[4]) & (center[..., 2] < ts[5])
     return {"pred_mask": torch.from_numpy(mask) & valid, "nms_mask": torch.from_numpy(mask), "scores": scores, "labels": labels,
             "aabb": torch.from_numpy(aabb)}
+
+
+# --------------------------------------------------------------------------- #
+# f-1  AddRayPE + tokeniser (model/ray_positional_encoding.py:61-139,
+#      utils/encoding_utils.py:15-100, model/parq_lightning.py:72-85)
+# --------------------------------------------------------------------------- #
+def _pose_parts(P):
+    P = torch.as_tensor(P, dtype=torch.float32)
+    return P[..., :9].reshape(P.shape[:-1] + (3, 3)), P[..., 9:]
+
+
+def _pose_inv(P):
+    R, t = _pose_parts(P)
+    Rt = R.transpose(-1, -2)
+    return torch.cat([Rt.flatten(-2), -(Rt @ t.unsqueeze(-1)).squeeze(-1)], -1)
+
+
+def _pose_mul(A, B):
+    RA, tA = _pose_parts(A)
+    RB, tB = _pose_parts(B)
+    return torch.cat([(RA @ RB).flatten(-2), tA + (RA @ tB.unsqueeze(-1)).squeeze(-1)], -1)
+
+
+def _pose_apply(P, pts):
+    R, t = _pose_parts(P)
+    return pts @ R.transpose(-1, -2) + t.unsqueeze(-2)
+
+
+def ray_depth_planes(num_samples=64, min_depth=0.25, max_depth=5.25):
+    """utils/encoding_utils.py:82-88: log-spaced depth planes, fp32 torch arithmetic."""
+    ramp = torch.linspace(0, 1, num_samples)
+    mn, mx = torch.tensor([min_depth])[0], torch.tensor([max_depth])[0]
+    return torch.exp(torch.log(mn) + torch.log(mx / mn) * ramp)
+
+
+def ray_features(camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local, H, W,
+                 ray_points_scale=(-3, 3, -2, 0.5, 0.25, 5.25), num_samples=64, min_depth=0.25, max_depth=5.25):
+    """The (B*T, H, W, 3*num_samples) input of AddRayPE's encoder (ray_positional_encoding.py:76-128):
+    pixel grid (x = 0..W-1, y = 0..H-1, encoding_utils.py:15-20) -> unproject (wrappers.py:523-549) -> points at the
+    depth planes -> pseudo-camera frame -> snippet-local frame -> normalise by ray_points_scale -> inverse sigmoid."""
+    B, T = T_camera_pseudoCam.shape[:2]
+    cam = camera.reshape(B * T, 6).float()
+    xs = torch.linspace(0.0, W, W + 1)[:-1]
+    ys = torch.linspace(0.0, H, H + 1)[:-1]
+    xx, yy = torch.meshgrid(xs, ys, indexing="xy")
+    uv = torch.stack([xx, yy], -1).reshape(1, H * W, 2)
+    rays = (uv - cam[:, None, 4:6]) / cam[:, None, 2:4]
+    rays = torch.cat([rays, torch.ones(B * T, H * W, 1)], -1)
+    pts = rays.unsqueeze(-2) * ray_depth_planes(num_samples, min_depth, max_depth).view(1, 1, num_samples, 1)
+    pts = pts.view(B * T, -1, 3)
+    pts = _pose_apply(_pose_inv(T_camera_pseudoCam.reshape(B * T, 12)), pts)
+    T_local_pseudoCam = _pose_mul(_pose_inv(T_world_local), T_world_pseudoCam).reshape(B * T, 12)
+    pts = _pose_apply(T_local_pseudoCam, pts).view(B * T, H, W, num_samples, 3)
+    s = [float(v) for v in ray_points_scale]
+    pts = torch.stack([(pts[..., 0] - s[0]) / (s[1] - s[0]), (pts[..., 1] - s[2]) / (s[3] - s[2]),
+                       (pts[..., 2] - s[4]) / (s[5] - s[4])], -1)
+    return inverse_sigmoid(pts).reshape(B * T, H, W, 3 * num_samples)
+
+
+def add_ray_pe(images_feat, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local, sd, **kw):
+    """AddRayPE.forward (ray_positional_encoding.py:61-139) + the tokeniser of PARQ.forward (parq_lightning.py:75-85).
+    images_feat (B,T,C,H,W); sd holds encoder.{0,2}.{weight,bias}.  Returns (encoding (B,T,C,H,W), tokens (B,T*H*W,C))."""
+    with torch.no_grad():
+        B, T, C, H, W = images_feat.shape
+        f = ray_features(camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local, H, W, **kw)
+        enc = F.linear(F.relu(F.linear(f, sd["encoder.0.weight"], sd["encoder.0.bias"])), sd["encoder.2.weight"], sd["encoder.2.bias"])
+        enc = enc.view(B, T, H, W, C).permute(0, 1, 4, 2, 3)
+        tokens = (images_feat + enc).permute(0, 1, 3, 4, 2).reshape(B, T * H * W, C)
+        return enc.contiguous(), tokens.contiguous()

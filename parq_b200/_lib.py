@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libparq_b200.so")
 PARQ_FLAG_SKIP_KV = 1
 PARQ_FLAG_WEIGHT_LO = 2
 PARQ_FLAG_NO_PDL = 4
+PARQ_RAYPE_SPLIT_HIDDEN = 8
 PARQ_NMS_SAME_CLASS = 1
 PARQ_NMS_NO_TRACK_SCALE = 2
 
@@ -20,7 +21,8 @@ EXPORTS = [
     "parq_version", "parq_last_error", "parq_packed_bytes", "parq_workspace_bytes", "parq_pack_weights",
     "parq_pose_chain", "parq_project_sample", "parq_kv_project", "parq_decoder_forward",
     "parq_gemm_bf16", "parq_attention_scratch_bytes", "parq_attention",
-    "parq_parse_pred", "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect", "parq_workspace_offset",
+    "parq_parse_pred", "parq_raype_packed_bytes", "parq_raype_workspace_bytes", "parq_raype_pack_weights",
+    "parq_raype_forward", "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect", "parq_workspace_offset",
 ]
 PROFILE_TAGS = ("kv_proj", "project_sample", "gemm", "self_attn", "cross_attn", "combine", "rowwise")
 
@@ -100,6 +102,14 @@ def load():
     lib.parq_parse_pred.restype = C.c_int
     lib.parq_parse_pred.argtypes = [f32p, f32p, f32p, f32p, i32, i32, i32, C.POINTER(C.c_float), C.c_double, u32, vp, vp, f32p, vp,
                                     f32p, vp]
+    lib.parq_raype_packed_bytes.restype = sz
+    lib.parq_raype_packed_bytes.argtypes = [i32, i32]
+    lib.parq_raype_workspace_bytes.restype = sz
+    lib.parq_raype_workspace_bytes.argtypes = [i32] * 6
+    lib.parq_raype_pack_weights.restype = C.c_int
+    lib.parq_raype_pack_weights.argtypes = [i32, i32, f32p, f32p, f32p, f32p, vp, sz, vp]
+    lib.parq_raype_forward.restype = C.c_int
+    lib.parq_raype_forward.argtypes = [i32] * 6 + [f32p] * 6 + [C.POINTER(C.c_float), vp, vp, sz, vp, f32p, u32, vp]
     lib.parq_workspace_offset.restype = C.c_longlong
     lib.parq_workspace_offset.argtypes = [C.POINTER(ParqShape), C.c_char_p]
     lib.parq_kernel_launches.restype = C.c_ulonglong

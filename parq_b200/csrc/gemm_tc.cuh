@@ -45,6 +45,13 @@ struct GemmEpilogue {
   // kernel streams is one contiguous 64 KB piece of HBM.
   int kv_tiled;
   int kv_Nk, kv_ntile, kv_H;
+  // Channels-first companions of a token-major product (rows = tokens (bt, pixel), columns = channels):
+  //   nchw_out[(bt*N + col)*HW + pixel] = value                    (fp32; AddRayPE's (B,T,C,H,W) encoding)
+  //   value += nchw_add[(bt*N + col)*HW + pixel]                    (fp32 backbone features, before out_f32 / out_lp)
+  const float* nchw_add;
+  float* nchw_out;
+  int nchw_HW;
+  int add_tma;         // the addend is staged through shared memory by TMA (third tensor map; needs HW % 4 == 0)
 };
 
 // element offset of the 32x32 chunk whose first row / column are (row0, col0) in a tiled K / V^T cache, and its row pitch
@@ -109,9 +116,13 @@ __device__ __forceinline__ void gemm_flush_stage(const uint32_t* stage, T* out, 
 // then fp32 and/or 16-bit outputs (bf16 or fp16; optionally the bf16 residual "lo" of the split layout).
 // Full chunks go through the per-warp shared-memory stage for coalesced stores; a ragged last chunk
 // (N not a multiple of 32) is written directly with per-element guards.
+// kNchw selects a lean instantiation for the token-major products with channels-first companions (AddRayPE producer):
+// only bias / ReLU, nchw_add / nchw_out and a plain bf16 output exist there, which leaves the registers to keep all
+// 32 addend loads of a chunk in flight; the general instantiation carries everything else and no channels-first code.
+template <bool kNchw>
 __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], const float* sbias, float row_bias,
                                                  long long row0, int lane, int col0, int M, int N, uint32_t* stage, float& gsum,
-                                                 float& gsq) {
+                                                 float& gsq, const float* sadd = nullptr, int rowin = 0) {
   const long long row = row0 + lane;
   const bool row_ok = row < M;
   const int rows_valid = M - row0 < 32 ? static_cast<int>(M - row0) : 32;
@@ -130,6 +141,44 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   }
   const bool full = (col0 + 32 <= N);
+  if constexpr (kNchw) {
+   if ((ep.nchw_add != nullptr || ep.nchw_out != nullptr) && row_ok) {
+    // for a fixed column the 32 lanes (consecutive tokens = consecutive pixels) touch one contiguous 128-byte run
+    const long long bt = row / ep.nchw_HW;
+    const long long off = (bt * N + col0) * ep.nchw_HW + (row - bt * ep.nchw_HW);
+    if (ep.nchw_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (full || col0 + i < N) ep.nchw_out[off + static_cast<long long>(i) * ep.nchw_HW] = v[i];
+    }
+    if (sadd != nullptr) {
+      // addend chunk staged by TMA as [32 channels][128 tile rows] fp32: conflict-free column reads
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += sadd[i * 128 + rowin];
+    } else if (ep.nchw_add != nullptr) {
+      // tiles that straddle two images: straight from global memory (a loop of its own, so the 32 loads are
+      // independent of the stores above)
+      const float* __restrict__ add = ep.nchw_add + off;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (full || col0 + i < N) v[i] += __ldg(add + static_cast<long long>(i) * ep.nchw_HW);
+    }
+   }
+    if (ep.out_lp != nullptr) {      // plain bf16 rows (the channels-last tokens)
+      uint16_t* obase = reinterpret_cast<uint16_t*>(ep.out_lp) + row0 * ep.ld_lp + col0;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) stage[lane * 33 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        __syncwarp();
+        gemm_flush_stage<16>(stage, obase, ep.ld_lp, rows_valid, lane);
+        __syncwarp();
+      } else if (row_ok) {
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < N) obase[lane * ep.ld_lp + i] = __bfloat16_as_ushort(__float2bfloat16_rn(v[i]));
+      }
+    }
+    return;
+  }
   if (ep.gn_out != nullptr && row_ok) {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
@@ -204,15 +253,24 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
   }
 }
 
+template <bool kNchw>
 __global__ void __launch_bounds__(gemm::THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using namespace gemm;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
   // ring layouts: plain = 4 stages, A tiles then B tiles; dual-A = 3 stages of [A_hi | A_lo | B] (same 192 KB)
   const bool dual = p.dual_a != 0;
-  const int nst = dual ? 3 : STAGES;
+  // Channels-first addend through TMA (kNchw only): the plain ring shrinks to 3 stages and the freed A stage
+  // (16 KB) and B stage (32 KB) become three 16 KB addend buffers [32 channels][128 rows] fp32.
+  const bool add_tma = kNchw && p.ep.add_tma != 0 && p.ep.nchw_add != nullptr && !dual;
+  const int nst = (dual || add_tma) ? 3 : STAGES;
+  uint64_t* add_full = full_bar + 16;      // [3], byte offset 128 of the barrier block
+  uint64_t* add_empty = add_full + 3;      // [3]
+  auto add_buf = [&](int i) { return reinterpret_cast<float*>(i == 0 ? smem + 3 * A_BYTES : smem + STAGES * A_BYTES + 3 * B_BYTES + (i - 1) * 16384); };
+  auto tile_fast = [&](int m0) { return add_tma && (m0 % p.ep.nchw_HW) + BM <= p.ep.nchw_HW; };
   const uint32_t stage_tx = dual ? 2 * A_BYTES + B_BYTES : A_BYTES + B_BYTES;
   auto a_ptr = [&](int st, int which) { return dual ? smem + st * (2 * A_BYTES + B_BYTES) + which * A_BYTES : smem + st * A_BYTES; };
   auto b_ptr = [&](int st) { return dual ? smem + st * (2 * A_BYTES + B_BYTES) + 2 * A_BYTES : smem + STAGES * A_BYTES + st * B_BYTES; };
@@ -238,6 +296,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 128);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&add_full[i], 1);
+      mbar_init(&add_empty[i], 128);
     }
     fence_mbar_init();
   }
@@ -355,6 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x - 128;      // 0..127
     const bool col_bias = (p.ep.bias != nullptr) && !p.ep.bias_per_row;
     int lt = 0;
+    int add_cc = 0;                        // addend chunks consumed (ring of 3 buffers)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       int m0, n0;
       tile_origin(tile, m0, n0);
@@ -377,17 +440,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       uint32_t r0[32], r1[32];
       float gsum = 0.f, gsq = 0.f;
+      const bool fast = tile_fast(m0);
       tmem_ld32(taddr, r0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c += 2) {
         tmem_wait_ld();
         tmem_ld32(taddr + (c + 1) * 32, r1);                 // next chunk in flight while this one is stored
         int col0 = n0 + c * 32;
-        if (col0 < p.N) gemm_store_chunk(p.ep, r0, col_bias ? sbias + acc * BN + c * 32 : nullptr, row_bias, row0, lane, col0, p.M, p.N, stage, gsum, gsq);
+        if (col0 < p.N) {
+          const float* sadd = nullptr;
+          if (fast) { mbar_wait(&add_full[add_cc % 3], (add_cc / 3) & 1); sadd = add_buf(add_cc % 3); }
+          gemm_store_chunk<kNchw>(p.ep, r0, col_bias ? sbias + acc * BN + c * 32 : nullptr, row_bias, row0, lane, col0, p.M, p.N, stage, gsum, gsq, sadd, et);
+          if (fast) { mbar_arrive(&add_empty[add_cc % 3]); ++add_cc; }
+        }
         tmem_wait_ld();
         if (c + 2 < BN / 32) tmem_ld32(taddr + (c + 2) * 32, r0);
         col0 += 32;
-        if (col0 < p.N) gemm_store_chunk(p.ep, r1, col_bias ? sbias + acc * BN + (c + 1) * 32 : nullptr, row_bias, row0, lane, col0, p.M, p.N, stage, gsum, gsq);
+        if (col0 < p.N) {
+          const float* sadd = nullptr;
+          if (fast) { mbar_wait(&add_full[add_cc % 3], (add_cc / 3) & 1); sadd = add_buf(add_cc % 3); }
+          gemm_store_chunk<kNchw>(p.ep, r1, col_bias ? sbias + acc * BN + (c + 1) * 32 : nullptr, row_bias, row0, lane, col0, p.M, p.N, stage, gsum, gsq, sadd, et);
+          if (fast) { mbar_arrive(&add_empty[add_cc % 3]); ++add_cc; }
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
@@ -413,6 +487,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2 || warp == 3) {
     pdl_wait();
     pdl_launch_dependents();
+    if (add_tma && warp == 2 && lane == 0) {
+      // addend producer: one TMA box {128 pixels, 32 channels} per epilogue chunk, up to three chunks ahead of the
+      // epilogue warps (also across tiles: the features do not depend on the MMA)
+      int cc = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m0, n0;
+        tile_origin(tile, m0, n0);
+        if (!tile_fast(m0)) continue;
+        const int bt = m0 / p.ep.nchw_HW, pix0 = m0 - bt * p.ep.nchw_HW;
+        for (int c = 0; c < BN / 32 && n0 + c * 32 < p.N; ++c, ++cc) {
+          const int buf = cc % 3;
+          mbar_wait(&add_empty[buf], ((cc / 3) & 1) ^ 1);
+          mbar_expect_tx(&add_full[buf], 32 * 128 * 4);
+          tma_load_2d(add_buf(buf), &tmC, &add_full[buf], pix0, bt * p.N + n0 + c * 32);
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();

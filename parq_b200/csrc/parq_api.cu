@@ -13,6 +13,7 @@
 #include "gemm_tc.cuh"
 #include "parse_pred.cuh"
 #include "project_sample.cuh"
+#include "raype.cuh"
 #include "rowwise.cuh"
 
 namespace parq {
@@ -154,6 +155,20 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
   return PARQ_OK;
 }
 
+// 2-D map over a row-major fp32 matrix without swizzle: box = box_cols x box_rows (the channels-first addend of gemm_tc.cuh)
+static int make_map_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(PARQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PARQ_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", static_cast<int>(r));
+  return PARQ_OK;
+}
+
 // ---------------------------------------------------------------------------------- launchers --
 static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t a_cols, const void* Bw, uint64_t b_rows,
                        uint64_t b_cols, const GemmParams& gp, int tag = TAG_GEMM) {
@@ -164,16 +179,26 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
   TRY(make_map(&tmB, Bw, b_rows, b_cols, b_cols, gemm::BN));
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
     attr_set = true;
   }
   GemmParams gpl = gp;
+  CUtensorMap tmC = tmA;                    // placeholder unless the channels-first addend goes through TMA
+  gpl.ep.add_tma = 0;
+  if (gp.ep.nchw_add != nullptr && gp.ep.nchw_HW % 4 == 0 && (reinterpret_cast<uintptr_t>(gp.ep.nchw_add) & 15) == 0 && gp.M % gp.ep.nchw_HW == 0) {
+    TRY(make_map_f32(&tmC, gp.ep.nchw_add, static_cast<uint64_t>(gp.M / gp.ep.nchw_HW) * gp.N, gp.ep.nchw_HW, 128, 32));
+    gpl.ep.add_tma = 1;
+  }
   gpl.dual_a = (gp.nterms == 2 && gp.b_koff[0] == gp.b_koff[1] && gp.a_koff[0] != gp.a_koff[1] && !g_no_dual) ? 1 : 0;
   const int tiles = ((gp.M + gemm::BM - 1) / gemm::BM) * ((gp.N + gemm::BN - 1) / gemm::BN);
   const int grid = tiles < device_info().sms ? tiles : device_info().sms;
   {
     ProfScope ps(tag, st);
-    launch_k(gemm_tc_kernel, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, gpl);
+    if (gp.ep.nchw_add != nullptr || gp.ep.nchw_out != nullptr)
+      launch_k(gemm_tc_kernel<true>, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, tmC, gpl);
+    else
+      launch_k(gemm_tc_kernel<false>, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, tmC, gpl);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
@@ -628,6 +653,140 @@ int parq_project_sample(const ParqShape* shape, const void* tokens_bf16, const f
     project_sample_kernel<<<shape->B * shape->Nq / SAMPLE_QPB, shape->C / 8, sample_smem(shape->T), static_cast<cudaStream_t>(stream)>>>(sp);
   }
   CUDA_TRY(cudaGetLastError());
+  return PARQ_OK;
+}
+
+// ---- f-1: AddRayPE + tokeniser ---------------------------------------------------------------------------------
+struct RayPacked { size_t w0, w2, b0, b2, lo_flag, total; };
+static RayPacked raype_packed_layout(int C, int n) {
+  RayPacked r;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  r.w0 = take(static_cast<size_t>(C) * 2 * 3 * n * 2);
+  r.w2 = take(static_cast<size_t>(C) * 2 * C * 2);
+  r.b0 = take(static_cast<size_t>(C) * 4);
+  r.b2 = take(static_cast<size_t>(C) * 4);
+  r.lo_flag = take(4);
+  r.total = off;
+  return r;
+}
+struct RayWorkspace { size_t aff, feat, hidden, total; };
+static RayWorkspace raype_workspace_layout(int B, int T, int H, int W, int C, int n) {
+  RayWorkspace r;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t ntok = static_cast<size_t>(B) * T * H * W;
+  r.aff = take(static_cast<size_t>(B) * T * 12 * 4);
+  r.feat = take(ntok * 2 * 3 * n * 2);
+  r.hidden = take(ntok * 2 * C * 2);      // [hi | lo] when PARQ_RAYPE_SPLIT_HIDDEN, else hi only
+  r.total = off;
+  return r;
+}
+static int raype_check(int B, int T, int H, int W, int C, int n) {
+  if (B < 1 || T < 1 || H < 1 || W < 1) return fail(PARQ_ERR_SHAPE, "non-positive dimension");
+  if (C < 64 || C % 64 != 0) return fail(PARQ_ERR_SHAPE, "C=%d must be a positive multiple of 64", C);
+  if (n < 1 || (3 * n) % 64 != 0) return fail(PARQ_ERR_SHAPE, "3*num_samples=%d must be a multiple of 64", 3 * n);
+  if (static_cast<long long>(B) * T * H * W > 0x7fffffffLL - 512) return fail(PARQ_ERR_SHAPE, "too many pixels for 32-bit TMA coordinates");
+  return PARQ_OK;
+}
+
+size_t parq_raype_packed_bytes(int C, int num_samples) {
+  if (raype_check(1, 1, 1, 1, C, num_samples) != PARQ_OK) return 0;
+  return raype_packed_layout(C, num_samples).total;
+}
+size_t parq_raype_workspace_bytes(int B, int T, int H, int W, int C, int num_samples) {
+  if (raype_check(B, T, H, W, C, num_samples) != PARQ_OK) return 0;
+  return raype_workspace_layout(B, T, H, W, C, num_samples).total;
+}
+
+int parq_raype_pack_weights(int C, int num_samples, const float* w0, const float* b0, const float* w2, const float* b2, void* packed,
+                            size_t packed_bytes, void* stream) {
+  TRY(raype_check(1, 1, 1, 1, C, num_samples));
+  if (!w0 || !b0 || !w2 || !b2 || !packed) return fail(PARQ_ERR_SHAPE, "null pointer");
+  const RayPacked P = raype_packed_layout(C, num_samples);
+  if (packed_bytes < P.total) return fail(PARQ_ERR_WORKSPACE, "packed buffer too small: need %zu, have %zu", P.total, packed_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* pk = static_cast<uint8_t*>(packed);
+  int* flag = reinterpret_cast<int*>(pk + P.lo_flag);
+  CUDA_TRY(cudaMemsetAsync(flag, 0, 4, st));
+  const int F = 3 * num_samples;
+  split_weight_kernel<<<(C * F + 255) / 256, 256, 0, st>>>(w0, C, F, 1.f, reinterpret_cast<__nv_bfloat16*>(pk + P.w0), flag);
+  split_weight_kernel<<<(C * C + 255) / 256, 256, 0, st>>>(w2, C, C, 1.f, reinterpret_cast<__nv_bfloat16*>(pk + P.w2), flag);
+  copy_scale_kernel<<<(C + 255) / 256, 256, 0, st>>>(b0, reinterpret_cast<float*>(pk + P.b0), C, 1.f);
+  copy_scale_kernel<<<(C + 255) / 256, 256, 0, st>>>(b2, reinterpret_cast<float*>(pk + P.b2), C, 1.f);
+  CUDA_TRY(cudaGetLastError());
+  int w_lo = 0;
+  CUDA_TRY(cudaMemcpyAsync(&w_lo, flag, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return w_lo != 0 ? 1 : 0;
+}
+
+int parq_raype_forward(int B, int T, int H, int W, int C, int num_samples, const float* feat_nchw, const float* camera,
+                       const float* T_cp, const float* T_wp, const float* T_wl, const float* depth_planes, const float* ray_points_scale,
+                       const void* packed, void* workspace, size_t workspace_bytes, void* tokens_bf16, float* encoding_nchw,
+                       uint32_t flags, void* stream) {
+  TRY(require_sm100());
+  TRY(raype_check(B, T, H, W, C, num_samples));
+  if (!camera || !T_cp || !T_wp || !T_wl || !depth_planes || !ray_points_scale || !packed || !workspace)
+    return fail(PARQ_ERR_SHAPE, "null pointer");
+  if (!tokens_bf16 && !encoding_nchw) return fail(PARQ_ERR_SHAPE, "need a tokens or an encoding output");
+  if (tokens_bf16 && !feat_nchw) return fail(PARQ_ERR_SHAPE, "tokens = features + encoding needs the feature maps");
+  const RayWorkspace Wk = raype_workspace_layout(B, T, H, W, C, num_samples);
+  if (workspace_bytes < Wk.total) return fail(PARQ_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", Wk.total, workspace_bytes);
+  const RayPacked P = raype_packed_layout(C, num_samples);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const bool w_lo = (flags & PARQ_FLAG_WEIGHT_LO) != 0;
+  const int F = 3 * num_samples;
+  const long long ntok = static_cast<long long>(B) * T * H * W;
+  {
+    ProfScope ps(TAG_ROWWISE, st, 2);
+    raype_affine_kernel<<<(B * T + 127) / 128, 128, 0, st>>>(T_cp, T_wp, T_wl, reinterpret_cast<float*>(ws + Wk.aff), B, T);
+    RayFeatParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.camera = camera; rp.aff = reinterpret_cast<const float*>(ws + Wk.aff); rp.depth = depth_planes;
+    rp.out = reinterpret_cast<__nv_bfloat16*>(ws + Wk.feat);
+    rp.BT = B * T; rp.H = H; rp.W = W; rp.n = num_samples;
+    for (int i = 0; i < 3; ++i) {
+      rp.lo[i] = ray_points_scale[2 * i];
+      rp.span[i] = static_cast<float>(static_cast<double>(ray_points_scale[2 * i + 1]) - static_cast<double>(ray_points_scale[2 * i]));
+    }
+    const long long nthreads = ntok * num_samples;
+    ray_features_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, st>>>(rp);
+  }
+  CUDA_TRY(cudaGetLastError());
+  // layer 0: relu(W0 f + b0), inputs as an exact [hi|lo] split (positions are precision-critical), hidden kept in bf16
+  GemmParams g;
+  memset(&g, 0, sizeof(g));
+  g.M = static_cast<int>(ntok); g.N = C;
+  term_offsets(g, F, w_lo, 0);
+  g.ep = epilogue_none();
+  g.ep.bias = reinterpret_cast<const float*>(pk + P.b0); g.ep.relu = 1;
+  const bool split_hidden = (flags & PARQ_RAYPE_SPLIT_HIDDEN) != 0;
+  g.ep.out_lp = ws + Wk.hidden; g.ep.ld_lp = split_hidden ? 2 * C : C;
+  g.ep.lp_lo_off = split_hidden ? C : 0;
+  TRY(launch_gemm(st, ws + Wk.feat, ntok, 2 * F, pk + P.w0, C, 2 * F, g));
+  // layer 2: W2 h + b2 (+ channels-first features) -> channels-last bf16 tokens and / or the channels-first fp32 encoding
+  memset(&g, 0, sizeof(g));
+  g.M = static_cast<int>(ntok); g.N = C;
+  if (split_hidden) {
+    term_offsets(g, C, w_lo, 0);                      // h_hi W + h_lo W (+ h_hi W_lo)
+  } else {
+    g.K = C;
+    g.nterms = w_lo ? 2 : 1;
+    g.const_operand = 2;
+    g.a_koff[0] = 0; g.b_koff[0] = 0; g.a_koff[1] = 0; g.b_koff[1] = C;
+  }
+  g.ep = epilogue_none();
+  g.ep.bias = reinterpret_cast<const float*>(pk + P.b2);
+  g.ep.nchw_HW = H * W;
+  g.ep.nchw_out = encoding_nchw;
+  if (tokens_bf16) {
+    g.ep.nchw_add = feat_nchw;
+    g.ep.out_lp = tokens_bf16; g.ep.ld_lp = C;
+  }
+  TRY(launch_gemm(st, ws + Wk.hidden, ntok, split_hidden ? 2 * C : C, pk + P.w2, C, 2 * C, g));
   return PARQ_OK;
 }
 

@@ -138,6 +138,26 @@ def make_tokens(B, T, H, W, C=DEC_DIM, seed=0, smooth=True):
     return bf16_round(out)
 
 
+def make_raype_weights(seed=0, dim=DEC_DIM, num_samples=64, bf16_exact=True):
+    """State dict of the reference's AddRayPE encoder (model/ray_positional_encoding.py:55-59):
+    Linear(3*num_samples, dim) -> ReLU -> Linear(dim, dim), torch's default Linear init families."""
+    g = torch.Generator().manual_seed(7000003 * seed + 29)
+    sd = OrderedDict()
+    for name, (fo, fi) in (("encoder.0", (dim, 3 * num_samples)), ("encoder.2", (dim, dim))):
+        bound = 1.0 / math.sqrt(fi)
+        w = (torch.rand(fo, fi, generator=g) * 2 - 1) * bound
+        sd[name + ".weight"] = (bf16_round(w) if bf16_exact else w).contiguous()
+        sd[name + ".bias"] = ((torch.rand(fo, generator=g) * 2 - 1) * bound).contiguous()
+    return sd
+
+
+def make_features(B, T, H, W, C=DEC_DIM, seed=0):
+    """(B, T, C, H, W) fp32 backbone-style feature maps (the layout ResnetFPN hands to AddRayPE,
+    model/resnet_fpn.py:73-85): the same smooth field as make_tokens, channels-first."""
+    tok = make_tokens(B, T, H, W, C, seed=seed + 500)
+    return tok.view(B, T, H, W, C).permute(0, 1, 4, 2, 3).contiguous()
+
+
 def _rot(axis, ang):
     c, s = torch.cos(ang), torch.sin(ang)
     o, z = torch.ones_like(ang), torch.zeros_like(ang)

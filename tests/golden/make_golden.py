@@ -29,6 +29,11 @@ CASES = {
     "ragged_wild": (1, 2, 10, 14, 128, 1, True, True),
     "white_noise": (1, 4, 15, 20, 256, 2, False, False),
 }
+RAYPE_CASES = {
+    # AddRayPE + tokeniser (f-1): (B, T, H, W, seed)
+    "raype_small": (2, 3, 12, 16, 6),
+    "raype_c1_view": (1, 2, 60, 80, 7),
+}
 PROJ_CASES = {
     # projection-only cases at benchmark geometry: (B, T, H, W, Nq, seed, wild)
     "proj_c1": (1, 8, 60, 80, 256, 3, False),
@@ -76,6 +81,25 @@ def main():
         data["nms_mask"] = np.asarray(ns.decoder_module.nms(parsed["obbs_pred"], scores, 9, 0.1, "nms_3d_faster"))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
         print(name, {k: v.shape for k, v in data.items() if hasattr(v, "shape")})
+    import importlib.util
+    from oracle.ref_loader import REFERENCE_ROOT
+    spec = importlib.util.spec_from_file_location("model.ray_positional_encoding",
+                                                  os.path.join(REFERENCE_ROOT, "model", "ray_positional_encoding.py"))
+    rpe = importlib.util.module_from_spec(spec)
+    sys.modules["model.ray_positional_encoding"] = rpe
+    spec.loader.exec_module(rpe)
+    for name, (B, T, H, W, seed) in RAYPE_CASES.items():
+        sd = I.make_raype_weights(seed)
+        ref = rpe.AddRayPE(1024, [-3, 3, -2, 0.5, 0.25, 5.25], 64, 0.25, 5.25).eval()      # config/eval.yaml:30-35
+        ref.load_state_dict(sd, strict=True)
+        feat = I.make_features(B, T, H, W, seed=seed)
+        cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+        with torch.no_grad():
+            enc = ref(feat, ns.Camera(cam._data), ns.Pose(Tcp._data), ns.Pose(Twp._data), ns.Pose(Twl._data))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), shape=np.array([B, T, H, W, seed]),
+                            inputs_sum=np.array(I.tensor_checksum(feat, cam._data, Tcp._data, Twp._data, Twl._data, *[sd[k] for k in sorted(sd)])),
+                            encoding=enc[:, :, ::FEAT_STRIDE].numpy())
+        print(name, tuple(enc.shape), "max |enc| %.3f" % enc.abs().max().item())
     for name, (B, T, H, W, Nq, seed, wild) in PROJ_CASES.items():
         tokens = I.make_tokens(B, T, H, W, seed=seed)
         cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed, wild=wild)

@@ -403,3 +403,32 @@ def test_streaming_window_shape(dev):
     torch.cuda.synchronize()
     assert all(torch.isfinite(o["center_unnormalized"]).all() for o in outs)
     assert not torch.equal(outs[0]["center_unnormalized"], outs[1]["center_unnormalized"])
+
+
+# ------------------------------------------- f-1: AddRayPE + tokeniser fused producer ----
+@pytest.mark.parametrize("name", ["raype_small", "raype_c1_view"])
+def test_add_ray_pe_against_reference_golden(dev, name):
+    from parq_b200.raype import AddRayPEB200
+    gold = load_golden(name)
+    B, T, H, W, seed = [int(x) for x in gold["shape"]]
+    sd = I.make_raype_weights(seed)
+    m = AddRayPEB200(1024, [-3, 3, -2, 0.5, 0.25, 5.25], 64, 0.25, 5.25).eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    feat = I.make_features(B, T, H, W, seed=seed)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+    enc = m(feat.to(dev), cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
+    tokens = m.tokens(feat.to(dev), cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
+    torch.cuda.synchronize()
+    assert enc.shape == (B, T, 1024, H, W) and enc.dtype == torch.float32
+    # forward(): both encoder layers consume exact [hi|lo] splits of their inputs -> the 1e-3 bar of the decoder
+    assert relerr(enc.cpu()[:, :, ::16], gold["encoding"]) <= TOL
+    enc_o, tok_o = O.add_ray_pe(feat, cam._data, Tcp._data, Twp._data, Twl._data, sd)
+    assert relerr(enc.cpu(), enc_o) <= TOL
+    # tokens(): plain-bf16 hidden layer, features + encoding rounded once to bf16 (the decoder's input precision):
+    # within one bf16 ulp of the value plus the bf16-hidden error of the encoding (3e-3 of its range)
+    assert tokens.shape == (B, T * H * W, 1024) and tokens.dtype == torch.bfloat16
+    d = (tokens.float().cpu() - tok_o).abs()
+    assert (d <= tok_o.abs() * 2.0 ** -8 + 3e-3 * enc_o.abs().max()).all()
+    with pytest.raises(NotImplementedError):
+        m(feat, cam, Tcp, Twp, Twl)                       # CPU tensors: refuse, never fall back

@@ -134,3 +134,15 @@ def test_accelerate_patches_the_reference_module_in_place():
         ref(torch.zeros(1, 2 * 12 * 16, 1024), cam, Tcp, Twp, Twl)
     with pytest.raises(NotImplementedError):
         ref.train()(torch.zeros(1, 2 * 12 * 16, 1024), cam, Tcp, Twp, Twl)
+
+
+def test_add_ray_pe_module_mirrors_reference_parameters():
+    from parq_b200.raype import AddRayPEB200
+    m = AddRayPEB200(1024, [-3, 3, -2, 0.5, 0.25, 5.25], 64, 0.25, 5.25).eval()
+    sd = I.make_raype_weights(1)
+    assert list(m.state_dict().keys()) == list(sd.keys()) == ["encoder.0.weight", "encoder.0.bias", "encoder.2.weight", "encoder.2.bias"]
+    m.load_state_dict(sd, strict=True)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 1, 1024, 2, 2), torch.zeros(1, 1, 6), torch.zeros(1, 1, 12), torch.zeros(1, 1, 12), torch.zeros(1, 1, 12))
+    planes = m._depth_planes("cpu")
+    assert torch.equal(planes, O.ray_depth_planes(64, 0.25, 5.25)) and abs(planes[0].item() - 0.25) < 1e-6 and abs(planes[-1].item() - 5.25) < 1e-5

@@ -87,3 +87,18 @@ def test_oracle_parse_pred_matches_reference_detection_sets(name):
     assert np.array_equal(obb[..., 18], r["labels"].numpy().astype(np.float32))
     aabb = O.box_corners_local(last["center_unnormalized"], last["size_unnormalized"], last["ortho6d"])
     assert np.allclose(np.concatenate([aabb.min(2)[0].numpy(), aabb.max(2)[0].numpy()], -1), r["aabb"].numpy(), atol=0)
+
+
+@pytest.mark.parametrize("name", ["raype_small", "raype_c1_view"])
+def test_oracle_add_ray_pe_matches_reference(name):
+    # f-1: AddRayPE encoding of the unmodified reference module (make_golden.py) against the oracle restatement
+    from parq_b200 import inputs as I
+    gold = load_golden(name)
+    B, T, H, W, seed = [int(x) for x in gold["shape"]]
+    sd = I.make_raype_weights(seed)
+    feat = I.make_features(B, T, H, W, seed=seed)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+    assert I.tensor_checksum(feat, cam._data, Tcp._data, Twp._data, Twl._data, *[sd[k] for k in sorted(sd)]) == str(gold["inputs_sum"])
+    enc, tokens = O.add_ray_pe(feat, cam._data, Tcp._data, Twp._data, Twl._data, sd)
+    assert relerr(enc[:, :, ::16], gold["encoding"]) <= 2e-6
+    assert torch.equal(tokens.view(B, T, H, W, 1024), (feat + enc).permute(0, 1, 3, 4, 2))

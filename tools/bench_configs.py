@@ -72,8 +72,36 @@ def c5(windows=200):
                       "p99_ms": lat[int(0.99 * len(lat)) - 1], "min_ms": lat[0], "max_ms": lat[-1]}), flush=True)
 
 
+def raype(steps=10):
+    """f-1 producer at config-2 size: 16 clips x 8 views x 60x80 pixels -> bf16 tokens."""
+    from parq_b200.raype import AddRayPEB200
+    B, T, H, W = 16, 8, 60, 80
+    m = AddRayPEB200(1024, [-3, 3, -2, 0.5, 0.25, 5.25], 64, 0.25, 5.25).eval()
+    m.load_state_dict(I.make_raype_weights(0), strict=True)
+    m = m.to(dev)
+    feat = torch.randn(B, T, 1024, H, W, device=dev)
+    cam, Tcp, Twp, Twl = (t.to(dev) for t in I.make_geometry(B, T, H, W, seed=0))
+    for fn, tag in ((m.tokens, "tokens (bf16 hidden)"), (m.forward, "encoding (split hidden)")):
+        for _ in range(3):
+            fn(feat, cam, Tcp, Twp, Twl)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn(feat, cam, Tcp, Twp, Twl)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        ntok = B * T * H * W
+        gf = 2.0 * ntok * 1024 * (2 * 192 + (1024 if "tokens" in tag else 2048)) / 1e9
+        print(json.dumps({"config": "f-1 AddRayPE producer, 16 clips x 8 views x 60x80 -> " + tag, "ms_per_batch": ms, "clips_per_s": B / ms * 1e3,
+                          "tensor_GF": gf, "TFLOPs": gf / ms}), flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c4", "c5"]
+    which = sys.argv[1:] or ["c4", "c5", "raype"]
+    if "raype" in which:
+        raype()
     if "c4" in which:
         c4()
     if "c5" in which:
