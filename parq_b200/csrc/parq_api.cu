@@ -11,6 +11,7 @@
 #include "../../include/parq_b200.h"
 #include "attn_tc.cuh"
 #include "gemm_tc.cuh"
+#include "gemm2_tc.cuh"
 #include "parse_pred.cuh"
 #include "project_sample.cuh"
 #include "raype.cuh"
@@ -101,26 +102,42 @@ static int require_sm100() {
 // ptx.cuh): the next kernel's prologue overlaps the tail of the current one, also inside a captured graph.
 // The stand-alone entry points launch plainly (their inputs may come from the caller's previous kernel).
 static thread_local bool g_pdl = false;
-static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;   // A/B switch for the shared-B ring layout
+static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
+static const bool g_no_pair = getenv("PARQ_NO_PAIR") != nullptr;       // A/B switch: single-CTA GEMM instead of the CTA-pair kernel   // A/B switch for the shared-B ring layout
 struct PdlScope {
   bool prev;
   explicit PdlScope(bool on) : prev(g_pdl) { g_pdl = on; }
   ~PdlScope() { g_pdl = prev; }
 };
 template <typename... KArgs, typename... Args>
-static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+static void launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (g_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_kc(kernel, grid, block, smem, st, 1, static_cast<Args&&>(args)...);
 }
 
 // ------------------------------------------------------------------------------ TMA tensor maps --
@@ -174,13 +191,17 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
                        uint64_t b_cols, const GemmParams& gp, int tag = TAG_GEMM) {
   if (gp.K <= 0 || gp.K % gemm::BK != 0) return fail(PARQ_ERR_SHAPE, "GEMM K=%d must be a positive multiple of 64", gp.K);
   if (gp.nterms < 1 || gp.nterms > 3) return fail(PARQ_ERR_SHAPE, "GEMM nterms=%d out of range", gp.nterms);
+  // CTA-pair kernel (gemm2_tc.cuh) unless switched off: each CTA stages half of the B tile
+  const bool pairk = !g_no_pair && device_info().sms >= 2;
   CUtensorMap tmA, tmB;
   TRY(make_map(&tmA, A, a_rows, a_cols, a_cols, gemm::BM));
-  TRY(make_map(&tmB, Bw, b_rows, b_cols, b_cols, gemm::BN));
+  TRY(make_map(&tmB, Bw, b_rows, b_cols, b_cols, pairk ? gemm2::BN / 2 : gemm::BN));
   static thread_local bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::SMEM_BYTES));
     attr_set = true;
   }
   GemmParams gpl = gp;
@@ -195,7 +216,15 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
   const int grid = tiles < device_info().sms ? tiles : device_info().sms;
   {
     ProfScope ps(tag, st);
-    if (gp.ep.nchw_add != nullptr || gp.ep.nchw_out != nullptr)
+    const bool nchw = gp.ep.nchw_add != nullptr || gp.ep.nchw_out != nullptr;
+    if (pairk) {
+      const int ptiles = ((gp.M + 2 * gemm2::BM - 1) / (2 * gemm2::BM)) * ((gp.N + gemm2::BN - 1) / gemm2::BN);
+      const int pgrid = 2 * (ptiles < device_info().sms / 2 ? ptiles : device_info().sms / 2);
+      if (nchw)
+        launch_kc(gemm2_tc_kernel<true>, dim3(pgrid), dim3(gemm2::THREADS), gemm2::SMEM_BYTES, st, 2, tmA, tmB, tmC, gpl);
+      else
+        launch_kc(gemm2_tc_kernel<false>, dim3(pgrid), dim3(gemm2::THREADS), gemm2::SMEM_BYTES, st, 2, tmA, tmB, tmC, gpl);
+    } else if (nchw)
       launch_k(gemm_tc_kernel<true>, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, tmC, gpl);
     else
       launch_k(gemm_tc_kernel<false>, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, tmC, gpl);
@@ -446,6 +475,9 @@ static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, c
   GemmParams gk;
   memset(&gk, 0, sizeof(gk));
   gk.M = static_cast<int>(Nt);  gk.N = C;  gk.K = C;
+  // w_lo: weights that are not bf16-exact keep a low-order term (second pass over the tokens).  K and V^T are stored
+  // in bf16, so that term is of the size of the storage rounding; PARQ_FLAG_KV_HI_ONLY drops it (measured: parity
+  // error 5e-4 -> 9e-4 of the 1e-3 bar, K/V projection 3.7 -> 2.3 ms at config 2), the default keeps it.
   gk.nterms = w_lo ? 2 : 1;
   gk.const_operand = 2;
   gk.a_koff[0] = 0; gk.b_koff[0] = 0; gk.a_koff[1] = 0; gk.b_koff[1] = C;
@@ -860,7 +892,7 @@ int parq_kv_project(const ParqShape* shape, const void* tokens_bf16, const void*
   if (workspace_bytes < W.total) return fail(PARQ_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", W.total, workspace_bytes);
   const Packed P = packed_layout(*shape);
   return kv_project(*shape, static_cast<cudaStream_t>(stream), tokens_bf16, static_cast<const uint8_t*>(packed), P,
-                    (flags & PARQ_FLAG_WEIGHT_LO) != 0, static_cast<uint8_t*>(workspace), W);
+                    (flags & PARQ_FLAG_WEIGHT_LO) != 0 && !(flags & PARQ_FLAG_KV_HI_ONLY), static_cast<uint8_t*>(workspace), W);
 }
 
 int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const float* camera, const float* T_cp, const float* T_wp,
@@ -890,7 +922,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   { ProfScope ps(TAG_ROWWISE, st); launch_k(pose_chain_kernel, dim3((s.B * s.T + 127) / 128), dim3(128), 0, st, T_cp, T_wp, T_wl, F32(W.T_cl), s.B, s.T); }
   CUDA_TRY(cudaGetLastError());
   // K4: hoisted K / V^T projection of the image tokens (iteration invariant)
-  if (!(flags & PARQ_FLAG_SKIP_KV)) TRY(kv_project(s, st, tokens_bf16, pk, P, w_lo, ws, W));
+  if (!(flags & PARQ_FLAG_SKIP_KV)) TRY(kv_project(s, st, tokens_bf16, pk, P, w_lo && !(flags & PARQ_FLAG_KV_HI_ONLY), ws, W));
 
   SampleParams sp;
   fill_sample_params(sp, s);

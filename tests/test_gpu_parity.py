@@ -432,3 +432,26 @@ def test_add_ray_pe_against_reference_golden(dev, name):
     assert (d <= tok_o.abs() * 2.0 ** -8 + 3e-3 * enc_o.abs().max()).all()
     with pytest.raises(NotImplementedError):
         m(feat, cam, Tcp, Twp, Twl)                       # CPU tensors: refuse, never fall back
+
+
+def test_decoder_with_fp32_weights_against_oracle(dev):
+    # released checkpoints are not bf16-representable: parq_pack_weights then keeps a low-order weight term and the
+    # GEMMs of the fp32 residual stream run their third term (A_hi x W_lo)
+    B, T, H, W, Nq, seed, iters = 2, 3, 12, 16, 256, 61, 3
+    sd = I.make_weights(seed, Nq, bf16_exact=False)
+    tokens = I.make_tokens(B, T, H, W, seed=seed)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+    c = dict(tokens=tokens, camera=cam._data, T_cp=Tcp._data, T_wp=Twp._data, T_wl=Twl._data, H=H, W=W)
+    outs, auxs = O.decoder_forward(tokens, cam._data, Tcp._data, Twp._data, Twl._data, sd, iters=iters, return_aux=True)
+    refs = O.refs_from_outputs(outs, sd)
+    eng = DecoderEngine(sd, dev, iters=iters)
+    assert eng.weight_lo
+    got = _engine_forward(eng, c, dev, forced_refs=refs.to(dev), debug=True)
+    errs = {}
+    for i in range(iters):
+        assert bit_equal(got["center_im"][i], auxs[i]["center_im"])
+        errs[("decoder_out", i)] = relerr(got["decoder_out"][i].cpu(), auxs[i]["decoder_out"])
+        for k in ("pred_logits", "center_unnormalized", "ortho6d", "sem_cls_prob"):
+            errs[(k, i)] = relerr(got[k][i].cpu(), outs[i][k])
+    print({k: "%.2e" % v for k, v in errs.items()})
+    assert max(errs.values()) <= TOL, max(errs, key=errs.get)

@@ -17,7 +17,8 @@ H = a[3] if len(a) > 3 else 60
 W = a[4] if len(a) > 4 else 80
 Nq = a[5] if len(a) > 5 else 256
 dev = torch.device("cuda:0")
-eng = DecoderEngine(I.make_weights(0, Nq), dev)
+eng = DecoderEngine(I.make_weights(0, Nq, bf16_exact=not os.environ.get('PARQ_FP32_WEIGHTS')), dev)
+print('weight_lo', eng.weight_lo)
 tokens = torch.empty(B, T * H * W, 1024, dtype=torch.bfloat16, device=dev)
 for b in range(B):
     tokens[b] = I.make_tokens(1, T, H, W, seed=1000 + b)[0].to(dev)
