@@ -103,6 +103,7 @@ static int require_sm100() {
 // The stand-alone entry points launch plainly (their inputs may come from the caller's previous kernel).
 static thread_local bool g_pdl = false;
 static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
+static const bool g_force_pair = getenv("PARQ_FORCE_PAIR") != nullptr;   // every GEMM on the CTA-pair kernel (tests)
 static const bool g_no_pair = getenv("PARQ_NO_PAIR") != nullptr;       // A/B switch: single-CTA GEMM instead of the CTA-pair kernel   // A/B switch for the shared-B ring layout
 struct PdlScope {
   bool prev;
@@ -191,8 +192,11 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
                        uint64_t b_cols, const GemmParams& gp, int tag = TAG_GEMM) {
   if (gp.K <= 0 || gp.K % gemm::BK != 0) return fail(PARQ_ERR_SHAPE, "GEMM K=%d must be a positive multiple of 64", gp.K);
   if (gp.nterms < 1 || gp.nterms > 3) return fail(PARQ_ERR_SHAPE, "GEMM nterms=%d out of range", gp.nterms);
-  // CTA-pair kernel (gemm2_tc.cuh) unless switched off: each CTA stages half of the B tile
-  const bool pairk = !g_no_pair && device_info().sms >= 2;
+  // CTA-pair kernel (gemm2_tc.cuh, each CTA stages half of the B tile) for the multi-wave GEMMs (hoisted K / V^T
+  // projection, AddRayPE encoder: +6 % measured); the one-wave per-iteration GEMMs stay on the single-CTA kernel, whose
+  // shorter prologue (no cluster barriers) is worth more there (-6 % with the pair kernel)
+  const long long tiles1 = static_cast<long long>((gp.M + gemm::BM - 1) / gemm::BM) * ((gp.N + gemm::BN - 1) / gemm::BN);
+  const bool pairk = !g_no_pair && device_info().sms >= 2 && (tiles1 >= 2LL * device_info().sms || g_force_pair);
   CUtensorMap tmA, tmB;
   TRY(make_map(&tmA, A, a_rows, a_cols, a_cols, gemm::BM));
   TRY(make_map(&tmB, Bw, b_rows, b_cols, b_cols, pairk ? gemm2::BN / 2 : gemm::BN));
