@@ -10,6 +10,7 @@
 
 #include "../../include/parq_b200.h"
 #include "attn_tc.cuh"
+#include "attn2_tc.cuh"
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
 #include "parse_pred.cuh"
@@ -104,6 +105,7 @@ static int require_sm100() {
 static thread_local bool g_pdl = false;
 static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
 static const bool g_force_pair = getenv("PARQ_FORCE_PAIR") != nullptr;   // every GEMM on the CTA-pair kernel (tests)
+static const bool g_no_pair_attn = getenv("PARQ_NO_PAIR_ATTN") != nullptr;   // A/B switch: single-CTA attention kernel
 static const bool g_no_pair = getenv("PARQ_NO_PAIR") != nullptr;       // A/B switch: single-CTA GEMM instead of the CTA-pair kernel   // A/B switch for the shared-B ring layout
 struct PdlScope {
   bool prev;
@@ -111,7 +113,7 @@ struct PdlScope {
   ~PdlScope() { g_pdl = prev; }
 };
 template <typename... KArgs, typename... Args>
-static void launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+static void launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, dim3 cluster, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -125,11 +127,11 @@ static void launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
   }
-  if (cluster > 1) {
+  if (cluster.x * cluster.y * cluster.z > 1) {
     attr[n].id = cudaLaunchAttributeClusterDimension;
-    attr[n].val.clusterDim.x = cluster;
-    attr[n].val.clusterDim.y = 1;
-    attr[n].val.clusterDim.z = 1;
+    attr[n].val.clusterDim.x = cluster.x;
+    attr[n].val.clusterDim.y = cluster.y;
+    attr[n].val.clusterDim.z = cluster.z;
     ++n;
   }
   cfg.attrs = attr;
@@ -138,7 +140,7 @@ static void launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
 }
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  launch_kc(kernel, grid, block, smem, st, 1, static_cast<Args&&>(args)...);
+  launch_kc(kernel, grid, block, smem, st, dim3(1, 1, 1), static_cast<Args&&>(args)...);
 }
 
 // ------------------------------------------------------------------------------ TMA tensor maps --
@@ -225,9 +227,9 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
       const int ptiles = ((gp.M + 2 * gemm2::BM - 1) / (2 * gemm2::BM)) * ((gp.N + gemm2::BN - 1) / gemm2::BN);
       const int pgrid = 2 * (ptiles < device_info().sms / 2 ? ptiles : device_info().sms / 2);
       if (nchw)
-        launch_kc(gemm2_tc_kernel<true>, dim3(pgrid), dim3(gemm2::THREADS), gemm2::SMEM_BYTES, st, 2, tmA, tmB, tmC, gpl);
+        launch_kc(gemm2_tc_kernel<true>, dim3(pgrid), dim3(gemm2::THREADS), gemm2::SMEM_BYTES, st, dim3(2, 1, 1), tmA, tmB, tmC, gpl);
       else
-        launch_kc(gemm2_tc_kernel<false>, dim3(pgrid), dim3(gemm2::THREADS), gemm2::SMEM_BYTES, st, 2, tmA, tmB, tmC, gpl);
+        launch_kc(gemm2_tc_kernel<false>, dim3(pgrid), dim3(gemm2::THREADS), gemm2::SMEM_BYTES, st, dim3(2, 1, 1), tmA, tmB, tmC, gpl);
     } else if (nchw)
       launch_k(gemm_tc_kernel<true>, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, tmC, gpl);
     else
@@ -278,16 +280,19 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
     return fail(PARQ_ERR_WORKSPACE, "attention scratch too small: need %zu, have %zu", attn_scratch_bytes(B, H, Nq, plan.nsplit),
                 scratch_bytes);
   const uint64_t C = static_cast<uint64_t>(H) * 256;
+  // CTA-pair kernel (attn2_tc.cuh): the two 128-query tiles of 256 queries share every K / V^T tile, each CTA stages half
+  const bool pairk = !g_no_pair_attn && Nq % (2 * attn::BQ) == 0 && device_info().sms >= 2;
+  const uint32_t kbox = pairk ? attn::BKEY / 2 : attn::BKEY, vbox = pairk ? 128 : 256;
   CUtensorMap tmQ, tmK, tmV;
   TRY(make_map(&tmQ, Q, static_cast<uint64_t>(B) * Nq, C, ldq, attn::BQ));
   if (kv_tiled) {
     // tile-contiguous caches written by the K / V^T projection GEMMs (GemmEpilogue::kv_tiled)
     const uint64_t blocks = static_cast<uint64_t>(B) * ntiles * H;
-    TRY(make_map(&tmK, K, blocks * attn::BKEY, 256, 256, attn::BKEY));
-    TRY(make_map(&tmV, Vt, blocks * 256, attn::BKEY, attn::BKEY, 256));
+    TRY(make_map(&tmK, K, blocks * attn::BKEY, 256, 256, kbox));
+    TRY(make_map(&tmV, Vt, blocks * 256, attn::BKEY, attn::BKEY, vbox));
   } else {
-    TRY(make_map(&tmK, K, static_cast<uint64_t>(B) * Nk, C, ldk, attn::BKEY));
-    TRY(make_map(&tmV, Vt, C, static_cast<uint64_t>(B) * Nk, ldv, 256));
+    TRY(make_map(&tmK, K, static_cast<uint64_t>(B) * Nk, C, ldk, kbox));
+    TRY(make_map(&tmV, Vt, C, static_cast<uint64_t>(B) * Nk, ldv, vbox));
   }
   AttnParams ap;
   ap.B = B; ap.H = H; ap.Nq = Nq; ap.Nk = Nk;
@@ -304,12 +309,19 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(attn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(attn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid(plan.nsplit, Nq / attn::BQ, B * H);
   {
     ProfScope ps(fp16 ? TAG_SELF_ATTN : TAG_CROSS_ATTN, st);
-    if (fp16)
+    const dim3 pgrid(Nq / attn::BQ, plan.nsplit, B * H);        // the CTA pair = the two query tiles, adjacent in x
+    if (pairk && fp16)
+      launch_kc(attn2_tc_kernel<true>, pgrid, dim3(attn::THREADS), attn::SMEM_BYTES, st, dim3(2, 1, 1), tmQ, tmK, tmV, ap);
+    else if (pairk)
+      launch_kc(attn2_tc_kernel<false>, pgrid, dim3(attn::THREADS), attn::SMEM_BYTES, st, dim3(2, 1, 1), tmQ, tmK, tmV, ap);
+    else if (fp16)
       launch_k(attn_tc_kernel<true>, grid, dim3(attn::THREADS), attn::SMEM_BYTES, st, tmQ, tmK, tmV, ap);
     else
       launch_k(attn_tc_kernel<false>, grid, dim3(attn::THREADS), attn::SMEM_BYTES, st, tmQ, tmK, tmV, ap);
