@@ -302,7 +302,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps,
                     "note": "PARQDecoderB200.forward on pinned host tokens (bf16) + poses, double-buffered H2D on a copy stream, D2H of the last-iteration detections"},
             "gpu_launches": launches,
-            "roofline": {"kernel": "attn_tc_kernel<bf16> (cross-attention over %d image tokens)" % Nk, "bound": "tensor",
+            "roofline": {"kernel": "attn2_tc_kernel<bf16> (CTA-pair flash cross-attention over %d image tokens)" % Nk, "bound": "tensor",
                          "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sustained"]) if ach else None,
                          "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                          "flops_per_launch": flops, "ms_per_launch": ca_ms / max(ca_n, 1), "launches_timed": ca_n, "traffic": traffic},
@@ -311,7 +311,7 @@ def run_ours(args):
                                   "frac": samp_bytes / (ps_ms / max(ps_n, 1) * 1e-3) / 1e9 / pk["hbm"] if ps_n else None,
                                   "bytes_per_launch": samp_bytes, "in_bounds_corners_per_launch": n_inb, "valid_view_fraction": valid_frac,
                                   "ms_per_launch": ps_ms / max(ps_n, 1)},
-            "roofline_kv_proj": {"kernel": "gemm_tc_kernel (K and V^T projection, 2 launches/step)", "bound": "tensor",
+            "roofline_kv_proj": {"kernel": "gemm2_tc_kernel (CTA-pair GEMM: K and V^T projection, 2 launches/step)", "bound": "tensor",
                                  "achieved": (4.0 * B * Nk * Cc * Cc) / (kv_ms / max(kv_n // 2, 1) * 1e-3) / 1e12 if kv_n else None,
                                  "peak": pk["tf_sustained"], "unit": "TFLOP/s"},
             "breakdown_ms_per_step": {k: round(v[0], 4) for k, v in breakdown.items() if k != "_dropped"},

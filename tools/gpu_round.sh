@@ -19,15 +19,15 @@ print(d["breakdown_ms_per_step"]); print(d["clocks"]); print(d.get("cpu_baseline
 PY
       ;;
     launches)
-      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_$TAG.csv \
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$TAG.csv \
         python bench.py --steps 3 --warmup 3 > gpurun_out/launches_$TAG.log 2>&1
       tail -3 gpurun_out/launches_$TAG.log ;;
     full)
       timeout 900 ncu --set full --clock-control none --import-source on \
-        -k regex:"attn_tc|project_sample|attn_combine|heads_final|add_ln|gn_apply|posemb" -c 14 -f -o gpurun_out/prof_${TAG}_iter \
+        -k regex:"attn2?_tc|project_sample|attn_combine|heads_final|add_ln|gn_apply|posemb" -c 14 -f -o gpurun_out/prof_${TAG}_iter \
         python tools/prof_step.py 1 > gpurun_out/prof_${TAG}_iter.log 2>&1
       tail -2 gpurun_out/prof_${TAG}_iter.log
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 6 -f -o gpurun_out/prof_${TAG}_gemm \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm2?_tc" -c 6 -f -o gpurun_out/prof_${TAG}_gemm \
         python tools/prof_step.py 1 > gpurun_out/prof_${TAG}_gemm.log 2>&1
       tail -2 gpurun_out/prof_${TAG}_gemm.log ;;
   esac
