@@ -119,6 +119,13 @@ int parq_decoder_forward(const ParqShape *shape, const void *tokens_bf16, const 
                          const void *packed, void *workspace, size_t workspace_bytes, const ParqOutputs *out,
                          uint32_t flags, void *stream);
 
+/* "Next" row f-3: the FPN upsample + concat of ResnetFPN.forward (model/resnet_fpn.py:73-80): the four pyramid levels
+ * l0..l3, each (BT, channels_per_level, h_l, w_l) fp32 channels-first with level_hw = HOST array {h0,w0,h1,w1,h2,w2,h3,w3},
+ * are bilinearly resized (F.interpolate(mode="bilinear"), align_corners=False) to the size of `target_level` and
+ * concatenated along channels into out_nchw (BT, 4*channels_per_level, H, W) -- the `all_features` tensor. */
+int parq_fpn_concat(const float *l0, const float *l1, const float *l2, const float *l3, const int32_t *level_hw, int BT,
+                    int channels_per_level, int target_level, float *out_nchw, void *stream);
+
 /* "Next" row f-1: AddRayPE.forward (model/ray_positional_encoding.py:61-139; utils/encoding_utils.py:15-100) fused with
  * the tokeniser of PARQ.forward (model/parq_lightning.py:75-85).  feat_nchw (B,T,C,H,W) fp32 backbone features (may be
  * NULL when only the encoding is wanted), depth_planes (num_samples) device floats (exp(log(min)+log(max/min)*linspace)),

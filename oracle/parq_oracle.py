@@ -471,3 +471,13 @@ def add_ray_pe(images_feat, camera, T_camera_pseudoCam, T_world_pseudoCam, T_wor
         enc = enc.view(B, T, H, W, C).permute(0, 1, 4, 2, 3)
         tokens = (images_feat + enc).permute(0, 1, 3, 4, 2).reshape(B, T * H * W, C)
         return enc.contiguous(), tokens.contiguous()
+
+
+# --------------------------------------------------------------------------- #
+# f-3  FPN upsample + concat (model/resnet_fpn.py:73-90)
+# --------------------------------------------------------------------------- #
+def fpn_concat(features, layer=0):
+    """ResnetFPN.forward :73-80: every pyramid level resized to the size of level ``layer`` with
+    F.interpolate(mode="bilinear") (align_corners=False), concatenated along channels."""
+    size = features[str(layer)].shape[-2:]
+    return torch.cat([F.interpolate(features[str(l)], size, mode="bilinear") for l in range(4)], dim=1)

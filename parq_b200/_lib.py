@@ -22,7 +22,7 @@ EXPORTS = [
     "parq_version", "parq_last_error", "parq_packed_bytes", "parq_workspace_bytes", "parq_pack_weights",
     "parq_pose_chain", "parq_project_sample", "parq_kv_project", "parq_decoder_forward",
     "parq_gemm_bf16", "parq_attention_scratch_bytes", "parq_attention",
-    "parq_parse_pred", "parq_raype_packed_bytes", "parq_raype_workspace_bytes", "parq_raype_pack_weights",
+    "parq_parse_pred", "parq_fpn_concat", "parq_raype_packed_bytes", "parq_raype_workspace_bytes", "parq_raype_pack_weights",
     "parq_raype_forward", "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect", "parq_workspace_offset",
 ]
 PROFILE_TAGS = ("kv_proj", "project_sample", "gemm", "self_attn", "cross_attn", "combine", "rowwise")
@@ -103,6 +103,8 @@ def load():
     lib.parq_parse_pred.restype = C.c_int
     lib.parq_parse_pred.argtypes = [f32p, f32p, f32p, f32p, i32, i32, i32, C.POINTER(C.c_float), C.c_double, u32, vp, vp, f32p, vp,
                                     f32p, vp]
+    lib.parq_fpn_concat.restype = C.c_int
+    lib.parq_fpn_concat.argtypes = [f32p, f32p, f32p, f32p, C.POINTER(C.c_int32), i32, i32, i32, f32p, vp]
     lib.parq_raype_packed_bytes.restype = sz
     lib.parq_raype_packed_bytes.argtypes = [i32, i32]
     lib.parq_raype_workspace_bytes.restype = sz

@@ -11,6 +11,7 @@
 #include "../../include/parq_b200.h"
 #include "attn_tc.cuh"
 #include "attn2_tc.cuh"
+#include "fpn.cuh"
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
 #include "parse_pred.cuh"
@@ -699,6 +700,33 @@ int parq_project_sample(const ParqShape* shape, const void* tokens_bf16, const f
   {
     ProfScope ps(TAG_SAMPLE, static_cast<cudaStream_t>(stream));
     project_sample_kernel<<<shape->B * shape->Nq / SAMPLE_QPB, shape->C / 8, sample_smem(shape->T), static_cast<cudaStream_t>(stream)>>>(sp);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PARQ_OK;
+}
+
+// ---- f-3: FPN upsample + concat ---------------------------------------------------------------------------------
+int parq_fpn_concat(const float* l0, const float* l1, const float* l2, const float* l3, const int32_t* level_hw, int BT, int channels_per_level,
+                    int target_level, float* out_nchw, void* stream) {
+  TRY(require_sm100());
+  if (!l0 || !l1 || !l2 || !l3 || !level_hw || !out_nchw) return fail(PARQ_ERR_SHAPE, "null pointer");
+  if (BT < 1 || channels_per_level < 1 || target_level < 0 || target_level > 3) return fail(PARQ_ERR_SHAPE, "bad fpn_concat arguments");
+  FpnParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.level[0] = l0; fp.level[1] = l1; fp.level[2] = l2; fp.level[3] = l3;
+  for (int l = 0; l < 4; ++l) {
+    fp.h[l] = level_hw[2 * l];
+    fp.w[l] = level_hw[2 * l + 1];
+    if (fp.h[l] < 1 || fp.w[l] < 1) return fail(PARQ_ERR_SHAPE, "non-positive level size");
+  }
+  fp.BT = BT; fp.Cl = channels_per_level; fp.H = fp.h[target_level]; fp.W = fp.w[target_level];
+  fp.out = out_nchw;
+  const long long total = static_cast<long long>(BT) * 4 * channels_per_level * fp.H * fp.W;
+  const long long blocks = (total + 255) / 256;
+  const int grid = static_cast<int>(blocks < 148LL * 32 ? blocks : 148LL * 32);
+  {
+    ProfScope ps(TAG_ROWWISE, static_cast<cudaStream_t>(stream));
+    fpn_concat_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(fp);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;

@@ -158,6 +158,17 @@ def make_features(B, T, H, W, C=DEC_DIM, seed=0):
     return tok.view(B, T, H, W, C).permute(0, 1, 4, 2, 3).contiguous()
 
 
+def make_pyramid(N, H, W, Cl=256, seed=0):
+    """The four FPN levels a torchvision resnet_fpn_backbone returns for level-0 size (H, W):
+    {"0": (N,Cl,H,W), "1": ceil/2, "2": ceil/4, "3": ceil/8} fp32 (model/resnet_fpn.py:66-75)."""
+    g = torch.Generator().manual_seed(9000011 * seed + 3)
+    out, h, w = {}, H, W
+    for l in range(4):
+        out[str(l)] = torch.randn(N, Cl, h, w, generator=g)
+        h, w = (h + 1) // 2, (w + 1) // 2
+    return out
+
+
 def _rot(axis, ang):
     c, s = torch.cos(ang), torch.sin(ang)
     o, z = torch.ones_like(ang), torch.zeros_like(ang)

@@ -100,6 +100,26 @@ def main():
                             inputs_sum=np.array(I.tensor_checksum(feat, cam._data, Tcp._data, Twp._data, Twl._data, *[sd[k] for k in sorted(sd)])),
                             encoding=enc[:, :, ::FEAT_STRIDE].numpy())
         print(name, tuple(enc.shape), "max |enc| %.3f" % enc.abs().max().item())
+    # f-3: the concat part of the reference's ResnetFPN.forward (model/resnet_fpn.py:56-91), run UNMODIFIED on an
+    # instance whose backbone is replaced by a stub that returns a seeded pyramid (the torchvision backbone itself is
+    # out of scope and needs downloaded weights)
+    spec = importlib.util.spec_from_file_location("model.resnet_fpn", os.path.join(REFERENCE_ROOT, "model", "resnet_fpn.py"))
+    rfpn = importlib.util.module_from_spec(spec)
+    sys.modules["model.resnet_fpn"] = rfpn
+    spec.loader.exec_module(rfpn)
+    for name, (B, T, H, W, seed) in {"fpn_small": (1, 2, 60, 80, 8), "fpn_odd": (2, 1, 15, 21, 9)}.items():
+        pyr = I.make_pyramid(B * T, H, W, seed=seed)
+        obj = rfpn.ResnetFPN.__new__(rfpn.ResnetFPN)
+        torch.nn.Module.__init__(obj)
+        obj.resnet_fpn, obj.transform, obj.freeze, obj.layer = (lambda x: pyr), (lambda x: x), False, "0"
+        cam = I.make_geometry(B, T, H * 4, W * 4, seed=seed)[0]
+        with torch.no_grad():
+            batch = obj.forward({"rgb_img": torch.zeros(B, T, 3, 4 * H, 4 * W), "camera": ns.Camera(cam._data)})
+        af = batch["all_features"]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), shape=np.array([B, T, H, W, seed]),
+                            inputs_sum=np.array(I.tensor_checksum(*[pyr[str(l)] for l in range(4)])),
+                            all_features=af[:, :, ::FEAT_STRIDE].numpy(), camera_feature=batch["camera_feature"]._data.numpy())
+        print(name, tuple(af.shape))
     for name, (B, T, H, W, Nq, seed, wild) in PROJ_CASES.items():
         tokens = I.make_tokens(B, T, H, W, seed=seed)
         cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed, wild=wild)

@@ -455,3 +455,52 @@ def test_decoder_with_fp32_weights_against_oracle(dev):
             errs[(k, i)] = relerr(got[k][i].cpu(), outs[i][k])
     print({k: "%.2e" % v for k, v in errs.items()})
     assert max(errs.values()) <= TOL, max(errs, key=errs.get)
+
+
+# --------------------------------------------------- f-3: FPN upsample + concat writer ----
+@pytest.mark.parametrize("name", ["fpn_small", "fpn_odd"])
+def test_fpn_concat_against_reference_golden(dev, name):
+    from parq_b200.fpn import fpn_concat
+    gold = load_golden(name)
+    B, T, H, W, seed = [int(x) for x in gold["shape"]]
+    pyr = I.make_pyramid(B * T, H, W, seed=seed)
+    got = fpn_concat({k: v.to(dev) for k, v in pyr.items()})
+    torch.cuda.synchronize()
+    assert got.shape == (B * T, 1024, H, W)
+    got = got.view(B, T, 1024, H, W).cpu()
+    assert bit_equal(got[:, :, :256], pyr["0"].view(B, T, 256, H, W))                      # the target level is an exact copy
+    assert relerr(got[:, :, ::16], gold["all_features"]) <= 1e-6
+    assert relerr(got, O.fpn_concat(pyr).view(B, T, 1024, H, W)) <= 1e-6
+    other = fpn_concat({k: v.to(dev) for k, v in pyr.items()}, layer=1).cpu()                # a coarser target level (down- and up-sampling)
+    assert relerr(other, O.fpn_concat(pyr, layer=1)) <= 1e-6
+
+
+def test_pipeline_fpn_raype_decoder_nms_chain(dev):
+    # the hot path with its three "next" rows chained on the device, as PARQ.forward / update_metrics would run them:
+    # pyramid -> fpn_concat (f-3) -> AddRayPEB200.tokens (f-1) -> PARQDecoderB200 -> parse_pred (f-2)
+    from parq_b200.fpn import camera_feature, fpn_concat
+    from parq_b200.raype import AddRayPEB200
+    B, T, H, W, Nq, seed = 1, 2, 12, 16, 128, 71
+    pyr = I.make_pyramid(B * T, H, W, seed=seed)
+    cam_img, Tcp, Twp, Twl = I.make_geometry(B, T, 4 * H, 4 * W, seed=seed)
+    cam = camera_feature(cam_img)                                      # image camera -> feature-map camera (1/4)
+    feats = fpn_concat({k: v.to(dev) for k, v in pyr.items()}).view(B, T, 1024, H, W)
+    rpe = AddRayPEB200(1024, [-3, 3, -2, 0.5, 0.25, 5.25], 64, 0.25, 5.25).eval()
+    rsd = I.make_raype_weights(seed)
+    rpe.load_state_dict(rsd, strict=True)
+    tokens = rpe.to(dev).tokens(feats, cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
+    dec = PARQDecoderB200(default_cfg(Nq)).eval()
+    sd = I.make_weights(seed, Nq)
+    dec.load_state_dict(sd, strict=True)
+    outs = dec.to(dev)(tokens, cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
+    parsed = dec.parse_pred(outs)
+    torch.cuda.synchronize()
+    # oracle chain up to the tokens, then the oracle decoder on OUR bf16 tokens (identical inputs) for iteration 0
+    enc_o, tok_o = O.add_ray_pe(O.fpn_concat(pyr).view(B, T, 1024, H, W), cam._data, Tcp._data, Twp._data, Twl._data, rsd)
+    d = (tokens.float().cpu() - tok_o).abs()
+    assert (d <= tok_o.abs() * 2.0 ** -8 + 3e-3 * enc_o.abs().max()).all()
+    ref = O.decoder_forward(tokens.float().cpu(), cam._data, Tcp._data, Twp._data, Twl._data, sd, iters=1)
+    for k in ("pred_logits", "center_unnormalized", "ortho6d", "sem_cls_prob"):
+        assert relerr(outs[0][k].cpu(), ref[0][k]) <= TOL, k
+    want = O.parse_pred({k: v.cpu() for k, v in outs[-1].items()})
+    assert torch.equal(parsed["pred_mask"].cpu(), want["pred_mask"]) and torch.equal(parsed["nms_mask"].cpu(), want["nms_mask"])

@@ -102,3 +102,18 @@ def test_oracle_add_ray_pe_matches_reference(name):
     enc, tokens = O.add_ray_pe(feat, cam._data, Tcp._data, Twp._data, Twl._data, sd)
     assert relerr(enc[:, :, ::16], gold["encoding"]) <= 2e-6
     assert torch.equal(tokens.view(B, T, H, W, 1024), (feat + enc).permute(0, 1, 3, 4, 2))
+
+
+@pytest.mark.parametrize("name", ["fpn_small", "fpn_odd"])
+def test_oracle_fpn_concat_matches_reference(name):
+    # f-3: `all_features` / `camera_feature` of the reference's own ResnetFPN.forward on a stubbed backbone (make_golden.py)
+    from parq_b200 import inputs as I
+    from parq_b200.fpn import camera_feature
+    gold = load_golden(name)
+    B, T, H, W, seed = [int(x) for x in gold["shape"]]
+    pyr = I.make_pyramid(B * T, H, W, seed=seed)
+    assert I.tensor_checksum(*[pyr[str(l)] for l in range(4)]) == str(gold["inputs_sum"])
+    af = O.fpn_concat(pyr).view(B, T, 1024, H, W)
+    assert bit_equal(af[:, :, ::16], gold["all_features"])
+    cam = I.make_geometry(B, T, H * 4, W * 4, seed=seed)[0]
+    assert bit_equal(camera_feature(cam)._data, gold["camera_feature"])
