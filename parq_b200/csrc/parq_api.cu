@@ -721,12 +721,16 @@ int parq_fpn_concat(const float* l0, const float* l1, const float* l2, const flo
   }
   fp.BT = BT; fp.Cl = channels_per_level; fp.H = fp.h[target_level]; fp.W = fp.w[target_level];
   fp.out = out_nchw;
-  const long long total = static_cast<long long>(BT) * 4 * channels_per_level * fp.H * fp.W;
-  const long long blocks = (total + 255) / 256;
-  const int grid = static_cast<int>(blocks < 148LL * 32 ? blocks : 148LL * 32);
-  {
+  const long long planes = static_cast<long long>(BT) * 4 * channels_per_level;
+  if (planes > 0x7fffffffLL) return fail(PARQ_ERR_SHAPE, "too many feature planes");
+  // grid.y is limited to 65535 planes per launch
+  for (long long p0 = 0; p0 < planes; p0 += 65535) {
+    const int np = static_cast<int>(planes - p0 < 65535 ? planes - p0 : 65535);
+    FpnParams part = fp;
+    // a launch covers planes [p0, p0+np): shift the output and let the kernel see plane indices from p0 via BT-relative pointers
+    part.plane0 = static_cast<int>(p0);
     ProfScope ps(TAG_ROWWISE, static_cast<cudaStream_t>(stream));
-    fpn_concat_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(fp);
+    fpn_concat_kernel<<<dim3((fp.H * fp.W + 1023) / 1024, np), 256, 0, static_cast<cudaStream_t>(stream)>>>(part);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;

@@ -50,7 +50,7 @@ class AddRayPEB200(nn.Module):
             self._packed, self._flags, self._depth, self._key = packed, (_lib.PARQ_FLAG_WEIGHT_LO if rc else 0), self._depth_planes(device), key
         return lib
 
-    def _run(self, images_feat, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local, want_tokens, want_encoding):
+    def _run(self, images_feat, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local, want_tokens, want_encoding, out=None):
         if self.training:
             raise NotImplementedError("AddRayPEB200 is inference-only: call .eval() (no training fallback exists)")
         if images_feat.device.type != "cuda":
@@ -65,7 +65,11 @@ class AddRayPEB200(nn.Module):
         nws = lib.parq_raype_workspace_bytes(B, T, H, W, Cc, self.num_samples)
         if self._ws is None or self._ws.numel() < nws:
             self._ws = torch.empty(nws, dtype=torch.uint8, device=dev)
-        tokens = torch.empty(B, T * H * W, Cc, dtype=torch.bfloat16, device=dev) if want_tokens else None
+        tokens = None
+        if want_tokens:
+            tokens = out if out is not None else torch.empty(B, T * H * W, Cc, dtype=torch.bfloat16, device=dev)
+            if tuple(tokens.shape) != (B, T * H * W, Cc) or tokens.dtype != torch.bfloat16 or not tokens.is_contiguous() or tokens.device != dev:
+                raise ValueError("out must be a contiguous (B, T*H*W, C) bf16 tensor on the features' device")
         enc = torch.empty(B, T, Cc, H, W, dtype=torch.float32, device=dev) if want_encoding else None
         scale = (C.c_float * 6)(*self.ray_points_scale)
         with torch.cuda.device(dev), torch.no_grad():
@@ -80,6 +84,7 @@ class AddRayPEB200(nn.Module):
         (hidden layer kept as an exact bf16 split: fp32-grade result)."""
         return self._run(images_feat, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local, False, True)[1]
 
-    def tokens(self, images_feat, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local):
-        """Fused producer: (B, T*H*W, C) bf16 channels-last tokens = features + encoding, the decoder's input."""
-        return self._run(images_feat, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local, True, False)[0]
+    def tokens(self, images_feat, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local, out=None):
+        """Fused producer: (B, T*H*W, C) bf16 channels-last tokens = features + encoding, the decoder's input.
+        ``out``: optional preallocated token buffer (a fixed address lets the decoder replay one captured graph)."""
+        return self._run(images_feat, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local, True, False, out)[0]
