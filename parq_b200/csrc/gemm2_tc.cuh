@@ -129,6 +129,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
+  __syncthreads();                         // CTA-level ordering of the TMEM-address write (also what racecheck models)
   cluster_sync_all();                      // barriers of both CTAs initialised, TMEM of both allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
