@@ -504,3 +504,26 @@ def test_pipeline_fpn_raype_decoder_nms_chain(dev):
         assert relerr(outs[0][k].cpu(), ref[0][k]) <= TOL, k
     want = O.parse_pred({k: v.cpu() for k, v in outs[-1].items()})
     assert torch.equal(parsed["pred_mask"].cpu(), want["pred_mask"]) and torch.equal(parsed["nms_mask"].cpu(), want["nms_mask"])
+
+
+def test_accelerate_hook_runs_the_library(dev):
+    # accelerate() patches an instance in place; on the GPU box the reference class is not importable,
+    # so the module with the reference's attribute names stands in for it
+    from parq_b200.decoder import accelerate
+    gold = load_golden("small")
+    c = regenerate_case(gold)
+    m = PARQDecoderB200(default_cfg(c["Nq"])).eval()
+    m.load_state_dict(c["sd"], strict=True)
+    m = accelerate(m.to(dev), feature_hw=(c["H"], c["W"]), use_cuda_graph=True)
+    cam, Tcp, Twp, Twl = I.make_geometry(c["B"], c["T"], c["H"], c["W"], seed=c["seed"])
+    args = (c["tokens"].to(dev).bfloat16(), cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
+    for _ in range(2):
+        out = m(*args)
+    torch.cuda.synchronize()
+    assert len(out) == 8 and set(out[0].keys()) == set(OUT_KEYS)
+    for k in OUT_KEYS:
+        assert relerr(out[0][k].cpu(), gold[k][0]) <= TOL, k
+    before = _lib.load().parq_kernel_launches()
+    m.forward.use_cuda_graph = False
+    m(*args)
+    assert _lib.load().parq_kernel_launches() - before > 100          # the CUDA library did the work
