@@ -169,7 +169,9 @@ int parq_gemm_bf16(const void *A, int64_t a_rows, int64_t a_cols, const void *Bw
                    int64_t lp_lo_off, void *stream);
 
 /* softmax(Q K^T) V for head_dim 256: Q (B*Nq, H*256) pre-scaled, K (B*Nk, H*256), Vt (H*256, ldv) 16-bit
- * (bf16, or fp16 when fp16 != 0); out_split (B*Nq, 2*H*256) bf16 [hi|lo]; scratch >= parq_attention_scratch_bytes. */
+ * (bf16, or fp16 when fp16 != 0); out_split (B*Nq, 2*H*256) bf16 [hi|lo]; scratch >= parq_attention_scratch_bytes.
+ * force_nsplit: > 0 fixes the number of key splits, 0 lets the library choose (stream-K schedule for long key
+ * sequences, else a split-KV grid), < 0 forces the stream-K schedule (needs Nq % 256 == 0). */
 size_t parq_attention_scratch_bytes(int B, int H, int Nq, int Nk);
 int parq_attention(const void *Q, int64_t ldq, const void *K, int64_t ldk, const void *Vt, int64_t ldv, int B, int H,
                    int Nq, int Nk, int fp16, void *scratch, size_t scratch_bytes, void *out_split, int force_nsplit,

@@ -1,0 +1,423 @@
+// Stream-K scheduling of the CTA-pair flash attention (attn2_tc.cuh) for the cross-attention.
+//
+// attn2 launches (key splits x query pairs x clips x heads) CTAs -- 1024 at config 2, 6.9 waves of 148 -- and every CTA
+// pays its own prologue (barrier init, 2-CTA TMEM allocation, two cluster barriers, Q load) and its own epilogue (128 KB
+// of partial O), and the merge kernel then re-reads 134 MB of partials.  Here the grid is ONE CTA pair per SM pair.
+// The work is the flat list of (item, key tile) units, item = (clip, head, 256-query pair); pair p owns the contiguous
+// unit range [U p / P, U (p+1) / P): perfectly balanced, one prologue per SM, and an item is cut only where a range
+// ends, so there are at most P + items partial outputs (148 x 256 rows instead of 1024 x 128) -- items that fall
+// completely inside one range are normalised and written directly.
+//
+// A pair walks its range as SEGMENTS (one per item it touches).  The K / V^T ring, the S / P double buffer and the
+// pv_done phases simply continue across segments (a global tile counter g supplies buffer indices and parities); per
+// segment the producer reloads Q once the previous segment's MMAs have retired (q_empty), the first P.V of a segment
+// overwrites O only after the previous segment's epilogue has drained it (o_free), and the softmax warps restart
+// their running max / sum.  Everything else is attn2_tc.cuh.
+#pragma once
+#include "attn2_tc.cuh"
+
+namespace parq {
+
+struct Attn3Params {
+  int B, H, Nq, Nk;
+  int qpairs;              // Nq / 256
+  int ntiles;              // key tiles per item
+  long long units;         // items * ntiles
+  int npairs;              // CTA pairs in the grid (== gridDim.y)
+  int slots;               // partial slots per pair
+  float* o_part;           // [(pair*slots + seg)*256 + row][256]
+  float2* ml_part;         // [(pair*slots + seg)*256 + row] = (m, l)
+  __nv_bfloat16* out;      // (B*Nq, 2*H*256) [hi|lo]: direct output of whole-item segments
+  int kv_const, kv_tiled;
+};
+
+__device__ __forceinline__ long long sk_unit_begin(long long units, int npairs, int pair) {
+  return units * pair / npairs;
+}
+
+template <bool kFp16>
+__global__ void __launch_bounds__(attn::THREADS, 1)
+attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const Attn3Params p) {
+  using namespace attn;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* ring = smem + Q_BYTES;
+  uint64_t* kv_full = reinterpret_cast<uint64_t*>(ring + NS * STAGE_BYTES);
+  uint64_t* kv_empty = kv_full + NS;
+  uint64_t* q_full = kv_empty + NS;
+  uint64_t* s_full = q_full + 1;     // [2]
+  uint64_t* p_full = s_full + 2;     // [2]
+  uint64_t* pv_done = p_full + 2;    // [1]
+  uint64_t* q_empty = pv_done + 1;   // [1] all MMAs of a segment retired: Q may be overwritten
+  uint64_t* o_free = q_empty + 1;    // [1] (leader's copy is live) the segment's O has been read by both CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();      // == blockIdx.x: which 128-query half of the item's 256 queries
+  const bool leader = rank == 0;
+  const int pair = blockIdx.y;
+  const long long u0 = sk_unit_begin(p.units, p.npairs, pair), u1 = sk_unit_begin(p.units, p.npairs, pair + 1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 256);
+    }
+    mbar_init(pv_done, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, 256);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_O = tmem_base + 256;
+
+  // segment walk shared by all roles: item, first tile, number of tiles
+  struct Seg { int item, ta, n; };
+  auto seg_at = [&](long long u) {
+    Seg s;
+    s.item = static_cast<int>(u / p.ntiles);
+    s.ta = static_cast<int>(u - static_cast<long long>(s.item) * p.ntiles);
+    const long long left = u1 - u;
+    s.n = static_cast<int>(left < p.ntiles - s.ta ? left : p.ntiles - s.ta);
+    return s;
+  };
+  auto item_bh = [&](int item, int& b, int& h, int& qt) {
+    const int qp = item % p.qpairs, bh = item / p.qpairs;
+    b = bh / p.H;
+    h = bh - b * p.H;
+    qt = qp * 2 + static_cast<int>(rank);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {                      // ---------------- TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_k = [&](int b, int h, int tile) {
+        const int row = (p.kv_tiled ? ((b * p.ntiles + tile) * p.H + h) * BKEY : b * p.Nk + tile * BKEY) + static_cast<int>(rank) * (BKEY / 2);
+        const int col = p.kv_tiled ? 0 : h * DH;
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        if (leader) mbar_expect_tx(&kv_full[stage], 2 * STAGE_BYTES);
+        uint8_t* dst = ring + stage * STAGE_BYTES;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_load_2d_pair(dst + c * 8192, &tmK, &kv_full[stage], col + c * 64, row);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      };
+      auto load_v = [&](int b, int h, int tile) {
+        const int col = p.kv_tiled ? 0 : b * p.Nk + tile * BKEY;
+        const int row = (p.kv_tiled ? ((b * p.ntiles + tile) * p.H + h) * DH : h * DH) + static_cast<int>(rank) * (DH / 2);
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        if (leader) mbar_expect_tx(&kv_full[stage], 2 * STAGE_BYTES);
+        uint8_t* dst = ring + stage * STAGE_BYTES;
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc) tma_load_2d_pair(dst + kc * 16384, &tmV, &kv_full[stage], col + kc * 64, row);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      };
+      int segi = 0;
+      for (long long u = u0; u < u1; ++segi) {
+        const Seg s = seg_at(u);
+        int b, h, qt;
+        item_bh(s.item, b, h, qt);
+        // ring order per segment: K(0), [K(j+1), V(j)] ...  The first two key tiles of the FIRST segment are
+        // requested before the programmatic-dependency wait when K / V^T are an old cache; Q follows the wait.
+        const bool early = segi == 0 && p.kv_const != 0;
+        if (early) {
+          load_k(b, h, s.ta);
+          if (s.n > 1) load_k(b, h, s.ta + 1);
+        }
+        if (segi == 0) {
+          pdl_wait();
+          pdl_launch_dependents();
+        } else {
+          mbar_wait(q_empty, (segi - 1) & 1);           // the previous segment's MMAs no longer read Q
+        }
+        if (leader) mbar_expect_tx(q_full, 2 * Q_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_load_2d_pair(sQ + c * (BQ * 128), &tmQ, q_full, h * DH + c * 64, b * p.Nq + qt * BQ);
+        if (!early) load_k(b, h, s.ta);
+        for (int j = 0; j < s.n; ++j) {
+          if (j + 1 < s.n && !(early && j == 0)) load_k(b, h, s.ta + j + 1);
+          load_v(b, h, s.ta + j);
+        }
+        u += s.n;
+      }
+    } else {
+      pdl_wait();
+      pdl_launch_dependents();
+    }
+  } else if (warp == 1) {
+    pdl_wait();
+    pdl_launch_dependents();
+    if (lane == 0 && leader) {            // ---------------- MMA issuer (leader CTA only, M = 256 over the pair)
+      constexpr uint32_t fmt = kFp16 ? 0u : 1u;
+      constexpr uint32_t idesc_s = umma_idesc(2 * BQ, BKEY, fmt);
+      constexpr uint32_t idesc_pv = umma_idesc(2 * BQ, DH, fmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_s = [&](int buf) {
+        const uint32_t d_tmem = tmem_base + buf * 128;
+        mbar_wait(&kv_full[stage], phase);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(ring + stage * STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint64_t qd = umma_desc_sw128(q_addr + c * (BQ * 128));
+          const uint64_t kd = umma_desc_sw128(k_addr + c * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_pair(d_tmem, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0);
+        }
+        umma_commit_pair(&kv_empty[stage]);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+        umma_commit_pair(&s_full[buf]);
+      };
+      int g = 0;                          // tiles issued so far by this pair (buffer index / parities)
+      int segi = 0;
+      for (long long u = u0; u < u1; ++segi) {
+        const Seg s = seg_at(u);
+        mbar_wait(q_full, segi & 1);
+        tc_fence_after();
+        issue_s(g & 1);
+        for (int j = 0; j < s.n; ++j, ++g) {
+          if (j + 1 < s.n) issue_s((g + 1) & 1);
+          const int buf = g & 1;
+          mbar_wait(&p_full[buf], (g >> 1) & 1);
+          if (j == 0 && segi > 0) mbar_wait(o_free, (segi - 1) & 1);    // the previous segment's O has been drained
+          tc_fence_after();
+          const uint32_t p_tmem = tmem_base + buf * 128;
+          mbar_wait(&kv_full[stage], phase);
+          tc_fence_after();
+#pragma unroll
+          for (int kc = 0; kc < 2; ++kc) {
+            const uint64_t vd = umma_desc_sw128(smem_u32(ring + stage * STAGE_BYTES + kc * 16384));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ts_pair(tmem_O, p_tmem + kc * 32 + k * 8, vd + 2 * k, idesc_pv, (j | kc | k) != 0);
+          }
+          umma_commit_pair(&kv_empty[stage]);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+          umma_commit_pair(pv_done);
+        }
+        umma_commit_pair(q_empty);        // every MMA of the segment retired: Q (and the S buffers) are free
+        u += s.n;
+      }
+    }
+  } else if (warp >= 4) {                 // ---------------- softmax / correction / epilogue (both CTAs)
+    pdl_wait();
+    pdl_launch_dependents();
+    const int q = warp - 4;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    int g = 0;
+    int segi = 0;
+    for (long long u = u0; u < u1; ++segi) {
+      const Seg s = seg_at(u);
+      int b, h, qt;
+      item_bh(s.item, b, h, qt);
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < s.n; ++j, ++g) {
+        const int buf = g & 1;
+        mbar_wait(&s_full[buf], (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t s_tmem = tmem_base + lane_base + buf * 128;
+        uint32_t su[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&su[c * 32]));
+        tmem_wait_ld();
+        const int nvalid = p.Nk - (s.ta + j) * BKEY;
+        if (nvalid < BKEY) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= nvalid) su[i] = 0xff800000u;
+        }
+        float tmax = __uint_as_float(su[0]);
+#pragma unroll
+        for (int i = 1; i < 128; ++i) tmax = fmaxf(tmax, __uint_as_float(su[i]));
+        tmax *= LOG2E;
+        // Every completion of pv_done is observed exactly once and in order (global tile counter g): tile g consumes
+        // the completion of P(g-1)V(g-1) here before touching O, or at the end of the iteration; for the first tile
+        // of a segment that completion was consumed by the previous segment's epilogue.
+        bool pv_seen = (j == 0);
+        if (j == 0) {
+          m_run = tmax;
+        } else if (__any_sync(0xffffffffu, tmax > m_run + RESCALE_THRESHOLD)) {
+          mbar_wait(pv_done, (g - 1) & 1);
+          pv_seen = true;
+          tc_fence_after();
+          const float m_new = fmaxf(m_run, tmax);
+          const float alpha = fast_exp2(m_run - m_new);
+#pragma unroll 1
+          for (int c = 0; c < DH / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_base + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_base + c * 32, o);
+          }
+          l_run *= alpha;
+          m_run = m_new;
+        }
+        float lsum = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i]), LOG2E, -m_run));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i + 1]), LOG2E, -m_run));
+            lsum += p0 + p1;
+            pk[i] = kFp16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
+          }
+          tmem_st32(s_tmem + half * 32, pk);
+        }
+        l_run += lsum;
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive_leader(&p_full[buf]);
+        if (!pv_seen) mbar_wait(pv_done, (g - 1) & 1);
+      }
+      // segment epilogue: g tiles issued so far, the last one is g-1
+      mbar_wait(pv_done, (g - 1) & 1);
+      tc_fence_after();
+      if (s.ta == 0 && s.n == p.ntiles) {
+        // the whole item was processed here: normalise and emit the [hi|lo] operand of the out-projection directly
+        const float inv = 1.f / l_run;
+        const int C = p.H * DH;
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.Nq + qt * BQ + q * 32 + lane) * (2 * C) + h * DH;
+#pragma unroll 1
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_base + c * 32, o);
+          tmem_wait_ld();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v0 = __uint_as_float(o[2 * i]) * inv, v1 = __uint_as_float(o[2 * i + 1]) * inv;
+            hi[i] = pack_bf16x2(v0, v1);
+            lo[i] = pack_bf16x2(v0 - __uint_as_float(hi[i] << 16), v1 - __uint_as_float(hi[i] & 0xFFFF0000u));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            reinterpret_cast<uint4*>(dst + c * 32)[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            reinterpret_cast<uint4*>(dst + C + c * 32)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          }
+        }
+      } else {
+        // un-normalised O, m, l of this segment for attn3_combine_kernel
+        const long long part = (static_cast<long long>(pair) * p.slots + segi) * 256 + static_cast<int>(rank) * BQ + q * 32 + lane;
+        float* orow = p.o_part + part * DH;
+#pragma unroll 1
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_base + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(orow + c * 32)[i] =
+                make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
+                            __uint_as_float(o[4 * i + 3]));
+        }
+        p.ml_part[part] = make_float2(m_run, l_run);
+      }
+      tc_fence_before();
+      mbar_arrive_leader(o_free);         // this CTA's O rows are read: the next segment may overwrite them
+      u += s.n;
+    }
+  }
+
+  if (warp == 2 || warp == 3) {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// Merge the segments of every item that was cut at a range boundary (items processed by a single pair were written
+// directly and are skipped): out = sum_s 2^(m_s-M) O_s / sum_s 2^(m_s-M) l_s as the exact bf16 split [hi | lo].
+// One block per (item, 32 of its 256 query rows): the 64-bit range arithmetic that locates the item's pieces runs once
+// per block; 64 threads per row, a thread owns 4 consecutive channels.
+constexpr int SK_COMBINE_ROWS = 32;
+constexpr int SK_MAX_PAIRS = 128;        // CTA pairs the schedule may use (74 on a B200)
+
+__global__ void __launch_bounds__(256)
+attn3_combine_kernel(const Attn3Params p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int item = blockIdx.x / (256 / SK_COMBINE_ROWS);
+  const int r0 = (blockIdx.x % (256 / SK_COMBINE_ROWS)) * SK_COMBINE_ROWS;      // first row of this block inside the item
+  __shared__ int s_np;
+  __shared__ long long s_slot[SK_MAX_PAIRS];                // first row of every piece of the item in o_part / ml_part (<= npairs pieces)
+  if (threadIdx.x == 0) {
+    const long long ua = static_cast<long long>(item) * p.ntiles, ub = ua + p.ntiles - 1;      // first / last unit of the item
+    auto pair_of = [&](long long u) {
+      int pr = static_cast<int>(u * p.npairs / p.units);
+      while (sk_unit_begin(p.units, p.npairs, pr + 1) <= u) ++pr;
+      while (sk_unit_begin(p.units, p.npairs, pr) > u) --pr;
+      return pr;
+    };
+    const int pa = pair_of(ua), pb = pair_of(ub);
+    s_np = pb - pa + 1;
+    for (int pr = pa; pr <= pb; ++pr) {
+      const int seg = item - static_cast<int>(sk_unit_begin(p.units, p.npairs, pr) / p.ntiles);
+      s_slot[pr - pa] = (static_cast<long long>(pr) * p.slots + seg) * 256;
+    }
+  }
+  __syncthreads();
+  const int np = s_np;
+  if (np == 1) return;                                       // whole item in one range: written directly
+  const int qp = item % p.qpairs, bh = item / p.qpairs;
+  const int b = bh / p.H, h = bh - b * p.H;
+  const int C = p.H * 256;
+  const int d = (threadIdx.x & 63) * 4;
+  for (int r = r0 + (threadIdx.x >> 6); r < r0 + SK_COMBINE_ROWS; r += 4) {
+    float M = -INFINITY;
+    for (int i = 0; i < np; ++i) M = fmaxf(M, __ldg(&p.ml_part[s_slot[i] + r].x));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float L = 0.f;
+    for (int i = 0; i < np; ++i) {
+      const long long idx = s_slot[i] + r;
+      const float2 ml = __ldg(&p.ml_part[idx]);
+      const float4 o = __ldg(reinterpret_cast<const float4*>(p.o_part + idx * 256 + d));
+      const float w = exp2f(ml.x - M);
+      L += w * ml.y;
+      acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
+    }
+    const float inv = 1.f / L;
+    const float v[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+    const uint32_t h0 = pack_bf16x2(v[0], v[1]), h1 = pack_bf16x2(v[2], v[3]);
+    const uint32_t l0 = pack_bf16x2(v[0] - __uint_as_float(h0 << 16), v[1] - __uint_as_float(h0 & 0xFFFF0000u));
+    const uint32_t l1 = pack_bf16x2(v[2] - __uint_as_float(h1 << 16), v[3] - __uint_as_float(h1 & 0xFFFF0000u));
+    const long long row = static_cast<long long>(b) * p.Nq + qp * 256 + r;
+    __nv_bfloat16* dst = p.out + row * (2 * C) + h * 256 + d;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(dst + C) = make_uint2(l0, l1);
+  }
+}
+
+}  // namespace parq

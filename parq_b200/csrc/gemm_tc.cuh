@@ -198,9 +198,9 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
         if (col0 + i < N) o[i] = v[i];
     }
   }
-  if (ep.out_lp != nullptr && ep.kv_tiled != 0) {
+  if (ep.out_lp != nullptr && ep.kv_tiled != 0 && ep.kv_Nk % 32 == 0) {
     // tile-contiguous K / V^T cache: the chunk is a dense 32 x 32 block with its own origin and pitch
-    // (host guarantees Nk % 32 == 0 and N % 32 == 0, so chunks are full and never straddle a key tile)
+    // (Nk % 32 == 0 and N % 32 == 0: chunks are full and never straddle a key tile or a clip)
     int ld;
     uint16_t* dst = reinterpret_cast<uint16_t*>(ep.out_lp) + kv_tiled_base(ep, row0, col0, ld);
 #pragma unroll
@@ -208,6 +208,26 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
     __syncwarp();
     gemm_flush_stage<16>(stage, dst, ld, rows_valid, lane);
     __syncwarp();
+  } else if (ep.out_lp != nullptr && ep.kv_tiled != 0) {
+    // ragged clips (Nk % 32 != 0): a chunk may straddle a key tile or a clip, every element finds its own place
+    if (row_ok) {
+      uint16_t* base = reinterpret_cast<uint16_t*>(ep.out_lp);
+      if (ep.kv_tiled == 1) {               // this thread's token row: 32 consecutive channels of one head
+        int ld;
+        uint16_t* dst = base + kv_tiled_base(ep, row, col0, ld);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (full || col0 + i < N) dst[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v[i]));
+      } else {                               // this thread's channel row: 32 consecutive tokens
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          if (full || col0 + i < N) {
+            int ld;
+            base[kv_tiled_base(ep, row, col0 + i, ld)] = __bfloat16_as_ushort(__float2bfloat16_rn(v[i]));
+          }
+        }
+      }
+    }
   } else if (ep.out_lp != nullptr) {
     uint16_t* obase = reinterpret_cast<uint16_t*>(ep.out_lp) + row0 * ep.ld_lp + col0;
     uint32_t w[16];

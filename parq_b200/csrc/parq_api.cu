@@ -11,6 +11,7 @@
 #include "../../include/parq_b200.h"
 #include "attn_tc.cuh"
 #include "attn2_tc.cuh"
+#include "attn3_tc.cuh"
 #include "fpn.cuh"
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
@@ -106,6 +107,7 @@ static int require_sm100() {
 static thread_local bool g_pdl = false;
 static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
 static const bool g_force_pair = getenv("PARQ_FORCE_PAIR") != nullptr;   // every GEMM on the CTA-pair kernel (tests)
+static const bool g_no_streamk = getenv("PARQ_NO_STREAMK") != nullptr;       // A/B switch: split-KV grid instead of the stream-K schedule
 static const bool g_no_pair_attn = getenv("PARQ_NO_PAIR_ATTN") != nullptr;   // A/B switch: single-CTA attention kernel
 static const bool g_no_pair = getenv("PARQ_NO_PAIR") != nullptr;       // A/B switch: single-CTA GEMM instead of the CTA-pair kernel   // A/B switch for the shared-B ring layout
 struct PdlScope {
@@ -271,15 +273,29 @@ static size_t attn_scratch_bytes(int B, int H, int Nq, int nsplit) {
   return align_up(rows * 256 * sizeof(float), 256) + align_up(rows * sizeof(float2), 256);
 }
 
+// scratch of the stream-K schedule (attn3_tc.cuh): one slot of 256 rows per (pair, segment)
+static size_t streamk_scratch_bytes(int B, int H, int Nq, int Nk, int sms) {
+  if (Nq % (2 * attn::BQ) != 0 || sms < 2) return 0;
+  const long long ntiles = (Nk + attn::BKEY - 1) / attn::BKEY;
+  const long long units = static_cast<long long>(B) * H * (Nq / (2 * attn::BQ)) * ntiles;
+  const long long cap = sms / 2 < SK_MAX_PAIRS ? sms / 2 : SK_MAX_PAIRS;
+  const long long npairs = units < cap ? units : cap;
+  const long long per = (units + npairs - 1) / npairs;
+  const size_t rows = static_cast<size_t>(npairs) * ((per + ntiles - 1) / ntiles + 1) * 256;
+  return align_up(rows * 256 * sizeof(float), 256) + align_up(rows * sizeof(float2), 256);
+}
+
 static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const void* K, uint64_t ldk, const void* Vt,
                             uint64_t ldv, int B, int H, int Nq, int Nk, bool fp16, void* scratch, size_t scratch_bytes,
                             __nv_bfloat16* out_split, int force_nsplit, bool kv_const = false, bool kv_tiled = false) {
   if (Nq % attn::BQ != 0) return fail(PARQ_ERR_SHAPE, "Nq=%d must be a multiple of 128", Nq);
   const int ntiles = (Nk + attn::BKEY - 1) / attn::BKEY;
-  const SplitPlan plan = plan_split(B * H * (Nq / attn::BQ), ntiles, device_info().sms, force_nsplit);
+  const SplitPlan plan = plan_split(B * H * (Nq / attn::BQ), ntiles, device_info().sms, force_nsplit < 0 ? 0 : force_nsplit);
   if (attn_scratch_bytes(B, H, Nq, plan.nsplit) > scratch_bytes)
     return fail(PARQ_ERR_WORKSPACE, "attention scratch too small: need %zu, have %zu", attn_scratch_bytes(B, H, Nq, plan.nsplit),
                 scratch_bytes);
+  if (!kv_tiled && B > 1 && Nk % 8 != 0)
+    return fail(PARQ_ERR_SHAPE, "plain V^T layout: clip b starts at column b*Nk, TMA needs 16-byte aligned box origins -> Nk %% 8 == 0 (Nk=%d)", Nk);
   const uint64_t C = static_cast<uint64_t>(H) * 256;
   // CTA-pair kernel (attn2_tc.cuh): the two 128-query tiles of 256 queries share every K / V^T tile, each CTA stages half
   const bool pairk = !g_no_pair_attn && Nq % (2 * attn::BQ) == 0 && device_info().sms >= 2;
@@ -294,6 +310,49 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
   } else {
     TRY(make_map(&tmK, K, static_cast<uint64_t>(B) * Nk, C, ldk, kbox));
     TRY(make_map(&tmV, Vt, C, static_cast<uint64_t>(B) * Nk, ldv, vbox));
+  }
+  static thread_local bool attr_set3 = false;
+  if (!attr_set3) {
+    CUDA_TRY(cudaFuncSetAttribute(attn3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(attn3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+    attr_set3 = true;
+  }
+  // Stream-K schedule (attn3_tc.cuh) for long key sequences: one CTA pair per SM pair walks a contiguous range of
+  // (item, key tile) units; used when every pair gets at least 8 tiles and no split count was forced by the caller.
+  if (pairk && !g_no_streamk && force_nsplit <= 0) {
+    Attn3Params sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.B = B; sp.H = H; sp.Nq = Nq; sp.Nk = Nk;
+    sp.qpairs = Nq / (2 * attn::BQ);
+    sp.ntiles = ntiles;
+    sp.units = static_cast<long long>(B) * H * sp.qpairs * ntiles;
+    const long long maxp = device_info().sms / 2 < SK_MAX_PAIRS ? device_info().sms / 2 : SK_MAX_PAIRS;
+    sp.npairs = static_cast<int>(sp.units < maxp ? sp.units : maxp);
+    const long long per = (sp.units + sp.npairs - 1) / sp.npairs;
+    sp.slots = static_cast<int>((per + ntiles - 1) / ntiles + 1);
+    const size_t rows3 = static_cast<size_t>(sp.npairs) * sp.slots * 256;
+    const size_t need3 = align_up(rows3 * 256 * sizeof(float), 256) + align_up(rows3 * sizeof(float2), 256);
+    if ((per >= 8 || force_nsplit < 0) && need3 <= scratch_bytes) {
+      sp.o_part = reinterpret_cast<float*>(scratch);
+      sp.ml_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(scratch) + align_up(rows3 * 256 * sizeof(float), 256));
+      sp.out = out_split;
+      sp.kv_const = kv_const ? 1 : 0;
+      sp.kv_tiled = kv_tiled ? 1 : 0;
+      {
+        ProfScope ps(fp16 ? TAG_SELF_ATTN : TAG_CROSS_ATTN, st);
+        if (fp16)
+          launch_kc(attn3_tc_kernel<true>, dim3(2, sp.npairs, 1), dim3(attn::THREADS), attn::SMEM_BYTES, st, dim3(2, 1, 1), tmQ, tmK, tmV, sp);
+        else
+          launch_kc(attn3_tc_kernel<false>, dim3(2, sp.npairs, 1), dim3(attn::THREADS), attn::SMEM_BYTES, st, dim3(2, 1, 1), tmQ, tmK, tmV, sp);
+      }
+      CUDA_TRY(cudaGetLastError());
+      {
+        ProfScope ps(TAG_COMBINE, st);
+        launch_k(attn3_combine_kernel, dim3(B * H * sp.qpairs * (256 / SK_COMBINE_ROWS)), dim3(256), 0, st, sp);
+      }
+      CUDA_TRY(cudaGetLastError());
+      return PARQ_OK;
+    }
   }
   AttnParams ap;
   ap.B = B; ap.H = H; ap.Nq = Nq; ap.Nk = Nk;
@@ -416,7 +475,7 @@ static Workspace workspace_layout(const ParqShape& s, int sms) {
   w.ldv = align_up(Nt, 64);
   w.ldvs = align_up(R, 64);
   w.ntile = static_cast<int>((Nk + attn::BKEY - 1) / attn::BKEY);
-  w.kv_tiled = (Nk % 32 == 0) ? 1 : 0;
+  w.kv_tiled = 1;            // every Nk: ragged clips (Nk % 32 != 0) take the per-element path of the GEMM epilogue
   const size_t cache = w.kv_tiled ? static_cast<size_t>(s.B) * w.ntile * attn::BKEY * C * 2 : 0;
   w.Kc = take(w.kv_tiled ? cache : Nt * C * 2);
   w.Vt = take(w.kv_tiled ? cache : C * w.ldv * 2);
@@ -435,6 +494,8 @@ static Workspace workspace_layout(const ParqShape& s, int sms) {
   w.self = plan_split(s.B * s.heads * qtiles, (s.Nq + attn::BKEY - 1) / attn::BKEY, sms, 0);
   const int smax = w.cross.nsplit > w.self.nsplit ? w.cross.nsplit : w.self.nsplit;
   w.scratch_bytes = attn_scratch_bytes(s.B, s.heads, s.Nq, smax);
+  const size_t sk = streamk_scratch_bytes(s.B, s.heads, s.Nq, static_cast<int>(Nk), sms);
+  if (sk > w.scratch_bytes) w.scratch_bytes = sk;
   w.scratch = take(w.scratch_bytes);
   w.a_attn = take(R * 2 * C * 2);
   w.y = take(R * C * 4);
@@ -920,7 +981,8 @@ int parq_gemm_bf16(const void* A, int64_t a_rows, int64_t a_cols, const void* Bw
 
 size_t parq_attention_scratch_bytes(int B, int H, int Nq, int Nk) {
   const int ntiles = (Nk + attn::BKEY - 1) / attn::BKEY;
-  return attn_scratch_bytes(B, H, Nq, ntiles < 32 ? ntiles : 32);
+  const size_t a = attn_scratch_bytes(B, H, Nq, ntiles < 32 ? ntiles : 32), b = streamk_scratch_bytes(B, H, Nq, Nk, device_info().sms);
+  return a > b ? a : b;
 }
 
 int parq_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* Vt, int64_t ldv, int B, int H, int Nq, int Nk,
@@ -1040,7 +1102,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       TRY(launch_gemm(st, ws + W.a_x1pe, R, 2 * C, pk + P.ca_q, C, 2 * C, g));
       const int Nk = s.T * s.H * s.W;
       TRY(launch_attention(st, ws + W.q_c, C, ws + W.Kc, C, ws + W.Vt, W.ldv, s.B, s.heads, s.Nq, Nk, false, ws + W.scratch,
-                           W.scratch_bytes, BF(W.a_attn), W.cross.nsplit, /*kv_const=*/true, W.kv_tiled != 0));
+                           W.scratch_bytes, BF(W.a_attn), /*library's choice: stream-K or the planned split*/ 0, /*kv_const=*/true,
+                           W.kv_tiled != 0));
       memset(&g, 0, sizeof(g));
       g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
       g.ep = epilogue_none(); g.ep.bias = PF(P.ca_out_b);

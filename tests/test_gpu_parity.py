@@ -198,6 +198,21 @@ def test_attention_against_fp32_softmax(dev, B, H, Nq, Nk, fp16, nsplit):
     assert _attention(dev, B, H, Nq, Nk, fp16, nsplit, seed=Nk) <= (2e-3 if fp16 else 1e-2)
 
 
+@pytest.mark.parametrize("B,H,Nq,Nk", [(2, 4, 256, 4000), (1, 2, 512, 1500), (3, 1, 256, 136), (16, 4, 256, 2048)])
+def test_attention_stream_k_schedule(dev, B, H, Nq, Nk):
+    # nsplit = -1 forces the stream-K schedule: segments that start / end in the middle of an item, items merged from
+    # two or three partials, items written directly, ragged last key tiles
+    assert _attention(dev, B, H, Nq, Nk, False, -1, seed=Nk + B) <= 1e-2
+
+
+def test_attention_plain_layout_alignment_is_checked(dev):
+    # stand-alone entry point with plain K / V^T matrices: clip b's keys start at column b*Nk of V^T, which TMA can only
+    # address at 16-byte granularity -> refused with an error instead of faulting (the decoder's tiled caches have no
+    # such restriction, see test_decoder_ragged_clip_sizes)
+    with pytest.raises(_lib.ParqError, match="Nk"):
+        _attention(dev, 3, 1, 256, 129, False, 0, seed=1)
+
+
 def test_attention_lazy_rescale_path(dev):
     assert _attention(dev, 1, 2, 128, 1024, False, 1, seed=3, scale=4.0, spike=True) <= 1e-2
 
@@ -527,3 +542,22 @@ def test_accelerate_hook_runs_the_library(dev):
     m.forward.use_cuda_graph = False
     m(*args)
     assert _lib.load().parq_kernel_launches() - before > 100          # the CUDA library did the work
+
+
+def test_decoder_ragged_clip_sizes(dev):
+    # Nk = T*H*W = 105 keys per clip, two clips: no alignment of any kind (key tiles, clips and 32-token chunks all
+    # straddle); the K / V^T projection takes the per-element path of the GEMM epilogue
+    B, T, H, W, Nq, seed, iters = 2, 3, 5, 7, 128, 81, 2
+    sd = I.make_weights(seed, Nq)
+    tokens = I.make_tokens(B, T, H, W, seed=seed)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+    c = dict(tokens=tokens, camera=cam._data, T_cp=Tcp._data, T_wp=Twp._data, T_wl=Twl._data, H=H, W=W)
+    outs, auxs = O.decoder_forward(tokens, cam._data, Tcp._data, Twp._data, Twl._data, sd, iters=iters, return_aux=True)
+    refs = O.refs_from_outputs(outs, sd)
+    eng = DecoderEngine(sd, dev, iters=iters)
+    got = _engine_forward(eng, c, dev, forced_refs=refs.to(dev), debug=True)
+    for i in range(iters):
+        assert bit_equal(got["center_im"][i], auxs[i]["center_im"])
+        assert relerr(got["features"][i].cpu(), auxs[i]["features"]) <= FEAT_TOL
+        for k in ("pred_logits", "center_unnormalized", "ortho6d", "sem_cls_prob"):
+            assert relerr(got[k][i].cpu(), outs[i][k]) <= TOL, (k, i)
