@@ -219,7 +219,7 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
         for (int i = 0; i < 32; ++i)
           if (full || col0 + i < N) dst[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v[i]));
       } else {                               // this thread's channel row: 32 consecutive tokens
-#pragma unroll 4
+#pragma unroll                               // (full unroll: a dynamic index would push v[] into local memory)
         for (int i = 0; i < 32; ++i) {
           if (full || col0 + i < N) {
             int ld;

@@ -146,3 +146,21 @@ def test_add_ray_pe_module_mirrors_reference_parameters():
         m(torch.zeros(1, 1, 1024, 2, 2), torch.zeros(1, 1, 6), torch.zeros(1, 1, 12), torch.zeros(1, 1, 12), torch.zeros(1, 1, 12))
     planes = m._depth_planes("cpu")
     assert torch.equal(planes, O.ray_depth_planes(64, 0.25, 5.25)) and abs(planes[0].item() - 0.25) < 1e-6 and abs(planes[-1].item() - 5.25) < 1e-5
+
+
+def test_tensor_kernels_keep_their_state_in_registers(tmp_path):
+    # a dynamically indexed array in an epilogue silently moves it to local memory (it cost the K/V projection 40 % once):
+    # the GEMM and attention kernels must compile without a stack frame and without spills
+    import subprocess
+    from parq_b200 import build
+    out = str(tmp_path / "probe.so")
+    cmd = [build._nvcc()] + build.NVCC_FLAGS + ["-Xptxas", "-v", "-o", out, os.path.join(build.CSRC, "parq_api.cu")]
+    log = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout.splitlines()
+    seen = 0
+    for i, line in enumerate(log):
+        m = re.search(r"Compiling entry function '(\w+)'", line)
+        if m and re.search(r"gemm2?_tc_kernel|attn[23]?_tc_kernel", m.group(1)):
+            props = log[i + 2]
+            assert "0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads" in props, (m.group(1), props)
+            seen += 1
+    assert seen == 10          # 2 + 2 GEMM and 2 + 2 + 2 attention instantiations

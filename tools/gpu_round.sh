@@ -24,7 +24,7 @@ PY
       tail -3 gpurun_out/launches_$TAG.log ;;
     full)
       timeout 900 ncu --set full --clock-control none --import-source on \
-        -k regex:"attn2?_tc|project_sample|attn_combine|heads_final|add_ln|gn_apply|posemb" -c 14 -f -o gpurun_out/prof_${TAG}_iter \
+        -k regex:"attn[23]?_tc|attn3_combine|project_sample|attn_combine|heads_final|add_ln|gn_apply|posemb" -c 14 -f -o gpurun_out/prof_${TAG}_iter \
         python tools/prof_step.py 1 > gpurun_out/prof_${TAG}_iter.log 2>&1
       tail -2 gpurun_out/prof_${TAG}_iter.log
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm2?_tc" -c 6 -f -o gpurun_out/prof_${TAG}_gemm \
