@@ -302,7 +302,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps,
                     "note": "PARQDecoderB200.forward on pinned host tokens (bf16) + poses, double-buffered H2D on a copy stream, D2H of the last-iteration detections"},
             "gpu_launches": launches,
-            "roofline": {"kernel": "attn2_tc_kernel<bf16> (CTA-pair flash cross-attention over %d image tokens)" % Nk, "bound": "tensor",
+            "roofline": {"kernel": "attn3_tc_kernel<bf16> (CTA-pair flash cross-attention, stream-K schedule, over %d image tokens)" % Nk, "bound": "tensor",
                          "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sustained"]) if ach else None,
                          "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                          "flops_per_launch": flops, "ms_per_launch": ca_ms / max(ca_n, 1), "launches_timed": ca_n, "traffic": traffic},
