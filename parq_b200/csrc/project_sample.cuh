@@ -146,8 +146,13 @@ project_sample_kernel(const SampleParams p) {
     if (t == 0 && p.coord_pos != nullptr && !early) {
       p.coord_pos[row * 3 + 0] = px; p.coord_pos[row * 3 + 1] = py; p.coord_pos[row * 3 + 2] = pz;
     }
-    const float* Tc = p.T_cl + (static_cast<long long>(b) * p.T + t) * 12;
-    const float* cam = p.camera + (static_cast<long long>(b) * p.T + t) * 6;
+    // pose (12 floats, 48-byte rows) and camera (6 floats, 24-byte rows) as vector loads: 6 requests instead of 18
+    const float4* Tc4 = reinterpret_cast<const float4*>(p.T_cl + (static_cast<long long>(b) * p.T + t) * 12);
+    const float2* cam2 = reinterpret_cast<const float2*>(p.camera + (static_cast<long long>(b) * p.T + t) * 6);
+    const float4 t0 = __ldg(Tc4), t1 = __ldg(Tc4 + 1), t2 = __ldg(Tc4 + 2);
+    const float2 c0 = __ldg(cam2), c1 = __ldg(cam2 + 1), c2 = __ldg(cam2 + 2);
+    const float Tc[12] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w};
+    const float cam[6] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y};
     float pc[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
