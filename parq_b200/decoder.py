@@ -174,10 +174,11 @@ class DecoderEngine:
         return self._ref0_cache
 
     def forward(self, tokens, camera, T_cp, T_wp, T_wl, H, W, forced_refs=None, ref0=None, debug=False, skip_kv=False,
-                graph=False, pdl=True):
+                graph=False, pdl=True, ln_fusion=False):
         """tokens (B, T*H*W, C) bf16 (fp32 is rounded to bf16); camera (B,T,6); poses (B,T,12)/(B,1,12) fp32.
         Returns a dict of stacked per-iteration tensors (iters, B, Nq, n).
 
+        ``ln_fusion=True`` selects the experimental cluster-fused GEMM + LayerNorm kernels (same results, slower at config 2).
         ``pdl=False`` launches the kernels in plain stream order instead of with programmatic dependent launch.
         ``graph=True`` replays the whole forward (~180 kernel launches) as ONE CUDA graph captured on first
         use for this exact set of input buffers; the returned tensors are then static buffers that the next
@@ -200,7 +201,8 @@ class DecoderEngine:
         fr = f32(forced_refs) if forced_refs is not None else None
         if fr is not None and tuple(fr.shape) != (self.iters, B, self.Nq, 3):
             raise ValueError("forced_refs must be (iters, B, Nq, 3)")
-        flags = self.flags | (_lib.PARQ_FLAG_SKIP_KV if skip_kv else 0) | (0 if pdl else _lib.PARQ_FLAG_NO_PDL)
+        flags = self.flags | (_lib.PARQ_FLAG_SKIP_KV if skip_kv else 0) | (0 if pdl else _lib.PARQ_FLAG_NO_PDL) | \
+            (_lib.PARQ_FLAG_LN_FUSION if ln_fusion else 0)
         if graph:
             key = (tokens.data_ptr(), camera.data_ptr(), T_cp.data_ptr(), T_wp.data_ptr(), T_wl.data_ptr(), ref0.data_ptr(),
                    fr.data_ptr() if fr is not None else 0, B, T, H, W, flags, bool(debug), ws.data_ptr())
