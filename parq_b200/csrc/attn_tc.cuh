@@ -1,4 +1,6 @@
-// Flash-style attention for head_dim 256 on tcgen05/TMEM (sm_100a), split over keys.
+// Flash-style attention for head_dim 256 on tcgen05/TMEM (sm_100a), split over keys -- the single-CTA kernel.
+// (attn2_tc.cuh is the same algorithm on a CTA pair with cta_group::2, attn3_tc.cuh adds the stream-K schedule;
+//  this one serves query counts that are not a multiple of 256 and defines the shared constants.)
 //
 // Replaces nn.MultiheadAttention's softmax(QK^T)V of the PARQ decoder layer
 // (reference transformer_parq.py:372-382; torch multi_head_attention_forward),
@@ -23,6 +25,8 @@
 //   Q   [B*Nq , H*256]   rows = queries, pre-scaled by 1/sqrt(256)
 //   K   [B*Nk , H*256]   rows = keys
 //   V^T [H*256, ldv  ]   rows = channels, columns = keys of all clips (b*Nk + key)
+// or, for the decoder's cross-attention (kv_tiled), the tile-contiguous caches written by the projection GEMM:
+//   K   [clip*tile][head][128 keys][256 ch],  V^T [clip*tile][head][256 ch][128 keys]
 // Output: un-normalised partial O (fp32), running max m (log2 units) and sum l per
 // (clip, head, split, query); attn_combine_kernel merges the splits.
 #pragma once

@@ -14,11 +14,13 @@
 // ((a0*b0 + a1*b1) + a2*b2) without FMA, the point transform as fma(p2,r2,fma(p1,r1,p0*r0)) + t,
 // then x/z (IEEE divide), *f, +c.  Never compile this file with --use_fast_math.
 //
-// Memory behaviour: the gather is HBM/L2 bound.  A warp owns 256 consecutive channels of one
-// (clip, query); every lane moves 16-byte vectors (8 bf16 channels), so each bilinear corner is a
-// fully coalesced 512-byte request and the two horizontally adjacent corners form one contiguous
-// 2*C*2-byte segment.  Per-view projection parameters are computed once by lane t and broadcast with
-// warp shuffles; four views (16 independent 16-byte loads per lane) are kept in flight.
+// Memory behaviour: the gather is HBM/L2 bound.  A block handles four queries: one THREAD per (query, view)
+// pair projects once into shared memory (the IEEE-exact projection is instruction-heavy), then warp w owns
+// channels [256w, 256w+256) of every query; every lane moves 16-byte vectors (8 bf16 channels), so each
+// bilinear corner is a fully coalesced 512-byte request and the two horizontally adjacent corners form one
+// contiguous 2*C*2-byte segment.  Views without an in-bounds corner cost nothing (compacted by a ballot), two
+// views (8 independent 16-byte loads per lane) are in flight, and the first loads of the next query are issued
+// before the epilogue of the current one.
 #pragma once
 #include "ptx.cuh"
 
