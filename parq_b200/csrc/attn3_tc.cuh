@@ -219,8 +219,10 @@ attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (++stage == NS) { stage = 0; phase ^= 1; }
           umma_commit_pair(pv_done);
         }
-        umma_commit_pair(q_empty);        // every MMA of the segment retired: Q (and the S buffers) are free
         u += s.n;
+        // every MMA of the segment retired: Q may be reloaded.  Not after the last segment: nobody would wait for it, and
+        // a multicast arrival must not be in flight towards a CTA that is about to leave.
+        if (u < u1) umma_commit_pair(q_empty);
       }
     }
   } else if (warp >= 4) {                 // ---------------- softmax / correction / epilogue (both CTAs)
