@@ -179,8 +179,9 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int tile = pair; tile < num_tiles; tile += npair) {
         int m0, n0;
         tile_origin(tile, m0, n0);
+        const int asplit = (p.a_split_n > 0 && n0 >= p.a_split_n) ? p.a_split_off : 0;
         for (int t = 0; t < nterm_loops; ++t) {
-          const int ak = a_off(t), bk = b_off(t);
+          const int ak = a_off(t) + asplit, bk = b_off(t);
           for (int kb = 0; kb < kb_per_term; ++kb) {
             const bool prefetched = pre > 0;
             if (!prefetched) {
@@ -191,7 +192,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             if (!(prefetched && p.const_operand == 1)) {
               tma_load_2d_pair(a_ptr(stage, 0), &tmA, &full_bar[stage], ak + kb * BK, m0);
-              if (dual) tma_load_2d_pair(a_ptr(stage, 1), &tmA, &full_bar[stage], a_off(1) + kb * BK, m0);
+              if (dual) tma_load_2d_pair(a_ptr(stage, 1), &tmA, &full_bar[stage], a_off(1) + asplit + kb * BK, m0);
             }
             if (!(prefetched && p.const_operand == 2))
               tma_load_2d_pair(b_ptr(stage), &tmB, &full_bar[stage], bk + kb * BK, n0 + static_cast<int>(rank) * (BN / 2));

@@ -76,6 +76,8 @@ struct GemmParams {
   int a_koff[3];       // element offset of each term along A's K axis
   int b_koff[3];
   int const_operand;   // 1: A holds constants (weights), 2: B does -- its first tiles are fetched before the PDL wait
+  int a_split_n;       // > 0: output columns >= a_split_n read A at an extra K offset of a_split_off (two independent
+  int a_split_off;     //      products that share M, e.g. the centre / rotation head layers, as ONE launch)
   int dual_a;          // nterms == 2 with the SAME B segment (A_hi W + A_lo W): a ring stage holds both A tiles and one B
                        // tile, so W is fetched from L2 once per k-block instead of twice (3 stages of 64 KB)
   GemmEpilogue ep;
@@ -374,8 +376,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m0, n0;
         tile_origin(tile, m0, n0);
+        const int asplit = (p.a_split_n > 0 && n0 >= p.a_split_n) ? p.a_split_off : 0;
         for (int t = 0; t < nterm_loops; ++t) {
-          const int ak = a_off(t), bk = b_off(t);
+          const int ak = a_off(t) + asplit, bk = b_off(t);
           for (int kb = 0; kb < kb_per_term; ++kb) {
             const bool prefetched = pre > 0;       // first k-blocks of this CTA's first tile
             if (!prefetched) {
@@ -386,7 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (!(prefetched && p.const_operand == 1)) {
               tma_load_2d(a_ptr(stage, 0), &tmA, &full_bar[stage], ak + kb * BK, m0);
-              if (dual) tma_load_2d(a_ptr(stage, 1), &tmA, &full_bar[stage], a_off(1) + kb * BK, m0);
+              if (dual) tma_load_2d(a_ptr(stage, 1), &tmA, &full_bar[stage], a_off(1) + asplit + kb * BK, m0);
             }
             if (!(prefetched && p.const_operand == 2)) tma_load_2d(b_ptr(stage), &tmB, &full_bar[stage], bk + kb * BK, n0);
             if (++stage == nst) { stage = 0; phase ^= 1; }

@@ -1190,14 +1190,15 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       { ProfScope ps(TAG_ROWWISE, st); launch_k(gn_apply_kernel, dim3(R), dim3(256), 0, st, F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1),
                                                PF(P.ctr1_g), PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1)); }
       CUDA_TRY(cudaGetLastError());
-      for (int hd = 0; hd < 2; ++hd) {
-        memset(&g, 0, sizeof(g));
-        g.M = R; g.N = C; term_offsets(g, C, w_lo, hd * 2 * C);
-        g.ep = epilogue_none();
-        g.ep.out_f32 = F32(W.h2) + hd * C; g.ep.ld_f32 = 2 * C;
-        g.ep.gn_out = reinterpret_cast<double2*>(ws + W.gn2) + hd * (C / 256); g.ep.gn_stride = GN_SLOTS_PER_MTILE;
-        TRY(launch_gemm(st, ws + W.a_h1, R, 4 * C, pk + (hd == 0 ? P.ctr4 : P.rot4), C, 2 * C, g));
-      }
+      // second hidden layer of the centre and rotation heads as ONE launch: the two weight matrices are adjacent in the
+      // packed buffer (one B operand of 2C rows), output columns >= C read the rotation half of a_h1
+      memset(&g, 0, sizeof(g));
+      g.M = R; g.N = 2 * C; term_offsets(g, C, w_lo, 0);
+      g.a_split_n = C; g.a_split_off = 2 * C;
+      g.ep = epilogue_none();
+      g.ep.out_f32 = F32(W.h2); g.ep.ld_f32 = 2 * C;
+      g.ep.gn_out = reinterpret_cast<double2*>(ws + W.gn2); g.ep.gn_stride = GN_SLOTS_PER_MTILE;
+      TRY(launch_gemm(st, ws + W.a_h1, R, 4 * C, pk + P.ctr4, 2 * C, 2 * C, g));
       hp.x = x3; hp.h2 = F32(W.h2); hp.partial = reinterpret_cast<const double2*>(ws + W.gn2);
       hp.gamma_c = PF(P.ctr5_g); hp.beta_c = PF(P.ctr5_b); hp.gamma_r = PF(P.rot5_g); hp.beta_r = PF(P.rot5_b);
       hp.w_cls = PF(P.cls_w); hp.b_cls = PF(P.cls_b); hp.w_size = PF(P.size_w); hp.b_size = PF(P.size_b);
