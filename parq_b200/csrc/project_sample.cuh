@@ -261,6 +261,13 @@ project_sample_kernel(const SampleParams p) {
       p.coord_pos[r * 3 + a] = __fadd_rn(__fmul_rn(p.ref[r * 3 + a], p.span[a]), p.lo[a]);
     }
   }
+  if (p.a_xpe != nullptr) {
+    // pull the positional features of the block's later queries towards the SM now (no registers involved): their
+    // loads at the top of each query then hit instead of adding an L2 round trip per query
+#pragma unroll
+    for (int qi = 1; qi < SAMPLE_QPB; ++qi)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.pe + static_cast<long long>(row0 + qi) * p.C + ch));
+  }
 #pragma unroll 1
   for (int qi = 0; qi < SAMPLE_QPB; ++qi) {
     const int row = row0 + qi;
