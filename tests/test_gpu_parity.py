@@ -579,3 +579,40 @@ def test_cluster_fused_layernorm_path_matches_default(dev):
         assert relerr(fused["decoder_out"][i], base["decoder_out"][i]) <= 2e-4
         for k in ("pred_logits", "center_unnormalized", "ortho6d", "sem_cls_prob"):
             assert relerr(fused[k][i].cpu(), gold[k][i]) <= TOL, (k, i)
+
+
+def test_free_running_divergence_report(dev):
+    """the free-running recurrence (no teacher forcing) is reported, not gated, next to the oracle's own
+    sensitivity: the oracle re-run on tokens perturbed by a relative 1e-6 (fp32 rounding scale) and 2^-9 (bf16 operand
+    rounding scale, what the tensor-core attention does to Q/K/V).  Written to gpurun_out/free_running.md."""
+    import os
+    B, T, H, W, Nq, seed = 1, 8, 30, 40, 256, 33
+    sd = I.make_weights(seed, Nq)
+    tokens = I.make_tokens(B, T, H, W, seed=seed)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+    c = dict(tokens=tokens, camera=cam._data, T_cp=Tcp._data, T_wp=Twp._data, T_wl=Twl._data, H=H, W=W)
+    run = lambda tk: O.decoder_forward(tk, cam._data, Tcp._data, Twp._data, Twl._data, sd)
+    base = run(tokens)
+    g = torch.Generator().manual_seed(seed)
+    noise = torch.randn(tokens.shape, generator=g)
+    pert = {"1e-6": run(tokens.float() * (1 + 1e-6 * noise)), "2^-9": run(tokens.float() * (1 + 2.0 ** -9 * noise))}
+    free = _engine_forward(DecoderEngine(sd, dev), c, dev)
+    keys = ("center_unnormalized", "pred_logits")
+    lines = ["| iteration | " + " | ".join("GPU free-running %s" % k for k in keys) + " | " +
+             " | ".join("oracle, tokens x(1+%s n) %s" % (p, k) for p in pert for k in keys) + " |",
+             "|---|" + "---|" * (len(keys) * (1 + len(pert)))]
+    for i in range(8):
+        row = [relerr(free[k][i].cpu(), base[i][k]) for k in keys]
+        row += [relerr(pert[p][i][k], base[i][k]) for p in pert for k in keys]
+        assert all(np.isfinite(row))
+        lines.append("| %d | " % i + " | ".join("%.2e" % v for v in row) + " |")
+    assert relerr(free["center_unnormalized"][0].cpu(), base[0]["center_unnormalized"]) <= TOL
+    report = "\n".join(lines)
+    print("\n" + report)
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/free_running.md", "w") as f:
+            f.write("max|d|/max|ref| per iteration vs the fp32 oracle, 1 clip x 8 views x 30x40, 256 queries (tests/test_gpu_parity.py::"
+                    "test_free_running_divergence_report)\n\n" + report + "\n")
+    except OSError:
+        pass
