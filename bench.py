@@ -7,8 +7,8 @@
 
 A step = one pass of the whole decoder (hoisted K/V projection + 8 recurrent iterations) over one batch of
 16 synthetic clips per GPU (8 views of 60x80 tokens x 1024 channels, 256 queries).  Prints ONE JSON line.
-`--impl reference` times the CPU port of the reference's own decoder (oracle/parq_oracle.py, reference op
-order incl. the per-iteration K/V re-projection) on the host cores for a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference PARQDecoder.forward (from /root/reference, or its bytecode tree
+oracle/_ref on the GPU box) on the host cores for a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -86,59 +86,179 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ reference arm --
-def oracle_clip_inputs(seed=100):
+# The UNMODIFIED reference (model/parq_decoder.py:30 PARQDecoder, imported by oracle/ref_loader.py from /root/reference
+# or, on the GPU box, from the bytecode tree oracle/_ref that oracle/build_ref.py compiled from it) on the host cores.
+def reference_clip_inputs(B=1, seed=100):
     from parq_b200 import inputs as I
     sd = I.make_weights(0, CFG["queries"])
-    tokens = I.make_tokens(1, CFG["views"], CFG["H"], CFG["W"], seed=seed)
-    cam, Tcp, Twp, Twl = I.make_geometry(1, CFG["views"], CFG["H"], CFG["W"], seed=seed)
+    tokens = I.make_tokens(B, CFG["views"], CFG["H"], CFG["W"], seed=seed)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, CFG["views"], CFG["H"], CFG["W"], seed=seed)
     return sd, tokens, cam._data, Tcp._data, Twp._data, Twl._data
 
 
-def time_oracle(iters, reps, threads):
-    """Seconds per clip of the reference-order CPU decoder on `threads` host threads; `iters` of the 8
-    iterations are executed (every iteration is identical work) and the time is scaled to a full clip."""
-    from oracle import parq_oracle as O
+def reference_runner(dec_layers, device="cpu", B=1):
+    """Returns (callable running one PARQDecoder.forward over B clips, kind).  kind = "reference" when the real module
+    is importable, else "port" (oracle/parq_oracle.py in the reference's op order)."""
+    sd, tokens, cam, Tcp, Twp, Twl = reference_clip_inputs(B)
+    try:
+        from oracle import ref_loader as RL
+        ns = RL.load_reference()
+        m = RL.build_decoder(sd, CFG["queries"], dec_layers, device=device)
+        args = (tokens.to(device), ns.Camera(cam.to(device)), ns.Pose(Tcp.to(device)), ns.Pose(Twp.to(device)), ns.Pose(Twl.to(device)))
+
+        def run():
+            with torch.no_grad():
+                return m(*args)
+        return run, "reference"
+    except Exception as e:                                   # no reference tree: fall back to the port, and say so
+        print("reference module unavailable (%s): timing the oracle port" % e, file=sys.stderr)
+        from oracle import parq_oracle as O
+
+        def run():
+            return O.decoder_forward(tokens, cam, Tcp, Twp, Twl, sd, iters=dec_layers, hoist_kv=False)
+        return run, "port"
+
+
+def time_cpu_reference(threads):
+    """PARQDecoder.forward, fp32, eval, no_grad, all host threads, config-1 shape (1 clip, 8 views of
+    60x80 tokens, 256 queries, 8 iterations); 1 warm-up + 3 timed runs, median.  Returns (seconds per clip, kind)."""
     torch.set_num_threads(threads)
-    sd, tokens, cam, Tcp, Twp, Twl = oracle_clip_inputs()
-    best = None
-    for _ in range(reps):
+    run, kind = reference_runner(CFG["iterations"])
+    run()
+    ts = []
+    for _ in range(3):
         t0 = time.perf_counter()
-        O.decoder_forward(tokens, cam, Tcp, Twp, Twl, sd, iters=iters, hoist_kv=False)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return best * CFG["iterations"] / iters
+        run()
+        ts.append(time.perf_counter() - t0)
+    return statistics.median(ts), kind
+
+
+def time_c1_pipeline(threads):
+    """BASELINE.json configs[0]: random-init torchvision ResNet50-FPN + the reference's AddRayPE + PARQDecoder on the host
+    cores for 1 clip of 8 views 240x320 (model/resnet_fpn.py:16-91, ray_positional_encoding.py:61, parq_lightning.py:68-88).
+    The backbone is built with pretrained=False (no network).  1 warm-up + 3 timed, median seconds per clip, or None."""
+    try:
+        from oracle import ref_loader as RL
+        from parq_b200 import inputs as I
+        from torchvision.models.detection.backbone_utils import resnet_fpn_backbone
+        import einops
+        ns = RL.load_reference()
+        torch.set_num_threads(threads)
+        T, H, W = CFG["views"], CFG["H"], CFG["W"]
+        torch.manual_seed(0)
+        try:
+            body = resnet_fpn_backbone(backbone_name="resnet50", weights=None, trainable_layers=5).eval()
+        except TypeError:
+            body = resnet_fpn_backbone("resnet50", pretrained=False, trainable_layers=5).eval()
+        rfpn = RL.load_resnet_fpn()
+        fpn = rfpn.ResnetFPN.__new__(rfpn.ResnetFPN)          # the reference's forward (upsample + concat + camera scale) around
+        torch.nn.Module.__init__(fpn)                         # a random-init backbone: its __init__ downloads weights
+        from torchvision import transforms
+        fpn.resnet_fpn, fpn.freeze, fpn.layer = body, False, "0"
+        fpn.transform = transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+        rpe = RL.load_add_ray_pe()(1024, [-3, 3, -2, 0.5, 0.25, 5.25], 64, 0.25, 5.25).eval()
+        rpe.load_state_dict(I.make_raype_weights(0), strict=True)
+        dec = RL.build_decoder(I.make_weights(0, CFG["queries"]), CFG["queries"], CFG["iterations"])
+        cam, Tcp, Twp, Twl = I.make_geometry(1, T, 4 * H, 4 * W, seed=100)
+        g = torch.Generator().manual_seed(100)
+        batch0 = {"rgb_img": torch.rand(1, T, 3, 4 * H, 4 * W, generator=g), "camera": ns.Camera(cam._data)}
+        poses = [ns.Pose(Tcp._data), ns.Pose(Twp._data), ns.Pose(Twl._data)]
+
+        def run():
+            with torch.no_grad():
+                batch = fpn(dict(batch0))
+                enc = rpe(batch["all_features"], batch["camera_feature"], *poses)
+                feat = batch["all_features"] + enc
+                tok = einops.rearrange(einops.rearrange(feat, "b t c h w -> b t h w c"), "b t h w c -> b (t h w) c")
+                return dec(tok.contiguous(), batch["camera_feature"], *poses)
+        run()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            run()
+            ts.append(time.perf_counter() - t0)
+        return statistics.median(ts)
+    except Exception as e:
+        print("config-1 pipeline baseline unavailable: %s" % e, file=sys.stderr)
+        return None
+
+
+def gpu_torch_baseline(dev, B):
+    """"the bar is stock PyTorch (ATen/cuBLAS/cuDNN) on the same B200".  The unmodified reference module on
+    the GPU, same batch as our arm (B clips, tokens resident), 1 warm-up + 3 timed forwards (CUDA events), median:
+    fp32 with TF32 off (the parity-grade setting), fp32 with TF32 allowed, and bf16 autocast."""
+    res = {}
+    try:
+        run, kind = reference_runner(CFG["iterations"], device=dev, B=B)
+        if kind != "reference":
+            return {"unavailable": "reference module not importable on this box"}
+        old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        for name, tf32, amp in (("fp32_tf32_off", False, False), ("tf32", True, False), ("bf16_autocast", True, True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            ts = []
+            for i in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                    run()
+                e1.record()
+                torch.cuda.synchronize()
+                if i:
+                    ts.append(e0.elapsed_time(e1))
+            ms = statistics.median(ts)
+            res[name] = {"clips_per_s": B / (ms * 1e-3), "ms_per_step": ms}
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        res["what"] = ("unmodified reference PARQDecoder.forward (model/parq_decoder.py:134) through stock PyTorch on this GPU, %d clips "
+                       "resident on the device, 1 warm-up + 3 timed, median" % B)
+    except Exception as e:
+        res["unavailable"] = "%s: %s" % (type(e).__name__, e)
+    finally:
+        torch.cuda.empty_cache()
+    return res
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import parq_oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd, tokens, cam, Tcp, Twp, Twl = oracle_clip_inputs()
-    # size the per-step sample so that (steps + warmup) steps end within ~4 minutes
+    # size the per-step sample so that (steps + warmup) steps end within ~4 minutes: the reference is built with
+    # DEC_LAYERS = iters (every recurrent iteration is identical work) and the time is scaled to the 8 of the workload
+    run1, kind = reference_runner(1)
+    run1()
     t0 = time.perf_counter()
-    O.decoder_forward(tokens, cam, Tcp, Twp, Twl, sd, iters=1, hoist_kv=False)
+    run1()
     t_it = time.perf_counter() - t0
     total = args.steps + args.warmup
     iters = max(1, min(CFG["iterations"], int(240.0 / max(total * t_it, 1e-6))))
+    run, kind = reference_runner(iters)
     for _ in range(args.warmup):
-        O.decoder_forward(tokens, cam, Tcp, Twp, Twl, sd, iters=iters, hoist_kv=False)
+        run()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.decoder_forward(tokens, cam, Tcp, Twp, Twl, sd, iters=iters, hoist_kv=False)
+        run()
     dt = (time.perf_counter() - t0) / args.steps
     sec_per_clip = dt * CFG["iterations"] / iters
     value = 1.0 / sec_per_clip
-    sample = ("1 clip per step (8 views x 4800 tokens x 1024 ch, 256 queries), %d of 8 recurrent iterations executed and scaled to 8; "
-              "reference op order (K/V projection repeated every iteration), fp32, torch CPU" % iters)
+    what = "the unmodified reference PARQDecoder.forward (model/parq_decoder.py:134-163)" if kind == "reference" else \
+        "the oracle port in the reference's op order (K/V projection repeated every iteration)"
+    sample = ("1 clip per step (8 views x 4800 tokens x 1024 ch, 256 queries), %d of 8 recurrent iterations executed "
+              "(DEC_LAYERS=%d) and scaled to 8; %s, fp32, torch CPU, %d threads" % (iters, iters, what, threads))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.gpus == 1:
+        c1 = time_c1_pipeline(threads)
+        if c1 is not None:
+            line["config1_pipeline"] = {"seconds_per_clip": c1, "clips_per_s": 1.0 / c1,
+                                        "what": "BASELINE.json configs[0]: random-init ResNet50-FPN + reference AddRayPE + PARQDecoder, "
+                                                "1 clip x 8 views 240x320, fp32 CPU, 1 warm-up + 3 timed, median"}
     print(json.dumps(line), flush=True)
 
 
@@ -279,6 +399,8 @@ def run_ours(args):
         dist.all_reduce(lt)
         launches = int(lt.item())
 
+    gpu_torch = gpu_torch_baseline(dev, B) if (world == 1 and rank == 0) else None
+
     if rank == 0:
         pk = peaks()
         step_ms = ms / args.steps
@@ -319,10 +441,12 @@ def run_ours(args):
         }
         if world == 1:
             threads = os.cpu_count() or 1
-            sec = time_oracle(iters=2, reps=1, threads=threads)
-            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "1 clip (8 views x 4800 tokens x 1024 ch, 256 queries), 2 of 8 iterations timed and scaled to 8; "
-                                              "oracle port in the reference's op order (K/V re-projected every iteration), fp32 torch CPU"}
+            sec, kind = time_cpu_reference(threads)
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": "1 clip (8 views x 4800 tokens x 1024 ch, 256 queries, all 8 iterations), 1 warm-up + 3 timed, median; "
+                                              + ("the unmodified reference PARQDecoder.forward" if kind == "reference" else "oracle port, reference op order")
+                                              + ", fp32 torch CPU"}
+            line["gpu_torch_baseline"] = gpu_torch
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,9 +1,10 @@
 """Loader for the UNMODIFIED reference decoder (test infrastructure only).
 
-Only usable where /root/reference exists (the build container).  It is used by
-tests/golden/make_golden.py to produce the committed fixtures and by the
-CPU-side tests that pin oracle/parq_oracle.py against the real reference.
-Nothing in the product path (parq_b200/) may import this module.
+Looks for the reference in /root/reference (sources, the build container) and, when that is absent
+(the GPU box), in oracle/_ref -- the sourceless bytecode tree oracle/build_ref.py compiles from the same
+files.  It is used by tests/golden/make_golden.py to produce the committed fixtures, by the tests that pin
+oracle/parq_oracle.py and the CUDA path against the real reference, and by bench.py's reference arm /
+cpu_baseline / gpu_torch_baseline legs.  Nothing in the product path (parq_b200/) may import this module.
 
 The reference needs two sys.modules stubs to import under torch>=2
 (SURVEY.md App. C): `torch._six` (utils/wrappers.py:31) and
@@ -11,16 +12,31 @@ The reference needs two sys.modules stubs to import under torch>=2
 `model` package is registered empty so model/__init__.py (which needs real
 Lightning) is bypassed.
 """
+import importlib.machinery
 import importlib.util
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PARQ_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    for cand in (os.environ.get("PARQ_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and (os.path.isfile(os.path.join(cand, "model", "parq_decoder.py")) or
+                     os.path.isfile(os.path.join(cand, "model", "parq_decoder.pyc"))):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
+# "source": the reference tree itself; "bytecode": oracle/_ref (same modules, compiled, unmodified)
+REFERENCE_KIND = "source" if os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "parq_decoder.py")) else "bytecode"
 
 
 def reference_available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "parq_decoder.py"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "parq_decoder.py")) or \
+        os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "parq_decoder.pyc"))
 
 
 class _NS(dict):
@@ -42,9 +58,25 @@ def decoder_cfg(num_queries=256, dec_layers=8, for_vis=False):
 _loaded = {}
 
 
+def load_module(name):
+    """Execute reference module `name` (e.g. "model.resnet_fpn") from its .py, or from its .pyc in oracle/_ref."""
+    if name in sys.modules and name in _loaded:
+        return sys.modules[name]
+    base = os.path.join(REFERENCE_ROOT, *name.split("."))
+    if os.path.isfile(base + ".py"):
+        spec = importlib.util.spec_from_file_location(name, base + ".py")
+    else:
+        spec = importlib.util.spec_from_loader(name, importlib.machinery.SourcelessFileLoader(name, base + ".pyc"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    _loaded[name] = m
+    return m
+
+
 def load_reference():
     """Returns a namespace with the reference's PARQDecoder, project, Pose, Camera."""
-    if _loaded:
+    if "ns" in _loaded:
         return _loaded["ns"]
     if not reference_available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
@@ -64,17 +96,30 @@ def load_reference():
     pkg.__path__ = [os.path.join(REFERENCE_ROOT, "model")]
     sys.modules["model"] = pkg
 
-    def _load(name, path):
-        spec = importlib.util.spec_from_file_location(name, path)
-        m = importlib.util.module_from_spec(spec)
-        sys.modules[name] = m
-        spec.loader.exec_module(m)
-        return m
-
     import utils as ref_utils  # reference utils/wrappers.py
-    dec = _load("model.parq_decoder", os.path.join(REFERENCE_ROOT, "model", "parq_decoder.py"))
+    dec = load_module("model.parq_decoder")
     tp = sys.modules["model.transformer_parq"]
     ns = types.SimpleNamespace(PARQDecoder=dec.PARQDecoder, project=tp.project, transformer_parq=tp,
                                Pose=ref_utils.Pose, Camera=ref_utils.Camera, Obb3D=ref_utils.Obb3D, decoder_module=dec)
     _loaded["ns"] = ns
     return ns
+
+
+def load_add_ray_pe():
+    """The reference's AddRayPE class (model/ray_positional_encoding.py:29)."""
+    load_reference()
+    return load_module("model.ray_positional_encoding").AddRayPE
+
+
+def load_resnet_fpn():
+    """The reference's model/resnet_fpn.py module (ResnetFPN :16; needs torchvision)."""
+    load_reference()
+    return load_module("model.resnet_fpn")
+
+
+def build_decoder(sd, num_queries=256, dec_layers=8, for_vis=False, device="cpu"):
+    """An instance of the unmodified PARQDecoder (model/parq_decoder.py:30) in eval mode with the given state dict."""
+    ns = load_reference()
+    m = ns.PARQDecoder(decoder_cfg(num_queries, dec_layers, for_vis)).eval()
+    m.load_state_dict(sd, strict=True)
+    return m.to(device)

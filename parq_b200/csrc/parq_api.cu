@@ -8,6 +8,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "../../include/parq_b200.h"
 #include "attn_tc.cuh"
 #include "attn2_tc.cuh"
@@ -15,7 +18,6 @@
 #include "fpn.cuh"
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
-#include "gemm_ln.cuh"
 #include "parse_pred.cuh"
 #include "project_sample.cuh"
 #include "raype.cuh"
@@ -80,11 +82,22 @@ struct DeviceInfo {
   int ok = 0;     // 0 unknown, 1 sm_100, -1 other arch / error
   int sms = 148;
 };
+constexpr int MAX_DEVICES = 64;
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
+// cached per device ordinal (a thread may drive several GPUs one after the other)
 static DeviceInfo& device_info() {
-  static thread_local DeviceInfo info;
+  static DeviceInfo infos[MAX_DEVICES];
+  static std::mutex mu;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(mu);
+  DeviceInfo& info = infos[dev];
   if (info.ok == 0) {
-    int dev = 0, major = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
+    int major = 0, sms = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
       info.ok = (major == 10) ? 1 : -1;
       info.sms = sms > 0 ? sms : 148;
@@ -95,6 +108,28 @@ static DeviceInfo& device_info() {
   }
   return info;
 }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) property of a kernel: the opt-in is
+// remembered per (device ordinal, kernel), not per thread.
+static int ensure_dyn_smem(const void* fn, size_t bytes) {
+  struct Entry { const void* fn; size_t bytes; };
+  static std::vector<Entry> tab[MAX_DEVICES];
+  static std::mutex mu;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(mu);
+  for (Entry& e : tab[dev]) {
+    if (e.fn == fn) {
+      if (e.bytes >= bytes) return PARQ_OK;
+      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+      e.bytes = bytes;
+      return PARQ_OK;
+    }
+  }
+  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  tab[dev].push_back(Entry{fn, bytes});
+  return PARQ_OK;
+}
+#define OPT_IN_SMEM(kernel, bytes) TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kernel), bytes))
+
 static int require_sm100() {
   DeviceInfo& d = device_info();
   if (d.ok != 1) return fail(PARQ_ERR_ARCH, "parq_b200 requires an sm_100 (B200) device; no fallback path exists");
@@ -206,14 +241,10 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
   CUtensorMap tmA, tmB;
   TRY(make_map(&tmA, A, a_rows, a_cols, a_cols, gemm::BM));
   TRY(make_map(&tmB, Bw, b_rows, b_cols, b_cols, pairk ? gemm2::BN / 2 : gemm::BN));
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(gemm2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(gemm2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2::SMEM_BYTES));
-    attr_set = true;
-  }
+  OPT_IN_SMEM(gemm_tc_kernel<false>, gemm::SMEM_BYTES);
+  OPT_IN_SMEM(gemm_tc_kernel<true>, gemm::SMEM_BYTES);
+  OPT_IN_SMEM(gemm2_tc_kernel<false>, gemm2::SMEM_BYTES);
+  OPT_IN_SMEM(gemm2_tc_kernel<true>, gemm2::SMEM_BYTES);
   GemmParams gpl = gp;
   CUtensorMap tmC = tmA;                    // placeholder unless the channels-first addend goes through TMA
   gpl.ep.add_tma = 0;
@@ -238,39 +269,6 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
       launch_k(gemm_tc_kernel<true>, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, tmC, gpl);
     else
       launch_k(gemm_tc_kernel<false>, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, tmC, gpl);
-  }
-  CUDA_TRY(cudaGetLastError());
-  return PARQ_OK;
-}
-
-// Linear + residual + LayerNorm in one launch (gemm_ln.cuh): A = [hi|lo] activations (R, 2K), W packed [hi|lo] (1024, 2K)
-static int launch_gemm_ln(cudaStream_t st, const void* A, int R, int K, const void* Wp, bool w_lo, const float* bias, const float* resid,
-                          const float* gamma, const float* beta, const float* pe, float* x_out, __nv_bfloat16* a_x, __nv_bfloat16* a_xpe) {
-  if (K <= 0 || K % gemm::BK != 0) return fail(PARQ_ERR_SHAPE, "GEMM K=%d must be a positive multiple of 64", K);
-  CUtensorMap tmA, tmB;
-  TRY(make_map(&tmA, A, R, 2 * K, 2 * K, gemm::BM));
-  TRY(make_map(&tmB, Wp, gemmln::N, 2 * K, 2 * K, gemm::BN));
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemmln::SMEM_BYTES));
-    attr_set = true;
-  }
-  GemmLnParams lp;
-  memset(&lp, 0, sizeof(lp));
-  lp.M = R; lp.K = K;
-  lp.nterms = w_lo ? 3 : 2;
-  lp.a_koff[0] = 0; lp.b_koff[0] = 0;
-  lp.a_koff[1] = K; lp.b_koff[1] = 0;
-  lp.a_koff[2] = 0; lp.b_koff[2] = K;
-  lp.dual_a = (!w_lo && !g_no_dual) ? 1 : 0;
-  lp.bias = bias; lp.resid = resid; lp.gamma = gamma; lp.beta = beta; lp.pe = pe;
-  lp.x_out = x_out; lp.a_x = a_x; lp.a_xpe = a_xpe;
-  const int tiles_m = (R + gemm::BM - 1) / gemm::BM;
-  const int maxc = device_info().sms / gemmln::CLUSTER;
-  const int nclusters = tiles_m < maxc ? tiles_m : maxc;
-  {
-    ProfScope ps(TAG_GEMM, st);
-    launch_kc(gemm_ln_kernel, dim3(nclusters * gemmln::CLUSTER), dim3(gemm::THREADS), gemmln::SMEM_BYTES, st, dim3(gemmln::CLUSTER, 1, 1), tmA, tmB, lp);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
@@ -345,12 +343,8 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
     TRY(make_map(&tmK, K, static_cast<uint64_t>(B) * Nk, C, ldk, kbox));
     TRY(make_map(&tmV, Vt, C, static_cast<uint64_t>(B) * Nk, ldv, vbox));
   }
-  static thread_local bool attr_set3 = false;
-  if (!attr_set3) {
-    CUDA_TRY(cudaFuncSetAttribute(attn3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(attn3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-    attr_set3 = true;
-  }
+  OPT_IN_SMEM(attn3_tc_kernel<false>, attn::SMEM_BYTES);
+  OPT_IN_SMEM(attn3_tc_kernel<true>, attn::SMEM_BYTES);
   // Stream-K schedule (attn3_tc.cuh) for long key sequences: one CTA pair per SM pair walks a contiguous range of
   // (item, key tile) units; used when every pair gets at least 8 tiles and no split count was forced by the caller.
   if (pairk && !g_no_streamk && force_nsplit <= 0) {
@@ -399,14 +393,10 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
   const size_t rows = static_cast<size_t>(B) * H * plan.nsplit * Nq;
   ap.o_part = reinterpret_cast<float*>(scratch);
   ap.ml_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(scratch) + align_up(rows * 256 * sizeof(float), 256));
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(attn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(attn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-    attr_set = true;
-  }
+  OPT_IN_SMEM(attn_tc_kernel<false>, attn::SMEM_BYTES);
+  OPT_IN_SMEM(attn_tc_kernel<true>, attn::SMEM_BYTES);
+  OPT_IN_SMEM(attn2_tc_kernel<false>, attn::SMEM_BYTES);
+  OPT_IN_SMEM(attn2_tc_kernel<true>, attn::SMEM_BYTES);
   dim3 grid(plan.nsplit, Nq / attn::BQ, B * H);
   {
     ProfScope ps(fp16 ? TAG_SELF_ATTN : TAG_CROSS_ATTN, st);
@@ -984,11 +974,7 @@ int parq_parse_pred(const float* center, const float* size, const float* ortho6d
   int P = 32;
   while (P < K) P <<= 1;
   const size_t smem = parse_pred_smem(P);
-  static thread_local size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    CUDA_TRY(cudaFuncSetAttribute(parse_pred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem = smem;
-  }
+  OPT_IN_SMEM(parse_pred_kernel, smem);
   {
     ProfScope ps(TAG_ROWWISE, static_cast<cudaStream_t>(stream));
     launch_k(parse_pred_kernel, dim3(B), dim3((K + 31) / 32 * 32), smem, static_cast<cudaStream_t>(stream), pp, P);
@@ -1057,8 +1043,6 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const bool w_lo = (flags & PARQ_FLAG_WEIGHT_LO) != 0;
   const PdlScope pdl((flags & PARQ_FLAG_NO_PDL) == 0);
-  // Opt-in (measured slower at config 2, see gemm_ln.cuh): residual + LayerNorm inside the out-projection / FFN GEMMs
-  const bool ln_fused = (flags & PARQ_FLAG_LN_FUSION) != 0 && device_info().sms >= gemmln::CLUSTER;      // C == 1024 is enforced by check_shape
   const int C = s.C, F = s.ffn, R = s.B * s.Nq;
   auto F32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto BF = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
@@ -1120,19 +1104,14 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       TRY(launch_gemm(st, pk + P.sa_v, C, 2 * C, ws + W.a_x, R, 2 * C, g));
       TRY(launch_attention(st, ws + W.qk_s, 2 * C, ws + W.qk_s + static_cast<size_t>(C) * 2, 2 * C, ws + W.vt_s, W.ldvs, s.B, s.heads,
                            s.Nq, s.Nq, true, ws + W.scratch, W.scratch_bytes, BF(W.a_attn), W.self.nsplit));
-      if (ln_fused) {
-        TRY(launch_gemm_ln(st, ws + W.a_attn, R, C, pk + P.sa_out, w_lo, PF(P.sa_out_b), x0, PF(P.ln1_g), PF(P.ln1_b), F32(W.pe), F32(W.x1), nullptr,
-                           BF(W.a_x1pe)));
-      } else {
-        memset(&g, 0, sizeof(g));
-        g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
-        g.ep = epilogue_none(); g.ep.bias = PF(P.sa_out_b);
-        g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
-        TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.sa_out, C, 2 * C, g));
-        { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, x0, F32(W.y), PF(P.ln1_g), PF(P.ln1_b), F32(W.pe), F32(W.x1),
-                                                 nullptr, BF(W.a_x1pe), R); }
-        CUDA_TRY(cudaGetLastError());
-      }
+      memset(&g, 0, sizeof(g));
+      g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.sa_out_b);
+      g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
+      TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.sa_out, C, 2 * C, g));
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, x0, F32(W.y), PF(P.ln1_g), PF(P.ln1_b), F32(W.pe), F32(W.x1),
+                                               nullptr, BF(W.a_x1pe), R); }
+      CUDA_TRY(cudaGetLastError());
     }
     // K5: cross-attention over all image tokens (bf16 operands), out-projection, residual + LN2
     {
@@ -1145,19 +1124,14 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       TRY(launch_attention(st, ws + W.q_c, C, ws + W.Kc, C, ws + W.Vt, W.ldv, s.B, s.heads, s.Nq, Nk, false, ws + W.scratch,
                            W.scratch_bytes, BF(W.a_attn), /*library's choice: stream-K or the planned split*/ 0, /*kv_const=*/true,
                            W.kv_tiled != 0));
-      if (ln_fused) {
-        TRY(launch_gemm_ln(st, ws + W.a_attn, R, C, pk + P.ca_out, w_lo, PF(P.ca_out_b), F32(W.x1), PF(P.ln2_g), PF(P.ln2_b), nullptr, F32(W.x2),
-                           BF(W.a_x2), nullptr));
-      } else {
-        memset(&g, 0, sizeof(g));
-        g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
-        g.ep = epilogue_none(); g.ep.bias = PF(P.ca_out_b);
-        g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
-        TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.ca_out, C, 2 * C, g));
-        { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x1), F32(W.y), PF(P.ln2_g), PF(P.ln2_b), nullptr, F32(W.x2),
-                                                 BF(W.a_x2), nullptr, R); }
-        CUDA_TRY(cudaGetLastError());
-      }
+      memset(&g, 0, sizeof(g));
+      g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.ca_out_b);
+      g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
+      TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.ca_out, C, 2 * C, g));
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x1), F32(W.y), PF(P.ln2_g), PF(P.ln2_b), nullptr, F32(W.x2),
+                                               BF(W.a_x2), nullptr, R); }
+      CUDA_TRY(cudaGetLastError());
     }
     // K6: FFN, residual + LN3
     float* x3 = out->decoder_out ? out->decoder_out + static_cast<size_t>(it) * R * C : F32(W.x3);
@@ -1167,17 +1141,13 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.lin1_b); g.ep.relu = 1;
       g.ep.out_lp = ws + W.a_ffn; g.ep.ld_lp = 2 * F; g.ep.lp_lo_off = F;
       TRY(launch_gemm(st, ws + W.a_x2, R, 2 * C, pk + P.lin1, F, 2 * C, g));
-      if (ln_fused) {
-        TRY(launch_gemm_ln(st, ws + W.a_ffn, R, F, pk + P.lin2, w_lo, PF(P.lin2_b), F32(W.x2), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr));
-      } else {
-        memset(&g, 0, sizeof(g));
-        g.M = R; g.N = C; term_offsets(g, F, w_lo, 0);
-        g.ep = epilogue_none(); g.ep.bias = PF(P.lin2_b);
-        g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
-        TRY(launch_gemm(st, ws + W.a_ffn, R, 2 * F, pk + P.lin2, C, 2 * F, g));
-        { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x2), F32(W.y), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr, R); }
-        CUDA_TRY(cudaGetLastError());
-      }
+      memset(&g, 0, sizeof(g));
+      g.M = R; g.N = C; term_offsets(g, F, w_lo, 0);
+      g.ep = epilogue_none(); g.ep.bias = PF(P.lin2_b);
+      g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
+      TRY(launch_gemm(st, ws + W.a_ffn, R, 2 * F, pk + P.lin2, C, 2 * F, g));
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x2), F32(W.y), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr, R); }
+      CUDA_TRY(cudaGetLastError());
     }
     // K7: heads (two hidden layers with per-clip GroupNorm) + box update
     {
@@ -1214,11 +1184,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       { ProfScope ps(TAG_ROWWISE, st); {
         const int rpb = (R + device_info().sms - 1) / device_info().sms;     // rows per block: one block per SM
         const size_t hsm = static_cast<size_t>(HEADS_SLOTS + 4) * C * sizeof(float);
-        static thread_local bool hattr = false;
-        if (!hattr) {
-          cudaFuncSetAttribute(heads_final_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hsm));
-          hattr = true;
-        }
+        OPT_IN_SMEM(heads_final_kernel<1024>, hsm);
         launch_k(heads_final_kernel<1024>, dim3((R + rpb - 1) / rpb), dim3(512), hsm, st, hp, rpb);
       } }
       CUDA_TRY(cudaGetLastError());

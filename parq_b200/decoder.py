@@ -30,6 +30,34 @@ MEAN_SIZE = (
     (1.68820774, 0.76637348, 0.89351734), (0.85305378, 0.43925023, 0.51612006),
     (1.0, 1.0, 1.0), (1.0, 1.0, 1.0))
 
+_SCAN2CAD_CLASSES = ("chair", "table", "cabinet", "trash bin", "bookshelf", "display", "sofa", "bathtub", "other")
+
+
+def load_mean_size(path, num_cls=10):
+    """Mean-size table of a ``MEAN_SIZE_PATH`` file in the format of the reference's data/average_scan2cad.txt
+    ("name[,alias...]: [x y z] " per line), with BoxProcessor.init_mean_size's selection rule
+    (utils/parq_utils.py:45-88): for each of the 9 ScanNet classes the first line whose alias list contains the
+    class name, then two rows of ones ("other" when no line names it, and "non-object").  Returns (num_cls, 3) float64."""
+    table = []
+    with open(path, "r") as f:
+        for line in f:
+            if ": " not in line:
+                continue
+            names, vec = line.split(": ", 1)
+            vals = [float(x) for x in vec.strip().strip("[]").split()]
+            table.append((names.split(","), vals[:3]))
+    rows = []
+    for cls in _SCAN2CAD_CLASSES:
+        for names, vals in table:
+            if cls in names:
+                rows.append(vals)
+                break
+    rows += [[1.0, 1.0, 1.0], [1.0, 1.0, 1.0]]
+    if len(rows) < num_cls:
+        raise ValueError("%s yields %d mean-size rows, the classifier has %d classes" % (path, len(rows), num_cls))
+    return torch.tensor(rows, dtype=torch.float64)[:num_cls]
+
+
 OUTPUT_KEYS = (("pred_logits", None), ("center_unnormalized", 3), ("size_unnormalized", 3), ("ortho6d", 6),
                ("sem_cls_prob", None), ("coord_pos", 3))
 
@@ -70,7 +98,9 @@ def make_shape(B, T, H, W, C_, Nq, heads, ffn, iters, num_cls, scale):
 class DecoderEngine:
     """Packed weights + workspace + calls into the C ABI for one device."""
 
-    def __init__(self, state_dict, device, heads=4, num_cls=10, scale=(-3, 3, -2, 0.5, 0.25, 5.25), iters=8):
+    def __init__(self, state_dict, device, heads=4, num_cls=10, scale=(-3, 3, -2, 0.5, 0.25, 5.25), iters=8, mean_size=None):
+        """``mean_size``: (>= num_cls, 3) table of BoxProcessor.mean_size_arr (float64 in the reference); default = the
+        table of the reference's data/average_scan2cad.txt."""
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -109,7 +139,10 @@ class DecoderEngine:
             t = sd[key].detach().to(self.device, torch.float32).contiguous()
             keep[field] = t
             setattr(w, field, t.data_ptr())
-        keep["mean_size"] = torch.tensor(MEAN_SIZE, dtype=torch.float64)[: num_cls].float().to(self.device).contiguous()
+        ms = torch.tensor(MEAN_SIZE, dtype=torch.float64) if mean_size is None else torch.as_tensor(mean_size).detach().cpu().double()
+        if ms.dim() != 2 or ms.shape[0] < num_cls or ms.shape[1] != 3:
+            raise ValueError("mean_size must be (>= %d, 3), got %s" % (num_cls, tuple(ms.shape)))
+        keep["mean_size"] = ms[: num_cls].float().to(self.device).contiguous()      # .float() of the float64 table, parq_utils.py:98
         keep["dim_t"] = _dim_t(self.device).contiguous()
         w.mean_size = keep["mean_size"].data_ptr()
         w.dim_t = keep["dim_t"].data_ptr()
@@ -174,59 +207,93 @@ class DecoderEngine:
         return self._ref0_cache
 
     def forward(self, tokens, camera, T_cp, T_wp, T_wl, H, W, forced_refs=None, ref0=None, debug=False, skip_kv=False,
-                graph=False, pdl=True, ln_fusion=False):
+                graph=False, pdl=True):
         """tokens (B, T*H*W, C) bf16 (fp32 is rounded to bf16); camera (B,T,6); poses (B,T,12)/(B,1,12) fp32.
         Returns a dict of stacked per-iteration tensors (iters, B, Nq, n).
 
-        ``ln_fusion=True`` selects the experimental cluster-fused GEMM + LayerNorm kernels (same results, slower at config 2).
         ``pdl=False`` launches the kernels in plain stream order instead of with programmatic dependent launch.
-        ``graph=True`` replays the whole forward (~180 kernel launches) as ONE CUDA graph captured on first
-        use for this exact set of input buffers; the returned tensors are then static buffers that the next
-        replay overwrites."""
+        ``graph=True`` replays the whole forward as ONE CUDA graph captured on first use per shape (see
+        ``_forward_graph``); the returned tensors are then static buffers that the next replay overwrites."""
         if tokens.device != self.device:
             raise NotImplementedError("tokens must live on %s (no host or cross-device fallback)" % self.device)
         B, T = T_cp.shape[0], T_cp.shape[1]
         if tokens.dim() != 3 or tokens.shape[0] != B or tokens.shape[1] != T * H * W or tokens.shape[2] != self.C:
             raise ValueError("tokens must be (B=%d, T*H*W=%d, C=%d), got %s" % (B, T * H * W, self.C, tuple(tokens.shape)))
+        if T_wl.shape[1] != 1:
+            raise ValueError("T_world_local must have shape (B, 1, 12)")
+        if forced_refs is not None and tuple(forced_refs.shape) != (self.iters, B, self.Nq, 3):
+            raise ValueError("forced_refs must be (iters, B, Nq, 3)")
+        shape = self._shape(B, T, H, W)
+        ws = self._workspace(shape, (B, T, H, W))
+        flags = self.flags | (_lib.PARQ_FLAG_SKIP_KV if skip_kv else 0) | (0 if pdl else _lib.PARQ_FLAG_NO_PDL)
+        if graph:
+            return self._forward_graph(shape, ws, flags, tokens, camera, T_cp, T_wp, T_wl, forced_refs, ref0, debug)
         if tokens.dtype != torch.bfloat16:
             tokens = tokens.to(torch.bfloat16)
         tokens = tokens.contiguous()
         f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
         camera, T_cp, T_wp, T_wl = f32(camera), f32(T_cp), f32(T_wp), f32(T_wl)
-        if T_wl.shape[1] != 1:
-            raise ValueError("T_world_local must have shape (B, 1, 12)")
-        shape = self._shape(B, T, H, W)
-        ws = self._workspace(shape, (B, T, H, W))
         ref0 = self._ref0(B) if ref0 is None else f32(ref0)
         fr = f32(forced_refs) if forced_refs is not None else None
-        if fr is not None and tuple(fr.shape) != (self.iters, B, self.Nq, 3):
-            raise ValueError("forced_refs must be (iters, B, Nq, 3)")
-        flags = self.flags | (_lib.PARQ_FLAG_SKIP_KV if skip_kv else 0) | (0 if pdl else _lib.PARQ_FLAG_NO_PDL) | \
-            (_lib.PARQ_FLAG_LN_FUSION if ln_fusion else 0)
-        if graph:
-            key = (tokens.data_ptr(), camera.data_ptr(), T_cp.data_ptr(), T_wp.data_ptr(), T_wl.data_ptr(), ref0.data_ptr(),
-                   fr.data_ptr() if fr is not None else 0, B, T, H, W, flags, bool(debug), ws.data_ptr())
-            entry = self._graphs.get(key)
+        outs, po = self._alloc_outputs(B, T, debug)
+        self._launch(shape, tokens, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags)
+        # keep inputs alive until the stream the kernels were launched on has consumed them
+        st = torch.cuda.current_stream(self.device)
+        for t in (tokens, camera, T_cp, T_wp, T_wl, ref0, fr):
+            if t is not None:
+                t.record_stream(st)
+        if "center_valid" in outs:
+            outs["center_valid"] = outs["center_valid"].bool()
+        return outs
+
+    def _forward_graph(self, shape, ws, flags, tokens, camera, T_cp, T_wp, T_wl, forced_refs, ref0, debug):
+        """Replay of the whole forward as ONE CUDA graph.  A graph is captured per (shape, flags, token source): the small
+        inputs (camera, poses, reference points) are always copied into static buffers owned by the entry, so fresh
+        temporaries, non-contiguous slices or dtype conversions on the caller's side never miss the cache.  Tokens that are
+        already contiguous bf16 are consumed in place (keyed by their address: no 1.26 GB copy per step at config 2);
+        tokens that need a conversion anyway (fp32 from the reference pipeline) are converted straight into one static
+        bf16 buffer per shape."""
+        B, T, H, W = shape.B, shape.T, shape.H, shape.W
+        in_place = tokens.dtype == torch.bfloat16 and tokens.is_contiguous()
+        key = (tokens.data_ptr() if in_place else "static", B, T, H, W, flags, bool(debug), forced_refs is not None, ref0 is not None,
+               ws.data_ptr())
+        entry = self._graphs.get(key)
+        with torch.cuda.device(self.device):
             if entry is None:
+                dev = self.device
+                st = {"tokens": tokens if in_place else torch.empty(tokens.shape, dtype=torch.bfloat16, device=dev),
+                      "camera": torch.empty(B, T, 6, dtype=torch.float32, device=dev),
+                      "T_cp": torch.empty(B, T, 12, dtype=torch.float32, device=dev),
+                      "T_wp": torch.empty(B, T, 12, dtype=torch.float32, device=dev),
+                      "T_wl": torch.empty(B, 1, 12, dtype=torch.float32, device=dev),
+                      "ref0": self._ref0(B) if ref0 is None else torch.empty(B, self.Nq, 3, dtype=torch.float32, device=dev),
+                      "fr": None if forced_refs is None else torch.empty(self.iters, B, self.Nq, 3, dtype=torch.float32, device=dev)}
+                entry = {"static": st, "graph": None, "outs": None}
+            st = entry["static"]
+            if not in_place:
+                st["tokens"].copy_(tokens)                     # the fp32 -> bf16 rounding the eager path does with .to()
+            for name, src in (("camera", camera), ("T_cp", T_cp), ("T_wp", T_wp), ("T_wl", T_wl)):
+                st[name].copy_(src.detach().reshape(st[name].shape))
+            if ref0 is not None:
+                st["ref0"].copy_(ref0.detach())
+            if forced_refs is not None:
+                st["fr"].copy_(forced_refs.detach())
+            if entry["graph"] is None:
                 outs, po = self._alloc_outputs(B, T, debug)
-                self._launch(shape, tokens, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags)   # lazy one-off setup outside capture
+                args = (shape, st["tokens"], st["camera"], st["T_cp"], st["T_wp"], st["T_wl"], st["ref0"], st["fr"], ws, po, flags)
+                self._launch(*args)                            # lazy one-off setup (smem opt-ins) outside the capture
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._launch(shape, tokens, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags)
+                    self._launch(*args)
                 if len(self._graphs) >= 8:
                     self._graphs.pop(next(iter(self._graphs)))
-                entry = (g, outs, (tokens, camera, T_cp, T_wp, T_wl, ref0, fr))     # keep the captured buffers alive
+                entry["graph"], entry["outs"] = g, outs
+                if in_place:
+                    st["tokens"] = None                        # address-keyed: do not pin the caller's buffer
                 self._graphs[key] = entry
-            entry[0].replay()
-            outs = dict(entry[1])
-        else:
-            outs, po = self._alloc_outputs(B, T, debug)
-            self._launch(shape, tokens, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags)
-            # keep inputs alive until the stream has consumed them
-            for t in (tokens, camera, T_cp, T_wp, T_wl, ref0, fr):
-                if t is not None:
-                    t.record_stream(torch.cuda.current_stream())
+            entry["graph"].replay()
+        outs = dict(entry["outs"])
         if "center_valid" in outs:
             outs["center_valid"] = outs["center_valid"].bool()
         return outs
@@ -287,11 +354,15 @@ def project(tokens, query_pos, T_camera_local, camera, H, W):
     return feat, cim, val.bool()
 
 
-def parse_pred(out_dict, track_scale=(-1.5, 1.5, -2, 1, 0, 2), num_semcls=9, for_vis=False):
+def parse_pred(out_dict, track_scale=(-1.5, 1.5, -2, 1, 0, 2), num_semcls=9, for_vis=False, enable_nms=True):
     """Device-side ``PARQDecoder.parse_pred`` (reference model/parq_decoder.py:372-424, NMS of utils/nms.py):
     takes the list of per-iteration dicts (or the last dict), uses the last iteration, and returns that dict with
     ``obbs_pred`` (Obb3D (B,Nq)), ``pred_mask`` (B,Nq) bool added -- plus ``scores``, ``labels``, ``nms_mask``.
     No host round trip: one kernel launch, one CTA per clip."""
+    if not enable_nms:
+        # the reference leaves `pred_mask` unbound when ENABLE_NMS is false (parq_decoder.py:415-422 -> UnboundLocalError):
+        # there is no defined behaviour to reproduce
+        raise NotImplementedError("ENABLE_NMS=False is undefined in the reference's parse_pred (pred_mask is never assigned)")
     last = dict(out_dict[-1] if isinstance(out_dict, (list, tuple)) else out_dict)
     lib = _lib.load()
     f32 = lambda t: t.detach().float().contiguous()
@@ -332,6 +403,10 @@ def accelerate(decoder, feature_hw=None, use_cuda_graph=False):
     iters = dec.num_layers
     scale = [float(x) for x in dec.scale]
     num_cls = decoder.mlp_heads["sem_cls_head"].layers[0].weight.shape[0]
+    # BoxProcessor's table as the module itself loaded it from cfg.MEAN_SIZE_PATH (utils/parq_utils.py:45-88)
+    mean_size = getattr(getattr(decoder, "box_processor", None), "mean_size_arr", None)
+    if mean_size is None:
+        mean_size = getattr(decoder, "mean_size_arr", None)
     state = {"engine": None, "key": None}
 
     def forward(intput_tokens, camera, T_camera_pseudoCam, T_world_pseudoCam, T_world_local):
@@ -348,7 +423,7 @@ def accelerate(decoder, feature_hw=None, use_cuda_graph=False):
         key = (str(intput_tokens.device),) + tuple((p.data_ptr(), p._version) for p in decoder.parameters())
         if state["engine"] is None or state["key"] != key:
             state["engine"] = DecoderEngine(decoder.state_dict(), intput_tokens.device, heads=heads, num_cls=num_cls,
-                                            scale=scale, iters=iters)
+                                            scale=scale, iters=iters, mean_size=mean_size)
             state["key"] = key
         with torch.no_grad():
             outs = state["engine"].forward(intput_tokens, cam, raw(T_camera_pseudoCam), raw(T_world_pseudoCam),
@@ -396,6 +471,10 @@ class PARQDecoderB200(nn.Module):
             raise NotImplementedError("DEC_DIM, QUERIES_DIM and DIM_IN must agree")
         D = tr.DEC_DIM
         self.heads, self.iters, self.scale = tr.DEC_HEADS, tr.DEC_LAYERS, list(tr.SCALE)
+        # BoxProcessor.mean_size_arr: from cfg.MEAN_SIZE_PATH when given, else the table of the reference's
+        # data/average_scan2cad.txt (the file every shipped config points at) built in above
+        path = getattr(cfg, "MEAN_SIZE_PATH", None)
+        self.mean_size_arr = load_mean_size(path, cfg.NUM_SEMCLS + 1) if path else torch.tensor(MEAN_SIZE, dtype=torch.float64)
         self.mlp_heads = nn.ModuleDict([
             ("sem_cls_head", _head(D, cfg.NUM_SEMCLS + 1, [], 0.3)),
             ("center_head", _head(D, 3, [D, D], 0.0)),
@@ -430,7 +509,7 @@ class PARQDecoderB200(nn.Module):
         key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
         if self._engine is None or self._engine_key != key:
             self._engine = DecoderEngine(self.state_dict(), device, heads=self.heads, num_cls=self.num_semcls + 1,
-                                         scale=self.scale, iters=self.iters)
+                                         scale=self.scale, iters=self.iters, mean_size=self.mean_size_arr)
             self._engine_key = key
         return self._engine
 
@@ -457,4 +536,4 @@ class PARQDecoderB200(nn.Module):
 
     def parse_pred(self, out_dict):
         """Same contract as the reference's ``parse_pred`` (parq_decoder.py:372-424), computed on the device."""
-        return parse_pred(out_dict, self.track_scale, self.num_semcls, self.for_vis)
+        return parse_pred(out_dict, self.track_scale, self.num_semcls, self.for_vis, self.enable_nms)

@@ -63,7 +63,7 @@ class AddRayPEB200(nn.Module):
         f32 = lambda t: raw(t).detach().to(dev, torch.float32).contiguous()
         feat, cam, Tcp, Twp, Twl = f32(images_feat), f32(camera), f32(T_camera_pseudoCam), f32(T_world_pseudoCam), f32(T_world_local)
         nws = lib.parq_raype_workspace_bytes(B, T, H, W, Cc, self.num_samples)
-        if self._ws is None or self._ws.numel() < nws:
+        if self._ws is None or self._ws.numel() < nws or self._ws.device != dev:
             self._ws = torch.empty(nws, dtype=torch.uint8, device=dev)
         tokens = None
         if want_tokens:

@@ -81,13 +81,8 @@ def main():
         data["nms_mask"] = np.asarray(ns.decoder_module.nms(parsed["obbs_pred"], scores, 9, 0.1, "nms_3d_faster"))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
         print(name, {k: v.shape for k, v in data.items() if hasattr(v, "shape")})
-    import importlib.util
-    from oracle.ref_loader import REFERENCE_ROOT
-    spec = importlib.util.spec_from_file_location("model.ray_positional_encoding",
-                                                  os.path.join(REFERENCE_ROOT, "model", "ray_positional_encoding.py"))
-    rpe = importlib.util.module_from_spec(spec)
-    sys.modules["model.ray_positional_encoding"] = rpe
-    spec.loader.exec_module(rpe)
+    from oracle.ref_loader import load_module
+    rpe = load_module("model.ray_positional_encoding")
     for name, (B, T, H, W, seed) in RAYPE_CASES.items():
         sd = I.make_raype_weights(seed)
         ref = rpe.AddRayPE(1024, [-3, 3, -2, 0.5, 0.25, 5.25], 64, 0.25, 5.25).eval()      # config/eval.yaml:30-35
@@ -103,10 +98,7 @@ def main():
     # f-3: the concat part of the reference's ResnetFPN.forward (model/resnet_fpn.py:56-91), run UNMODIFIED on an
     # instance whose backbone is replaced by a stub that returns a seeded pyramid (the torchvision backbone itself is
     # out of scope and needs downloaded weights)
-    spec = importlib.util.spec_from_file_location("model.resnet_fpn", os.path.join(REFERENCE_ROOT, "model", "resnet_fpn.py"))
-    rfpn = importlib.util.module_from_spec(spec)
-    sys.modules["model.resnet_fpn"] = rfpn
-    spec.loader.exec_module(rfpn)
+    rfpn = load_module("model.resnet_fpn")
     for name, (B, T, H, W, seed) in {"fpn_small": (1, 2, 60, 80, 8), "fpn_odd": (2, 1, 15, 21, 9)}.items():
         pyr = I.make_pyramid(B * T, H, W, seed=seed)
         obj = rfpn.ResnetFPN.__new__(rfpn.ResnetFPN)
