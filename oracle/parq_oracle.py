@@ -361,8 +361,10 @@ def box_corners_local(center, size, ortho6d):
     return c @ R.transpose(-1, -2) + center.unsqueeze(-2)
 
 
-def nms_3d_faster(boxes, overlap_threshold):
-    """utils/nms.py:141-179 (class-agnostic greedy NMS on AABBs, float64).  boxes (n, >=7): x1,y1,z1,x2,y2,z2,score."""
+def nms_3d_faster(boxes, overlap_threshold, same_class=False):
+    """utils/nms.py:141-179 (class-agnostic greedy NMS on AABBs, float64).  boxes (n, >=7): x1,y1,z1,x2,y2,z2,score.
+    same_class: nms_3d_faster_samecls (utils/nms.py:182-224) -- column 7 is the class, the overlap of two boxes of
+    different classes is multiplied by 0 before the threshold test."""
     x1, y1, z1, x2, y2, z2, score = (boxes[:, i] for i in range(7))
     area = (x2 - x1) * (y2 - y1) * (z2 - z1)
     order = np.argsort(score)
@@ -377,14 +379,17 @@ def nms_3d_faster(boxes, overlap_threshold):
         h = np.maximum(0, np.minimum(z2[i], z2[rest]) - np.maximum(z1[i], z1[rest]))
         inter = l * w * h
         o = inter / (area[i] + area[rest] - inter)
+        if same_class:
+            o = o * (boxes[i, 7] == boxes[rest, 7])
         order = np.delete(order, np.concatenate(([last - 1], np.where(o > overlap_threshold)[0])))
     return pick
 
 
-def parse_pred(last, track_scale=(-1.5, 1.5, -2, 1, 0, 2), num_semcls=9, overlap_threshold=0.1):
-    """PARQDecoder.parse_pred (parq_decoder.py:372-424) with FOR_VIS False / ENABLE_NMS True (config/eval.yaml):
-    scores, labels = max over ALL classes; AABB of the rotated corners; class-agnostic NMS over the
-    non-background boxes; pred_mask = nms & (x in (ts0,ts1)) & (z in (ts4,ts5)).
+def parse_pred(last, track_scale=(-1.5, 1.5, -2, 1, 0, 2), num_semcls=9, overlap_threshold=None, for_vis=False):
+    """PARQDecoder.parse_pred (parq_decoder.py:372-424) with ENABLE_NMS True (config/eval.yaml):
+    scores, labels = max over ALL classes; AABB of the rotated corners; NMS over the non-background boxes;
+    FOR_VIS False: class-agnostic NMS at IoU 0.1, pred_mask = nms & (x in (ts0,ts1)) & (z in (ts4,ts5));
+    FOR_VIS True (:407-421): same-class NMS at IoU 0.2 and no track-scale filter.
     Returns dict(pred_mask (B,K) bool, scores (B,K), labels (B,K), aabb (B,K,6) float64)."""
     center, size, o6, prob = (last[k].detach().float().cpu() for k in
                               ("center_unnormalized", "size_unnormalized", "ortho6d", "sem_cls_prob"))
@@ -393,13 +398,18 @@ def parse_pred(last, track_scale=(-1.5, 1.5, -2, 1, 0, 2), num_semcls=9, overlap
     B, K = scores.shape
     aabb = np.concatenate([corners.min(axis=2), corners.max(axis=2)], -1).astype(np.float64)     # (B,K,6)
     mask = np.zeros((B, K), dtype=bool)
+    if overlap_threshold is None:
+        overlap_threshold = 0.2 if for_vis else 0.1
     for b in range(B):
         fg = np.where(labels[b].numpy() != num_semcls)[0]
-        boxes = np.concatenate([aabb[b, fg], scores[b, fg].numpy().astype(np.float64)[:, None]], 1)
-        pick = nms_3d_faster(boxes, overlap_threshold)
+        boxes = np.concatenate([aabb[b, fg], scores[b, fg].numpy().astype(np.float64)[:, None],
+                                labels[b, fg].numpy().astype(np.float64)[:, None]], 1)
+        pick = nms_3d_faster(boxes, overlap_threshold, same_class=for_vis)
         mask[b, fg[pick]] = True
     ts = track_scale
     valid = (center[..., 0] > ts[0]) & (center[..., 0] < ts[1]) & (center[..., 2] > ts[4]) & (center[..., 2] < ts[5])
+    if for_vis:
+        valid = torch.ones_like(valid)
     return {"pred_mask": torch.from_numpy(mask) & valid, "nms_mask": torch.from_numpy(mask), "scores": scores, "labels": labels,
             "aabb": torch.from_numpy(aabb)}
 

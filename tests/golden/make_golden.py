@@ -79,6 +79,11 @@ def main():
         # the NMS decision alone (before the track-scale filter), from the reference's own nms() (utils/nms.py:20-32)
         scores = torch.max(outs[-1]["sem_cls_prob"], -1)[0]
         data["nms_mask"] = np.asarray(ns.decoder_module.nms(parsed["obbs_pred"], scores, 9, 0.1, "nms_3d_faster"))
+        # the FOR_VIS branch of the same unmodified method (:407-421): same-class NMS at IoU 0.2, no track-scale filter
+        ref.for_vis = True
+        parsed_vis = ref.parse_pred([dict(o) for o in outs])
+        ref.for_vis = False
+        data["pred_mask_vis"] = parsed_vis["pred_mask"].numpy()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
         print(name, {k: v.shape for k, v in data.items() if hasattr(v, "shape")})
     from oracle.ref_loader import load_module

@@ -309,16 +309,33 @@ def test_post_nms_detection_sets_identical(dev, name):
     assert flips <= 0.08 * gold["nms_mask"].size
 
 
+@pytest.mark.parametrize("name", ["small", "ragged_wild", "white_noise"])
+def test_parse_pred_for_vis_branch_against_reference_golden(dev, name):
+    # FOR_VIS=True (parq_decoder.py:407-421, utils/nms.py:182-224): same-class NMS at IoU 0.2, no track-scale filter --
+    # the reference's own tensors and the reference's own answer (make_golden.py, `pred_mask_vis`)
+    from parq_b200.decoder import parse_pred
+    gold = load_golden(name)
+    last = {k: torch.from_numpy(gold[k][-1]).to(dev) for k in ("center_unnormalized", "size_unnormalized", "ortho6d", "sem_cls_prob")}
+    got = parse_pred(last, for_vis=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(got["pred_mask"].cpu().numpy(), gold["pred_mask_vis"])
+    m = PARQDecoderB200(default_cfg(256))
+    m.for_vis = True
+    assert np.array_equal(m.parse_pred([last])["pred_mask"].cpu().numpy(), gold["pred_mask_vis"])
+    with pytest.raises(NotImplementedError):
+        parse_pred(last, enable_nms=False)
+
+
 def test_parse_pred_random_boxes_against_oracle(dev):
     from parq_b200.decoder import parse_pred
     g = torch.Generator().manual_seed(77)
-    for B, K, for_vis in ((16, 256, False), (3, 512, False), (2, 100, False)):
+    for B, K, for_vis in ((16, 256, False), (3, 512, False), (2, 100, False), (16, 256, True), (2, 100, True)):
         last = {"center_unnormalized": (torch.rand(B, K, 3, generator=g) - 0.5) * torch.tensor([4.0, 2.0, 3.0]) + torch.tensor([0.0, 0.0, 1.2]),
                 "size_unnormalized": torch.rand(B, K, 3, generator=g) * 1.2 + 0.2,
                 "ortho6d": torch.randn(B, K, 6, generator=g),
                 "sem_cls_prob": torch.softmax(3 * torch.randn(B, K, 10, generator=g), -1)}
-        want = O.parse_pred(last)
-        got = parse_pred({k: v.to(dev) for k, v in last.items()})
+        want = O.parse_pred(last, for_vis=for_vis)
+        got = parse_pred({k: v.to(dev) for k, v in last.items()}, for_vis=for_vis)
         torch.cuda.synchronize()
         assert torch.equal(got["labels"].cpu(), want["labels"]) and torch.equal(got["scores"].cpu(), want["scores"])
         assert torch.equal(got["nms_mask"].cpu(), want["nms_mask"]), (B, K)
@@ -522,26 +539,89 @@ def test_pipeline_fpn_raype_decoder_nms_chain(dev):
 
 
 def test_accelerate_hook_runs_the_library(dev):
-    # accelerate() patches an instance in place; on the GPU box the reference class is not importable,
-    # so the module with the reference's attribute names stands in for it
+    # accelerate() patches an instance of the REFERENCE's own PARQDecoder class in place.  The class comes
+    # from /root/reference in the build container and from its bytecode tree oracle/_ref on the GPU box; only when neither
+    # is present does the module with the reference's attribute names stand in for it.
+    from oracle import ref_loader as RL
     from parq_b200.decoder import accelerate
     gold = load_golden("small")
     c = regenerate_case(gold)
-    m = PARQDecoderB200(default_cfg(c["Nq"])).eval()
-    m.load_state_dict(c["sd"], strict=True)
-    m = accelerate(m.to(dev), feature_hw=(c["H"], c["W"]), use_cuda_graph=True)
     cam, Tcp, Twp, Twl = I.make_geometry(c["B"], c["T"], c["H"], c["W"], seed=c["seed"])
-    args = (c["tokens"].to(dev).bfloat16(), cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
-    for _ in range(2):
-        out = m(*args)
+    real = RL.reference_available()
+    if real:
+        ns = RL.load_reference()
+        m = RL.build_decoder(c["sd"], c["Nq"], device=dev)
+        assert type(m).__module__ == "model.parq_decoder" and type(m).__name__ == "PARQDecoder"
+        geo = (ns.Camera(cam._data.to(dev)), ns.Pose(Tcp._data.to(dev)), ns.Pose(Twp._data.to(dev)), ns.Pose(Twl._data.to(dev)))
+    else:
+        m = PARQDecoderB200(default_cfg(c["Nq"])).eval()
+        m.load_state_dict(c["sd"], strict=True)
+        m = m.to(dev)
+        geo = (cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
+    m = accelerate(m, use_cuda_graph=True)           # H, W read from the Camera like the reference does (transformer_parq.py:301)
+    # fp32 tokens, as parq_lightning.py:78-88 hands them over (the fixture's values are bf16-representable)
+    tok32 = c["tokens"].to(dev).float()
+    for _ in range(3):
+        out = m(tok32.clone(), *geo)                  # a fresh tensor every call: the graph cache must still hit
     torch.cuda.synchronize()
     assert len(out) == 8 and set(out[0].keys()) == set(OUT_KEYS)
-    for k in OUT_KEYS:
+    for k in OUT_KEYS:                                # iteration 0 is free of the recurrence: compare with the fixture
         assert relerr(out[0][k].cpu(), gold[k][0]) <= TOL, k
     before = _lib.load().parq_kernel_launches()
     m.forward.use_cuda_graph = False
-    m(*args)
+    out = m(tok32, *geo)
     assert _lib.load().parq_kernel_launches() - before > 100          # the CUDA library did the work
+    if real:
+        # everything else stays the reference's: its own parse_pred consumes our outputs (device Obb3D round trip and numpy NMS)
+        parsed = m.parse_pred([dict(o) for o in out])
+        ours = PARQDecoderB200(default_cfg(c["Nq"])).parse_pred([dict(o) for o in out])
+        assert np.array_equal(parsed["pred_mask"].cpu().numpy(), ours["pred_mask"].cpu().numpy())
+
+
+def test_graph_cache_is_keyed_by_shape_not_by_temporaries(dev):
+    # fp32 tokens / non-contiguous pose slices create fresh temporaries per call; the graph must be reused
+    gold = load_golden("small")
+    c = regenerate_case(gold)
+    eng = DecoderEngine(c["sd"], dev)
+    base = None
+    for i in range(4):
+        tok = c["tokens"].to(dev).float().clone()                     # new address every call, needs the bf16 conversion
+        poses = torch.stack([c["T_cp"], c["T_wp"]], 0).to(dev)         # slices of a stacked tensor
+        out = eng.forward(tok, c["camera"].to(dev), poses[0], poses[1], c["T_wl"].to(dev), c["H"], c["W"], graph=True)
+        torch.cuda.synchronize()
+        if base is None:
+            base = {k: v.clone() for k, v in out.items()}
+        for k in OUT_KEYS:
+            assert torch.equal(out[k], base[k]), k
+    assert len(eng._graphs) == 1
+    eager = eng.forward(c["tokens"].to(dev), c["camera"].to(dev), c["T_cp"].to(dev), c["T_wp"].to(dev), c["T_wl"].to(dev), c["H"], c["W"])
+    torch.cuda.synchronize()
+    for k in OUT_KEYS:
+        assert torch.equal(eager[k], base[k]), k
+
+
+def test_custom_mean_size_table_is_honoured(dev, tmp_path):
+    # MEAN_SIZE_PATH / box_processor.mean_size_arr must reach the kernels (size = exp(s) * mean_size[argmax])
+    from parq_b200.decoder import load_mean_size
+    gold = load_golden("small")
+    c = regenerate_case(gold)
+    path = tmp_path / "sizes.txt"
+    names = ["chair", "table", "cabinet", "trash can,trash bin", "bookshelf", "display,video display", "sofa,couch", "bathtub,tub"]
+    path.write_text("".join("%s: [%.8f %.8f %.8f] \n" % (n, 0.5 + 0.1 * i, 1.0 + 0.2 * i, 0.25 * (i + 1)) for i, n in enumerate(names)))
+    table = load_mean_size(str(path))
+    assert table.shape == (10, 3) and table[3, 0].item() == pytest.approx(0.8) and table[8:].eq(1).all()
+    cfg = default_cfg(c["Nq"])
+    cfg.MEAN_SIZE_PATH = str(path)
+    m = PARQDecoderB200(cfg).eval()
+    m.load_state_dict(c["sd"], strict=True)
+    m = m.to(dev)
+    cam, Tcp, Twp, Twl = I.make_geometry(c["B"], c["T"], c["H"], c["W"], seed=c["seed"])
+    out = m(c["tokens"].to(dev), cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
+    torch.cuda.synchronize()
+    cls = torch.from_numpy(gold["sem_cls_prob"][0]).argmax(-1)
+    same = out[0]["sem_cls_prob"].cpu().argmax(-1) == cls
+    want = torch.from_numpy(gold["size_unnormalized"][0]) / torch.tensor(O.MEAN_SIZE, dtype=torch.float32)[cls] * table.float()[cls]
+    assert relerr(out[0]["size_unnormalized"].cpu()[same], want[same]) <= TOL
 
 
 def test_decoder_ragged_clip_sizes(dev):

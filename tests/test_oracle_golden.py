@@ -89,6 +89,16 @@ def test_oracle_parse_pred_matches_reference_detection_sets(name):
     assert np.allclose(np.concatenate([aabb.min(2)[0].numpy(), aabb.max(2)[0].numpy()], -1), r["aabb"].numpy(), atol=0)
 
 
+@pytest.mark.parametrize("name", ["small", "ragged_wild", "white_noise"])
+def test_oracle_parse_pred_for_vis_branch(name):
+    # FOR_VIS=True (parq_decoder.py:407-421): same-class NMS (utils/nms.py:182-224) at IoU 0.2, no track-scale filter
+    gold = load_golden(name)
+    last = {k: torch.from_numpy(gold[k][-1]) for k in ("center_unnormalized", "size_unnormalized", "ortho6d", "sem_cls_prob")}
+    r = O.parse_pred(last, for_vis=True)
+    assert np.array_equal(r["pred_mask"].numpy(), gold["pred_mask_vis"])
+    assert gold["pred_mask_vis"].sum() > gold["nms_mask"].sum()      # fewer suppressions than the class-agnostic NMS
+
+
 @pytest.mark.parametrize("name", ["raype_small", "raype_c1_view"])
 def test_oracle_add_ray_pe_matches_reference(name):
     # f-1: AddRayPE encoding of the unmodified reference module (make_golden.py) against the oracle restatement
