@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PARQ_ABI_VERSION 1
+#define PARQ_ABI_VERSION 2
 
 #define PARQ_OK 0
 #define PARQ_ERR_SHAPE (-1)       /* unsupported shape / alignment / null pointer */
@@ -101,23 +101,29 @@ int parq_pack_weights(const ParqShape *shape, const ParqWeightsF32 *w, void *pac
  * T_cp, T_wp (B,T,12), T_wl (B,1,12) -> T_cl (B,T,12). */
 int parq_pose_chain(const float *T_cp, const float *T_wp, const float *T_wl, float *T_cl, int B, int T, void *stream);
 
+/* fp32 tokens (parq_lightning.py:78-85 hands the decoder fp32) as an exact bf16 pair: hi = bf16(x), lo = bf16(x - hi),
+ * n elements (multiple of 4), 16-byte aligned buffers.  `hi` is the plane the K / V^T projection consumes; passing `lo`
+ * as tokens_lo_bf16 below makes the gather see x to 16 mantissa bits instead of 8. */
+int parq_split_tokens(const float *tokens_f32, void *hi_bf16, void *lo_bf16, long long n, void *stream);
+
 /* transformer_parq.project (:129-161) for normalised reference points `ref` (B,Nq,3):
- * tokens bf16 (B,T*H*W,C) -> features (B,Nq,C), center_im (B,T,Nq,2), center_valid (B,T,Nq), coord_pos (B,Nq,3).
- * Output pointers other than `features` may be NULL. */
-int parq_project_sample(const ParqShape *shape, const void *tokens_bf16, const float *ref, const float *T_cl,
-                        const float *camera, float *features, float *center_im, uint8_t *center_valid,
+ * tokens bf16 (B,T*H*W,C) [+ optional low-order plane tokens_lo_bf16, may be NULL] -> features (B,Nq,C),
+ * center_im (B,T,Nq,2), center_valid (B,T,Nq), coord_pos (B,Nq,3).  Output pointers other than `features` may be NULL. */
+int parq_project_sample(const ParqShape *shape, const void *tokens_bf16, const void *tokens_lo_bf16, const float *ref,
+                        const float *T_cl, const float *camera, float *features, float *center_im, uint8_t *center_valid,
                         float *coord_pos, void *stream);
 
 /* Hoisted cross-attention K / V^T projection of all image tokens into the workspace (once per clip batch). */
 int parq_kv_project(const ParqShape *shape, const void *tokens_bf16, const void *packed, void *workspace,
                     size_t workspace_bytes, uint32_t flags, void *stream);
 
-/* The whole recurrent decoder.  ref0 (B,Nq,3): normalised initial reference points (sigmoid(refpoint.weight)
- * repeated per clip).  forced_refs (iters,B,Nq,3) or NULL: teacher-forced reference points per iteration. */
-int parq_decoder_forward(const ParqShape *shape, const void *tokens_bf16, const float *camera, const float *T_cp,
-                         const float *T_wp, const float *T_wl, const float *ref0, const float *forced_refs,
-                         const void *packed, void *workspace, size_t workspace_bytes, const ParqOutputs *out,
-                         uint32_t flags, void *stream);
+/* The whole recurrent decoder.  tokens_lo_bf16: optional low-order token plane (parq_split_tokens) or NULL.
+ * ref0 (B,Nq,3): normalised initial reference points (sigmoid(refpoint.weight) repeated per clip).
+ * forced_refs (iters,B,Nq,3) or NULL: teacher-forced reference points per iteration. */
+int parq_decoder_forward(const ParqShape *shape, const void *tokens_bf16, const void *tokens_lo_bf16, const float *camera,
+                         const float *T_cp, const float *T_wp, const float *T_wl, const float *ref0,
+                         const float *forced_refs, const void *packed, void *workspace, size_t workspace_bytes,
+                         const ParqOutputs *out, uint32_t flags, void *stream);
 
 /* "Next" row f-3: the FPN upsample + concat of ResnetFPN.forward (model/resnet_fpn.py:73-80): the four pyramid levels
  * l0..l3, each (BT, channels_per_level, h_l, w_l) fp32 channels-first with level_hw = HOST array {h0,w0,h1,w1,h2,w2,h3,w3},

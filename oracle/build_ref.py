@@ -4,8 +4,10 @@ The reference (/root/reference, ymingxie/PARQ) is pure Python and does not exist
 recipe for a compiled reference applies: compile it from the sources WHERE THEY LIE, outputs only into
 ``oracle/_ref/`` (git-ignored, but it travels to the GPU box like our own built .so).  For Python the
 compiled artefact is CPython bytecode: every module below is compiled with ``py_compile`` straight from
-/root/reference into a sourceless ``.pyc`` tree -- no reference source file is copied into the repository.
-The build container and the GPU box run the same image (same CPython), so the bytecode loads there.
+/root/reference into a sourceless bytecode tree -- no reference source file is copied into the repository.
+The files carry the extension ``.pybc`` (the snapshot that ships the repository to the GPU box drops ``*.pyc``);
+oracle/ref_loader.py imports them through a small meta-path finder.  The build container and the GPU box run the
+same image (same CPython), so the bytecode loads there.
 
     python oracle/build_ref.py          # run in the build container; __graft_entry__.build() calls it
 
@@ -24,6 +26,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("PARQ_REFERENCE_SRC", "/root/reference")
 DST = os.path.join(HERE, "_ref")
+EXT = ".pybc"
 
 # modules on (or next to) the hot path; model/__init__.py and parq_lightning.py need real Lightning and are
 # bypassed by the loader exactly as in the build container
@@ -42,7 +45,7 @@ def available():
 
 def stale():
     for rel in MODULES:
-        out = os.path.join(DST, rel[:-3] + ".pyc")
+        out = os.path.join(DST, rel[:-3] + EXT)
         if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(os.path.join(SRC, rel)):
             return True
     return not all(os.path.exists(os.path.join(DST, d)) for d in DATA)
@@ -56,7 +59,7 @@ def build(force=False):
     if not force and not stale():
         return DST
     for rel in MODULES:
-        out = os.path.join(DST, rel[:-3] + ".pyc")
+        out = os.path.join(DST, rel[:-3] + EXT)
         os.makedirs(os.path.dirname(out), exist_ok=True)
         py_compile.compile(os.path.join(SRC, rel), cfile=out, dfile="<reference>/" + rel, doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)

@@ -12,6 +12,7 @@ The reference needs two sys.modules stubs to import under torch>=2
 `model` package is registered empty so model/__init__.py (which needs real
 Lightning) is bypassed.
 """
+import importlib.abc
 import importlib.machinery
 import importlib.util
 import os
@@ -19,12 +20,13 @@ import sys
 import types
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+BYTECODE_EXT = ".pybc"          # oracle/build_ref.py: sourceless bytecode under a name the GPU-box snapshot keeps
 
 
 def _find_root():
     for cand in (os.environ.get("PARQ_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
         if cand and (os.path.isfile(os.path.join(cand, "model", "parq_decoder.py")) or
-                     os.path.isfile(os.path.join(cand, "model", "parq_decoder.pyc"))):
+                     os.path.isfile(os.path.join(cand, "model", "parq_decoder" + BYTECODE_EXT))):
             return cand
     return "/root/reference"
 
@@ -36,7 +38,7 @@ REFERENCE_KIND = "source" if os.path.isfile(os.path.join(REFERENCE_ROOT, "model"
 
 def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "parq_decoder.py")) or \
-        os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "parq_decoder.pyc"))
+        os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "parq_decoder" + BYTECODE_EXT))
 
 
 class _NS(dict):
@@ -58,6 +60,27 @@ def decoder_cfg(num_queries=256, dec_layers=8, for_vis=False):
 _loaded = {}
 
 
+class _BytecodeFinder(importlib.abc.MetaPathFinder):
+    """Resolves `utils`, `utils.*` and `model.*` to the sourceless bytecode files of oracle/_ref."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, name, path=None, target=None):
+        parts = name.split(".")
+        if parts[0] not in ("utils", "model"):
+            return None
+        base = os.path.join(self.root, *parts)
+        init = os.path.join(base, "__init__" + BYTECODE_EXT)
+        if os.path.isfile(init):
+            return importlib.util.spec_from_file_location(name, init, loader=importlib.machinery.SourcelessFileLoader(name, init),
+                                                          submodule_search_locations=[base])
+        if os.path.isfile(base + BYTECODE_EXT):
+            return importlib.util.spec_from_file_location(name, base + BYTECODE_EXT,
+                                                          loader=importlib.machinery.SourcelessFileLoader(name, base + BYTECODE_EXT))
+        return None
+
+
 def load_module(name):
     """Execute reference module `name` (e.g. "model.resnet_fpn") from its .py, or from its .pyc in oracle/_ref."""
     if name in sys.modules and name in _loaded:
@@ -66,7 +89,7 @@ def load_module(name):
     if os.path.isfile(base + ".py"):
         spec = importlib.util.spec_from_file_location(name, base + ".py")
     else:
-        spec = importlib.util.spec_from_loader(name, importlib.machinery.SourcelessFileLoader(name, base + ".pyc"))
+        spec = _BytecodeFinder(REFERENCE_ROOT).find_spec(name)
     m = importlib.util.module_from_spec(spec)
     sys.modules[name] = m
     spec.loader.exec_module(m)
@@ -80,8 +103,11 @@ def load_reference():
         return _loaded["ns"]
     if not reference_available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if REFERENCE_KIND == "source":
+        if REFERENCE_ROOT not in sys.path:
+            sys.path.insert(0, REFERENCE_ROOT)
+    elif not any(isinstance(f, _BytecodeFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _BytecodeFinder(REFERENCE_ROOT))
     six = types.ModuleType("torch._six")
     six.string_classes = (str, bytes)
     sys.modules.setdefault("torch._six", six)

@@ -20,7 +20,7 @@ PARQ_NMS_NO_TRACK_SCALE = 2
 
 EXPORTS = [
     "parq_version", "parq_last_error", "parq_packed_bytes", "parq_workspace_bytes", "parq_pack_weights",
-    "parq_pose_chain", "parq_project_sample", "parq_kv_project", "parq_decoder_forward",
+    "parq_pose_chain", "parq_split_tokens", "parq_project_sample", "parq_kv_project", "parq_decoder_forward",
     "parq_gemm_bf16", "parq_attention_scratch_bytes", "parq_attention",
     "parq_parse_pred", "parq_fpn_concat", "parq_raype_packed_bytes", "parq_raype_workspace_bytes", "parq_raype_pack_weights",
     "parq_raype_forward", "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect", "parq_workspace_offset",
@@ -87,11 +87,13 @@ def load():
     lib.parq_pose_chain.restype = C.c_int
     lib.parq_pose_chain.argtypes = [f32p, f32p, f32p, f32p, i32, i32, vp]
     lib.parq_project_sample.restype = C.c_int
-    lib.parq_project_sample.argtypes = [C.POINTER(ParqShape), vp, f32p, f32p, f32p, f32p, f32p, vp, f32p, vp]
+    lib.parq_project_sample.argtypes = [C.POINTER(ParqShape), vp, vp, f32p, f32p, f32p, f32p, f32p, vp, f32p, vp]
+    lib.parq_split_tokens.restype = C.c_int
+    lib.parq_split_tokens.argtypes = [f32p, vp, vp, C.c_longlong, vp]
     lib.parq_kv_project.restype = C.c_int
     lib.parq_kv_project.argtypes = [C.POINTER(ParqShape), vp, vp, vp, sz, u32, vp]
     lib.parq_decoder_forward.restype = C.c_int
-    lib.parq_decoder_forward.argtypes = [C.POINTER(ParqShape), vp, f32p, f32p, f32p, f32p, f32p, f32p, vp, vp, sz,
+    lib.parq_decoder_forward.argtypes = [C.POINTER(ParqShape), vp, vp, f32p, f32p, f32p, f32p, f32p, f32p, vp, vp, sz,
                                          C.POINTER(ParqOutputs), u32, vp]
     lib.parq_gemm_bf16.restype = C.c_int
     lib.parq_gemm_bf16.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),

@@ -481,7 +481,7 @@ __global__ void copy_scale_kernel(const float* __restrict__ src, float* __restri
 
 // --------------------------------------------------------------------------- workspace layout --
 struct Workspace {
-  size_t Kc, Vt, T_cl, ref_cur, a_pos, a_peh, pe, x0, a_x, a_xpe, qk_s, vt_s, scratch, a_attn, y, x1, x2, x3, a_x1pe, q_c,
+  size_t Kc, Vt, T_cl, ref_cur, a_pos, a_peh, pe, a_x, a_xpe, qk_s, vt_s, scratch, a_attn, y, x1, x2, x3, a_x1pe, q_c,
       a_x2, a_ffn, a_x3, h1, a_h1, h2, gn1, gn2;
   size_t scratch_bytes, ldv, ldvs, total;
   int kv_tiled, ntile;      // tile-contiguous K / V^T caches (needs Nk % 32 == 0), key tiles per clip
@@ -508,7 +508,6 @@ static Workspace workspace_layout(const ParqShape& s, int sms) {
   w.a_pos = take(R * 768 * 2);
   w.a_peh = take(R * 2 * C * 2);
   w.pe = take(R * C * 4);
-  w.x0 = take(R * C * 4);
   w.a_x = take(R * 2 * C * 2);
   w.a_xpe = take(R * 2 * C * 2);
   w.qk_s = take(R * 2 * C * 2);
@@ -657,7 +656,7 @@ long long parq_workspace_offset(const ParqShape* shape, const char* name) {
   if (check_shape(shape) != PARQ_OK || name == nullptr) return -1;
   const Workspace W = workspace_layout(*shape, device_info().sms);
   const struct { const char* n; size_t off; } tab[] = {
-      {"Kc", W.Kc}, {"Vt", W.Vt}, {"T_cl", W.T_cl}, {"pe", W.pe}, {"x0", W.x0}, {"qk_s", W.qk_s}, {"vt_s", W.vt_s},
+      {"Kc", W.Kc}, {"Vt", W.Vt}, {"T_cl", W.T_cl}, {"pe", W.pe}, {"qk_s", W.qk_s}, {"vt_s", W.vt_s},
       {"a_attn", W.a_attn}, {"y", W.y}, {"x1", W.x1}, {"x2", W.x2}, {"x3", W.x3}, {"q_c", W.q_c}, {"h1", W.h1}, {"h2", W.h2},
       {"ldv", W.ldv}, {"ldvs", W.ldvs}, {"kv_tiled", static_cast<size_t>(W.kv_tiled)}, {"ntile", static_cast<size_t>(W.ntile)}, {"cross_nsplit", static_cast<size_t>(W.cross.nsplit)},
       {"self_nsplit", static_cast<size_t>(W.self.nsplit)}};
@@ -760,11 +759,33 @@ int parq_pose_chain(const float* T_cp, const float* T_wp, const float* T_wl, flo
   return PARQ_OK;
 }
 
-static size_t sample_smem(int T) { return static_cast<size_t>(SAMPLE_QPB) * T * sizeof(ViewTap); }
+static int launch_sample(cudaStream_t st, const SampleParams& sp) {
+  if (sp.T > sample::MAX_PAIRS) return fail(PARQ_ERR_SHAPE, "T=%d views: the sampling kernel supports up to %d", sp.T, sample::MAX_PAIRS);
+  if ((reinterpret_cast<uintptr_t>(sp.tokens) & 15) != 0 || (reinterpret_cast<uintptr_t>(sp.tokens_lo) & 15) != 0)
+    return fail(PARQ_ERR_SHAPE, "token planes must be 16-byte aligned (bulk copies)");
+  const size_t smem = sample::smem_bytes(sp.C, sp.slots);
+  OPT_IN_SMEM(project_sample_kernel, smem);
+  const int R = sp.B * sp.Nq;
+  {
+    ProfScope ps(TAG_SAMPLE, st);
+    launch_k(project_sample_kernel, dim3((R + sp.rows_per_cta - 1) / sp.rows_per_cta), dim3(sample::THREADS), smem, st, sp);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PARQ_OK;
+}
 
 static void fill_sample_params(SampleParams& sp, const ParqShape& s) {
   memset(&sp, 0, sizeof(sp));
   sp.B = s.B; sp.T = s.T; sp.H = s.H; sp.W = s.W; sp.C = s.C; sp.Nq = s.Nq;
+  // persistent grid: CTAS_PER_SM CTAs per SM, each with a contiguous range of queries and a ring that fills its share of
+  // the shared memory (12 slots of 8 KB at C = 1024)
+  const int R = s.B * s.Nq;
+  const int ctas = device_info().sms * sample::CTAS_PER_SM;
+  sp.rows_per_cta = (R + ctas - 1) / ctas;
+  const size_t budget = 110 * 1024;
+  int slots = sample::MAX_SLOTS;
+  while (slots > 2 && sample::smem_bytes(s.C, slots) > budget) --slots;
+  sp.slots = slots;
   for (int i = 0; i < 3; ++i) {
     // (hi - lo) is evaluated in double from the config floats, then enters the fp32 op as a scalar
     sp.span[i] = static_cast<float>(static_cast<double>(s.scale[2 * i + 1]) - static_cast<double>(s.scale[2 * i]));
@@ -772,19 +793,44 @@ static void fill_sample_params(SampleParams& sp, const ParqShape& s) {
   }
 }
 
-int parq_project_sample(const ParqShape* shape, const void* tokens_bf16, const float* ref, const float* T_cl, const float* camera,
-                        float* features, float* center_im, uint8_t* center_valid, float* coord_pos, void* stream) {
+int parq_project_sample(const ParqShape* shape, const void* tokens_bf16, const void* tokens_lo_bf16, const float* ref, const float* T_cl,
+                        const float* camera, float* features, float* center_im, uint8_t* center_valid, float* coord_pos, void* stream) {
   TRY(require_sm100());
   TRY(check_shape(shape));
   if (!tokens_bf16 || !ref || !T_cl || !camera || !features) return fail(PARQ_ERR_SHAPE, "null pointer");
   SampleParams sp;
   fill_sample_params(sp, *shape);
   sp.tokens = static_cast<const __nv_bfloat16*>(tokens_bf16);
+  sp.tokens_lo = static_cast<const __nv_bfloat16*>(tokens_lo_bf16);
   sp.ref = ref; sp.T_cl = T_cl; sp.camera = camera;
   sp.feat = features; sp.center_im = center_im; sp.valid = center_valid; sp.coord_pos = coord_pos;
+  return launch_sample(static_cast<cudaStream_t>(stream), sp);
+}
+
+// fp32 tokens -> exact bf16 pair: hi = bf16(x), lo = bf16(x - hi)  (x = hi + lo to 16 mantissa bits)
+__global__ void split_tokens_kernel(const float4* __restrict__ src, uint2* __restrict__ hi, uint2* __restrict__ lo, long long n4) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = src[i];
+    const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+    hi[i] = make_uint2(h0, h1);
+    lo[i] = make_uint2(pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xFFFF0000u)),
+                       pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xFFFF0000u)));
+  }
+}
+
+int parq_split_tokens(const float* tokens_f32, void* hi_bf16, void* lo_bf16, long long n, void* stream) {
+  TRY(require_sm100());
+  if (!tokens_f32 || !hi_bf16 || !lo_bf16 || n < 0 || n % 4 != 0) return fail(PARQ_ERR_SHAPE, "bad split_tokens arguments (n must be a multiple of 4)");
+  if (((reinterpret_cast<uintptr_t>(tokens_f32) | reinterpret_cast<uintptr_t>(hi_bf16) | reinterpret_cast<uintptr_t>(lo_bf16)) & 15) != 0)
+    return fail(PARQ_ERR_SHAPE, "split_tokens needs 16-byte aligned buffers");
+  if (n == 0) return PARQ_OK;
+  const long long n4 = n / 4;
+  const long long want = (n4 + 255) / 256;
+  const int blocks = static_cast<int>(want < 148LL * 16 ? want : 148LL * 16);
   {
-    ProfScope ps(TAG_SAMPLE, static_cast<cudaStream_t>(stream));
-    project_sample_kernel<<<shape->B * shape->Nq / SAMPLE_QPB, shape->C / 8, sample_smem(shape->T), static_cast<cudaStream_t>(stream)>>>(sp);
+    ProfScope ps(TAG_ROWWISE, static_cast<cudaStream_t>(stream));
+    split_tokens_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(tokens_f32), static_cast<uint2*>(hi_bf16),
+                                                                              static_cast<uint2*>(lo_bf16), n4);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
@@ -1025,8 +1071,8 @@ int parq_kv_project(const ParqShape* shape, const void* tokens_bf16, const void*
                     (flags & PARQ_FLAG_WEIGHT_LO) != 0 && !(flags & PARQ_FLAG_KV_HI_ONLY), static_cast<uint8_t*>(workspace), W);
 }
 
-int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const float* camera, const float* T_cp, const float* T_wp,
-                         const float* T_wl, const float* ref0, const float* forced_refs, const void* packed, void* workspace,
+int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const void* tokens_lo_bf16, const float* camera, const float* T_cp,
+                         const float* T_wp, const float* T_wl, const float* ref0, const float* forced_refs, const void* packed, void* workspace,
                          size_t workspace_bytes, const ParqOutputs* out, uint32_t flags, void* stream) {
   TRY(require_sm100());
   TRY(check_shape(shape));
@@ -1062,7 +1108,18 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
 
   for (int it = 0; it < s.iters; ++it) {
     const float* ref = forced_refs ? forced_refs + static_cast<size_t>(it) * R * 3 : (it == 0 ? ref0 : F32(W.ref_cur));
-    // K2: reference-point positional feature  pe = W2 relu(W1 posemb + b1) + b2
+    // K1: projection + multi-view bilinear gather -> the [hi|lo] split of the sampled features (the query content x)
+    sp.tokens = static_cast<const __nv_bfloat16*>(tokens_bf16);
+    sp.tokens_lo = static_cast<const __nv_bfloat16*>(tokens_lo_bf16);
+    sp.ref = ref; sp.T_cl = F32(W.T_cl); sp.camera = camera;
+    sp.feat = out->features ? out->features + static_cast<size_t>(it) * R * C : nullptr;
+    sp.a_x = BF(W.a_x);
+    sp.center_im = out->center_im ? out->center_im + static_cast<size_t>(it) * s.B * s.T * s.Nq * 2 : nullptr;
+    sp.valid = out->center_valid ? out->center_valid + static_cast<size_t>(it) * s.B * s.T * s.Nq : nullptr;
+    sp.coord_pos = nullptr;
+    TRY(launch_sample(st, sp));
+    // K2: reference-point positional feature  pe = W2 relu(W1 posemb + b1) + b2; the second GEMM also emits the split of
+    // x + pe, the query / key input of the self-attention (transformer_parq.py:372)
     { ProfScope ps(TAG_ROWWISE, st); launch_k(posemb_kernel, dim3((R * 384 + 255) / 256), dim3(256), 0, st, ref, PF(P.dim_t), BF(W.a_pos), R); }
     CUDA_TRY(cudaGetLastError());
     {
@@ -1075,19 +1132,9 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
       g.ep = epilogue_none(); g.ep.bias = PF(P.pe2_b);
       g.ep.out_f32 = F32(W.pe); g.ep.ld_f32 = C;
+      g.ep.add_split = BF(W.a_x); g.ep.out_sum_split = BF(W.a_xpe); g.ep.ld_split = 2 * C; g.ep.split_lo_off = C;
       TRY(launch_gemm(st, ws + W.a_peh, R, 2 * C, pk + P.pe2, C, 2 * C, g));
     }
-    // K1: projection + multi-view bilinear gather (+pe, + operand splits)
-    sp.tokens = static_cast<const __nv_bfloat16*>(tokens_bf16);
-    sp.ref = ref; sp.T_cl = F32(W.T_cl); sp.camera = camera; sp.pe = F32(W.pe);
-    sp.feat = out->features ? out->features + static_cast<size_t>(it) * R * C : F32(W.x0);
-    sp.a_x = BF(W.a_x); sp.a_xpe = BF(W.a_xpe);
-    sp.center_im = out->center_im ? out->center_im + static_cast<size_t>(it) * s.B * s.T * s.Nq * 2 : nullptr;
-    sp.valid = out->center_valid ? out->center_valid + static_cast<size_t>(it) * s.B * s.T * s.Nq : nullptr;
-    sp.coord_pos = nullptr;
-    { ProfScope ps(TAG_SAMPLE, st); launch_k(project_sample_kernel, dim3(R / SAMPLE_QPB), dim3(C / 8), sample_smem(s.T), st, sp); }
-    CUDA_TRY(cudaGetLastError());
-    const float* x0 = sp.feat;
     // K3: self-attention among the queries (fp16 operands), out-projection, residual + LN1
     {
       GemmParams g; memset(&g, 0, sizeof(g));
@@ -1109,8 +1156,9 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.sa_out_b);
       g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
       TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.sa_out, C, 2 * C, g));
-      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, x0, F32(W.y), PF(P.ln1_g), PF(P.ln1_b), F32(W.pe), F32(W.x1),
-                                               nullptr, BF(W.a_x1pe), R); }
+      // the residual x is read back from its [hi|lo] split (the only form in which the sampled features are stored)
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, static_cast<const float*>(nullptr), BF(W.a_x), F32(W.y),
+                                               PF(P.ln1_g), PF(P.ln1_b), F32(W.pe), F32(W.x1), nullptr, BF(W.a_x1pe), R); }
       CUDA_TRY(cudaGetLastError());
     }
     // K5: cross-attention over all image tokens (bf16 operands), out-projection, residual + LN2
@@ -1129,7 +1177,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.ca_out_b);
       g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
       TRY(launch_gemm(st, ws + W.a_attn, R, 2 * C, pk + P.ca_out, C, 2 * C, g));
-      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x1), F32(W.y), PF(P.ln2_g), PF(P.ln2_b), nullptr, F32(W.x2),
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x1), static_cast<const __nv_bfloat16*>(nullptr), F32(W.y), PF(P.ln2_g), PF(P.ln2_b), nullptr, F32(W.x2),
                                                BF(W.a_x2), nullptr, R); }
       CUDA_TRY(cudaGetLastError());
     }
@@ -1146,7 +1194,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.lin2_b);
       g.ep.out_f32 = F32(W.y); g.ep.ld_f32 = C;
       TRY(launch_gemm(st, ws + W.a_ffn, R, 2 * F, pk + P.lin2, C, 2 * F, g));
-      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x2), F32(W.y), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr, R); }
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x2), static_cast<const __nv_bfloat16*>(nullptr), F32(W.y), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr, R); }
       CUDA_TRY(cudaGetLastError());
     }
     // K7: heads (two hidden layers with per-clip GroupNorm) + box update

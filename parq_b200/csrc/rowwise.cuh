@@ -53,11 +53,13 @@ __global__ void posemb_kernel(const float* __restrict__ ref, const float* __rest
 // eps 1e-5, biased variance.  One warp per row.  Also emits the bf16 split of x_out and, when pe is
 // given, of x_out + pe (the cross-attention query input, transformer_parq.py:377).
 // ---------------------------------------------------------------------------------------------
+// The residual input is either fp32 (x_in) or, when x_in is null, the [hi|lo] bf16 split x_in_split (R, 2C) -- the form in
+// which the sampled features leave the sampling kernel (hi + lo carries 16 mantissa bits, exactly what the GEMMs saw).
 template <int C>
 __global__ void __launch_bounds__(256)
-add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y, const float* __restrict__ gamma,
-              const float* __restrict__ beta, const float* __restrict__ pe, float* __restrict__ x_out,
-              __nv_bfloat16* __restrict__ a_x, __nv_bfloat16* __restrict__ a_xpe, int R) {
+add_ln_kernel(const float* __restrict__ x_in, const __nv_bfloat16* __restrict__ x_in_split, const float* __restrict__ y,
+              const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ pe,
+              float* __restrict__ x_out, __nv_bfloat16* __restrict__ a_x, __nv_bfloat16* __restrict__ a_xpe, int R) {
   constexpr int PASSES = C / 256;          // a lane owns 8 consecutive channels per pass
   pdl_wait();
   pdl_launch_dependents();
@@ -70,7 +72,17 @@ add_ln_kernel(const float* __restrict__ x_in, const float* __restrict__ y, const
 #pragma unroll
   for (int i = 0; i < PASSES; ++i) {
     const int c = (i * 32 + lane) * 8;
-    const float4 a0 = *reinterpret_cast<const float4*>(x_in + base + c), a1 = *reinterpret_cast<const float4*>(x_in + base + c + 4);
+    float4 a0, a1;
+    if (x_in != nullptr) {
+      a0 = *reinterpret_cast<const float4*>(x_in + base + c);
+      a1 = *reinterpret_cast<const float4*>(x_in + base + c + 4);
+    } else {
+      const uint4 h = *reinterpret_cast<const uint4*>(x_in_split + 2 * base + c), l = *reinterpret_cast<const uint4*>(x_in_split + 2 * base + C + c);
+      a0 = make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16), __uint_as_float(h.x & 0xFFFF0000u) + __uint_as_float(l.x & 0xFFFF0000u),
+                       __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16), __uint_as_float(h.y & 0xFFFF0000u) + __uint_as_float(l.y & 0xFFFF0000u));
+      a1 = make_float4(__uint_as_float(h.z << 16) + __uint_as_float(l.z << 16), __uint_as_float(h.z & 0xFFFF0000u) + __uint_as_float(l.z & 0xFFFF0000u),
+                       __uint_as_float(h.w << 16) + __uint_as_float(l.w << 16), __uint_as_float(h.w & 0xFFFF0000u) + __uint_as_float(l.w & 0xFFFF0000u));
+    }
     const float4 b0 = *reinterpret_cast<const float4*>(y + base + c), b1 = *reinterpret_cast<const float4*>(y + base + c + 4);
     v[i][0] = a0.x + b0.x; v[i][1] = a0.y + b0.y; v[i][2] = a0.z + b0.z; v[i][3] = a0.w + b0.w;
     v[i][4] = a1.x + b1.x; v[i][5] = a1.y + b1.y; v[i][6] = a1.z + b1.z; v[i][7] = a1.w + b1.w;

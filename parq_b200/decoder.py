@@ -194,11 +194,23 @@ class DecoderEngine:
             setattr(po, k, outs[k].data_ptr())
         return outs, po
 
-    def _launch(self, shape, tokens, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags):
+    def _launch(self, shape, tokens, tokens_lo, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags):
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.parq_decoder_forward(C.byref(shape), _ptr(tokens), _ptr(camera), _ptr(T_cp), _ptr(T_wp), _ptr(T_wl),
-                                                     _ptr(ref0), _ptr(fr), _ptr(self.packed), _ptr(ws), ws.numel(), C.byref(po),
+            _lib.check(self.lib.parq_decoder_forward(C.byref(shape), _ptr(tokens), _ptr(tokens_lo), _ptr(camera), _ptr(T_cp), _ptr(T_wp),
+                                                     _ptr(T_wl), _ptr(ref0), _ptr(fr), _ptr(self.packed), _ptr(ws), ws.numel(), C.byref(po),
                                                      flags, _stream()), "parq_decoder_forward")
+
+    def _split_tokens(self, tokens, hi=None, lo=None):
+        """fp32 tokens -> exact bf16 pair (hi, lo) on the device (parq_split_tokens): K / V^T are projected from `hi`
+        (they are stored in bf16 anyway), the gather reads hi + lo, so the sampled query content -- which enters the fp32
+        residual stream directly -- sees the caller's fp32 values to 16 mantissa bits."""
+        tokens = tokens.detach().contiguous()
+        hi = torch.empty(tokens.shape, dtype=torch.bfloat16, device=self.device) if hi is None else hi
+        lo = torch.empty(tokens.shape, dtype=torch.bfloat16, device=self.device) if lo is None else lo
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.parq_split_tokens(_ptr(tokens), _ptr(hi), _ptr(lo), tokens.numel(), _stream()), "parq_split_tokens")
+        tokens.record_stream(torch.cuda.current_stream(self.device))
+        return hi, lo
 
     def _ref0(self, B):
         # sigmoid(refpoint.weight) repeated per clip (reference transformer_parq.py:121,309); cached per batch size
@@ -208,7 +220,8 @@ class DecoderEngine:
 
     def forward(self, tokens, camera, T_cp, T_wp, T_wl, H, W, forced_refs=None, ref0=None, debug=False, skip_kv=False,
                 graph=False, pdl=True):
-        """tokens (B, T*H*W, C) bf16 (fp32 is rounded to bf16); camera (B,T,6); poses (B,T,12)/(B,1,12) fp32.
+        """tokens (B, T*H*W, C) bf16, or fp32 (split on the device into an exact bf16 pair, see ``_split_tokens``);
+        camera (B,T,6); poses (B,T,12)/(B,1,12) fp32.
         Returns a dict of stacked per-iteration tensors (iters, B, Nq, n).
 
         ``pdl=False`` launches the kernels in plain stream order instead of with programmatic dependent launch.
@@ -228,7 +241,10 @@ class DecoderEngine:
         flags = self.flags | (_lib.PARQ_FLAG_SKIP_KV if skip_kv else 0) | (0 if pdl else _lib.PARQ_FLAG_NO_PDL)
         if graph:
             return self._forward_graph(shape, ws, flags, tokens, camera, T_cp, T_wp, T_wl, forced_refs, ref0, debug)
-        if tokens.dtype != torch.bfloat16:
+        tokens_lo = None
+        if tokens.dtype == torch.float32:
+            tokens, tokens_lo = self._split_tokens(tokens)
+        elif tokens.dtype != torch.bfloat16:
             tokens = tokens.to(torch.bfloat16)
         tokens = tokens.contiguous()
         f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
@@ -236,10 +252,10 @@ class DecoderEngine:
         ref0 = self._ref0(B) if ref0 is None else f32(ref0)
         fr = f32(forced_refs) if forced_refs is not None else None
         outs, po = self._alloc_outputs(B, T, debug)
-        self._launch(shape, tokens, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags)
+        self._launch(shape, tokens, tokens_lo, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags)
         # keep inputs alive until the stream the kernels were launched on has consumed them
         st = torch.cuda.current_stream(self.device)
-        for t in (tokens, camera, T_cp, T_wp, T_wl, ref0, fr):
+        for t in (tokens, tokens_lo, camera, T_cp, T_wp, T_wl, ref0, fr):
             if t is not None:
                 t.record_stream(st)
         if "center_valid" in outs:
@@ -251,17 +267,19 @@ class DecoderEngine:
         inputs (camera, poses, reference points) are always copied into static buffers owned by the entry, so fresh
         temporaries, non-contiguous slices or dtype conversions on the caller's side never miss the cache.  Tokens that are
         already contiguous bf16 are consumed in place (keyed by their address: no 1.26 GB copy per step at config 2);
-        tokens that need a conversion anyway (fp32 from the reference pipeline) are converted straight into one static
-        bf16 buffer per shape."""
+        tokens that need a conversion anyway (fp32 from the reference pipeline) are split straight into one static
+        bf16 (hi, lo) pair per shape."""
         B, T, H, W = shape.B, shape.T, shape.H, shape.W
         in_place = tokens.dtype == torch.bfloat16 and tokens.is_contiguous()
-        key = (tokens.data_ptr() if in_place else "static", B, T, H, W, flags, bool(debug), forced_refs is not None, ref0 is not None,
+        split = tokens.dtype == torch.float32
+        key = (tokens.data_ptr() if in_place else ("split" if split else "static"), B, T, H, W, flags, bool(debug), forced_refs is not None, ref0 is not None,
                ws.data_ptr())
         entry = self._graphs.get(key)
         with torch.cuda.device(self.device):
             if entry is None:
                 dev = self.device
                 st = {"tokens": tokens if in_place else torch.empty(tokens.shape, dtype=torch.bfloat16, device=dev),
+                      "tokens_lo": torch.empty(tokens.shape, dtype=torch.bfloat16, device=dev) if split else None,
                       "camera": torch.empty(B, T, 6, dtype=torch.float32, device=dev),
                       "T_cp": torch.empty(B, T, 12, dtype=torch.float32, device=dev),
                       "T_wp": torch.empty(B, T, 12, dtype=torch.float32, device=dev),
@@ -270,8 +288,10 @@ class DecoderEngine:
                       "fr": None if forced_refs is None else torch.empty(self.iters, B, self.Nq, 3, dtype=torch.float32, device=dev)}
                 entry = {"static": st, "graph": None, "outs": None}
             st = entry["static"]
-            if not in_place:
-                st["tokens"].copy_(tokens)                     # the fp32 -> bf16 rounding the eager path does with .to()
+            if split:
+                self._split_tokens(tokens, st["tokens"], st["tokens_lo"])
+            elif not in_place:
+                st["tokens"].copy_(tokens)
             for name, src in (("camera", camera), ("T_cp", T_cp), ("T_wp", T_wp), ("T_wl", T_wl)):
                 st[name].copy_(src.detach().reshape(st[name].shape))
             if ref0 is not None:
@@ -280,7 +300,7 @@ class DecoderEngine:
                 st["fr"].copy_(forced_refs.detach())
             if entry["graph"] is None:
                 outs, po = self._alloc_outputs(B, T, debug)
-                args = (shape, st["tokens"], st["camera"], st["T_cp"], st["T_wp"], st["T_wl"], st["ref0"], st["fr"], ws, po, flags)
+                args = (shape, st["tokens"], st["tokens_lo"], st["camera"], st["T_cp"], st["T_wp"], st["T_wl"], st["ref0"], st["fr"], ws, po, flags)
                 self._launch(*args)                            # lazy one-off setup (smem opt-ins) outside the capture
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
@@ -338,7 +358,13 @@ def project(tokens, query_pos, T_camera_local, camera, H, W):
     cam = raw(camera).float().contiguous()
     B, T = T_cl.shape[:2]
     Nq, Cc = query_pos.shape[1], tokens.shape[-1]
-    if tokens.dtype != torch.bfloat16:
+    tokens_lo = None
+    if tokens.dtype == torch.float32:
+        t32 = tokens.contiguous()
+        tokens, tokens_lo = torch.empty_like(t32, dtype=torch.bfloat16), torch.empty_like(t32, dtype=torch.bfloat16)
+        with torch.cuda.device(t32.device):
+            _lib.check(lib.parq_split_tokens(_ptr(t32), _ptr(tokens), _ptr(tokens_lo), t32.numel(), _stream()), "parq_split_tokens")
+    elif tokens.dtype != torch.bfloat16:
         tokens = tokens.to(torch.bfloat16)
     tokens = tokens.contiguous()
     q = query_pos.float().contiguous()
@@ -349,7 +375,7 @@ def project(tokens, query_pos, T_camera_local, camera, H, W):
     cim = torch.empty(B, T, Nq, 2, dtype=torch.float32, device=dev)
     val = torch.empty(B, T, Nq, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.parq_project_sample(C.byref(shape), _ptr(tokens), _ptr(q), _ptr(T_cl), _ptr(cam), _ptr(feat), _ptr(cim),
+        _lib.check(lib.parq_project_sample(C.byref(shape), _ptr(tokens), _ptr(tokens_lo), _ptr(q), _ptr(T_cl), _ptr(cam), _ptr(feat), _ptr(cim),
                                            _ptr(val), None, _stream()), "parq_project_sample")
     return feat, cim, val.bool()
 

@@ -80,7 +80,7 @@ def test_library_exports_every_declared_symbol():
     assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
     for n in names:
         assert hasattr(lib, n), "libparq_b200.so does not export " + n
-    assert lib.parq_version() == 1
+    assert lib.parq_version() == 2
 
 
 def test_shape_validation_without_gpu():

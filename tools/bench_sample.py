@@ -27,7 +27,7 @@ def run(tag, tokens, ref, Tcl, cam, B, T, H, W, reps=50):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(lib.parq_project_sample(C.byref(shape), _ptr(tokens), _ptr(ref), _ptr(Tcl), _ptr(cam), _ptr(feat), _ptr(cim), _ptr(val),
+        _lib.check(lib.parq_project_sample(C.byref(shape), _ptr(tokens), None, _ptr(ref), _ptr(Tcl), _ptr(cam), _ptr(feat), _ptr(cim), _ptr(val),
                                            None, _stream()), "ps")
         e1.record()
         torch.cuda.synchronize()
