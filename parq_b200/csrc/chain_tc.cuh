@@ -1,0 +1,521 @@
+// Chained tcgen05 GEMMs for the row-local part of a decoder iteration (sm_100a).
+//
+// Between the attention kernels an iteration is a chain of linear layers in which every output row depends only
+// on the same row of the input (reference transformer_parq.py:365-386, 176-180, 211-281):
+//     P:  pe0 -> ReLU -> pe2 (+x -> x+pe) -> self-attention Q|K projection
+//     A:  self-attention out-projection + residual + LayerNorm1 (+pe) -> cross-attention Q projection
+//     B:  cross-attention out-projection + residual + LayerNorm2 -> FFN linear1 + ReLU -> linear2 + residual +
+//         LayerNorm3 -> first layer of the centre / rotation heads (+ GroupNorm tile sums)
+// As separate launches each link is a one-wave GEMM of 128 CTAs whose launch latency, pipeline fill and epilogue
+// are fully exposed (25-37 us for ~10 us of tensor work), plus a row-wise LayerNorm kernel after three of them.
+// Here a CLUSTER OF 4 CTAs owns a block of 128 rows for the whole chain: CTA r computes columns [r N/4, (r+1) N/4)
+// of every stage with the same TMA -> smem ring -> tcgen05.mma (TMEM accumulator) pipeline as gemm_tc.cuh, the
+// stage's output goes to global memory (it stays in L2), and the next stage streams it back as its A operand as
+// soon as all four CTAs have signalled "stage done" on a cluster-scope mbarrier.  Weight tiles of the next stage
+// are requested while the current stage's epilogue is still running.
+//   LayerNorm inside a stage: the rows of z = acc + bias + residual are spread over the four CTAs (and two
+// epilogue warps per row); every thread reduces its 96-128 values to (mean, M2), writes that pair into all four
+// CTAs' shared memory (DSMEM), and after a cluster-scope mbarrier combines the 8 partials of its row in a fixed
+// order (Chan's parallel variance: deterministic, no cancellation).  z waits in TMEM (written back in place).
+//   Activations enter the tensor cores as an exact bf16 [hi|lo] split (see gemm_tc.cuh); every stage that feeds
+// another GEMM emits that split directly.
+#pragma once
+#include <cuda.h>
+
+#include "gemm2_tc.cuh"
+#include "ptx.cuh"
+
+namespace parq {
+
+enum ChainEpilogue {
+  CH_EP_LN = 0,     // y = LayerNorm(acc + bias + residual) * gamma + beta -> out_f32, a_out = split(y), a_out_pe = split(y + pe)
+  CH_EP_SPLIT = 1,  // v = [relu](acc + bias) -> a_out = split(v)
+  CH_EP_LP = 2,     // v = acc + bias -> out_lp (bf16 / fp16)
+  CH_EP_F32 = 3,    // v = acc + bias -> out_f32 [, GroupNorm tile sums] [, out_sum_split = split(v + add_split)]
+};
+
+struct ChainStage {
+  int N, K;                  // output columns of the stage (all four CTAs), K per term (multiple of 64)
+  int tile_n, tiles;         // per CTA: `tiles` accumulator tiles of `tile_n` columns; tiles * tile_n = N / 4
+  int nterms, a_koff[3], b_koff[3], dual_a;
+  int ep, relu, lp_fp16;
+  const float* bias;                   // (N) or null
+  const float* resid_f32;              // LN: (M, N) fp32 residual, or null
+  const __nv_bfloat16* resid_split;    // LN: (M, 2N) [hi|lo] residual, or null
+  const float* gamma;
+  const float* beta;
+  const float* pe;                     // LN: optional (M, N)
+  float* out_f32;                      // (M, N)
+  __nv_bfloat16* a_out;                // (M, 2N) [hi|lo], or null
+  __nv_bfloat16* a_out_pe;             // LN only, or null
+  void* out_lp;                        // CH_EP_LP: (M, ld_lp) 16-bit
+  long long ld_lp;
+  double2* gn_out;                     // CH_EP_F32: optional (sum, sum of squares) per 128 x 256 tile, slot m_tile * gn_stride + n0 / 256
+  int gn_stride;
+  const __nv_bfloat16* add_split;      // CH_EP_F32: optional (M, 2N) [hi|lo] addend ...
+  __nv_bfloat16* out_sum_split;        // ... and the split of (v + addend)
+};
+
+namespace chain {
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int CLUSTER = 4;
+constexpr int MAX_STAGES = 4;
+constexpr int THREADS = 384;           // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-11 epilogue
+constexpr int EPI_WARPS = 8;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = 256 * BK * 2;  // 32 KB
+constexpr int RING_BYTES = 4 * (A_BYTES + B_BYTES);
+constexpr int VEC_COLS = 512;          // columns of one CTA in a stage (bias / gamma / beta staging)
+constexpr int SMEM_BYTES = 1024 + RING_BYTES + 512 /*barriers*/ + 2 * CLUSTER * BM * 8 /*row statistics*/ + 3 * VEC_COLS * 4 + 256 /*GN sums*/;
+}  // namespace chain
+
+struct ChainParams {
+  int M, nstages;
+  ChainStage st[chain::MAX_STAGES];
+};
+struct ChainMaps {
+  CUtensorMap a[chain::MAX_STAGES], b[chain::MAX_STAGES];
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+// generic-proxy writes (st.global of the epilogue) <-> async-proxy reads (TMA loads of the next stage), all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// 8 fp32 -> 8 bf16 "hi" at dst and 8 bf16 residuals at dst + lo_off (16-byte stores)
+__device__ __forceinline__ void chain_store_split8(__nv_bfloat16* dst, long long lo_off, const float* v) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    lo[i] = pack_bf16x2(v[2 * i] - __uint_as_float(hi[i] << 16), v[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u));
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+__device__ __forceinline__ void chain_load_split8(const __nv_bfloat16* src, long long lo_off, float* v) {
+  const uint4 h = *reinterpret_cast<const uint4*>(src), l = *reinterpret_cast<const uint4*>(src + lo_off);
+  const uint32_t hs[4] = {h.x, h.y, h.z, h.w}, ls[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(hs[i] << 16) + __uint_as_float(ls[i] << 16);
+    v[2 * i + 1] = __uint_as_float(hs[i] & 0xFFFF0000u) + __uint_as_float(ls[i] & 0xFFFF0000u);
+  }
+}
+
+// grid = 4 * (M / 128) CTAs in clusters of 4 along x; M % 128 == 0.
+__global__ void __launch_bounds__(chain::THREADS, 1)
+chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
+  using namespace chain;
+  extern __shared__ uint8_t smem_raw_c[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_c) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES);   // [4]
+  uint64_t* empty_bar = full_bar + 4;                                    // [4]
+  uint64_t* tfull_bar = empty_bar + 4;                                   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                                  // [2]
+  uint64_t* xbar = tempty_bar + 2;        // row statistics of all four CTAs have arrived
+  uint64_t* dbar = xbar + 1;              // the stage's outputs of all four CTAs are in global memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dbar + 1);
+  float2* s_part = reinterpret_cast<float2*>(smem + RING_BYTES + 512);   // [2 * CLUSTER][BM] (mean, M2) partials
+  float* s_vec = reinterpret_cast<float*>(s_part + 2 * CLUSTER * BM);    // [3][VEC_COLS] bias | gamma | beta
+  double* s_gn = reinterpret_cast<double*>(s_vec + 3 * VEC_COLS);        // [EPI_WARPS][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int m0 = (blockIdx.x / CLUSTER) * BM;
+  // every stage of a chain uses the same ring geometry: dual-A (3 slots of [A_hi | A_lo | B]) or plain (4 slots of A + B)
+  const bool dual = p.st[0].dual_a != 0;
+  const int nst = dual ? 3 : 4;
+  auto a_ptr = [&](int st, int which) { return dual ? smem + st * (2 * A_BYTES + B_BYTES) + which * A_BYTES : smem + st * A_BYTES; };
+  auto b_ptr = [&](int st) { return dual ? smem + st * (2 * A_BYTES + B_BYTES) + 2 * A_BYTES : smem + 4 * A_BYTES + st * B_BYTES; };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      tma_prefetch_desc(&maps.a[s]);
+      tma_prefetch_desc(&maps.b[s]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], EPI_WARPS);
+    }
+    mbar_init(xbar, CLUSTER * EPI_WARPS);
+    mbar_init(dbar, CLUSTER * EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_sync_all();                      // the peers' barriers exist before anyone arrives on them
+
+  if (warp == 0) {
+    if (lane == 0) {                       // ---------------------------------------------------- TMA producer
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < p.nstages; ++s) {
+        const ChainStage& S = p.st[s];
+        const int kb_per_term = S.K / BK;
+        const int nterm_loops = dual ? 1 : S.nterms;
+        const int num_kb = kb_per_term * nterm_loops;
+        const uint32_t b_bytes = static_cast<uint32_t>(S.tile_n) * BK * 2;
+        const uint32_t stage_tx = (dual ? 2 * A_BYTES : A_BYTES) + b_bytes;
+        const int n_base = static_cast<int>(rank) * (S.N / CLUSTER);
+        auto a_off = [&](int t) { return t == 0 ? S.a_koff[0] : (t == 1 ? S.a_koff[1] : S.a_koff[2]); };
+        auto b_off = [&](int t) { return t == 0 ? S.b_koff[0] : (t == 1 ? S.b_koff[1] : S.b_koff[2]); };
+        // weights do not depend on the previous stage (or kernel): the B tiles of the first ring slots are requested
+        // before the wait, the A tiles of the same slots after it
+        const int total = num_kb * S.tiles;
+        const int pre = total < nst ? total : nst;
+        {
+          int ps = slot;
+          uint32_t pp = phase;
+          for (int i = 0; i < pre; ++i) {
+            const int j = i / num_kb, r = i % num_kb, t = r / kb_per_term, kb = r % kb_per_term;
+            mbar_wait(&empty_bar[ps], pp ^ 1);
+            mbar_expect_tx(&full_bar[ps], stage_tx);
+            tma_load_2d(b_ptr(ps), &maps.b[s], &full_bar[ps], b_off(t) + kb * BK, n_base + j * S.tile_n);
+            if (++ps == nst) { ps = 0; pp ^= 1; }
+          }
+        }
+        if (s == 0) {
+          pdl_wait();
+          pdl_launch_dependents();
+        } else {
+          mbar_wait_cluster(dbar, (s - 1) & 1);
+          fence_proxy_async_all();
+        }
+        int idx = 0;
+        for (int j = 0; j < S.tiles; ++j) {
+          const int n0 = n_base + j * S.tile_n;
+          for (int t = 0; t < nterm_loops; ++t) {
+            for (int kb = 0; kb < kb_per_term; ++kb, ++idx) {
+              if (idx >= pre) {
+                mbar_wait(&empty_bar[slot], phase ^ 1);
+                mbar_expect_tx(&full_bar[slot], stage_tx);
+                tma_load_2d(b_ptr(slot), &maps.b[s], &full_bar[slot], b_off(t) + kb * BK, n0);
+              }
+              tma_load_2d(a_ptr(slot, 0), &maps.a[s], &full_bar[slot], a_off(t) + kb * BK, m0);
+              if (dual) tma_load_2d(a_ptr(slot, 1), &maps.a[s], &full_bar[slot], a_off(1) + kb * BK, m0);
+              if (++slot == nst) { slot = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else {
+      pdl_wait();
+      pdl_launch_dependents();
+    }
+  } else if (warp == 1) {
+    pdl_wait();
+    pdl_launch_dependents();
+    if (lane == 0) {                       // ---------------------------------------------------- MMA issuer
+      int slot = 0;
+      uint32_t phase = 0;
+      int cnt = 0;
+      for (int s = 0; s < p.nstages; ++s) {
+        const ChainStage& S = p.st[s];
+        const int num_kb = (S.K / BK) * (dual ? 1 : S.nterms);
+        const uint32_t idesc = umma_idesc(BM, static_cast<uint32_t>(S.tile_n), 1);
+        for (int j = 0; j < S.tiles; ++j, ++cnt) {
+          const int acc = cnt & 1;
+          mbar_wait(&tempty_bar[acc], ((cnt >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 256;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[slot], phase);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(a_ptr(slot, 0)));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(b_ptr(slot)));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (dual) {
+              const uint64_t adesc1 = umma_desc_sw128(smem_u32(a_ptr(slot, 1)));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_ss(d_tmem, adesc1 + 2 * k, bdesc + 2 * k, idesc, 1u);
+            }
+            umma_commit(&empty_bar[slot]);
+            if (++slot == nst) { slot = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[acc]);
+        }
+      }
+    }
+  } else if (warp >= 4) {                  // ---------------------------------------------------- epilogue warps
+    pdl_wait();
+    pdl_launch_dependents();
+    const int e = warp - 4;
+    const int q = e & 3;                   // TMEM lane quadrant == warp % 4
+    const int h = e >> 2;                  // which half of the tile's columns
+    const int et = threadIdx.x - 128;      // 0..255
+    const int rin = q * 32 + lane;         // row inside the block
+    const long long row = m0 + rin;
+    int cnt = 0, nln = 0;
+    uint32_t xaddr[CLUSTER], daddr[CLUSTER];
+#pragma unroll
+    for (int c = 0; c < CLUSTER; ++c) {
+      xaddr[c] = mapa_u32(smem_u32(xbar), c);
+      daddr[c] = mapa_u32(smem_u32(dbar), c);
+    }
+    for (int s = 0; s < p.nstages; ++s) {
+      const ChainStage& S = p.st[s];
+      const int ncta = S.N / CLUSTER;                        // columns of this CTA
+      const int n_base = static_cast<int>(rank) * ncta;
+      const int half = S.tile_n / 2, nchunks = half / 32;
+      // stage the per-column vectors of this CTA's columns
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // the previous stage no longer reads s_vec
+      for (int i = et; i < ncta; i += 256) {
+        s_vec[i] = S.bias != nullptr ? __ldg(S.bias + n_base + i) : 0.f;
+        if (S.ep == CH_EP_LN) {
+          s_vec[VEC_COLS + i] = __ldg(S.gamma + n_base + i);
+          s_vec[2 * VEC_COLS + i] = __ldg(S.beta + n_base + i);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int j = 0; j < S.tiles; ++j, ++cnt) {
+        const int acc = cnt & 1;
+        const int cl0 = j * S.tile_n + h * half;             // first column of this warp inside the CTA's columns
+        const int col0 = n_base + cl0;                       // ... and in the stage's output
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + h * half;
+        mbar_wait(&tfull_bar[acc], (cnt >> 1) & 1);
+        tc_fence_after();
+        uint32_t r[32];
+        if (S.ep == CH_EP_LN) {
+          // ---- pass 1: z = acc + bias + residual, running (mean, M2) over this thread's columns, z back into TMEM
+          float mean = 0.f, M2 = 0.f, n = 0.f;
+          for (int c = 0; c < nchunks; ++c) {
+            tmem_ld32(taddr + c * 32, r);
+            float z[32];
+            if (S.resid_f32 != nullptr) {
+              const float4* rp = reinterpret_cast<const float4*>(S.resid_f32 + row * S.N + col0 + c * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 v = rp[i];
+                z[4 * i] = v.x; z[4 * i + 1] = v.y; z[4 * i + 2] = v.z; z[4 * i + 3] = v.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) chain_load_split8(S.resid_split + row * 2 * S.N + col0 + c * 32 + 8 * i, S.N, z + 8 * i);
+            }
+            tmem_wait_ld();
+            float cs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = reinterpret_cast<const float4*>(s_vec + cl0 + c * 32)[i];
+              z[4 * i] += __uint_as_float(r[4 * i]) + b4.x;
+              z[4 * i + 1] += __uint_as_float(r[4 * i + 1]) + b4.y;
+              z[4 * i + 2] += __uint_as_float(r[4 * i + 2]) + b4.z;
+              z[4 * i + 3] += __uint_as_float(r[4 * i + 3]) + b4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cs += z[i];
+            const float cm = cs * (1.f / 32.f);
+            float cM2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float d = z[i] - cm;
+              cM2 = fmaf(d, d, cM2);
+              r[i] = __float_as_uint(z[i]);
+            }
+            tmem_st32(taddr + c * 32, r);
+            const float nn = n + 32.f, delta = cm - mean;
+            mean += delta * (32.f / nn);
+            M2 += cM2 + delta * delta * (n * 32.f / nn);
+            n = nn;
+          }
+          tmem_wait_st();
+          // ---- exchange: this thread's partial into slot (rank, h) of every CTA of the cluster
+          {
+            const uint32_t local = smem_u32(s_part + (rank * 2 + h) * BM + rin);
+#pragma unroll
+            for (int c = 0; c < CLUSTER; ++c) st_cluster_f32x2(mapa_u32(local, c), mean, M2);
+          }
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < CLUSTER; ++c) mbar_arrive_cluster(xaddr[c]);
+          }
+          mbar_wait_cluster(xbar, nln & 1);
+          ++nln;
+          {
+            const float np = static_cast<float>(half);        // values per partial
+            float mt = 0.f, Mt = 0.f, nt = 0.f;
+#pragma unroll
+            for (int k = 0; k < 2 * CLUSTER; ++k) {
+              const float2 pk = s_part[k * BM + rin];
+              const float nn = nt + np, delta = pk.x - mt;
+              mt += delta * (np / nn);
+              Mt += pk.y + delta * delta * (nt * np / nn);
+              nt = nn;
+            }
+            mean = mt;
+            M2 = Mt / nt;                                      // biased variance
+          }
+          const float rstd = 1.f / sqrtf(M2 + 1e-5f);
+          // ---- pass 2: normalise, write the fp32 row and the operand splits
+          for (int c = 0; c < nchunks; ++c) {
+            tmem_ld32(taddr + c * 32, r);
+            tmem_wait_ld();
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 g4 = reinterpret_cast<const float4*>(s_vec + VEC_COLS + cl0 + c * 32)[i];
+              const float4 e4 = reinterpret_cast<const float4*>(s_vec + 2 * VEC_COLS + cl0 + c * 32)[i];
+              y[4 * i] = (__uint_as_float(r[4 * i]) - mean) * rstd * g4.x + e4.x;
+              y[4 * i + 1] = (__uint_as_float(r[4 * i + 1]) - mean) * rstd * g4.y + e4.y;
+              y[4 * i + 2] = (__uint_as_float(r[4 * i + 2]) - mean) * rstd * g4.z + e4.z;
+              y[4 * i + 3] = (__uint_as_float(r[4 * i + 3]) - mean) * rstd * g4.w + e4.w;
+            }
+            const long long o = row * S.N + col0 + c * 32;
+            if (S.out_f32 != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(S.out_f32 + o)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+            }
+            if (S.a_out != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) chain_store_split8(S.a_out + row * 2 * S.N + col0 + c * 32 + 8 * i, S.N, y + 8 * i);
+            }
+            if (S.a_out_pe != nullptr) {
+              const float4* pp = reinterpret_cast<const float4*>(S.pe + o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 v = pp[i];
+                y[4 * i] += v.x; y[4 * i + 1] += v.y; y[4 * i + 2] += v.z; y[4 * i + 3] += v.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) chain_store_split8(S.a_out_pe + row * 2 * S.N + col0 + c * 32 + 8 * i, S.N, y + 8 * i);
+            }
+          }
+        } else {
+          float gsum = 0.f, gsq = 0.f;
+          for (int c = 0; c < nchunks; ++c) {
+            tmem_ld32(taddr + c * 32, r);
+            tmem_wait_ld();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = reinterpret_cast<const float4*>(s_vec + cl0 + c * 32)[i];
+              v[4 * i] = __uint_as_float(r[4 * i]) + b4.x;
+              v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z;
+              v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+            }
+            if (S.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            const long long cc = col0 + c * 32;
+            if (S.ep == CH_EP_SPLIT) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) chain_store_split8(S.a_out + row * 2 * S.N + cc + 8 * i, S.N, v + 8 * i);
+            } else if (S.ep == CH_EP_LP) {
+              uint32_t w[16];
+              if (S.lp_fp16) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+              }
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(S.out_lp) + row * S.ld_lp + cc);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            } else {
+              if (S.gn_out != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { gsum += v[i]; gsq = fmaf(v[i], v[i], gsq); }
+              }
+              if (S.out_f32 != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  reinterpret_cast<float4*>(S.out_f32 + row * S.N + cc)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              }
+              if (S.add_split != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float a[8];
+                  chain_load_split8(S.add_split + row * 2 * S.N + cc + 8 * i, S.N, a);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) a[k] += v[8 * i + k];
+                  chain_store_split8(S.out_sum_split + row * 2 * S.N + cc + 8 * i, S.N, a);
+                }
+              }
+            }
+          }
+          if (S.ep == CH_EP_F32 && S.gn_out != nullptr) {
+            // deterministic tile statistics for the following GroupNorm: lanes -> warp (shuffles, double) -> 8 warps (smem)
+            double ds = gsum, dq = gsq;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              ds += __shfl_xor_sync(0xffffffffu, ds, o);
+              dq += __shfl_xor_sync(0xffffffffu, dq, o);
+            }
+            if (lane == 0) { s_gn[2 * e] = ds; s_gn[2 * e + 1] = dq; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) {
+              double a = 0.0, b = 0.0;
+              for (int k = 0; k < EPI_WARPS; ++k) { a += s_gn[2 * k]; b += s_gn[2 * k + 1]; }
+              S.gn_out[static_cast<long long>(m0 / BM) * S.gn_stride + (n_base + j * S.tile_n) / 256] = make_double2(a, b);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      // the stage's outputs of this warp are written: publish them to the TMA engines of the whole cluster
+      if (s + 1 < p.nstages) {
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < CLUSTER; ++c) mbar_arrive_cluster(daddr[c]);
+        }
+      }
+    }
+  } else {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // no CTA leaves while a peer may still signal its barriers or write its statistics
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace parq

@@ -15,6 +15,7 @@
 #include "attn_tc.cuh"
 #include "attn2_tc.cuh"
 #include "attn3_tc.cuh"
+#include "chain_tc.cuh"
 #include "fpn.cuh"
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
@@ -142,6 +143,7 @@ static int require_sm100() {
 // The stand-alone entry points launch plainly (their inputs may come from the caller's previous kernel).
 static thread_local bool g_pdl = false;
 static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
+static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;           // A/B switch: separate GEMM + LayerNorm launches instead of chain_tc.cuh
 static const bool g_force_pair = getenv("PARQ_FORCE_PAIR") != nullptr;   // every GEMM on the CTA-pair kernel (tests)
 static const bool g_no_streamk = getenv("PARQ_NO_STREAMK") != nullptr;       // A/B switch: split-KV grid instead of the stream-K schedule
 static const bool g_no_pair_attn = getenv("PARQ_NO_PAIR_ATTN") != nullptr;   // A/B switch: single-CTA attention kernel
@@ -272,6 +274,58 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
+}
+
+// ---- chained GEMMs (chain_tc.cuh): one cluster of 4 CTAs per 128 rows walks a list of dependent linear stages ----
+struct ChainBuilder {
+  ChainParams p;
+  ChainMaps m;
+  ChainBuilder(int M) {
+    memset(&p, 0, sizeof(p));
+    memset(&m, 0, sizeof(m));
+    p.M = M;
+  }
+};
+static bool chain_cols_ok(int N) {
+  const int ncta = N / chain::CLUSTER;
+  if (N % chain::CLUSTER != 0 || ncta > chain::VEC_COLS) return false;
+  return ncta <= 256 ? (ncta % 64 == 0) : (ncta % 256 == 0);
+}
+// A = [hi|lo] activations (M, a_cols), W = packed [hi|lo] weights (N, 2K); S carries N, K and the epilogue
+static int chain_add(ChainBuilder& cb, const void* A, uint64_t a_cols, const void* W, bool w_lo, ChainStage S) {
+  if (cb.p.nstages >= chain::MAX_STAGES) return fail(PARQ_ERR_SHAPE, "too many chain stages");
+  if (S.K <= 0 || S.K % chain::BK != 0 || !chain_cols_ok(S.N)) return fail(PARQ_ERR_SHAPE, "chain stage N=%d K=%d not supported", S.N, S.K);
+  const int ncta = S.N / chain::CLUSTER;
+  S.tile_n = ncta <= 256 ? ncta : 256;
+  S.tiles = ncta / S.tile_n;
+  S.nterms = w_lo ? 3 : 2;
+  S.a_koff[0] = 0;   S.b_koff[0] = 0;
+  S.a_koff[1] = S.K; S.b_koff[1] = 0;
+  S.a_koff[2] = 0;   S.b_koff[2] = S.K;
+  S.dual_a = (!w_lo && !g_no_dual) ? 1 : 0;
+  if (cb.p.nstages > 0 && cb.p.st[0].dual_a != S.dual_a) return fail(PARQ_ERR_SHAPE, "chain stages must share the ring geometry");
+  const int i = cb.p.nstages++;
+  TRY(make_map(&cb.m.a[i], A, cb.p.M, a_cols, a_cols, chain::BM));
+  TRY(make_map(&cb.m.b[i], W, S.N, 2 * static_cast<uint64_t>(S.K), 2 * static_cast<uint64_t>(S.K), S.tile_n));
+  cb.p.st[i] = S;
+  return PARQ_OK;
+}
+static int launch_chain(cudaStream_t st, const ChainBuilder& cb) {
+  if (cb.p.M % chain::BM != 0) return fail(PARQ_ERR_SHAPE, "chain kernel needs M %% 128 == 0 (M=%d)", cb.p.M);
+  OPT_IN_SMEM(chain_tc_kernel, chain::SMEM_BYTES);
+  {
+    ProfScope ps(TAG_GEMM, st);
+    launch_kc(chain_tc_kernel, dim3(chain::CLUSTER * (cb.p.M / chain::BM)), dim3(chain::THREADS), chain::SMEM_BYTES, st, dim3(chain::CLUSTER, 1, 1),
+              cb.m, cb.p);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PARQ_OK;
+}
+static ChainStage chain_stage(int N, int K, int ep, const float* bias) {
+  ChainStage S;
+  memset(&S, 0, sizeof(S));
+  S.N = N; S.K = K; S.ep = ep; S.bias = bias;
+  return S;
 }
 
 struct SplitPlan {
@@ -1090,6 +1144,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   const bool w_lo = (flags & PARQ_FLAG_WEIGHT_LO) != 0;
   const PdlScope pdl((flags & PARQ_FLAG_NO_PDL) == 0);
   const int C = s.C, F = s.ffn, R = s.B * s.Nq;
+  // the row-local linears of an iteration as three chained launches (chain_tc.cuh) instead of ten GEMMs + three LayerNorms
+  const bool chained = !(flags & PARQ_FLAG_NO_CHAIN) && !g_no_chain && chain_cols_ok(C) && chain_cols_ok(2 * C) && chain_cols_ok(F) && R % chain::BM == 0;
   auto F32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto BF = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
   auto PF = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
@@ -1118,10 +1174,73 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     sp.valid = out->center_valid ? out->center_valid + static_cast<size_t>(it) * s.B * s.T * s.Nq : nullptr;
     sp.coord_pos = nullptr;
     TRY(launch_sample(st, sp));
-    // K2: reference-point positional feature  pe = W2 relu(W1 posemb + b1) + b2; the second GEMM also emits the split of
-    // x + pe, the query / key input of the self-attention (transformer_parq.py:372)
+    float* x3 = out->decoder_out ? out->decoder_out + static_cast<size_t>(it) * R * C : F32(W.x3);
+    const int Nk = s.T * s.H * s.W;
     { ProfScope ps(TAG_ROWWISE, st); launch_k(posemb_kernel, dim3((R * 384 + 255) / 256), dim3(256), 0, st, ref, PF(P.dim_t), BF(W.a_pos), R); }
     CUDA_TRY(cudaGetLastError());
+    if (chained) {
+      // ---- chain P: pe = W2 relu(W1 posemb + b1) + b2 (+ x -> split(x + pe)) -> self-attention Q|K projection
+      {
+        ChainBuilder cb(R);
+        ChainStage S = chain_stage(C, 384, CH_EP_SPLIT, PF(P.pe0_b));
+        S.relu = 1; S.a_out = BF(W.a_peh);
+        TRY(chain_add(cb, ws + W.a_pos, 768, pk + P.pe0, w_lo, S));
+        S = chain_stage(C, C, CH_EP_F32, PF(P.pe2_b));
+        S.out_f32 = F32(W.pe); S.add_split = BF(W.a_x); S.out_sum_split = BF(W.a_xpe);
+        TRY(chain_add(cb, ws + W.a_peh, 2 * C, pk + P.pe2, w_lo, S));
+        S = chain_stage(2 * C, C, CH_EP_LP, PF(P.sa_qk_b));
+        S.out_lp = ws + W.qk_s; S.ld_lp = 2 * C; S.lp_fp16 = 1;
+        TRY(chain_add(cb, ws + W.a_xpe, 2 * C, pk + P.sa_qk, w_lo, S));
+        TRY(launch_chain(st, cb));
+      }
+      // V^T = Wv x^T + bv of the self-attention: weights are the A operand, activations the B operand
+      {
+        GemmParams g; memset(&g, 0, sizeof(g));
+        g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : 2; g.const_operand = 1;
+        g.a_koff[0] = 0; g.b_koff[0] = 0; g.a_koff[1] = 0; g.b_koff[1] = C; g.a_koff[2] = C; g.b_koff[2] = 0;
+        g.ep = epilogue_none(); g.ep.bias = PF(P.sa_v_b); g.ep.bias_per_row = 1;
+        g.ep.out_lp = ws + W.vt_s; g.ep.ld_lp = static_cast<long long>(W.ldvs); g.ep.lp_fp16 = 1;
+        TRY(launch_gemm(st, pk + P.sa_v, C, 2 * C, ws + W.a_x, R, 2 * C, g));
+      }
+      TRY(launch_attention(st, ws + W.qk_s, 2 * C, ws + W.qk_s + static_cast<size_t>(C) * 2, 2 * C, ws + W.vt_s, W.ldvs, s.B, s.heads,
+                           s.Nq, s.Nq, true, ws + W.scratch, W.scratch_bytes, BF(W.a_attn), W.self.nsplit));
+      // ---- chain A: self-attention out-projection + residual + LN1 (+pe) -> cross-attention Q projection
+      {
+        ChainBuilder cb(R);
+        ChainStage S = chain_stage(C, C, CH_EP_LN, PF(P.sa_out_b));
+        S.resid_split = BF(W.a_x); S.gamma = PF(P.ln1_g); S.beta = PF(P.ln1_b); S.pe = F32(W.pe);
+        S.out_f32 = F32(W.x1); S.a_out_pe = BF(W.a_x1pe);
+        TRY(chain_add(cb, ws + W.a_attn, 2 * C, pk + P.sa_out, w_lo, S));
+        S = chain_stage(C, C, CH_EP_LP, PF(P.ca_q_b));
+        S.out_lp = ws + W.q_c; S.ld_lp = C;
+        TRY(chain_add(cb, ws + W.a_x1pe, 2 * C, pk + P.ca_q, w_lo, S));
+        TRY(launch_chain(st, cb));
+      }
+      TRY(launch_attention(st, ws + W.q_c, C, ws + W.Kc, C, ws + W.Vt, W.ldv, s.B, s.heads, s.Nq, Nk, false, ws + W.scratch,
+                           W.scratch_bytes, BF(W.a_attn), /*library's choice: stream-K or the planned split*/ 0, /*kv_const=*/true,
+                           W.kv_tiled != 0));
+      // ---- chain B: cross-attention out-projection + residual + LN2 -> FFN -> + residual + LN3 -> first head layer
+      {
+        ChainBuilder cb(R);
+        ChainStage S = chain_stage(C, C, CH_EP_LN, PF(P.ca_out_b));
+        S.resid_f32 = F32(W.x1); S.gamma = PF(P.ln2_g); S.beta = PF(P.ln2_b);
+        S.out_f32 = F32(W.x2); S.a_out = BF(W.a_x2);
+        TRY(chain_add(cb, ws + W.a_attn, 2 * C, pk + P.ca_out, w_lo, S));
+        S = chain_stage(F, C, CH_EP_SPLIT, PF(P.lin1_b));
+        S.relu = 1; S.a_out = BF(W.a_ffn);
+        TRY(chain_add(cb, ws + W.a_x2, 2 * C, pk + P.lin1, w_lo, S));
+        S = chain_stage(C, F, CH_EP_LN, PF(P.lin2_b));
+        S.resid_f32 = F32(W.x2); S.gamma = PF(P.ln3_g); S.beta = PF(P.ln3_b);
+        S.out_f32 = x3; S.a_out = BF(W.a_x3);
+        TRY(chain_add(cb, ws + W.a_ffn, 2 * F, pk + P.lin2, w_lo, S));
+        S = chain_stage(2 * C, C, CH_EP_F32, nullptr);
+        S.out_f32 = F32(W.h1); S.gn_out = reinterpret_cast<double2*>(ws + W.gn1); S.gn_stride = GN_SLOTS_PER_MTILE;
+        TRY(chain_add(cb, ws + W.a_x3, 2 * C, pk + P.hd1, w_lo, S));
+        TRY(launch_chain(st, cb));
+      }
+    } else {
+    // K2: reference-point positional feature  pe = W2 relu(W1 posemb + b1) + b2; the second GEMM also emits the split of
+    // x + pe, the query / key input of the self-attention (transformer_parq.py:372)
     {
       GemmParams g; memset(&g, 0, sizeof(g));
       g.M = R; g.N = C; term_offsets(g, 384, w_lo, 0);
@@ -1168,7 +1287,6 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.ca_q_b);
       g.ep.out_lp = ws + W.q_c; g.ep.ld_lp = C;
       TRY(launch_gemm(st, ws + W.a_x1pe, R, 2 * C, pk + P.ca_q, C, 2 * C, g));
-      const int Nk = s.T * s.H * s.W;
       TRY(launch_attention(st, ws + W.q_c, C, ws + W.Kc, C, ws + W.Vt, W.ldv, s.B, s.heads, s.Nq, Nk, false, ws + W.scratch,
                            W.scratch_bytes, BF(W.a_attn), /*library's choice: stream-K or the planned split*/ 0, /*kv_const=*/true,
                            W.kv_tiled != 0));
@@ -1182,7 +1300,6 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       CUDA_TRY(cudaGetLastError());
     }
     // K6: FFN, residual + LN3
-    float* x3 = out->decoder_out ? out->decoder_out + static_cast<size_t>(it) * R * C : F32(W.x3);
     {
       GemmParams g; memset(&g, 0, sizeof(g));
       g.M = R; g.N = F; term_offsets(g, C, w_lo, 0);
@@ -1197,7 +1314,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       { ProfScope ps(TAG_ROWWISE, st); launch_k(add_ln_kernel<1024>, dim3((R + 3) / 4), dim3(128), 0, st, F32(W.x2), static_cast<const __nv_bfloat16*>(nullptr), F32(W.y), PF(P.ln3_g), PF(P.ln3_b), nullptr, x3, BF(W.a_x3), nullptr, R); }
       CUDA_TRY(cudaGetLastError());
     }
-    // K7: heads (two hidden layers with per-clip GroupNorm) + box update
+    // first hidden layer of the centre / rotation heads (one GEMM, N = 2C) with the GroupNorm tile sums in its epilogue
     {
       GemmParams g; memset(&g, 0, sizeof(g));
       g.M = R; g.N = 2 * C; term_offsets(g, C, w_lo, 0);
@@ -1205,6 +1322,11 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep.out_f32 = F32(W.h1); g.ep.ld_f32 = 2 * C;
       g.ep.gn_out = reinterpret_cast<double2*>(ws + W.gn1); g.ep.gn_stride = GN_SLOTS_PER_MTILE;
       TRY(launch_gemm(st, ws + W.a_x3, R, 2 * C, pk + P.hd1, 2 * C, 2 * C, g));
+    }
+    }   // !chained
+    // K7: heads (two hidden layers with per-clip GroupNorm) + box update
+    {
+      GemmParams g;
       { ProfScope ps(TAG_ROWWISE, st); launch_k(gn_apply_kernel, dim3(R), dim3(256), 0, st, F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1),
                                                PF(P.ctr1_g), PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1)); }
       CUDA_TRY(cudaGetLastError());

@@ -643,6 +643,31 @@ def test_decoder_ragged_clip_sizes(dev):
             assert relerr(got[k][i].cpu(), outs[i][k]) <= TOL, (k, i)
 
 
+def test_unchained_launch_sequence_matches_chained(dev):
+    # chain=False: one GEMM / LayerNorm launch per link (gemm_tc.cuh + add_ln_kernel) instead of the chained cluster kernel
+    # (chain_tc.cuh).  Both against the fixture; against each other they differ only by the summation order of the
+    # LayerNorm statistics (and a 1-ulp query change can flip a bf16 rounding inside the attention).
+    gold = load_golden("small")
+    c = regenerate_case(gold)
+    gold_outs = [{k: torch.from_numpy(gold[k][i]) for k in OUT_KEYS} for i in range(8)]
+    refs = O.refs_from_outputs(gold_outs, c["sd"]).to(dev)
+    eng = DecoderEngine(c["sd"], dev)
+    chained = {k: v.clone() for k, v in _engine_forward(eng, c, dev, forced_refs=refs, debug=True).items()}
+    plain = _engine_forward(eng, c, dev, forced_refs=refs, debug=True, chain=False)
+    for i in range(8):
+        assert relerr(plain["decoder_out"][i], chained["decoder_out"][i]) <= 2e-4
+        for k in ("pred_logits", "center_unnormalized", "ortho6d", "sem_cls_prob"):
+            assert relerr(plain[k][i].cpu(), gold[k][i]) <= TOL, (k, i)
+            assert relerr(chained[k][i].cpu(), gold[k][i]) <= TOL, (k, i)
+    # fp32 (checkpoint-style) weights: three-term GEMMs, plain 4-slot ring in the chained kernel
+    sd = I.make_weights(61, 256, bf16_exact=False)
+    eng = DecoderEngine(sd, dev, iters=2)
+    a = {k: v.clone() for k, v in _engine_forward(eng, c, dev, debug=True).items()}
+    b = _engine_forward(eng, c, dev, debug=True, chain=False)
+    assert relerr(a["decoder_out"][0], b["decoder_out"][0]) <= 2e-4
+    assert relerr(a["pred_logits"][0], b["pred_logits"][0]) <= 2e-4
+
+
 def test_free_running_divergence_report(dev):
     """the free-running recurrence (no teacher forcing) is reported, not gated, next to the oracle's own
     sensitivity: the oracle re-run on tokens perturbed by a relative 1e-6 (fp32 rounding scale) and 2^-9 (bf16 operand
