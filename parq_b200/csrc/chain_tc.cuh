@@ -67,7 +67,9 @@ constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_BYTES = 256 * BK * 2;  // 32 KB
 constexpr int RING_BYTES = 4 * (A_BYTES + B_BYTES);
 constexpr int VEC_COLS = 512;          // columns of one CTA in a stage (bias / gamma / beta staging)
-constexpr int SMEM_BYTES = 1024 + RING_BYTES + 512 /*barriers*/ + 2 * CLUSTER * BM * 8 /*row statistics*/ + 3 * VEC_COLS * 4 + 256 /*GN sums*/;
+constexpr int STAGE_WORDS = 32 * 17;   // per epilogue warp: 32 rows x 16 words (+1 pad) for coalesced global I/O
+constexpr int SMEM_BYTES = 1024 + RING_BYTES + 512 /*barriers*/ + 2 * CLUSTER * BM * 8 /*row statistics*/ + 3 * VEC_COLS * 4 + 256 /*GN sums*/ +
+                           EPI_WARPS * STAGE_WORDS * 4;
 }  // namespace chain
 
 struct ChainParams {
@@ -106,24 +108,78 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // generic-proxy writes (st.global of the epilogue) <-> async-proxy reads (TMA loads of the next stage), all state spaces
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// 8 fp32 -> 8 bf16 "hi" at dst and 8 bf16 residuals at dst + lo_off (16-byte stores)
-__device__ __forceinline__ void chain_store_split8(__nv_bfloat16* dst, long long lo_off, const float* v) {
-  uint32_t hi[4], lo[4];
+// ---- coalesced global I/O of the epilogue ------------------------------------------------------------------------
+// An epilogue thread owns one ROW of the accumulator (TMEM lane = row); written naively, every 16-byte global access of a
+// warp would touch 32 different rows (32 sectors per instruction).  Each warp therefore moves 32 rows x 16 words through
+// a padded shared-memory tile: towards memory 4 lanes cover 64 contiguous bytes of a row (8 rows per instruction),
+// towards the thread lane r reads / writes row r with stride 17 (conflict free).
+// g points at [first row of the warp][first word of the 16-word block]; ldw = row pitch in 32-bit words.
+__device__ __forceinline__ void chain_flush16(const uint32_t* stage, uint32_t* g, long long ldw, int lane) {
+  __syncwarp();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-    lo[i] = pack_bf16x2(v[2 * i] - __uint_as_float(hi[i] << 16), v[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u));
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), w = (lane & 3) * 4;
+    const uint32_t* sp = stage + r * 17 + w;
+    *reinterpret_cast<uint4*>(g + r * ldw + w) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
   }
-  *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  __syncwarp();
 }
-__device__ __forceinline__ void chain_load_split8(const __nv_bfloat16* src, long long lo_off, float* v) {
-  const uint4 h = *reinterpret_cast<const uint4*>(src), l = *reinterpret_cast<const uint4*>(src + lo_off);
-  const uint32_t hs[4] = {h.x, h.y, h.z, h.w}, ls[4] = {l.x, l.y, l.z, l.w};
+__device__ __forceinline__ void chain_fetch16(uint32_t* stage, const uint32_t* g, long long ldw, int lane) {
+  __syncwarp();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[2 * i] = __uint_as_float(hs[i] << 16) + __uint_as_float(ls[i] << 16);
-    v[2 * i + 1] = __uint_as_float(hs[i] & 0xFFFF0000u) + __uint_as_float(ls[i] & 0xFFFF0000u);
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), w = (lane & 3) * 4;
+    const uint4 v = *reinterpret_cast<const uint4*>(g + r * ldw + w);
+    uint32_t* sp = stage + r * 17 + w;
+    sp[0] = v.x; sp[1] = v.y; sp[2] = v.z; sp[3] = v.w;
+  }
+  __syncwarp();
+}
+// 32 fp32 values of this lane's row -> global (row pitch ld elements); g = [warp's first row][first column of the chunk]
+__device__ __forceinline__ void chain_store_f32x32(uint32_t* stage, float* g, long long ld, const float* v, int lane) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) stage[lane * 17 + i] = __float_as_uint(v[hf * 16 + i]);
+    chain_flush16(stage, reinterpret_cast<uint32_t*>(g) + hf * 16, ld, lane);
+  }
+}
+__device__ __forceinline__ void chain_load_f32x32(uint32_t* stage, const float* g, long long ld, float* v, int lane) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    chain_fetch16(stage, reinterpret_cast<const uint32_t*>(g) + hf * 16, ld, lane);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[hf * 16 + i] = __uint_as_float(stage[lane * 17 + i]);
+  }
+}
+// 32 values -> bf16 "hi" at g and bf16 residuals at g + lo_off (row pitch ld bf16 elements)
+__device__ __forceinline__ void chain_store_split32(uint32_t* stage, __nv_bfloat16* g, long long ld, long long lo_off, const float* v, int lane) {
+  uint32_t lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t h = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    lo[i] = pack_bf16x2(v[2 * i] - __uint_as_float(h << 16), v[2 * i + 1] - __uint_as_float(h & 0xFFFF0000u));
+    stage[lane * 17 + i] = h;
+  }
+  chain_flush16(stage, reinterpret_cast<uint32_t*>(g), ld / 2, lane);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) stage[lane * 17 + i] = lo[i];
+  chain_flush16(stage, reinterpret_cast<uint32_t*>(g + lo_off), ld / 2, lane);
+}
+// v[i] (+)= hi + lo of a [hi|lo] split
+template <bool kAccumulate>
+__device__ __forceinline__ void chain_load_split32(uint32_t* stage, const __nv_bfloat16* g, long long ld, long long lo_off, float* v, int lane) {
+  chain_fetch16(stage, reinterpret_cast<const uint32_t*>(g), ld / 2, lane);
+  uint32_t h[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) h[i] = stage[lane * 17 + i];
+  chain_fetch16(stage, reinterpret_cast<const uint32_t*>(g + lo_off), ld / 2, lane);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t l = stage[lane * 17 + i];
+    const float a = __uint_as_float(h[i] << 16) + __uint_as_float(l << 16);
+    const float b = __uint_as_float(h[i] & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u);
+    if (kAccumulate) { v[2 * i] += a; v[2 * i + 1] += b; } else { v[2 * i] = a; v[2 * i + 1] = b; }
   }
 }
 
@@ -143,6 +199,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
   float2* s_part = reinterpret_cast<float2*>(smem + RING_BYTES + 512);   // [2 * CLUSTER][BM] (mean, M2) partials
   float* s_vec = reinterpret_cast<float*>(s_part + 2 * CLUSTER * BM);    // [3][VEC_COLS] bias | gamma | beta
   double* s_gn = reinterpret_cast<double*>(s_vec + 3 * VEC_COLS);        // [EPI_WARPS][2]
+  uint32_t* s_stage = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_gn) + 256);   // [EPI_WARPS][STAGE_WORDS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -279,7 +336,8 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
     const int h = e >> 2;                  // which half of the tile's columns
     const int et = threadIdx.x - 128;      // 0..255
     const int rin = q * 32 + lane;         // row inside the block
-    const long long row = m0 + rin;
+    const long long wrow0 = m0 + q * 32;   // first row of this warp
+    uint32_t* stage = s_stage + e * STAGE_WORDS;
     int cnt = 0, nln = 0;
     uint32_t xaddr[CLUSTER], daddr[CLUSTER];
 #pragma unroll
@@ -316,17 +374,10 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
           for (int c = 0; c < nchunks; ++c) {
             tmem_ld32(taddr + c * 32, r);
             float z[32];
-            if (S.resid_f32 != nullptr) {
-              const float4* rp = reinterpret_cast<const float4*>(S.resid_f32 + row * S.N + col0 + c * 32);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 v = rp[i];
-                z[4 * i] = v.x; z[4 * i + 1] = v.y; z[4 * i + 2] = v.z; z[4 * i + 3] = v.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) chain_load_split8(S.resid_split + row * 2 * S.N + col0 + c * 32 + 8 * i, S.N, z + 8 * i);
-            }
+            if (S.resid_f32 != nullptr)
+              chain_load_f32x32(stage, S.resid_f32 + wrow0 * S.N + col0 + c * 32, S.N, z, lane);
+            else
+              chain_load_split32<false>(stage, S.resid_split + wrow0 * 2 * S.N + col0 + c * 32, 2 * S.N, S.N, z, lane);
             tmem_wait_ld();
             float cs = 0.f;
 #pragma unroll
@@ -396,24 +447,15 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
               y[4 * i + 2] = (__uint_as_float(r[4 * i + 2]) - mean) * rstd * g4.z + e4.z;
               y[4 * i + 3] = (__uint_as_float(r[4 * i + 3]) - mean) * rstd * g4.w + e4.w;
             }
-            const long long o = row * S.N + col0 + c * 32;
-            if (S.out_f32 != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(S.out_f32 + o)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-            }
-            if (S.a_out != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) chain_store_split8(S.a_out + row * 2 * S.N + col0 + c * 32 + 8 * i, S.N, y + 8 * i);
-            }
+            const long long o = wrow0 * S.N + col0 + c * 32;
+            if (S.out_f32 != nullptr) chain_store_f32x32(stage, S.out_f32 + o, S.N, y, lane);
+            if (S.a_out != nullptr) chain_store_split32(stage, S.a_out + 2 * o - (col0 + c * 32), 2 * S.N, S.N, y, lane);
             if (S.a_out_pe != nullptr) {
-              const float4* pp = reinterpret_cast<const float4*>(S.pe + o);
+              float pv[32];
+              chain_load_f32x32(stage, S.pe + o, S.N, pv, lane);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 v = pp[i];
-                y[4 * i] += v.x; y[4 * i + 1] += v.y; y[4 * i + 2] += v.z; y[4 * i + 3] += v.w;
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) chain_store_split8(S.a_out_pe + row * 2 * S.N + col0 + c * 32 + 8 * i, S.N, y + 8 * i);
+              for (int i = 0; i < 32; ++i) y[i] += pv[i];
+              chain_store_split32(stage, S.a_out_pe + 2 * o - (col0 + c * 32), 2 * S.N, S.N, y, lane);
             }
           }
         } else {
@@ -436,8 +478,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
             }
             const long long cc = col0 + c * 32;
             if (S.ep == CH_EP_SPLIT) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) chain_store_split8(S.a_out + row * 2 * S.N + cc + 8 * i, S.N, v + 8 * i);
+              chain_store_split32(stage, S.a_out + wrow0 * 2 * S.N + cc, 2 * S.N, S.N, v, lane);
             } else if (S.ep == CH_EP_LP) {
               uint32_t w[16];
               if (S.lp_fp16) {
@@ -447,28 +488,18 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
               }
-              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(S.out_lp) + row * S.ld_lp + cc);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+              for (int i = 0; i < 16; ++i) stage[lane * 17 + i] = w[i];
+              chain_flush16(stage, reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(S.out_lp) + wrow0 * S.ld_lp + cc), S.ld_lp / 2, lane);
             } else {
               if (S.gn_out != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) { gsum += v[i]; gsq = fmaf(v[i], v[i], gsq); }
               }
-              if (S.out_f32 != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  reinterpret_cast<float4*>(S.out_f32 + row * S.N + cc)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-              }
+              if (S.out_f32 != nullptr) chain_store_f32x32(stage, S.out_f32 + wrow0 * S.N + cc, S.N, v, lane);
               if (S.add_split != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float a[8];
-                  chain_load_split8(S.add_split + row * 2 * S.N + cc + 8 * i, S.N, a);
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) a[k] += v[8 * i + k];
-                  chain_store_split8(S.out_sum_split + row * 2 * S.N + cc + 8 * i, S.N, a);
-                }
+                chain_load_split32<true>(stage, S.add_split + wrow0 * 2 * S.N + cc, 2 * S.N, S.N, v, lane);
+                chain_store_split32(stage, S.out_sum_split + wrow0 * 2 * S.N + cc, 2 * S.N, S.N, v, lane);
               }
             }
           }

@@ -814,15 +814,16 @@ int parq_pose_chain(const float* T_cp, const float* T_wp, const float* T_wl, flo
 }
 
 static int launch_sample(cudaStream_t st, const SampleParams& sp) {
-  if (sp.T > sample::MAX_PAIRS) return fail(PARQ_ERR_SHAPE, "T=%d views: the sampling kernel supports up to %d", sp.T, sample::MAX_PAIRS);
   if ((reinterpret_cast<uintptr_t>(sp.tokens) & 15) != 0 || (reinterpret_cast<uintptr_t>(sp.tokens_lo) & 15) != 0)
-    return fail(PARQ_ERR_SHAPE, "token planes must be 16-byte aligned (bulk copies)");
-  const size_t smem = sample::smem_bytes(sp.C, sp.slots);
-  OPT_IN_SMEM(project_sample_kernel, smem);
+    return fail(PARQ_ERR_SHAPE, "token planes must be 16-byte aligned");
   const int R = sp.B * sp.Nq;
+  const size_t smem = static_cast<size_t>(SAMPLE_QPB) * sp.T * sizeof(ViewTap);
   {
     ProfScope ps(TAG_SAMPLE, st);
-    launch_k(project_sample_kernel, dim3((R + sp.rows_per_cta - 1) / sp.rows_per_cta), dim3(sample::THREADS), smem, st, sp);
+    if (sp.tokens_lo != nullptr)
+      launch_k(project_sample_kernel<true>, dim3(R / SAMPLE_QPB), dim3(sp.C / 8), smem, st, sp);
+    else
+      launch_k(project_sample_kernel<false>, dim3(R / SAMPLE_QPB), dim3(sp.C / 8), smem, st, sp);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
@@ -831,15 +832,6 @@ static int launch_sample(cudaStream_t st, const SampleParams& sp) {
 static void fill_sample_params(SampleParams& sp, const ParqShape& s) {
   memset(&sp, 0, sizeof(sp));
   sp.B = s.B; sp.T = s.T; sp.H = s.H; sp.W = s.W; sp.C = s.C; sp.Nq = s.Nq;
-  // persistent grid: CTAS_PER_SM CTAs per SM, each with a contiguous range of queries and a ring that fills its share of
-  // the shared memory (12 slots of 8 KB at C = 1024)
-  const int R = s.B * s.Nq;
-  const int ctas = device_info().sms * sample::CTAS_PER_SM;
-  sp.rows_per_cta = (R + ctas - 1) / ctas;
-  const size_t budget = 110 * 1024;
-  int slots = sample::MAX_SLOTS;
-  while (slots > 2 && sample::smem_bytes(s.C, slots) > budget) --slots;
-  sp.slots = slots;
   for (int i = 0; i < 3; ++i) {
     // (hi - lo) is evaluated in double from the config floats, then enters the fp32 op as a scalar
     sp.span[i] = static_cast<float>(static_cast<double>(s.scale[2 * i + 1]) - static_cast<double>(s.scale[2 * i]));
@@ -1164,6 +1156,12 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
 
   for (int it = 0; it < s.iters; ++it) {
     const float* ref = forced_refs ? forced_refs + static_cast<size_t>(it) * R * 3 : (it == 0 ? ref0 : F32(W.ref_cur));
+    float* x3 = out->decoder_out ? out->decoder_out + static_cast<size_t>(it) * R * C : F32(W.x3);
+    const int Nk = s.T * s.H * s.W;
+    // sinusoidal embedding of the reference points (input of the reference-point MLP); launched BEFORE the sampling kernel so
+    // that the reference points are two launches old when the sampler projects them in its pre-wait prologue
+    { ProfScope ps(TAG_ROWWISE, st); launch_k(posemb_kernel, dim3((R * 384 + 255) / 256), dim3(256), 0, st, ref, PF(P.dim_t), BF(W.a_pos), R); }
+    CUDA_TRY(cudaGetLastError());
     // K1: projection + multi-view bilinear gather -> the [hi|lo] split of the sampled features (the query content x)
     sp.tokens = static_cast<const __nv_bfloat16*>(tokens_bf16);
     sp.tokens_lo = static_cast<const __nv_bfloat16*>(tokens_lo_bf16);
@@ -1174,10 +1172,6 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     sp.valid = out->center_valid ? out->center_valid + static_cast<size_t>(it) * s.B * s.T * s.Nq : nullptr;
     sp.coord_pos = nullptr;
     TRY(launch_sample(st, sp));
-    float* x3 = out->decoder_out ? out->decoder_out + static_cast<size_t>(it) * R * C : F32(W.x3);
-    const int Nk = s.T * s.H * s.W;
-    { ProfScope ps(TAG_ROWWISE, st); launch_k(posemb_kernel, dim3((R * 384 + 255) / 256), dim3(256), 0, st, ref, PF(P.dim_t), BF(W.a_pos), R); }
-    CUDA_TRY(cudaGetLastError());
     if (chained) {
       // ---- chain P: pe = W2 relu(W1 posemb + b1) + b2 (+ x -> split(x + pe)) -> self-attention Q|K projection
       {
