@@ -424,6 +424,40 @@ def run_ours(args):
         dist.all_reduce(lt)
         launches = int(lt.item())
 
+    # ---- the one collective of the path: device parse_pred + NMS on this rank's clips, then the
+    # all_gather of the fixed-size detections into global clip order (what rank 0 feeds the order-dependent F1 fusion,
+    # utils/f1_eval.py:293-352).  Verified against per-clip checksums that travel separately.
+    from parq_b200 import shard
+    model.use_cuda_graph = True
+    out = model(tokens, *geo)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    parsed = model.parse_pred(out)
+    local_det = {k: parsed[k] for k in shard.DETECTION_KEYS + ("pred_mask",)}
+    gathered = shard.gather_detections(local_det, world * B)
+    g1.record()
+    barrier()
+    gather_ms = g0.elapsed_time(g1)
+    chk = torch.stack([local_det[k].double().flatten(1).sum(1) for k in shard.DETECTION_KEYS + ("pred_mask",)], 1)     # (B, 5) per-clip sums
+    if world > 1:
+        chks = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(chks, chk)
+        chk_all = torch.cat(chks, 0)
+        t = torch.tensor([gather_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_ms = t.item()
+    else:
+        chk_all = chk
+    chk_g = torch.stack([gathered[k].double().flatten(1).sum(1) for k in shard.DETECTION_KEYS + ("pred_mask",)], 1)
+    gather_ok = bool(torch.equal(chk_g, chk_all)) and all(gathered[k].shape[0] == world * B for k in gathered) and \
+        all(torch.equal(gathered[k][rank * B:(rank + 1) * B], local_det[k]) for k in gathered)
+    gather_bytes = sum(v.numel() * v.element_size() for v in gathered.values())
+    detection_gather = {"ms": gather_ms, "bytes": gather_bytes, "nranks": world, "verified_global_clip_order": gather_ok,
+                        "kept_boxes_rank0": int(local_det["pred_mask"].sum().item()),
+                        "what": "parse_pred + NMS on the device for this rank's %d clips, then shard.gather_detections (one NCCL all_gather "
+                                "per tensor: centre, size, ortho6d, class probabilities, pred_mask) into global clip order" % B}
+
     gpu_torch = gpu_torch_baseline(dev, B) if (world == 1 and rank == 0) else None
 
     if rank == 0:
@@ -469,6 +503,7 @@ def run_ours(args):
             "roofline_kv_proj": {"kernel": "gemm2_tc_kernel (CTA-pair GEMM: K and V^T projection, 2 launches/step)", "bound": "tensor",
                                  "achieved": (4.0 * B * Nk * Cc * Cc) / (kv_ms / max(kv_n // 2, 1) * 1e-3) / 1e12 if kv_n else None,
                                  "peak": pk["tf_sustained"], "unit": "TFLOP/s"},
+            "detection_gather": detection_gather,
             "breakdown_ms_per_step": {k: round(v[0], 4) for k, v in breakdown.items() if k != "_dropped"},
             "breakdown_launches": {k: v[1] for k, v in breakdown.items() if k != "_dropped"},
         }

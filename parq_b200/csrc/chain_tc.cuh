@@ -28,7 +28,7 @@
 namespace parq {
 
 enum ChainEpilogue {
-  CH_EP_LN = 0,     // y = LayerNorm(acc + bias + residual) * gamma + beta -> out_f32, a_out = split(y), a_out_pe = split(y + pe)
+  CH_EP_LN = 0,     // y = LayerNorm(acc + bias + residual) * gamma + beta -> out_cm / out_f32, a_out = split(y), a_out_pe = split(y + pe)
   CH_EP_SPLIT = 1,  // v = [relu](acc + bias) -> a_out = split(v)
   CH_EP_LP = 2,     // v = acc + bias -> out_lp (bf16 / fp16)
   CH_EP_F32 = 3,    // v = acc + bias -> out_f32 [, GroupNorm tile sums] [, out_sum_split = split(v + add_split)]
@@ -40,12 +40,17 @@ struct ChainStage {
   int nterms, a_koff[3], b_koff[3], dual_a;
   int ep, relu, lp_fp16;
   const float* bias;                   // (N) or null
-  const float* resid_f32;              // LN: (M, N) fp32 residual, or null
-  const __nv_bfloat16* resid_split;    // LN: (M, 2N) [hi|lo] residual, or null
+  // "cm" = COLUMN-MAJOR fp32 scratch [N][M]: streams that are written and later read by the SAME epilogue thread (the
+  // residual stream x / x1 / x2 and the positional feature) -- a thread owns a row, so with rows contiguous every access
+  // of a warp is one 128-byte line and needs no staging; every N = C stage of every chain maps (row, column) to the
+  // same thread, also across launches.
+  const float* resid_cm;               // LN: residual
   const float* gamma;
   const float* beta;
-  const float* pe;                     // LN: optional (M, N)
-  float* out_f32;                      // (M, N)
+  const float* pe_cm;                  // LN: optional positional feature
+  float* out_cm;                       // LN: y; F32: value
+  float* add_cm_out;                   // F32 with add_split: the addend itself (hi + lo) as fp32
+  float* out_f32;                      // row-major (M, N) copy of y / value for consumers outside the chains, or null
   __nv_bfloat16* a_out;                // (M, 2N) [hi|lo], or null
   __nv_bfloat16* a_out_pe;             // LN only, or null
   void* out_lp;                        // CH_EP_LP: (M, ld_lp) 16-bit
@@ -67,8 +72,9 @@ constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_BYTES = 256 * BK * 2;  // 32 KB
 constexpr int RING_BYTES = 4 * (A_BYTES + B_BYTES);
 constexpr int VEC_COLS = 512;          // columns of one CTA in a stage (bias / gamma / beta staging)
-constexpr int STAGE_WORDS = 32 * 17;   // per epilogue warp: 32 rows x 16 words (+1 pad) for coalesced global I/O
-constexpr int SMEM_BYTES = 1024 + RING_BYTES + 512 /*barriers*/ + 2 * CLUSTER * BM * 8 /*row statistics*/ + 3 * VEC_COLS * 4 + 256 /*GN sums*/ +
+constexpr int LN_COLS = 256;           // columns of one CTA in a LayerNorm stage (gamma / beta staging)
+constexpr int STAGE_WORDS = 32 * 20;   // per epilogue warp: 32 rows x 16 words, row stride 20 (16-byte accesses, conflict free)
+constexpr int SMEM_BYTES = 1024 + RING_BYTES + 512 /*barriers*/ + 2 * CLUSTER * BM * 8 /*row statistics*/ + (VEC_COLS + 2 * LN_COLS) * 4 + 256 /*GN sums*/ +
                            EPI_WARPS * STAGE_WORDS * 4;
 }  // namespace chain
 
@@ -110,77 +116,72 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 
 // ---- coalesced global I/O of the epilogue ------------------------------------------------------------------------
 // An epilogue thread owns one ROW of the accumulator (TMEM lane = row); written naively, every 16-byte global access of a
-// warp would touch 32 different rows (32 sectors per instruction).  Each warp therefore moves 32 rows x 16 words through
-// a padded shared-memory tile: towards memory 4 lanes cover 64 contiguous bytes of a row (8 rows per instruction),
-// towards the thread lane r reads / writes row r with stride 17 (conflict free).
+// warp would touch 32 different rows.  Row-major tensors therefore move through a padded shared-memory tile per warp,
+// 32 rows x 16 words with a row stride of 20 words: the owner of row r reads / writes 16-byte pieces at r*20 + 4j
+// (conflict free per quarter warp), towards memory 4 lanes cover 64 contiguous bytes of a row (8 rows per instruction).
 // g points at [first row of the warp][first word of the 16-word block]; ldw = row pitch in 32-bit words.
+constexpr int CH_STRIDE = 20;
 __device__ __forceinline__ void chain_flush16(const uint32_t* stage, uint32_t* g, long long ldw, int lane) {
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int r = it * 8 + (lane >> 2), w = (lane & 3) * 4;
-    const uint32_t* sp = stage + r * 17 + w;
-    *reinterpret_cast<uint4*>(g + r * ldw + w) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+    *reinterpret_cast<uint4*>(g + r * ldw + w) = *reinterpret_cast<const uint4*>(stage + r * CH_STRIDE + w);
   }
   __syncwarp();
 }
-__device__ __forceinline__ void chain_fetch16(uint32_t* stage, const uint32_t* g, long long ldw, int lane) {
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int r = it * 8 + (lane >> 2), w = (lane & 3) * 4;
-    const uint4 v = *reinterpret_cast<const uint4*>(g + r * ldw + w);
-    uint32_t* sp = stage + r * 17 + w;
-    sp[0] = v.x; sp[1] = v.y; sp[2] = v.z; sp[3] = v.w;
-  }
-  __syncwarp();
-}
-// 32 fp32 values of this lane's row -> global (row pitch ld elements); g = [warp's first row][first column of the chunk]
+// 32 fp32 values of this lane's row -> row-major global (row pitch ld elements)
 __device__ __forceinline__ void chain_store_f32x32(uint32_t* stage, float* g, long long ld, const float* v, int lane) {
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) stage[lane * 17 + i] = __float_as_uint(v[hf * 16 + i]);
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<uint4*>(stage + lane * CH_STRIDE + 4 * i) =
+          make_uint4(__float_as_uint(v[hf * 16 + 4 * i]), __float_as_uint(v[hf * 16 + 4 * i + 1]), __float_as_uint(v[hf * 16 + 4 * i + 2]),
+                     __float_as_uint(v[hf * 16 + 4 * i + 3]));
     chain_flush16(stage, reinterpret_cast<uint32_t*>(g) + hf * 16, ld, lane);
   }
 }
-__device__ __forceinline__ void chain_load_f32x32(uint32_t* stage, const float* g, long long ld, float* v, int lane) {
+// 16 packed words of this lane's row (32 bf16 / fp16 values) -> row-major global (row pitch ld 16-bit elements)
+__device__ __forceinline__ void chain_store_w16(uint32_t* stage, void* g, long long ld, const uint32_t* w, int lane) {
 #pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    chain_fetch16(stage, reinterpret_cast<const uint32_t*>(g) + hf * 16, ld, lane);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[hf * 16 + i] = __uint_as_float(stage[lane * 17 + i]);
-  }
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + lane * CH_STRIDE + 4 * i) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  chain_flush16(stage, reinterpret_cast<uint32_t*>(g), ld / 2, lane);
 }
 // 32 values -> bf16 "hi" at g and bf16 residuals at g + lo_off (row pitch ld bf16 elements)
 __device__ __forceinline__ void chain_store_split32(uint32_t* stage, __nv_bfloat16* g, long long ld, long long lo_off, const float* v, int lane) {
-  uint32_t lo[16];
+  uint32_t hi[16], lo[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const uint32_t h = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-    lo[i] = pack_bf16x2(v[2 * i] - __uint_as_float(h << 16), v[2 * i + 1] - __uint_as_float(h & 0xFFFF0000u));
-    stage[lane * 17 + i] = h;
+    hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    lo[i] = pack_bf16x2(v[2 * i] - __uint_as_float(hi[i] << 16), v[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u));
   }
-  chain_flush16(stage, reinterpret_cast<uint32_t*>(g), ld / 2, lane);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) stage[lane * 17 + i] = lo[i];
-  chain_flush16(stage, reinterpret_cast<uint32_t*>(g + lo_off), ld / 2, lane);
+  chain_store_w16(stage, g, ld, hi, lane);
+  chain_store_w16(stage, g + lo_off, ld, lo, lane);
 }
-// v[i] (+)= hi + lo of a [hi|lo] split
-template <bool kAccumulate>
-__device__ __forceinline__ void chain_load_split32(uint32_t* stage, const __nv_bfloat16* g, long long ld, long long lo_off, float* v, int lane) {
-  chain_fetch16(stage, reinterpret_cast<const uint32_t*>(g), ld / 2, lane);
-  uint32_t h[16];
+// the 16-byte global loads of a 32-row x 16-word block (issued early, consumed by chain_unstage16)
+__device__ __forceinline__ void chain_issue16(uint4 (&t)[4], const uint32_t* g, long long ldw, int lane) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) h[i] = stage[lane * 17 + i];
-  chain_fetch16(stage, reinterpret_cast<const uint32_t*>(g + lo_off), ld / 2, lane);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const uint32_t l = stage[lane * 17 + i];
-    const float a = __uint_as_float(h[i] << 16) + __uint_as_float(l << 16);
-    const float b = __uint_as_float(h[i] & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u);
-    if (kAccumulate) { v[2 * i] += a; v[2 * i + 1] += b; } else { v[2 * i] = a; v[2 * i + 1] = b; }
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), w = (lane & 3) * 4;
+    t[it] = *reinterpret_cast<const uint4*>(g + r * ldw + w);
   }
+}
+// ... through the tile into the 16 words of this lane's row
+__device__ __forceinline__ void chain_unstage16(uint32_t* stage, const uint4 (&t)[4], uint32_t* w, int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), c = (lane & 3) * 4;
+    *reinterpret_cast<uint4*>(stage + r * CH_STRIDE + c) = t[it];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + lane * CH_STRIDE + 4 * i);
+    w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+  }
+  __syncwarp();
 }
 
 // grid = 4 * (M / 128) CTAs in clusters of 4 along x; M % 128 == 0.
@@ -197,8 +198,8 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
   uint64_t* dbar = xbar + 1;              // the stage's outputs of all four CTAs are in global memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dbar + 1);
   float2* s_part = reinterpret_cast<float2*>(smem + RING_BYTES + 512);   // [2 * CLUSTER][BM] (mean, M2) partials
-  float* s_vec = reinterpret_cast<float*>(s_part + 2 * CLUSTER * BM);    // [3][VEC_COLS] bias | gamma | beta
-  double* s_gn = reinterpret_cast<double*>(s_vec + 3 * VEC_COLS);        // [EPI_WARPS][2]
+  float* s_vec = reinterpret_cast<float*>(s_part + 2 * CLUSTER * BM);    // bias [VEC_COLS] | gamma [LN_COLS] | beta [LN_COLS]
+  double* s_gn = reinterpret_cast<double*>(s_vec + VEC_COLS + 2 * LN_COLS);   // [EPI_WARPS][2]
   uint32_t* s_stage = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_gn) + 256);   // [EPI_WARPS][STAGE_WORDS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -336,6 +337,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
     const int h = e >> 2;                  // which half of the tile's columns
     const int et = threadIdx.x - 128;      // 0..255
     const int rin = q * 32 + lane;         // row inside the block
+    const long long row = m0 + rin;
     const long long wrow0 = m0 + q * 32;   // first row of this warp
     uint32_t* stage = s_stage + e * STAGE_WORDS;
     int cnt = 0, nln = 0;
@@ -356,7 +358,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
         s_vec[i] = S.bias != nullptr ? __ldg(S.bias + n_base + i) : 0.f;
         if (S.ep == CH_EP_LN) {
           s_vec[VEC_COLS + i] = __ldg(S.gamma + n_base + i);
-          s_vec[2 * VEC_COLS + i] = __ldg(S.beta + n_base + i);
+          s_vec[VEC_COLS + LN_COLS + i] = __ldg(S.beta + n_base + i);
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -374,10 +376,11 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
           for (int c = 0; c < nchunks; ++c) {
             tmem_ld32(taddr + c * 32, r);
             float z[32];
-            if (S.resid_f32 != nullptr)
-              chain_load_f32x32(stage, S.resid_f32 + wrow0 * S.N + col0 + c * 32, S.N, z, lane);
-            else
-              chain_load_split32<false>(stage, S.resid_split + wrow0 * 2 * S.N + col0 + c * 32, 2 * S.N, S.N, z, lane);
+            {
+              const float* rp = S.resid_cm + static_cast<long long>(col0 + c * 32) * p.M + row;      // 32 independent, fully coalesced loads
+#pragma unroll
+              for (int i = 0; i < 32; ++i) z[i] = rp[static_cast<long long>(i) * p.M];
+            }
             tmem_wait_ld();
             float cs = 0.f;
 #pragma unroll
@@ -441,18 +444,26 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 g4 = reinterpret_cast<const float4*>(s_vec + VEC_COLS + cl0 + c * 32)[i];
-              const float4 e4 = reinterpret_cast<const float4*>(s_vec + 2 * VEC_COLS + cl0 + c * 32)[i];
+              const float4 e4 = reinterpret_cast<const float4*>(s_vec + VEC_COLS + LN_COLS + cl0 + c * 32)[i];
               y[4 * i] = (__uint_as_float(r[4 * i]) - mean) * rstd * g4.x + e4.x;
               y[4 * i + 1] = (__uint_as_float(r[4 * i + 1]) - mean) * rstd * g4.y + e4.y;
               y[4 * i + 2] = (__uint_as_float(r[4 * i + 2]) - mean) * rstd * g4.z + e4.z;
               y[4 * i + 3] = (__uint_as_float(r[4 * i + 3]) - mean) * rstd * g4.w + e4.w;
             }
             const long long o = wrow0 * S.N + col0 + c * 32;
+            const long long ocm = static_cast<long long>(col0 + c * 32) * p.M + row;
+            float pv[32];
+            if (S.a_out_pe != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) pv[i] = S.pe_cm[ocm + static_cast<long long>(i) * p.M];     // in flight during the stores below
+            }
+            if (S.out_cm != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) S.out_cm[ocm + static_cast<long long>(i) * p.M] = y[i];
+            }
             if (S.out_f32 != nullptr) chain_store_f32x32(stage, S.out_f32 + o, S.N, y, lane);
             if (S.a_out != nullptr) chain_store_split32(stage, S.a_out + 2 * o - (col0 + c * 32), 2 * S.N, S.N, y, lane);
             if (S.a_out_pe != nullptr) {
-              float pv[32];
-              chain_load_f32x32(stage, S.pe + o, S.N, pv, lane);
 #pragma unroll
               for (int i = 0; i < 32; ++i) y[i] += pv[i];
               chain_store_split32(stage, S.a_out_pe + 2 * o - (col0 + c * 32), 2 * S.N, S.N, y, lane);
@@ -462,6 +473,12 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
           float gsum = 0.f, gsq = 0.f;
           for (int c = 0; c < nchunks; ++c) {
             tmem_ld32(taddr + c * 32, r);
+            uint4 th[4], tl[4];
+            if (S.add_split != nullptr) {
+              const uint32_t* ag = reinterpret_cast<const uint32_t*>(S.add_split + wrow0 * 2 * S.N + col0 + c * 32);
+              chain_issue16(th, ag, S.N, lane);
+              chain_issue16(tl, ag + S.N / 2, S.N, lane);
+            }
             tmem_wait_ld();
             float v[32];
 #pragma unroll
@@ -488,18 +505,36 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
               }
-#pragma unroll
-              for (int i = 0; i < 16; ++i) stage[lane * 17 + i] = w[i];
-              chain_flush16(stage, reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(S.out_lp) + wrow0 * S.ld_lp + cc), S.ld_lp / 2, lane);
+              chain_store_w16(stage, reinterpret_cast<uint16_t*>(S.out_lp) + wrow0 * S.ld_lp + cc, S.ld_lp, w, lane);
             } else {
               if (S.gn_out != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) { gsum += v[i]; gsq = fmaf(v[i], v[i], gsq); }
               }
+              const long long ocm = cc * p.M + row;
+              if (S.out_cm != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) S.out_cm[ocm + static_cast<long long>(i) * p.M] = v[i];
+              }
               if (S.out_f32 != nullptr) chain_store_f32x32(stage, S.out_f32 + wrow0 * S.N + cc, S.N, v, lane);
               if (S.add_split != nullptr) {
-                chain_load_split32<true>(stage, S.add_split + wrow0 * 2 * S.N + cc, 2 * S.N, S.N, v, lane);
-                chain_store_split32(stage, S.out_sum_split + wrow0 * 2 * S.N + cc, 2 * S.N, S.N, v, lane);
+                // addend = hi + lo of a row-major split (its loads were issued before the accumulator wait)
+                uint32_t hw[16], lw[16];
+                chain_unstage16(stage, th, hw, lane);
+                chain_unstage16(stage, tl, lw, lane);
+                float a[32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  a[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+                  a[2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+                }
+                if (S.add_cm_out != nullptr) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) S.add_cm_out[ocm + static_cast<long long>(i) * p.M] = a[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) a[i] += v[i];
+                chain_store_split32(stage, S.out_sum_split + wrow0 * 2 * S.N + cc, 2 * S.N, S.N, a, lane);
               }
             }
           }

@@ -1179,8 +1179,9 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
         ChainStage S = chain_stage(C, 384, CH_EP_SPLIT, PF(P.pe0_b));
         S.relu = 1; S.a_out = BF(W.a_peh);
         TRY(chain_add(cb, ws + W.a_pos, 768, pk + P.pe0, w_lo, S));
+        // (column-major private streams of the chained path: W.pe = pe, W.y = x, W.x1 = x1, W.x2 = x2 -- see chain_tc.cuh)
         S = chain_stage(C, C, CH_EP_F32, PF(P.pe2_b));
-        S.out_f32 = F32(W.pe); S.add_split = BF(W.a_x); S.out_sum_split = BF(W.a_xpe);
+        S.out_cm = F32(W.pe); S.add_split = BF(W.a_x); S.out_sum_split = BF(W.a_xpe); S.add_cm_out = F32(W.y);
         TRY(chain_add(cb, ws + W.a_peh, 2 * C, pk + P.pe2, w_lo, S));
         S = chain_stage(2 * C, C, CH_EP_LP, PF(P.sa_qk_b));
         S.out_lp = ws + W.qk_s; S.ld_lp = 2 * C; S.lp_fp16 = 1;
@@ -1202,8 +1203,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       {
         ChainBuilder cb(R);
         ChainStage S = chain_stage(C, C, CH_EP_LN, PF(P.sa_out_b));
-        S.resid_split = BF(W.a_x); S.gamma = PF(P.ln1_g); S.beta = PF(P.ln1_b); S.pe = F32(W.pe);
-        S.out_f32 = F32(W.x1); S.a_out_pe = BF(W.a_x1pe);
+        S.resid_cm = F32(W.y); S.gamma = PF(P.ln1_g); S.beta = PF(P.ln1_b); S.pe_cm = F32(W.pe);
+        S.out_cm = F32(W.x1); S.a_out_pe = BF(W.a_x1pe);
         TRY(chain_add(cb, ws + W.a_attn, 2 * C, pk + P.sa_out, w_lo, S));
         S = chain_stage(C, C, CH_EP_LP, PF(P.ca_q_b));
         S.out_lp = ws + W.q_c; S.ld_lp = C;
@@ -1217,14 +1218,14 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       {
         ChainBuilder cb(R);
         ChainStage S = chain_stage(C, C, CH_EP_LN, PF(P.ca_out_b));
-        S.resid_f32 = F32(W.x1); S.gamma = PF(P.ln2_g); S.beta = PF(P.ln2_b);
-        S.out_f32 = F32(W.x2); S.a_out = BF(W.a_x2);
+        S.resid_cm = F32(W.x1); S.gamma = PF(P.ln2_g); S.beta = PF(P.ln2_b);
+        S.out_cm = F32(W.x2); S.a_out = BF(W.a_x2);
         TRY(chain_add(cb, ws + W.a_attn, 2 * C, pk + P.ca_out, w_lo, S));
         S = chain_stage(F, C, CH_EP_SPLIT, PF(P.lin1_b));
         S.relu = 1; S.a_out = BF(W.a_ffn);
         TRY(chain_add(cb, ws + W.a_x2, 2 * C, pk + P.lin1, w_lo, S));
         S = chain_stage(C, F, CH_EP_LN, PF(P.lin2_b));
-        S.resid_f32 = F32(W.x2); S.gamma = PF(P.ln3_g); S.beta = PF(P.ln3_b);
+        S.resid_cm = F32(W.x2); S.gamma = PF(P.ln3_g); S.beta = PF(P.ln3_b);
         S.out_f32 = x3; S.a_out = BF(W.a_x3);
         TRY(chain_add(cb, ws + W.a_ffn, 2 * F, pk + P.lin2, w_lo, S));
         S = chain_stage(2 * C, C, CH_EP_F32, nullptr);

@@ -32,20 +32,26 @@ def shard_batch(batch, rank, world_size):
 def gather_detections(last_iter, n_clips, group=None):
     """All-gather the last-iteration detections of every rank into global clip order.
 
-    ``last_iter``: dict with DETECTION_KEYS, each (local_clips, Nq, n).  Ranks may own
-    different numbers of clips (block partition of ``n_clips``); tensors are padded to the
-    largest block for the fixed-size collective and trimmed afterwards."""
+    ``last_iter``: dict with DETECTION_KEYS, each (local_clips, Nq, n) -- plus, when present, the (local_clips, Nq)
+    ``pred_mask`` of parse_pred (gathered as bytes).  Ranks may own different numbers of clips (block partition of
+    ``n_clips``); tensors are padded to the largest block for the fixed-size collective and trimmed afterwards."""
+    keys = DETECTION_KEYS + (("pred_mask",) if "pred_mask" in last_iter else ())
     if not dist.is_available() or not dist.is_initialized():
-        return {k: last_iter[k] for k in DETECTION_KEYS}
+        return {k: last_iter[k] for k in keys}
     world = dist.get_world_size(group)
     sizes = [clip_range(n_clips, r, world)[1] - clip_range(n_clips, r, world)[0] for r in range(world)]
     cap = max(sizes)
     out = {}
-    for k in DETECTION_KEYS:
+    for k in keys:
         t = last_iter[k].contiguous()
+        is_bool = t.dtype == torch.bool
+        if is_bool:
+            t = t.to(torch.uint8)
         pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         pad[: t.shape[0]] = t
         bufs = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(bufs, pad, group=group)
         out[k] = torch.cat([b[:n] for b, n in zip(bufs, sizes)], 0)
+        if is_bool:
+            out[k] = out[k].bool()
     return out

@@ -107,7 +107,7 @@ def main():
     t0.record()
     for b in batches:
         run_batch(*b, True)
-    last = {k: torch.cat([d[k] for d in dets], 0) for k in shard.DETECTION_KEYS}
+    last = {k: torch.cat([d[k] for d in dets], 0) for k in shard.DETECTION_KEYS + ("pred_mask",)}
     gathered = shard.gather_detections(last, args.clips)     # the single collective: detections in global clip order
     t1.record()
     barrier()
