@@ -118,6 +118,17 @@ int parq_project_sample(const ParqShape *shape, const void *tokens_bf16, const v
 int parq_kv_project(const ParqShape *shape, const void *tokens_bf16, const void *packed, void *workspace,
                     size_t workspace_bytes, uint32_t flags, void *stream);
 
+/* "Next" row f-4, streaming window: re-project K / V^T of `n_views` consecutive view slots [slot0, slot0 + n_views) of every
+ * clip from view_tokens_bf16 (B, n_views*H*W, C) into the workspace caches; the other views' K / V^T stay where they are.
+ * A sliding 8-view window then costs one view's projection per step instead of eight (datasets/transforms.py:191-208 slides
+ * the window by re-running everything).  Needs H*W % 32 == 0.  Follow with parq_decoder_forward(..., PARQ_FLAG_SKIP_KV). */
+int parq_kv_project_views(const ParqShape *shape, const void *view_tokens_bf16, int slot0, int n_views, const void *packed,
+                          void *workspace, size_t workspace_bytes, uint32_t flags, void *stream);
+
+/* Instrumentation of the chained GEMM kernel: clock64 stamps of its CTA 0 for the next <= 64 launches go to `buf`
+ * (device memory, 64 x 64 int64); NULL switches it off.  Read by tools/chain_timeline.py. */
+int parq_chain_debug(void *buf);
+
 /* The whole recurrent decoder.  tokens_lo_bf16: optional low-order token plane (parq_split_tokens) or NULL.
  * ref0 (B,Nq,3): normalised initial reference points (sigmoid(refpoint.weight) repeated per clip).
  * forced_refs (iters,B,Nq,3) or NULL: teacher-forced reference points per iteration. */

@@ -21,7 +21,7 @@ PARQ_NMS_NO_TRACK_SCALE = 2
 
 EXPORTS = [
     "parq_version", "parq_last_error", "parq_packed_bytes", "parq_workspace_bytes", "parq_pack_weights",
-    "parq_pose_chain", "parq_split_tokens", "parq_project_sample", "parq_kv_project", "parq_decoder_forward",
+    "parq_pose_chain", "parq_split_tokens", "parq_project_sample", "parq_kv_project", "parq_kv_project_views", "parq_chain_debug", "parq_decoder_forward",
     "parq_gemm_bf16", "parq_attention_scratch_bytes", "parq_attention",
     "parq_parse_pred", "parq_fpn_concat", "parq_raype_packed_bytes", "parq_raype_workspace_bytes", "parq_raype_pack_weights",
     "parq_raype_forward", "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect", "parq_workspace_offset",
@@ -93,6 +93,10 @@ def load():
     lib.parq_split_tokens.argtypes = [f32p, vp, vp, C.c_longlong, vp]
     lib.parq_kv_project.restype = C.c_int
     lib.parq_kv_project.argtypes = [C.POINTER(ParqShape), vp, vp, vp, sz, u32, vp]
+    lib.parq_kv_project_views.restype = C.c_int
+    lib.parq_kv_project_views.argtypes = [C.POINTER(ParqShape), vp, i32, i32, vp, vp, sz, u32, vp]
+    lib.parq_chain_debug.restype = C.c_int
+    lib.parq_chain_debug.argtypes = [vp]
     lib.parq_decoder_forward.restype = C.c_int
     lib.parq_decoder_forward.argtypes = [C.POINTER(ParqShape), vp, vp, f32p, f32p, f32p, f32p, f32p, f32p, vp, vp, sz,
                                          C.POINTER(ParqOutputs), u32, vp]

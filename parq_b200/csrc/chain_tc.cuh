@@ -80,6 +80,7 @@ constexpr int SMEM_BYTES = 1024 + RING_BYTES + 512 /*barriers*/ + 2 * CLUSTER * 
 
 struct ChainParams {
   int M, nstages;
+  long long* dbg;          // optional: clock64 stamps of CTA 0 (tools/chain_timeline.py), 64 slots per launch, or null
   ChainStage st[chain::MAX_STAGES];
 };
 struct ChainMaps {
@@ -184,6 +185,11 @@ __device__ __forceinline__ void chain_unstage16(uint32_t* stage, const uint4 (&t
   __syncwarp();
 }
 
+#define CHAIN_STAMP(slot)                                                        \
+  do {                                                                           \
+    if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[slot] = clock64();           \
+  } while (0)
+
 // grid = 4 * (M / 128) CTAs in clusters of 4 along x; M % 128 == 0.
 __global__ void __launch_bounds__(chain::THREADS, 1)
 chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
@@ -273,6 +279,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
           mbar_wait_cluster(dbar, (s - 1) & 1);
           fence_proxy_async_all();
         }
+        CHAIN_STAMP(s * 8 + 0);              // the A operand of this stage may be loaded
         int idx = 0;
         for (int j = 0; j < S.tiles; ++j) {
           const int n0 = n_base + j * S.tile_n;
@@ -312,6 +319,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
           const uint32_t d_tmem = tmem_base + acc * 256;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&full_bar[slot], phase);
+            if (kb == 0 && j == 0) CHAIN_STAMP(s * 8 + 1);   // first operands have landed
             tc_fence_after();
             const uint64_t adesc = umma_desc_sw128(smem_u32(a_ptr(slot, 0)));
             const uint64_t bdesc = umma_desc_sw128(smem_u32(b_ptr(slot)));
@@ -326,6 +334,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
             if (++slot == nst) { slot = 0; phase ^= 1; }
           }
           umma_commit(&tfull_bar[acc]);
+          if (j == S.tiles - 1) CHAIN_STAMP(s * 8 + 2);      // last MMA of the stage issued
         }
       }
     }
@@ -369,6 +378,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + h * half;
         mbar_wait(&tfull_bar[acc], (cnt >> 1) & 1);
         tc_fence_after();
+        if (et == 0 && j == S.tiles - 1) CHAIN_STAMP(s * 8 + 3);   // accumulator of the stage's last tile complete
         uint32_t r[32];
         if (S.ep == CH_EP_LN) {
           // ---- pass 1: z = acc + bias + residual, running (mean, M2) over this thread's columns, z back into TMEM
@@ -419,7 +429,9 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
 #pragma unroll
             for (int c = 0; c < CLUSTER; ++c) mbar_arrive_cluster(xaddr[c]);
           }
+          if (et == 0) CHAIN_STAMP(s * 8 + 4);                     // LayerNorm pass 1 done, partials sent
           mbar_wait_cluster(xbar, nln & 1);
+          if (et == 0) CHAIN_STAMP(s * 8 + 5);                     // all partials here
           ++nln;
           {
             const float np = static_cast<float>(half);        // values per partial
@@ -560,6 +572,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
+      if (et == 0) CHAIN_STAMP(s * 8 + 6);                         // epilogue of the stage done (this warp)
       // the stage's outputs of this warp are written: publish them to the TMA engines of the whole cluster
       if (s + 1 < p.nstages) {
         fence_proxy_async_all();

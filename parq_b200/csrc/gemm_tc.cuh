@@ -45,6 +45,7 @@ struct GemmEpilogue {
   // kernel streams is one contiguous 64 KB piece of HBM.
   int kv_tiled;
   int kv_Nk, kv_ntile, kv_H;
+  long long kv_tok_offset;   // added to the token index of a row / column: a GEMM over a sub-range of the tokens (one view of one clip)
   // Channels-first companions of a token-major product (rows = tokens (bt, pixel), columns = channels):
   //   nchw_out[(bt*N + col)*HW + pixel] = value                    (fp32; AddRayPE's (B,T,C,H,W) encoding)
   //   value += nchw_add[(bt*N + col)*HW + pixel]                    (fp32 backbone features, before out_f32 / out_lp)
@@ -63,7 +64,7 @@ struct GemmEpilogue {
 
 // element offset of the 32x32 chunk whose first row / column are (row0, col0) in a tiled K / V^T cache, and its row pitch
 __device__ __forceinline__ long long kv_tiled_base(const GemmEpilogue& ep, long long row0, int col0, int& ld) {
-  const long long tok = ep.kv_tiled == 1 ? row0 : col0;
+  const long long tok = (ep.kv_tiled == 1 ? row0 : col0) + ep.kv_tok_offset;
   const int chan = ep.kv_tiled == 1 ? col0 : static_cast<int>(row0);
   const long long b = tok / ep.kv_Nk;
   const int key = static_cast<int>(tok - b * ep.kv_Nk);

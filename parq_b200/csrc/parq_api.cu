@@ -310,7 +310,10 @@ static int chain_add(ChainBuilder& cb, const void* A, uint64_t a_cols, const voi
   cb.p.st[i] = S;
   return PARQ_OK;
 }
-static int launch_chain(cudaStream_t st, const ChainBuilder& cb) {
+static thread_local long long* g_chain_dbg = nullptr;     // parq_chain_debug: device buffer for clock stamps, 64 slots per chain launch
+static thread_local int g_chain_dbg_launch = 0;
+static int launch_chain(cudaStream_t st, ChainBuilder& cb) {
+  if (g_chain_dbg != nullptr && g_chain_dbg_launch < 64) cb.p.dbg = g_chain_dbg + 64 * g_chain_dbg_launch++;
   if (cb.p.M % chain::BM != 0) return fail(PARQ_ERR_SHAPE, "chain kernel needs M %% 128 == 0 (M=%d)", cb.p.M);
   OPT_IN_SMEM(chain_tc_kernel, chain::SMEM_BYTES);
   {
@@ -622,14 +625,16 @@ static GemmEpilogue epilogue_none() {
   return e;
 }
 
-static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, const uint8_t* pk, const Packed& P, bool w_lo,
-                      uint8_t* ws, const Workspace& W) {
+// K = tokens Wk^T + bk and V^T = Wv tokens^T + bv for `rows` consecutive tokens whose first one is token `tok0` of the batch
+// (token index = clip * Nk + key), written into the tile-contiguous caches of the workspace.
+static int kv_project_range(const ParqShape& s, cudaStream_t st, const void* tokens, long long rows, long long tok0, const uint8_t* pk,
+                            const Packed& P, bool w_lo, uint8_t* ws, const Workspace& W) {
   const int C = s.C;
-  const long long Nt = static_cast<long long>(s.B) * s.T * s.H * s.W;
-  // K = tokens Wk^T + bk : A = tokens (single bf16 term), B = Wk [hi|lo]
+  const int Nk = s.T * s.H * s.W;
+  // K: A = tokens (single bf16 term), B = Wk [hi|lo]
   GemmParams gk;
   memset(&gk, 0, sizeof(gk));
-  gk.M = static_cast<int>(Nt);  gk.N = C;  gk.K = C;
+  gk.M = static_cast<int>(rows);  gk.N = C;  gk.K = C;
   // w_lo: weights that are not bf16-exact keep a low-order term (second pass over the tokens).  K and V^T are stored
   // in bf16, so that term is of the size of the storage rounding; PARQ_FLAG_KV_HI_ONLY drops it (measured: parity
   // error 5e-4 -> 9e-4 of the 1e-3 bar, K/V projection 3.7 -> 2.3 ms at config 2), the default keeps it.
@@ -639,17 +644,12 @@ static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, c
   gk.ep = epilogue_none();
   gk.ep.bias = reinterpret_cast<const float*>(pk + P.ca_k_b);
   gk.ep.out_lp = ws + W.Kc;  gk.ep.ld_lp = C;
-  const int Nk = s.T * s.H * s.W;
-  if (W.kv_tiled) {
-    gk.ep.kv_tiled = 1; gk.ep.kv_Nk = Nk; gk.ep.kv_ntile = W.ntile; gk.ep.kv_H = s.heads;
-    // keys beyond Nk in a clip's last tile are never written: P is exactly 0 there, but 0 x garbage could be NaN
-    if (Nk % attn::BKEY != 0) CUDA_TRY(cudaMemsetAsync(ws + W.Vt, 0, static_cast<size_t>(s.B) * W.ntile * attn::BKEY * C * 2, st));
-  }
-  TRY(launch_gemm(st, tokens, Nt, C, pk + P.ca_k, C, 2 * C, gk, TAG_KV_PROJ));
-  // V^T = Wv tokens^T + bv (per row) : A = Wv [hi|lo], B = tokens
+  gk.ep.kv_tiled = 1; gk.ep.kv_Nk = Nk; gk.ep.kv_ntile = W.ntile; gk.ep.kv_H = s.heads; gk.ep.kv_tok_offset = tok0;
+  TRY(launch_gemm(st, tokens, rows, C, pk + P.ca_k, C, 2 * C, gk, TAG_KV_PROJ));
+  // V^T: A = Wv [hi|lo], B = tokens
   GemmParams gv;
   memset(&gv, 0, sizeof(gv));
-  gv.M = C;  gv.N = static_cast<int>(Nt);  gv.K = C;
+  gv.M = C;  gv.N = static_cast<int>(rows);  gv.K = C;
   gv.nterms = w_lo ? 2 : 1;
   gv.const_operand = 1;
   gv.a_koff[0] = 0; gv.b_koff[0] = 0; gv.a_koff[1] = C; gv.b_koff[1] = 0;
@@ -657,9 +657,18 @@ static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, c
   gv.ep.bias = reinterpret_cast<const float*>(pk + P.ca_v_b);
   gv.ep.bias_per_row = 1;
   gv.ep.out_lp = ws + W.Vt;  gv.ep.ld_lp = static_cast<long long>(W.ldv);
-  if (W.kv_tiled) { gv.ep.kv_tiled = 2; gv.ep.kv_Nk = Nk; gv.ep.kv_ntile = W.ntile; gv.ep.kv_H = s.heads; }
-  TRY(launch_gemm(st, pk + P.ca_v, C, 2 * C, tokens, Nt, C, gv, TAG_KV_PROJ));
+  gv.ep.kv_tiled = 2; gv.ep.kv_Nk = Nk; gv.ep.kv_ntile = W.ntile; gv.ep.kv_H = s.heads; gv.ep.kv_tok_offset = tok0;
+  TRY(launch_gemm(st, pk + P.ca_v, C, 2 * C, tokens, rows, C, gv, TAG_KV_PROJ));
   return PARQ_OK;
+}
+
+static int kv_project(const ParqShape& s, cudaStream_t st, const void* tokens, const uint8_t* pk, const Packed& P, bool w_lo,
+                      uint8_t* ws, const Workspace& W) {
+  const long long Nt = static_cast<long long>(s.B) * s.T * s.H * s.W;
+  const int Nk = s.T * s.H * s.W;
+  // keys beyond Nk in a clip's last tile are never written: P is exactly 0 there, but 0 x garbage could be NaN
+  if (Nk % attn::BKEY != 0) CUDA_TRY(cudaMemsetAsync(ws + W.Vt, 0, static_cast<size_t>(s.B) * W.ntile * attn::BKEY * s.C * 2, st));
+  return kv_project_range(s, st, tokens, Nt, 0, pk, P, w_lo, ws, W);
 }
 
 }  // namespace parq
@@ -1115,6 +1124,35 @@ int parq_kv_project(const ParqShape* shape, const void* tokens_bf16, const void*
   const Packed P = packed_layout(*shape);
   return kv_project(*shape, static_cast<cudaStream_t>(stream), tokens_bf16, static_cast<const uint8_t*>(packed), P,
                     (flags & PARQ_FLAG_WEIGHT_LO) != 0 && !(flags & PARQ_FLAG_KV_HI_ONLY), static_cast<uint8_t*>(workspace), W);
+}
+
+/* instrumentation: clock64 stamps of CTA 0 of the next <= 64 chain launches into buf (64 slots each); NULL switches it off */
+int parq_chain_debug(void* buf) {
+  g_chain_dbg = static_cast<long long*>(buf);
+  g_chain_dbg_launch = 0;
+  return PARQ_OK;
+}
+
+int parq_kv_project_views(const ParqShape* shape, const void* view_tokens_bf16, int slot0, int n_views, const void* packed, void* workspace,
+                          size_t workspace_bytes, uint32_t flags, void* stream) {
+  TRY(require_sm100());
+  TRY(check_shape(shape));
+  if (!view_tokens_bf16 || !packed || !workspace) return fail(PARQ_ERR_SHAPE, "null pointer");
+  const ParqShape& s = *shape;
+  if (slot0 < 0 || n_views < 1 || slot0 + n_views > s.T) return fail(PARQ_ERR_SHAPE, "view slots [%d, %d) outside the %d views of the window", slot0, slot0 + n_views, s.T);
+  const long long hw = static_cast<long long>(s.H) * s.W;
+  if (hw % 32 != 0) return fail(PARQ_ERR_SHAPE, "per-view K / V^T updates need H*W %% 32 == 0 (H*W = %lld)", hw);
+  const Workspace W = workspace_layout(s, device_info().sms);
+  if (workspace_bytes < W.total) return fail(PARQ_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", W.total, workspace_bytes);
+  const Packed P = packed_layout(s);
+  const bool w_lo = (flags & PARQ_FLAG_WEIGHT_LO) != 0 && !(flags & PARQ_FLAG_KV_HI_ONLY);
+  const long long rows = hw * n_views, Nk = hw * s.T;
+  for (int b = 0; b < s.B; ++b) {
+    const uint8_t* tok = static_cast<const uint8_t*>(view_tokens_bf16) + static_cast<size_t>(b) * rows * s.C * 2;
+    TRY(kv_project_range(s, static_cast<cudaStream_t>(stream), tok, rows, b * Nk + slot0 * hw, static_cast<const uint8_t*>(packed), P, w_lo,
+                         static_cast<uint8_t*>(workspace), W));
+  }
+  return PARQ_OK;
 }
 
 int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const void* tokens_lo_bf16, const float* camera, const float* T_cp,

@@ -164,3 +164,17 @@ def test_tensor_kernels_keep_their_state_in_registers(tmp_path):
             assert "0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads" in props, (m.group(1), props)
             seen += 1
     assert seen == 10          # 2 + 2 GEMM and 2 + 2 + 2 attention instantiations
+
+
+def test_streaming_pose_helpers_match_the_oracle():
+    # parq_b200/streaming.py re-expresses reference points with A<-L = T_wA^-1 o T_wL (plain torch, window-level glue)
+    from oracle import parq_oracle as O
+    from parq_b200 import inputs as I
+    from parq_b200.streaming import _pose_inv, _pose_mul
+    _, Tcp, Twp, Twl = I.make_geometry(2, 3, 12, 16, seed=3)
+    A, B = Twp._data[:, 0], Twp._data[:, 1]
+    got = _pose_mul(_pose_inv(A), B)
+    want = torch.from_numpy(O.pose_compose(O.pose_inverse(A.numpy()), B.numpy()))
+    assert torch.allclose(got, want, atol=1e-6)
+    eye = torch.tensor([1., 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]).expand(2, 12)
+    assert torch.allclose(_pose_mul(_pose_inv(A), A), eye, atol=1e-6)
