@@ -38,6 +38,7 @@ struct ChainStage {
   int N, K;                  // output columns of the stage (all four CTAs), K per term (multiple of 64)
   int tile_n, tiles;         // per CTA: `tiles` accumulator tiles of `tile_n` columns; tiles * tile_n = N / 4
   int nterms, a_koff[3], b_koff[3], dual_a;
+  int hi_only;               // dual-A ring only: skip the low-order activation term (outputs that are rounded to 16 bits anyway)
   int ep, relu, lp_fp16;
   const float* bias;                   // (N) or null
   // "cm" = COLUMN-MAJOR fp32 scratch [N][M]: streams that are written and later read by the SAME epilogue thread (the
@@ -253,7 +254,8 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
         const int nterm_loops = dual ? 1 : S.nterms;
         const int num_kb = kb_per_term * nterm_loops;
         const uint32_t b_bytes = static_cast<uint32_t>(S.tile_n) * BK * 2;
-        const uint32_t stage_tx = (dual ? 2 * A_BYTES : A_BYTES) + b_bytes;
+        const bool lo_term = dual && S.hi_only == 0;
+        const uint32_t stage_tx = (lo_term ? 2 * A_BYTES : A_BYTES) + b_bytes;
         const int n_base = static_cast<int>(rank) * (S.N / CLUSTER);
         auto a_off = [&](int t) { return t == 0 ? S.a_koff[0] : (t == 1 ? S.a_koff[1] : S.a_koff[2]); };
         auto b_off = [&](int t) { return t == 0 ? S.b_koff[0] : (t == 1 ? S.b_koff[1] : S.b_koff[2]); };
@@ -291,7 +293,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                 tma_load_2d(b_ptr(slot), &maps.b[s], &full_bar[slot], b_off(t) + kb * BK, n0);
               }
               tma_load_2d(a_ptr(slot, 0), &maps.a[s], &full_bar[slot], a_off(t) + kb * BK, m0);
-              if (dual) tma_load_2d(a_ptr(slot, 1), &maps.a[s], &full_bar[slot], a_off(1) + kb * BK, m0);
+              if (lo_term) tma_load_2d(a_ptr(slot, 1), &maps.a[s], &full_bar[slot], a_off(1) + kb * BK, m0);
               if (++slot == nst) { slot = 0; phase ^= 1; }
             }
           }
@@ -325,7 +327,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
             const uint64_t bdesc = umma_desc_sw128(smem_u32(b_ptr(slot)));
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            if (dual) {
+            if (dual && S.hi_only == 0) {
               const uint64_t adesc1 = umma_desc_sw128(smem_u32(a_ptr(slot, 1)));
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) umma_ss(d_tmem, adesc1 + 2 * k, bdesc + 2 * k, idesc, 1u);
@@ -384,6 +386,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
           // ---- pass 1: z = acc + bias + residual, running (mean, M2) over this thread's columns, z back into TMEM
           float mean = 0.f, M2 = 0.f, n = 0.f;
           for (int c = 0; c < nchunks; ++c) {
+            if (et == 0 && c == 1) CHAIN_STAMP(32 + s * 8 + 6);
             tmem_ld32(taddr + c * 32, r);
             float z[32];
             {
@@ -412,6 +415,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
               r[i] = __float_as_uint(z[i]);
             }
             tmem_st32(taddr + c * 32, r);
+            if (et == 0 && c == 1) CHAIN_STAMP(32 + s * 8 + 7);
             const float nn = n + 32.f, delta = cm - mean;
             mean += delta * (32.f / nn);
             M2 += cM2 + delta * delta * (n * 32.f / nn);
@@ -450,8 +454,10 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
           const float rstd = 1.f / sqrtf(M2 + 1e-5f);
           // ---- pass 2: normalise, write the fp32 row and the operand splits
           for (int c = 0; c < nchunks; ++c) {
+            if (et == 0 && c == 0) CHAIN_STAMP(32 + s * 8 + 0);
             tmem_ld32(taddr + c * 32, r);
             tmem_wait_ld();
+            if (et == 0 && c == 0) CHAIN_STAMP(32 + s * 8 + 1);
             float y[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -469,12 +475,16 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < 32; ++i) pv[i] = S.pe_cm[ocm + static_cast<long long>(i) * p.M];     // in flight during the stores below
             }
+            if (et == 0 && c == 0) CHAIN_STAMP(32 + s * 8 + 2);
             if (S.out_cm != nullptr) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) S.out_cm[ocm + static_cast<long long>(i) * p.M] = y[i];
             }
+            if (et == 0 && c == 0) CHAIN_STAMP(32 + s * 8 + 3);
             if (S.out_f32 != nullptr) chain_store_f32x32(stage, S.out_f32 + o, S.N, y, lane);
+            if (et == 0 && c == 0) CHAIN_STAMP(32 + s * 8 + 4);
             if (S.a_out != nullptr) chain_store_split32(stage, S.a_out + 2 * o - (col0 + c * 32), 2 * S.N, S.N, y, lane);
+            if (et == 0 && c == 0) CHAIN_STAMP(32 + s * 8 + 5);
             if (S.a_out_pe != nullptr) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) y[i] += pv[i];

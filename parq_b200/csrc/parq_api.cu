@@ -143,7 +143,10 @@ static int require_sm100() {
 // The stand-alone entry points launch plainly (their inputs may come from the caller's previous kernel).
 static thread_local bool g_pdl = false;
 static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
-static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;           // A/B switch: separate GEMM + LayerNorm launches instead of chain_tc.cuh
+static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;
+static const int g_chain_tile = getenv("PARQ_CHAIN_TILE") ? atoi(getenv("PARQ_CHAIN_TILE")) : 0;
+constexpr int HI_ONLY_DEFAULT = 0;
+static const int g_hi_only = getenv("PARQ_HI_ONLY") ? atoi(getenv("PARQ_HI_ONLY")) : 0;   // ablation: bit0 sa_qk, bit1 sa_v, bit2 ca_q use the hi activation term only           // A/B switch: separate GEMM + LayerNorm launches instead of chain_tc.cuh
 static const bool g_force_pair = getenv("PARQ_FORCE_PAIR") != nullptr;   // every GEMM on the CTA-pair kernel (tests)
 static const bool g_no_streamk = getenv("PARQ_NO_STREAMK") != nullptr;       // A/B switch: split-KV grid instead of the stream-K schedule
 static const bool g_no_pair_attn = getenv("PARQ_NO_PAIR_ATTN") != nullptr;   // A/B switch: single-CTA attention kernel
@@ -297,6 +300,9 @@ static int chain_add(ChainBuilder& cb, const void* A, uint64_t a_cols, const voi
   if (S.K <= 0 || S.K % chain::BK != 0 || !chain_cols_ok(S.N)) return fail(PARQ_ERR_SHAPE, "chain stage N=%d K=%d not supported", S.N, S.K);
   const int ncta = S.N / chain::CLUSTER;
   S.tile_n = ncta <= 256 ? ncta : 256;
+  // experiment (PARQ_CHAIN_TILE=128): narrower accumulator tiles for the stages without LayerNorm, so that the epilogue of
+  // tile j runs under the MMA of tile j+1 (the A operand is then streamed once per tile)
+  if (g_chain_tile > 0 && S.ep != CH_EP_LN && ncta % g_chain_tile == 0 && g_chain_tile % 64 == 0) S.tile_n = g_chain_tile;
   S.tiles = ncta / S.tile_n;
   S.nterms = w_lo ? 3 : 2;
   S.a_koff[0] = 0;   S.b_koff[0] = 0;
@@ -1175,6 +1181,9 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   const PdlScope pdl((flags & PARQ_FLAG_NO_PDL) == 0);
   const int C = s.C, F = s.ffn, R = s.B * s.Nq;
   // the row-local linears of an iteration as three chained launches (chain_tc.cuh) instead of ten GEMMs + three LayerNorms
+  // Low-order activation term of the three GEMMs whose output is rounded to 16 bits (self-attention Q|K and V^T in fp16,
+  // cross-attention Q in bf16): PARQ_HI_ONLY (environment) overrides the default for the ablation of DESIGN.md
+  const int hi_only = getenv("PARQ_HI_ONLY") ? g_hi_only : HI_ONLY_DEFAULT;
   const bool chained = !(flags & PARQ_FLAG_NO_CHAIN) && !g_no_chain && chain_cols_ok(C) && chain_cols_ok(2 * C) && chain_cols_ok(F) && R % chain::BM == 0;
   auto F32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto BF = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
@@ -1222,14 +1231,14 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
         S.out_cm = F32(W.pe); S.add_split = BF(W.a_x); S.out_sum_split = BF(W.a_xpe); S.add_cm_out = F32(W.y);
         TRY(chain_add(cb, ws + W.a_peh, 2 * C, pk + P.pe2, w_lo, S));
         S = chain_stage(2 * C, C, CH_EP_LP, PF(P.sa_qk_b));
-        S.out_lp = ws + W.qk_s; S.ld_lp = 2 * C; S.lp_fp16 = 1;
+        S.out_lp = ws + W.qk_s; S.ld_lp = 2 * C; S.lp_fp16 = 1; S.hi_only = (!w_lo && (hi_only & 1)) ? 1 : 0;
         TRY(chain_add(cb, ws + W.a_xpe, 2 * C, pk + P.sa_qk, w_lo, S));
         TRY(launch_chain(st, cb));
       }
       // V^T = Wv x^T + bv of the self-attention: weights are the A operand, activations the B operand
       {
         GemmParams g; memset(&g, 0, sizeof(g));
-        g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : 2; g.const_operand = 1;
+        g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : ((hi_only & 2) ? 1 : 2); g.const_operand = 1;
         g.a_koff[0] = 0; g.b_koff[0] = 0; g.a_koff[1] = 0; g.b_koff[1] = C; g.a_koff[2] = C; g.b_koff[2] = 0;
         g.ep = epilogue_none(); g.ep.bias = PF(P.sa_v_b); g.ep.bias_per_row = 1;
         g.ep.out_lp = ws + W.vt_s; g.ep.ld_lp = static_cast<long long>(W.ldvs); g.ep.lp_fp16 = 1;
@@ -1245,7 +1254,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
         S.out_cm = F32(W.x1); S.a_out_pe = BF(W.a_x1pe);
         TRY(chain_add(cb, ws + W.a_attn, 2 * C, pk + P.sa_out, w_lo, S));
         S = chain_stage(C, C, CH_EP_LP, PF(P.ca_q_b));
-        S.out_lp = ws + W.q_c; S.ld_lp = C;
+        S.out_lp = ws + W.q_c; S.ld_lp = C; S.hi_only = (!w_lo && (hi_only & 4)) ? 1 : 0;
         TRY(chain_add(cb, ws + W.a_x1pe, 2 * C, pk + P.ca_q, w_lo, S));
         TRY(launch_chain(st, cb));
       }

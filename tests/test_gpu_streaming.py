@@ -68,7 +68,7 @@ def test_streaming_cache_is_exact_and_matches_reference(dev):
 
 
 def test_streaming_anchor_frame_report(dev):
-    T, H, W, Nq, seed, n = 8, 30, 40, 256, 53, 12
+    T, H, W, Nq, seed, n = 8, 32, 40, 256, 53, 12
     sd = I.make_weights(seed, Nq)
     tokens, cam, Tcp, Twp = _stream_inputs(T, H, W, n, seed)
     eng = DecoderEngine(sd, dev)
@@ -112,6 +112,6 @@ def test_streaming_anchor_frame_report(dev):
         with open("gpurun_out/streaming_anchor.md", "w") as f:
             f.write("Anchor-frame streaming decode (tokens encoded once, reference points re-expressed) vs the exact per-window decode; "
                     "max|d|/max|ref|, random-init weights (the decoder is not frame-equivariant: the reference-point MLP and the box update see "
-                    "coordinates in another frame), 1 clip, 8-view window of 30x40 tokens sliding by one view\n\n" + report + "\n")
+                    "coordinates in another frame), 1 clip, 8-view window of 32x40 tokens sliding by one view\n\n" + report + "\n")
     except OSError:
         pass

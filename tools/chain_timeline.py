@@ -36,3 +36,7 @@ for launch in range(6):
         if not (st > 0).any():
             continue
         print("  stage %d: " % s + "  ".join("%s %+d" % (names[i], int(st[i]) - t0) for i in range(7) if int(st[i]) > 0))
+        fine = row[32 + s * 8: 32 + s * 8 + 8]
+        if (fine > 0).any():
+            fn = ["p2 c0 start", "tmem ld done", "normalised", "out_cm issued", "out_f32 stored", "a_out stored", "p1 c1 start", "p1 c1 tmem st"]
+            print("     fine: " + "  ".join("%s %+d" % (fn[i], int(fine[i]) - t0) for i in range(8) if int(fine[i]) > 0))
