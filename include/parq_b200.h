@@ -143,6 +143,9 @@ int parq_decoder_forward(const ParqShape *shape, const void *tokens_bf16, const 
  * concatenated along channels into out_nchw (BT, 4*channels_per_level, H, W) -- the `all_features` tensor. */
 int parq_fpn_concat(const float *l0, const float *l1, const float *l2, const float *l3, const int32_t *level_hw, int BT,
                     int channels_per_level, int target_level, float *out_nchw, void *stream);
+/* Same with bf16 pyramid levels (what an evaluation host ships over PCIe: 3.3 MB per view instead of 9.8 MB of tokens). */
+int parq_fpn_concat_bf16(const void *l0, const void *l1, const void *l2, const void *l3, const int32_t *level_hw, int BT,
+                         int channels_per_level, int target_level, float *out_nchw, void *stream);
 
 /* "Next" row f-1: AddRayPE.forward (model/ray_positional_encoding.py:61-139; utils/encoding_utils.py:15-100) fused with
  * the tokeniser of PARQ.forward (model/parq_lightning.py:75-85).  feat_nchw (B,T,C,H,W) fp32 backbone features (may be

@@ -144,7 +144,6 @@ static int require_sm100() {
 static thread_local bool g_pdl = false;
 static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
 static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;
-static const int g_chain_tile = getenv("PARQ_CHAIN_TILE") ? atoi(getenv("PARQ_CHAIN_TILE")) : 0;
 constexpr int HI_ONLY_DEFAULT = 0;
 static const int g_hi_only = getenv("PARQ_HI_ONLY") ? atoi(getenv("PARQ_HI_ONLY")) : 0;   // ablation: bit0 sa_qk, bit1 sa_v, bit2 ca_q use the hi activation term only           // A/B switch: separate GEMM + LayerNorm launches instead of chain_tc.cuh
 static const bool g_force_pair = getenv("PARQ_FORCE_PAIR") != nullptr;   // every GEMM on the CTA-pair kernel (tests)
@@ -300,9 +299,6 @@ static int chain_add(ChainBuilder& cb, const void* A, uint64_t a_cols, const voi
   if (S.K <= 0 || S.K % chain::BK != 0 || !chain_cols_ok(S.N)) return fail(PARQ_ERR_SHAPE, "chain stage N=%d K=%d not supported", S.N, S.K);
   const int ncta = S.N / chain::CLUSTER;
   S.tile_n = ncta <= 256 ? ncta : 256;
-  // experiment (PARQ_CHAIN_TILE=128): narrower accumulator tiles for the stages without LayerNorm, so that the epilogue of
-  // tile j runs under the MMA of tile j+1 (the A operand is then streamed once per tile)
-  if (g_chain_tile > 0 && S.ep != CH_EP_LN && ncta % g_chain_tile == 0 && g_chain_tile % 64 == 0) S.tile_n = g_chain_tile;
   S.tiles = ncta / S.tile_n;
   S.nterms = w_lo ? 3 : 2;
   S.a_koff[0] = 0;   S.b_koff[0] = 0;
@@ -898,14 +894,27 @@ int parq_split_tokens(const float* tokens_f32, void* hi_bf16, void* lo_bf16, lon
 }
 
 // ---- f-3: FPN upsample + concat ---------------------------------------------------------------------------------
+static int fpn_concat_impl(const void* l0, const void* l1, const void* l2, const void* l3, int in_bf16, const int32_t* level_hw, int BT,
+                           int channels_per_level, int target_level, float* out_nchw, void* stream);
+
 int parq_fpn_concat(const float* l0, const float* l1, const float* l2, const float* l3, const int32_t* level_hw, int BT, int channels_per_level,
                     int target_level, float* out_nchw, void* stream) {
+  return fpn_concat_impl(l0, l1, l2, l3, 0, level_hw, BT, channels_per_level, target_level, out_nchw, stream);
+}
+int parq_fpn_concat_bf16(const void* l0, const void* l1, const void* l2, const void* l3, const int32_t* level_hw, int BT, int channels_per_level,
+                         int target_level, float* out_nchw, void* stream) {
+  return fpn_concat_impl(l0, l1, l2, l3, 1, level_hw, BT, channels_per_level, target_level, out_nchw, stream);
+}
+
+static int fpn_concat_impl(const void* l0, const void* l1, const void* l2, const void* l3, int in_bf16, const int32_t* level_hw, int BT,
+                           int channels_per_level, int target_level, float* out_nchw, void* stream) {
   TRY(require_sm100());
   if (!l0 || !l1 || !l2 || !l3 || !level_hw || !out_nchw) return fail(PARQ_ERR_SHAPE, "null pointer");
   if (BT < 1 || channels_per_level < 1 || target_level < 0 || target_level > 3) return fail(PARQ_ERR_SHAPE, "bad fpn_concat arguments");
   FpnParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.level[0] = l0; fp.level[1] = l1; fp.level[2] = l2; fp.level[3] = l3;
+  fp.in_bf16 = in_bf16;
   for (int l = 0; l < 4; ++l) {
     fp.h[l] = level_hw[2 * l];
     fp.w[l] = level_hw[2 * l + 1];
@@ -922,7 +931,10 @@ int parq_fpn_concat(const float* l0, const float* l1, const float* l2, const flo
     // a launch covers planes [p0, p0+np): shift the output and let the kernel see plane indices from p0 via BT-relative pointers
     part.plane0 = static_cast<int>(p0);
     ProfScope ps(TAG_ROWWISE, static_cast<cudaStream_t>(stream));
-    fpn_concat_kernel<<<dim3((fp.H * fp.W + 1023) / 1024, np), 256, 0, static_cast<cudaStream_t>(stream)>>>(part);
+    if (in_bf16)
+      fpn_concat_kernel<__nv_bfloat16><<<dim3((fp.H * fp.W + 1023) / 1024, np), 256, 0, static_cast<cudaStream_t>(stream)>>>(part);
+    else
+      fpn_concat_kernel<float><<<dim3((fp.H * fp.W + 1023) / 1024, np), 256, 0, static_cast<cudaStream_t>(stream)>>>(part);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;

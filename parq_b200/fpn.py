@@ -10,13 +10,14 @@ from .wrappers import Camera, raw
 
 
 def fpn_concat(features, layer=0):
-    """``features``: the backbone's dict {"0": (N,Cl,h0,w0), "1": ..., "2": ..., "3": ...} fp32 CUDA tensors
+    """``features``: the backbone's dict {"0": (N,Cl,h0,w0), "1": ..., "2": ..., "3": ...} fp32 (or all-bf16) CUDA tensors
     (torchvision ``resnet_fpn_backbone`` output; "pool" is ignored).  Returns (N, 4*Cl, h_layer, w_layer) fp32 =
     ``torch.cat([F.interpolate(features[str(l)], features[str(layer)].shape[-2:], mode="bilinear") for l in range(4)], 1)``."""
     lv = [features[str(l)] for l in range(4)]
     if lv[0].device.type != "cuda":
         raise NotImplementedError("fpn_concat needs CUDA tensors on an sm_100 device (no CPU fallback)")
-    lv = [t.detach().float().contiguous() for t in lv]
+    bf16 = all(t.dtype == torch.bfloat16 for t in lv)
+    lv = [t.detach().contiguous() if bf16 else t.detach().float().contiguous() for t in lv]
     N, Cl = lv[0].shape[:2]
     if any(t.shape[0] != N or t.shape[1] != Cl or t.dim() != 4 for t in lv):
         raise ValueError("pyramid levels must be (N, Cl, h, w) with the same N and Cl")
@@ -24,8 +25,8 @@ def fpn_concat(features, layer=0):
     H, W = lv[int(layer)].shape[-2:]
     out = torch.empty(N, 4 * Cl, H, W, dtype=torch.float32, device=lv[0].device)
     with torch.cuda.device(out.device):
-        _lib.check(_lib.load().parq_fpn_concat(_ptr(lv[0]), _ptr(lv[1]), _ptr(lv[2]), _ptr(lv[3]), hw, N, Cl, int(layer), _ptr(out), _stream()),
-                   "parq_fpn_concat")
+        fn = _lib.load().parq_fpn_concat_bf16 if bf16 else _lib.load().parq_fpn_concat
+        _lib.check(fn(_ptr(lv[0]), _ptr(lv[1]), _ptr(lv[2]), _ptr(lv[3]), hw, N, Cl, int(layer), _ptr(out), _stream()), "parq_fpn_concat")
     return out
 
 

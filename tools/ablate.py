@@ -18,8 +18,6 @@ ROWS = [
     ("hi-only: sa_v", {"PARQ_HI_ONLY": "2"}),
     ("hi-only: ca_q", {"PARQ_HI_ONLY": "4"}),
     ("hi-only: sa_qk + sa_v + ca_q", {"PARQ_HI_ONLY": "7"}),
-    ("chain tiles of 128 columns", {"PARQ_CHAIN_TILE": "128"}),
-    ("chain tiles of 128 + hi-only all", {"PARQ_CHAIN_TILE": "128", "PARQ_HI_ONLY": "7"}),
     ("no chain (separate GEMM + LayerNorm launches)", {"PARQ_NO_CHAIN": "1"}),
 ]
 
