@@ -397,44 +397,6 @@ attn3_combine_kernel(const Attn3Params p) {
   const int b = bh / p.H, h = bh - b * p.H;
   const int C = p.H * 256;
   const int d = (threadIdx.x & 63) * 4;
-  // Items are cut into 2 (rarely 3) pieces: the common case keeps all loads of a thread's 8 rows in flight at once.
-  if (np == 2) {
-    constexpr int NR = SK_COMBINE_ROWS / 4;
-    float2 ml[NR][2];
-    float4 o[NR][2];
-#pragma unroll
-    for (int k = 0; k < NR; ++k) {
-      const int r = r0 + (threadIdx.x >> 6) + 4 * k;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const long long idx = s_slot[i] + r;
-        ml[k][i] = __ldg(&p.ml_part[idx]);
-        o[k][i] = __ldg(reinterpret_cast<const float4*>(p.o_part + idx * 256 + d));
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < NR; ++k) {
-      const int r = r0 + (threadIdx.x >> 6) + 4 * k;
-      const float M = fmaxf(ml[k][0].x, ml[k][1].x);
-      const float w0 = exp2f(ml[k][0].x - M), w1 = exp2f(ml[k][1].x - M);
-      float L = 0.f;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      L += w0 * ml[k][0].y;
-      acc.x += w0 * o[k][0].x; acc.y += w0 * o[k][0].y; acc.z += w0 * o[k][0].z; acc.w += w0 * o[k][0].w;
-      L += w1 * ml[k][1].y;
-      acc.x += w1 * o[k][1].x; acc.y += w1 * o[k][1].y; acc.z += w1 * o[k][1].z; acc.w += w1 * o[k][1].w;
-      const float inv = 1.f / L;
-      const float v[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
-      const uint32_t h0 = pack_bf16x2(v[0], v[1]), h1 = pack_bf16x2(v[2], v[3]);
-      const uint32_t l0 = pack_bf16x2(v[0] - __uint_as_float(h0 << 16), v[1] - __uint_as_float(h0 & 0xFFFF0000u));
-      const uint32_t l1 = pack_bf16x2(v[2] - __uint_as_float(h1 << 16), v[3] - __uint_as_float(h1 & 0xFFFF0000u));
-      const long long row = static_cast<long long>(b) * p.Nq + qp * 256 + r;
-      __nv_bfloat16* dst = p.out + row * (2 * C) + h * 256 + d;
-      *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(dst + C) = make_uint2(l0, l1);
-    }
-    return;
-  }
   for (int r = r0 + (threadIdx.x >> 6); r < r0 + SK_COMBINE_ROWS; r += 4) {
     float M = -INFINITY;
     for (int i = 0; i < np; ++i) M = fmaxf(M, __ldg(&p.ml_part[s_slot[i] + r].x));
