@@ -53,13 +53,6 @@ struct GemmEpilogue {
   float* nchw_out;
   int nchw_HW;
   int add_tma;         // the addend is staged through shared memory by TMA (third tensor map; needs HW % 4 == 0)
-  // Second 16-bit output: the bf16 [hi|lo] split of (value + addend), where the addend itself is stored as such a split
-  // (rows of ld_split elements, hi at column c, lo at column c + split_lo_off; same geometry for input and output).
-  // Used by the reference-point MLP: pe = W2 h + b2 goes out in fp32 AND x + pe (the self-attention query/key input,
-  // transformer_parq.py:372) goes out as a GEMM operand, x being the sampled features.  Needs N % 32 == 0.
-  const __nv_bfloat16* add_split;
-  __nv_bfloat16* out_sum_split;
-  long long ld_split, split_lo_off;
 };
 
 // element offset of the 32x32 chunk whose first row / column are (row0, col0) in a tiled K / V^T cache, and its row pitch
@@ -207,41 +200,6 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
       for (int i = 0; i < 32; ++i)
         if (col0 + i < N) o[i] = v[i];
     }
-  }
-  if (ep.add_split != nullptr) {
-    uint32_t hs[16], ls[16];
-    if (row_ok) {
-      const uint4* ah = reinterpret_cast<const uint4*>(ep.add_split + row * ep.ld_split + col0);
-      const uint4* al = reinterpret_cast<const uint4*>(ep.add_split + row * ep.ld_split + ep.split_lo_off + col0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 h = ah[i], l = al[i];
-        hs[4 * i] = h.x; hs[4 * i + 1] = h.y; hs[4 * i + 2] = h.z; hs[4 * i + 3] = h.w;
-        ls[4 * i] = l.x; ls[4 * i + 1] = l.y; ls[4 * i + 2] = l.z; ls[4 * i + 3] = l.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { hs[i] = 0u; ls[i] = 0u; }
-    }
-    __nv_bfloat16* obase = ep.out_sum_split + row0 * ep.ld_split + col0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float s0 = v[2 * i] + (__uint_as_float(hs[i] << 16) + __uint_as_float(ls[i] << 16));
-      const float s1 = v[2 * i + 1] + (__uint_as_float(hs[i] & 0xFFFF0000u) + __uint_as_float(ls[i] & 0xFFFF0000u));
-      const uint32_t h = pack_bf16x2(s0, s1);
-      hs[i] = h;
-      ls[i] = pack_bf16x2(s0 - __uint_as_float(h << 16), s1 - __uint_as_float(h & 0xFFFF0000u));
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) stage[lane * 33 + i] = hs[i];
-    __syncwarp();
-    gemm_flush_stage<16>(stage, reinterpret_cast<uint16_t*>(obase), ep.ld_split, rows_valid, lane);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) stage[lane * 33 + i] = ls[i];
-    __syncwarp();
-    gemm_flush_stage<16>(stage, reinterpret_cast<uint16_t*>(obase + ep.split_lo_off), ep.ld_split, rows_valid, lane);
-    __syncwarp();
   }
   if (ep.out_lp != nullptr && ep.kv_tiled != 0 && ep.kv_Nk % 32 == 0) {
     // tile-contiguous K / V^T cache: the chunk is a dense 32 x 32 block with its own origin and pitch

@@ -1305,8 +1305,9 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
       g.ep = epilogue_none(); g.ep.bias = PF(P.pe2_b);
       g.ep.out_f32 = F32(W.pe); g.ep.ld_f32 = C;
-      g.ep.add_split = BF(W.a_x); g.ep.out_sum_split = BF(W.a_xpe); g.ep.ld_split = 2 * C; g.ep.split_lo_off = C;
       TRY(launch_gemm(st, ws + W.a_peh, R, 2 * C, pk + P.pe2, C, 2 * C, g));
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(split_sum_kernel, dim3((R * (C / 8) + 255) / 256), dim3(256), 0, st, BF(W.a_x), F32(W.pe), BF(W.a_xpe), R, C); }
+      CUDA_TRY(cudaGetLastError());
     }
     // K3: self-attention among the queries (fp16 operands), out-projection, residual + LN1
     {

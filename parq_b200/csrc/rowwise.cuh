@@ -49,6 +49,31 @@ __global__ void posemb_kernel(const float* __restrict__ ref, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// a_sum = split(x + pe), x given as its [hi|lo] split (the sampled features), pe fp32: the query / key input of the
+// self-attention (reference transformer_parq.py:372) on the un-chained launch path.  One thread per 8 channels.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_sum_kernel(const __nv_bfloat16* __restrict__ a_x, const float* __restrict__ pe, __nv_bfloat16* __restrict__ a_sum, int R, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;       // 8-channel group
+  if (i >= static_cast<long long>(R) * C / 8) return;
+  const long long row = i / (C / 8);
+  const int c = static_cast<int>(i - row * (C / 8)) * 8;
+  const uint4 h = *reinterpret_cast<const uint4*>(a_x + row * 2 * C + c), l = *reinterpret_cast<const uint4*>(a_x + row * 2 * C + C + c);
+  const float4 p0 = *reinterpret_cast<const float4*>(pe + row * C + c), p1 = *reinterpret_cast<const float4*>(pe + row * C + c + 4);
+  const uint32_t hs[4] = {h.x, h.y, h.z, h.w}, ls[4] = {l.x, l.y, l.z, l.w};
+  const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[2 * k] = __uint_as_float(hs[k] << 16) + __uint_as_float(ls[k] << 16) + pv[2 * k];
+    v[2 * k + 1] = __uint_as_float(hs[k] & 0xFFFF0000u) + __uint_as_float(ls[k] & 0xFFFF0000u) + pv[2 * k + 1];
+  }
+  store_split8(a_sum + row * 2 * C + c, C, v);
+}
+
+// ---------------------------------------------------------------------------------------------
 // x_out = LayerNorm(x_in + y) (post-norm residual, reference transformer_parq.py:375-376, 381-385),
 // eps 1e-5, biased variance.  One warp per row.  Also emits the bf16 split of x_out and, when pe is
 // given, of x_out + pe (the cross-attention query input, transformer_parq.py:377).
