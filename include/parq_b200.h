@@ -84,6 +84,7 @@ typedef struct ParqOutputs {
 #define PARQ_FLAG_WEIGHT_LO 2u   /* parq_pack_weights returned 1: weights are not bf16-exact, use the 3-term GEMMs */
 #define PARQ_FLAG_KV_HI_ONLY 16u /* with WEIGHT_LO: project K / V^T with the high weight part only (they are stored in bf16 anyway) */
 #define PARQ_FLAG_NO_CHAIN 64u   /* per-iteration linears as separate GEMM + LayerNorm launches instead of the chained cluster kernel (A/B timing, tests) */
+#define PARQ_FLAG_FORCE_CHAIN 128u /* use the chained kernel also below its break-even batch (B*Nq < 2048 rows): tests */
 #define PARQ_FLAG_NO_PDL 4u      /* launch without programmatic dependent launch (plain stream order; for A/B timing) */
 
 int parq_version(void);

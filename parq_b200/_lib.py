@@ -15,6 +15,7 @@ PARQ_FLAG_WEIGHT_LO = 2
 PARQ_FLAG_NO_PDL = 4
 PARQ_FLAG_KV_HI_ONLY = 16
 PARQ_FLAG_NO_CHAIN = 64
+PARQ_FLAG_FORCE_CHAIN = 128
 PARQ_RAYPE_SPLIT_HIDDEN = 8
 PARQ_NMS_SAME_CLASS = 1
 PARQ_NMS_NO_TRACK_SCALE = 2

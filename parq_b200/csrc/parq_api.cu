@@ -144,6 +144,7 @@ static int require_sm100() {
 static thread_local bool g_pdl = false;
 static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
 static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;
+static const int g_chain_min_rows = getenv("PARQ_CHAIN_MIN_ROWS") ? atoi(getenv("PARQ_CHAIN_MIN_ROWS")) : 2048;
 constexpr int HI_ONLY_DEFAULT = 0;
 static const int g_hi_only = getenv("PARQ_HI_ONLY") ? atoi(getenv("PARQ_HI_ONLY")) : 0;   // ablation: bit0 sa_qk, bit1 sa_v, bit2 ca_q use the hi activation term only           // A/B switch: separate GEMM + LayerNorm launches instead of chain_tc.cuh
 static const bool g_force_pair = getenv("PARQ_FORCE_PAIR") != nullptr;   // every GEMM on the CTA-pair kernel (tests)
@@ -1196,7 +1197,10 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   // Low-order activation term of the three GEMMs whose output is rounded to 16 bits (self-attention Q|K and V^T in fp16,
   // cross-attention Q in bf16): PARQ_HI_ONLY (environment) overrides the default for the ablation of DESIGN.md
   const int hi_only = getenv("PARQ_HI_ONLY") ? g_hi_only : HI_ONLY_DEFAULT;
-  const bool chained = !(flags & PARQ_FLAG_NO_CHAIN) && !g_no_chain && chain_cols_ok(C) && chain_cols_ok(2 * C) && chain_cols_ok(F) && R % chain::BM == 0;
+  // It pays when the one-wave GEMMs it replaces fill the machine (R = 4096 rows at config 2: -0.46 ms per step); with a few
+  // hundred rows (one clip: 2-4 clusters) the separate launches are faster (measured at config 5: 2.7 vs 3.5 ms per window).
+  const bool chained = !(flags & PARQ_FLAG_NO_CHAIN) && !g_no_chain && chain_cols_ok(C) && chain_cols_ok(2 * C) && chain_cols_ok(F) && R % chain::BM == 0 &&
+                       (R >= g_chain_min_rows || (flags & PARQ_FLAG_FORCE_CHAIN));
   auto F32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto BF = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
   auto PF = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };

@@ -219,13 +219,14 @@ class DecoderEngine:
         return self._ref0_cache
 
     def forward(self, tokens, camera, T_cp, T_wp, T_wl, H, W, forced_refs=None, ref0=None, debug=False, skip_kv=False,
-                graph=False, pdl=True, chain=True):
+                graph=False, pdl=True, chain=None):
         """tokens (B, T*H*W, C) bf16, or fp32 (split on the device into an exact bf16 pair, see ``_split_tokens``);
         camera (B,T,6); poses (B,T,12)/(B,1,12) fp32.
         Returns a dict of stacked per-iteration tensors (iters, B, Nq, n).
 
-        ``chain=False`` runs the row-local linears of an iteration as separate GEMM + LayerNorm launches instead of the
-        chained cluster kernel (csrc/chain_tc.cuh); same results up to the summation order of the LayerNorm statistics.
+        ``chain``: True forces the chained cluster kernel (csrc/chain_tc.cuh) for the row-local linears of an iteration,
+        False forces separate GEMM + LayerNorm launches, None (default) lets the library choose (chained from B*Nq = 2048
+        rows); same results up to the summation order of the LayerNorm statistics.
         ``pdl=False`` launches the kernels in plain stream order instead of with programmatic dependent launch.
         ``graph=True`` replays the whole forward as ONE CUDA graph captured on first use per shape (see
         ``_forward_graph``); the returned tensors are then static buffers that the next replay overwrites."""
@@ -241,7 +242,7 @@ class DecoderEngine:
         shape = self._shape(B, T, H, W)
         ws = self._workspace(shape, (B, T, H, W))
         flags = self.flags | (_lib.PARQ_FLAG_SKIP_KV if skip_kv else 0) | (0 if pdl else _lib.PARQ_FLAG_NO_PDL) | \
-            (0 if chain else _lib.PARQ_FLAG_NO_CHAIN)
+            (0 if chain is None else (_lib.PARQ_FLAG_FORCE_CHAIN if chain else _lib.PARQ_FLAG_NO_CHAIN))
         if graph:
             return self._forward_graph(shape, ws, flags, tokens, camera, T_cp, T_wp, T_wl, forced_refs, ref0, debug)
         tokens_lo = None

@@ -67,8 +67,10 @@ def test_projection_edge_cases(dev):
 
 
 # ------------------------------------------------------- full decoder: teacher-forced ----
+@pytest.mark.parametrize("chain", [None, True], ids=["auto", "chained"])
 @pytest.mark.parametrize("name", ["small", "ragged_wild", "white_noise"])
-def test_decoder_against_reference_golden(dev, name):
+def test_decoder_against_reference_golden(dev, name, chain):
+    # chain=True forces the chained cluster kernel (chain_tc.cuh), which the library picks by itself only from 2048 rows
     gold = load_golden(name)
     c = regenerate_case(gold)
     sd = c["sd"]
@@ -76,7 +78,7 @@ def test_decoder_against_reference_golden(dev, name):
     gold_outs = [{k: torch.from_numpy(gold[k][i]) for k in OUT_KEYS} for i in range(iters)]
     refs = O.refs_from_outputs(gold_outs, sd)
     eng = DecoderEngine(sd, dev)
-    got = _engine_forward(eng, c, dev, forced_refs=refs.to(dev), debug=True)
+    got = _engine_forward(eng, c, dev, forced_refs=refs.to(dev), debug=True, chain=chain)
     flips = 0
     for i in range(iters):
         assert bit_equal(got["coord_pos"][i], gold["coord_pos"][i]), "iteration %d" % i
@@ -478,7 +480,7 @@ def test_decoder_with_fp32_weights_against_oracle(dev):
     refs = O.refs_from_outputs(outs, sd)
     eng = DecoderEngine(sd, dev, iters=iters)
     assert eng.weight_lo
-    got = _engine_forward(eng, c, dev, forced_refs=refs.to(dev), debug=True)
+    got = _engine_forward(eng, c, dev, forced_refs=refs.to(dev), debug=True, chain=True)     # three-term stages in the chained kernel
     errs = {}
     for i in range(iters):
         assert bit_equal(got["center_im"][i], auxs[i]["center_im"])
@@ -652,7 +654,7 @@ def test_unchained_launch_sequence_matches_chained(dev):
     gold_outs = [{k: torch.from_numpy(gold[k][i]) for k in OUT_KEYS} for i in range(8)]
     refs = O.refs_from_outputs(gold_outs, c["sd"]).to(dev)
     eng = DecoderEngine(c["sd"], dev)
-    chained = {k: v.clone() for k, v in _engine_forward(eng, c, dev, forced_refs=refs, debug=True).items()}
+    chained = {k: v.clone() for k, v in _engine_forward(eng, c, dev, forced_refs=refs, debug=True, chain=True).items()}
     plain = _engine_forward(eng, c, dev, forced_refs=refs, debug=True, chain=False)
     for i in range(8):
         assert relerr(plain["decoder_out"][i], chained["decoder_out"][i]) <= 2e-4
@@ -662,7 +664,7 @@ def test_unchained_launch_sequence_matches_chained(dev):
     # fp32 (checkpoint-style) weights: three-term GEMMs, plain 4-slot ring in the chained kernel
     sd = I.make_weights(61, 256, bf16_exact=False)
     eng = DecoderEngine(sd, dev, iters=2)
-    a = {k: v.clone() for k, v in _engine_forward(eng, c, dev, debug=True).items()}
+    a = {k: v.clone() for k, v in _engine_forward(eng, c, dev, debug=True, chain=True).items()}
     b = _engine_forward(eng, c, dev, debug=True, chain=False)
     assert relerr(a["decoder_out"][0], b["decoder_out"][0]) <= 2e-4
     assert relerr(a["pred_logits"][0], b["pred_logits"][0]) <= 2e-4
