@@ -254,10 +254,11 @@ def box_heads(x, ref, sd, scale):
             "ortho6d": ortho6d, "sem_cls_prob": prob, "coord_pos": coord_pos}
 
 
-def decoder_iteration(tokens, memory, ref, T_camera_local, camera, H, W, sd, heads=4, scale=None, kv=None):
+def decoder_iteration(tokens, memory, ref, T_camera_local, camera, H, W, sd, heads=4, scale=None, kv=None, layer=0):
     """One pass of the hot loop body (transformer_parq.py:311-332) for normalised
-    reference points ``ref`` (B,Nq,3).  Returns (out_dict, next_ref, aux)."""
-    L = "parq_module.decoder.layers.0."
+    reference points ``ref`` (B,Nq,3).  ``layer``: index of the decoder layer this iteration uses (0 when the
+    weights are shared, the iteration number otherwise, :311-314).  Returns (out_dict, next_ref, aux)."""
+    L = "parq_module.decoder.layers.%d." % layer
     P = "parq_module.decoder.position_encoder."
     pe = F.linear(F.relu(F.linear(pos2posemb3d(ref), sd[P + "0.weight"], sd[P + "0.bias"])), sd[P + "2.weight"], sd[P + "2.bias"])
     pe = pe.permute(1, 0, 2)
@@ -303,9 +304,11 @@ def decoder_forward(tokens, camera, T_camera_pseudoCam, T_world_pseudoCam, T_wor
         Tcl = camera_from_local(T_camera_pseudoCam.numpy(), T_world_pseudoCam.numpy(), T_world_local.numpy())
         memory = tokens.permute(1, 0, 2)
         E = tokens.shape[-1]
+        # SHARE_WEIGHTS False (transformer_parq.py:168-171): one layer per iteration, nothing to hoist
+        shared = "parq_module.decoder.layers.1.norm1.weight" not in sd
         L = "parq_module.decoder.layers.0.multihead_attn."
         kv = None
-        if hoist_kv:
+        if hoist_kv and shared:
             kv = (F.linear(memory, sd[L + "in_proj_weight"][E:2 * E], sd[L + "in_proj_bias"][E:2 * E]),
                   F.linear(memory, sd[L + "in_proj_weight"][2 * E:], sd[L + "in_proj_bias"][2 * E:]))
         ref = sd["refpoint.weight"].unsqueeze(0).repeat(B, 1, 1).sigmoid()
@@ -313,7 +316,7 @@ def decoder_forward(tokens, camera, T_camera_pseudoCam, T_world_pseudoCam, T_wor
         for it in range(iters):
             if forced_refs is not None:
                 ref = forced_refs[it]
-            out, ref, aux = decoder_iteration(tokens, memory, ref, Tcl, cam.numpy(), H, W, sd, heads, scale, kv)
+            out, ref, aux = decoder_iteration(tokens, memory, ref, Tcl, cam.numpy(), H, W, sd, heads, scale, kv, layer=0 if shared else it)
             outs.append(out)
             auxs.append(aux)
         return (outs, auxs) if return_aux else outs

@@ -45,7 +45,7 @@ class _NS(dict):
     __getattr__ = dict.__getitem__
 
 
-def decoder_cfg(num_queries=256, dec_layers=8, for_vis=False):
+def decoder_cfg(num_queries=256, dec_layers=8, for_vis=False, share_weights=True):
     """Attribute namespace with the MODEL.DECODER fields of config/eval.yaml:37-56."""
     return _NS(
         DIM_IN=1024, NUM_QUERIES=num_queries, NUM_SEMCLS=9, LOSS_WEIGHT=[5.0, 5.0, 5.0, 1.0],
@@ -54,7 +54,7 @@ def decoder_cfg(num_queries=256, dec_layers=8, for_vis=False):
         EVAL_TYPE="f1", CONF_THRESH=0.8, ENABLE_NMS=True,
         TRANSFORMER=_NS(DEC_DIM=1024, QUERIES_DIM=1024, DEC_HEADS=4, DEC_LAYERS=dec_layers,
                         DEC_FFN_DIM=768, DROPOUT_RATE=0.1,
-                        SCALE=[-3, 3, -2, 0.5, 0.25, 5.25], SHARE_WEIGHTS=True))
+                        SCALE=[-3, 3, -2, 0.5, 0.25, 5.25], SHARE_WEIGHTS=share_weights))
 
 
 _loaded = {}
@@ -144,8 +144,10 @@ def load_resnet_fpn():
 
 
 def build_decoder(sd, num_queries=256, dec_layers=8, for_vis=False, device="cpu"):
-    """An instance of the unmodified PARQDecoder (model/parq_decoder.py:30) in eval mode with the given state dict."""
+    """An instance of the unmodified PARQDecoder (model/parq_decoder.py:30) in eval mode with the given state dict
+    (SHARE_WEIGHTS False when the state dict carries more than one decoder layer)."""
     ns = load_reference()
-    m = ns.PARQDecoder(decoder_cfg(num_queries, dec_layers, for_vis)).eval()
+    shared = "parq_module.decoder.layers.1.norm1.weight" not in sd
+    m = ns.PARQDecoder(decoder_cfg(num_queries, dec_layers, for_vis, share_weights=shared)).eval()
     m.load_state_dict(sd, strict=True)
     return m.to(device)

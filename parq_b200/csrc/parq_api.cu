@@ -722,7 +722,7 @@ long long parq_workspace_offset(const ParqShape* shape, const char* name) {
   if (check_shape(shape) != PARQ_OK || name == nullptr) return -1;
   const Workspace W = workspace_layout(*shape, device_info().sms);
   const struct { const char* n; size_t off; } tab[] = {
-      {"Kc", W.Kc}, {"Vt", W.Vt}, {"T_cl", W.T_cl}, {"pe", W.pe}, {"qk_s", W.qk_s}, {"vt_s", W.vt_s},
+      {"Kc", W.Kc}, {"Vt", W.Vt}, {"T_cl", W.T_cl}, {"ref_cur", W.ref_cur}, {"pe", W.pe}, {"qk_s", W.qk_s}, {"vt_s", W.vt_s},
       {"a_attn", W.a_attn}, {"y", W.y}, {"x1", W.x1}, {"x2", W.x2}, {"x3", W.x3}, {"q_c", W.q_c}, {"h1", W.h1}, {"h2", W.h2},
       {"ldv", W.ldv}, {"ldvs", W.ldvs}, {"kv_tiled", static_cast<size_t>(W.kv_tiled)}, {"ntile", static_cast<size_t>(W.ntile)}, {"cross_nsplit", static_cast<size_t>(W.cross.nsplit)},
       {"self_nsplit", static_cast<size_t>(W.self.nsplit)}};

@@ -107,60 +107,77 @@ class DecoderEngine:
             raise NotImplementedError("parq_b200 runs on sm_100 CUDA devices only")
         self.heads, self.num_cls, self.scale, self.iters = heads, num_cls, tuple(float(x) for x in scale), iters
         sd = state_dict
-        L = "parq_module.decoder.layers.0."
         Pn = "parq_module.decoder.position_encoder."
         Hn = "mlp_heads."
-        self.C = sd[L + "norm1.weight"].shape[0]
-        self.ffn = sd[L + "linear1.weight"].shape[0]
+        L0 = "parq_module.decoder.layers.0."
+        self.C = sd[L0 + "norm1.weight"].shape[0]
+        self.ffn = sd[L0 + "linear1.weight"].shape[0]
         self.Nq = sd["refpoint.weight"].shape[0]
-        names = {
-            "pe0_w": Pn + "0.weight", "pe0_b": Pn + "0.bias", "pe2_w": Pn + "2.weight", "pe2_b": Pn + "2.bias",
-            "sa_in_w": L + "self_attn.in_proj_weight", "sa_in_b": L + "self_attn.in_proj_bias",
-            "sa_out_w": L + "self_attn.out_proj.weight", "sa_out_b": L + "self_attn.out_proj.bias",
-            "ca_in_w": L + "multihead_attn.in_proj_weight", "ca_in_b": L + "multihead_attn.in_proj_bias",
-            "ca_out_w": L + "multihead_attn.out_proj.weight", "ca_out_b": L + "multihead_attn.out_proj.bias",
-            "lin1_w": L + "linear1.weight", "lin1_b": L + "linear1.bias", "lin2_w": L + "linear2.weight", "lin2_b": L + "linear2.bias",
-            "ln1_g": L + "norm1.weight", "ln1_b": L + "norm1.bias", "ln2_g": L + "norm2.weight", "ln2_b": L + "norm2.bias",
-            "ln3_g": L + "norm3.weight", "ln3_b": L + "norm3.bias",
-            "cls_w": Hn + "sem_cls_head.layers.0.weight", "cls_b": Hn + "sem_cls_head.layers.0.bias",
-            "ctr0_w": Hn + "center_head.layers.0.weight", "ctr1_g": Hn + "center_head.layers.1.weight",
-            "ctr1_b": Hn + "center_head.layers.1.bias", "ctr4_w": Hn + "center_head.layers.4.weight",
-            "ctr5_g": Hn + "center_head.layers.5.weight", "ctr5_b": Hn + "center_head.layers.5.bias",
-            "ctr8_w": Hn + "center_head.layers.8.weight", "ctr8_b": Hn + "center_head.layers.8.bias",
-            "size_w": Hn + "size_head.layers.0.weight", "size_b": Hn + "size_head.layers.0.bias",
-            "rot0_w": Hn + "rotation_head.layers.0.weight", "rot1_g": Hn + "rotation_head.layers.1.weight",
-            "rot1_b": Hn + "rotation_head.layers.1.bias", "rot4_w": Hn + "rotation_head.layers.4.weight",
-            "rot5_g": Hn + "rotation_head.layers.5.weight", "rot5_b": Hn + "rotation_head.layers.5.bias",
-            "rot8_w": Hn + "rotation_head.layers.8.weight", "rot8_b": Hn + "rotation_head.layers.8.bias",
-        }
-        keep = {}
-        w = _lib.ParqWeightsF32()
-        for field, key in names.items():
-            t = sd[key].detach().to(self.device, torch.float32).contiguous()
-            keep[field] = t
-            setattr(w, field, t.data_ptr())
+        # SHARE_WEIGHTS False (transformer_parq.py:168-171, 311-314): one decoder layer per iteration.  The library's forward
+        # walks its iterations with ONE packed weight set, so un-shared layers are driven from here: one packed buffer per
+        # layer (position encoder and heads are shared) and one single-iteration call per layer.
+        self.n_layers = 1
+        while ("parq_module.decoder.layers.%d.norm1.weight" % self.n_layers) in sd:
+            self.n_layers += 1
+        if self.n_layers > 1 and self.n_layers != iters:
+            raise ValueError("state dict has %d distinct decoder layers but iters=%d" % (self.n_layers, iters))
+
+        def names_for(layer):
+            L = "parq_module.decoder.layers.%d." % layer
+            return {
+                "pe0_w": Pn + "0.weight", "pe0_b": Pn + "0.bias", "pe2_w": Pn + "2.weight", "pe2_b": Pn + "2.bias",
+                "sa_in_w": L + "self_attn.in_proj_weight", "sa_in_b": L + "self_attn.in_proj_bias",
+                "sa_out_w": L + "self_attn.out_proj.weight", "sa_out_b": L + "self_attn.out_proj.bias",
+                "ca_in_w": L + "multihead_attn.in_proj_weight", "ca_in_b": L + "multihead_attn.in_proj_bias",
+                "ca_out_w": L + "multihead_attn.out_proj.weight", "ca_out_b": L + "multihead_attn.out_proj.bias",
+                "lin1_w": L + "linear1.weight", "lin1_b": L + "linear1.bias", "lin2_w": L + "linear2.weight", "lin2_b": L + "linear2.bias",
+                "ln1_g": L + "norm1.weight", "ln1_b": L + "norm1.bias", "ln2_g": L + "norm2.weight", "ln2_b": L + "norm2.bias",
+                "ln3_g": L + "norm3.weight", "ln3_b": L + "norm3.bias",
+                "cls_w": Hn + "sem_cls_head.layers.0.weight", "cls_b": Hn + "sem_cls_head.layers.0.bias",
+                "ctr0_w": Hn + "center_head.layers.0.weight", "ctr1_g": Hn + "center_head.layers.1.weight",
+                "ctr1_b": Hn + "center_head.layers.1.bias", "ctr4_w": Hn + "center_head.layers.4.weight",
+                "ctr5_g": Hn + "center_head.layers.5.weight", "ctr5_b": Hn + "center_head.layers.5.bias",
+                "ctr8_w": Hn + "center_head.layers.8.weight", "ctr8_b": Hn + "center_head.layers.8.bias",
+                "size_w": Hn + "size_head.layers.0.weight", "size_b": Hn + "size_head.layers.0.bias",
+                "rot0_w": Hn + "rotation_head.layers.0.weight", "rot1_g": Hn + "rotation_head.layers.1.weight",
+                "rot1_b": Hn + "rotation_head.layers.1.bias", "rot4_w": Hn + "rotation_head.layers.4.weight",
+                "rot5_g": Hn + "rotation_head.layers.5.weight", "rot5_b": Hn + "rotation_head.layers.5.bias",
+                "rot8_w": Hn + "rotation_head.layers.8.weight", "rot8_b": Hn + "rotation_head.layers.8.bias",
+            }
+
         ms = torch.tensor(MEAN_SIZE, dtype=torch.float64) if mean_size is None else torch.as_tensor(mean_size).detach().cpu().double()
         if ms.dim() != 2 or ms.shape[0] < num_cls or ms.shape[1] != 3:
             raise ValueError("mean_size must be (>= %d, 3), got %s" % (num_cls, tuple(ms.shape)))
-        keep["mean_size"] = ms[: num_cls].float().to(self.device).contiguous()      # .float() of the float64 table, parq_utils.py:98
-        keep["dim_t"] = _dim_t(self.device).contiguous()
-        w.mean_size = keep["mean_size"].data_ptr()
-        w.dim_t = keep["dim_t"].data_ptr()
+        mean_size_dev = ms[: num_cls].float().to(self.device).contiguous()      # .float() of the float64 table, parq_utils.py:98
+        dim_t_dev = _dim_t(self.device).contiguous()
         self.refpoint = sd["refpoint.weight"].detach().to(self.device, torch.float32).contiguous()
         shape = self._shape(1, 1, 1, 1)
         nbytes = self.lib.parq_packed_bytes(C.byref(shape))
         if nbytes == 0:
             raise _lib.ParqError("parq_packed_bytes: " + self.lib.parq_last_error().decode())
-        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
-            rc = _lib.check(self.lib.parq_pack_weights(C.byref(shape), C.byref(w), _ptr(self.packed), nbytes, _stream()),
-                            "parq_pack_weights")
-        self.weight_lo = bool(rc)
+        self.packed_layers, lo_any = [], False
+        for layer in range(self.n_layers):
+            keep = {}
+            w = _lib.ParqWeightsF32()
+            for field, key in names_for(layer).items():
+                t = sd[key].detach().to(self.device, torch.float32).contiguous()
+                keep[field] = t
+                setattr(w, field, t.data_ptr())
+            w.mean_size = mean_size_dev.data_ptr()
+            w.dim_t = dim_t_dev.data_ptr()
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                rc = _lib.check(self.lib.parq_pack_weights(C.byref(shape), C.byref(w), _ptr(packed), nbytes, _stream()),
+                                "parq_pack_weights")
+            lo_any = lo_any or bool(rc)
+            self.packed_layers.append(packed)
+            del keep
+        self.packed = self.packed_layers[0]
+        self.weight_lo = lo_any
         self._ws = None
         self._ws_key = None
         self._graphs = {}
         self._ref0_cache = None
-        del keep
 
     def _shape(self, B, T, H, W):
         return make_shape(B, T, H, W, self.C, self.Nq, self.heads, self.ffn, self.iters, self.num_cls, self.scale)
@@ -194,11 +211,28 @@ class DecoderEngine:
             setattr(po, k, outs[k].data_ptr())
         return outs, po
 
-    def _launch(self, shape, tokens, tokens_lo, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags):
+    def _launch(self, shape, tokens, tokens_lo, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags, outs=None):
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.parq_decoder_forward(C.byref(shape), _ptr(tokens), _ptr(tokens_lo), _ptr(camera), _ptr(T_cp), _ptr(T_wp),
-                                                     _ptr(T_wl), _ptr(ref0), _ptr(fr), _ptr(self.packed), _ptr(ws), ws.numel(), C.byref(po),
-                                                     flags, _stream()), "parq_decoder_forward")
+            if self.n_layers == 1:
+                _lib.check(self.lib.parq_decoder_forward(C.byref(shape), _ptr(tokens), _ptr(tokens_lo), _ptr(camera), _ptr(T_cp), _ptr(T_wp),
+                                                         _ptr(T_wl), _ptr(ref0), _ptr(fr), _ptr(self.packed), _ptr(ws), ws.numel(), C.byref(po),
+                                                         flags, _stream()), "parq_decoder_forward")
+                return
+            # un-shared layers: one single-iteration call per layer; the next reference points stay in the workspace
+            # ("ref_cur"), K / V^T are re-projected with every layer's own weights (nothing is iteration invariant)
+            if flags & _lib.PARQ_FLAG_SKIP_KV:
+                raise NotImplementedError("skip_kv needs shared decoder layers (K / V^T depend on the layer)")
+            one = make_shape(shape.B, shape.T, shape.H, shape.W, self.C, self.Nq, self.heads, self.ffn, 1, self.num_cls, self.scale)
+            off = self.lib.parq_workspace_offset(C.byref(one), b"ref_cur")
+            ref_cur = ws[off: off + shape.B * self.Nq * 12]
+            for i in range(self.iters):
+                po_i = _lib.ParqOutputs()
+                for k, t in outs.items():
+                    setattr(po_i, k, t[i].data_ptr())
+                _lib.check(self.lib.parq_decoder_forward(C.byref(one), _ptr(tokens), _ptr(tokens_lo), _ptr(camera), _ptr(T_cp), _ptr(T_wp),
+                                                         _ptr(T_wl), _ptr(ref0 if i == 0 else ref_cur), _ptr(fr[i] if fr is not None else None),
+                                                         _ptr(self.packed_layers[i]), _ptr(ws), ws.numel(), C.byref(po_i), flags, _stream()),
+                           "parq_decoder_forward (layer %d)" % i)
 
     def _split_tokens(self, tokens, hi=None, lo=None):
         """fp32 tokens -> exact bf16 pair (hi, lo) on the device (parq_split_tokens): K / V^T are projected from `hi`
@@ -256,7 +290,7 @@ class DecoderEngine:
         ref0 = self._ref0(B) if ref0 is None else f32(ref0)
         fr = f32(forced_refs) if forced_refs is not None else None
         outs, po = self._alloc_outputs(B, T, debug)
-        self._launch(shape, tokens, tokens_lo, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags)
+        self._launch(shape, tokens, tokens_lo, camera, T_cp, T_wp, T_wl, ref0, fr, ws, po, flags, outs)
         # keep inputs alive until the stream the kernels were launched on has consumed them
         st = torch.cuda.current_stream(self.device)
         for t in (tokens, tokens_lo, camera, T_cp, T_wp, T_wl, ref0, fr):
@@ -304,7 +338,7 @@ class DecoderEngine:
                 st["fr"].copy_(forced_refs.detach())
             if entry["graph"] is None:
                 outs, po = self._alloc_outputs(B, T, debug)
-                args = (shape, st["tokens"], st["tokens_lo"], st["camera"], st["T_cp"], st["T_wp"], st["T_wl"], st["ref0"], st["fr"], ws, po, flags)
+                args = (shape, st["tokens"], st["tokens_lo"], st["camera"], st["T_cp"], st["T_wp"], st["T_wl"], st["ref0"], st["fr"], ws, po, flags, outs)
                 self._launch(*args)                            # lazy one-off setup (smem opt-ins) outside the capture
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
@@ -427,8 +461,8 @@ def accelerate(decoder, feature_hw=None, use_cuda_graph=False):
     iterations from ``num_layers``, scale from the decoder (transformer_parq.py:164-183)."""
     dec = decoder.parq_module.decoder
     layer = dec.layers[0]
-    if len(set(id(l) for l in dec.layers)) != 1:
-        raise NotImplementedError("only SHARE_WEIGHTS=True decoders (one layer reused every iteration) are supported")
+    if len(dec.layers) not in (1, dec.num_layers):
+        raise NotImplementedError("decoder has %d layers for %d iterations" % (len(dec.layers), dec.num_layers))
     heads = layer.self_attn.num_heads
     iters = dec.num_layers
     scale = [float(x) for x in dec.scale]
@@ -495,8 +529,9 @@ class PARQDecoderB200(nn.Module):
         tr = cfg.TRANSFORMER
         self.dim_in, self.num_queries, self.num_semcls = cfg.DIM_IN, cfg.NUM_QUERIES, cfg.NUM_SEMCLS
         self.for_vis, self.track_scale, self.enable_nms = cfg.FOR_VIS, cfg.TRACK_SCALE, cfg.ENABLE_NMS
-        if not cfg.SHARE_MLP_HEADS or not tr.SHARE_WEIGHTS:
-            raise NotImplementedError("only SHARE_MLP_HEADS=True / SHARE_WEIGHTS=True (the shipped configs) are supported")
+        if not cfg.SHARE_MLP_HEADS:
+            # the reference's own SHARE_MLP_HEADS=False branch references an undefined attribute (parq_decoder.py:119-123)
+            raise NotImplementedError("SHARE_MLP_HEADS=False does not construct in the reference either")
         if tr.DEC_DIM != cfg.DIM_IN or tr.QUERIES_DIM != tr.DEC_DIM:
             raise NotImplementedError("DEC_DIM, QUERIES_DIM and DIM_IN must agree")
         D = tr.DEC_DIM
@@ -511,14 +546,18 @@ class PARQDecoderB200(nn.Module):
             ("size_head", _head(D, 3, [], 0.3)),
             ("rotation_head", _head(D, 6, [D, D], 0.0)),
         ])
-        layer = _Params()
-        layer.self_attn = nn.MultiheadAttention(D, tr.DEC_HEADS, dropout=tr.DROPOUT_RATE)
-        layer.multihead_attn = nn.MultiheadAttention(D, tr.DEC_HEADS, dropout=tr.DROPOUT_RATE)
-        layer.linear1 = nn.Linear(D, tr.DEC_FFN_DIM)
-        layer.linear2 = nn.Linear(tr.DEC_FFN_DIM, D)
-        layer.norm1, layer.norm2, layer.norm3 = nn.LayerNorm(D), nn.LayerNorm(D), nn.LayerNorm(D)
+        def make_layer():
+            layer = _Params()
+            layer.self_attn = nn.MultiheadAttention(D, tr.DEC_HEADS, dropout=tr.DROPOUT_RATE)
+            layer.multihead_attn = nn.MultiheadAttention(D, tr.DEC_HEADS, dropout=tr.DROPOUT_RATE)
+            layer.linear1 = nn.Linear(D, tr.DEC_FFN_DIM)
+            layer.linear2 = nn.Linear(tr.DEC_FFN_DIM, D)
+            layer.norm1, layer.norm2, layer.norm3 = nn.LayerNorm(D), nn.LayerNorm(D), nn.LayerNorm(D)
+            return layer
+
         dec = _Params()
-        dec.layers = nn.ModuleList([layer])
+        # SHARE_WEIGHTS True: one layer reused every iteration; False: one layer per iteration (transformer_parq.py:168-171)
+        dec.layers = nn.ModuleList([make_layer() for _ in range(1 if tr.SHARE_WEIGHTS else tr.DEC_LAYERS)])
         dec.norm = nn.LayerNorm(D)        # present in checkpoints, never applied (transformer_parq.py:174)
         dec.position_encoder = nn.Sequential(nn.Linear(3 * POS_FEATS, D), nn.ReLU(), nn.Linear(D, D))
         dec.num_layers, dec.scale = tr.DEC_LAYERS, list(tr.SCALE)     # attribute names of the reference's TransformerDecoder

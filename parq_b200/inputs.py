@@ -83,7 +83,7 @@ def state_dict_spec(num_queries=256, dim=DEC_DIM, ffn=FFN_DIM, num_cls=NUM_CLS):
     return spec
 
 
-def make_weights(seed=0, num_queries=256, bf16_exact=True):
+def make_weights(seed=0, num_queries=256, bf16_exact=True, n_layers=1):
     """Random-init decoder weights as a state dict with the reference's 65 keys.
 
     Matrices use the reference's init families (xavier-uniform inside
@@ -92,11 +92,21 @@ def make_weights(seed=0, num_queries=256, bf16_exact=True):
     from their 0/1 defaults so that every bias/affine path is exercised by the
     parity tests.  With ``bf16_exact`` every matrix is rounded to
     bf16-representable fp32 so both sides of a parity test consume identical
-    values.
+    values.  ``n_layers`` > 1: SHARE_WEIGHTS False, one distinct decoder layer per iteration
+    (keys ``parq_module.decoder.layers.{i}.*``, transformer_parq.py:168-171).
     """
     g = torch.Generator().manual_seed(1000003 * seed + 17)
     sd = OrderedDict()
+    spec = []
     for key, shape in state_dict_spec(num_queries):
+        if key.startswith("parq_module.decoder.layers.0.") and n_layers > 1:
+            continue
+        spec.append((key, shape))
+    if n_layers > 1:
+        layer0 = [(k, sh) for k, sh in state_dict_spec(num_queries) if k.startswith("parq_module.decoder.layers.0.")]
+        at = next(i for i, (k, _) in enumerate(spec) if k.startswith("parq_module.decoder.norm."))
+        spec[at:at] = [(k.replace("layers.0.", "layers.%d." % i), sh) for i in range(n_layers) for k, sh in layer0]
+    for key, shape in spec:
         if key.startswith("parq_module.decoder.mlp_heads."):
             sd[key] = sd[key[len("parq_module.decoder."):]]      # alias, parq_decoder.py:66
             continue

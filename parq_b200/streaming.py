@@ -47,6 +47,8 @@ class StreamingWindow:
     def __init__(self, engine, T, H, W, B=1):
         if (H * W) % 32 != 0:
             raise ValueError("per-view K / V^T updates need H*W % 32 == 0")
+        if engine.n_layers != 1:
+            raise NotImplementedError("the K / V^T cache needs shared decoder layers (SHARE_WEIGHTS=True)")
         self.eng, self.B, self.T, self.H, self.W = engine, B, T, H, W
         dev, Cc = engine.device, engine.C
         self.tokens = torch.zeros(B, T * H * W, Cc, dtype=torch.bfloat16, device=dev)      # ring of view slots

@@ -86,6 +86,22 @@ def main():
         data["pred_mask_vis"] = parsed_vis["pred_mask"].numpy()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
         print(name, {k: v.shape for k, v in data.items() if hasattr(v, "shape")})
+    # SHARE_WEIGHTS False (transformer_parq.py:168-171, 311-314): one distinct decoder layer per iteration
+    for name, (B, T, H, W, Nq, seed, layers) in {"unshared": (1, 2, 10, 14, 128, 5, 3)}.items():
+        from oracle.ref_loader import build_decoder
+        sd = I.make_weights(seed, Nq, n_layers=layers)
+        ref = build_decoder(sd, Nq, layers)
+        tokens = I.make_tokens(B, T, H, W, seed=seed)
+        cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+        with torch.no_grad():
+            outs = ref(tokens, ns.Camera(cam._data), ns.Pose(Tcp._data), ns.Pose(Twp._data), ns.Pose(Twl._data))
+        data = {"shape": np.array([B, T, H, W, Nq, seed, layers]),
+                "weights_sum": np.array(I.tensor_checksum(*[sd[k] for k in sorted(sd)])),
+                "inputs_sum": np.array(I.tensor_checksum(tokens, cam._data, Tcp._data, Twp._data, Twl._data))}
+        for k in outs[0]:
+            data[k] = np.stack([o[k].numpy() for o in outs])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
+        print(name, {k: v.shape for k, v in data.items() if hasattr(v, "shape")})
     from oracle.ref_loader import load_module
     rpe = load_module("model.ray_positional_encoding")
     for name, (B, T, H, W, seed) in RAYPE_CASES.items():

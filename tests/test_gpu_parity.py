@@ -670,6 +670,36 @@ def test_unchained_launch_sequence_matches_chained(dev):
     assert relerr(a["pred_logits"][0], b["pred_logits"][0]) <= 2e-4
 
 
+def test_unshared_decoder_layers_against_reference_golden(dev):
+    # SHARE_WEIGHTS False: one distinct layer per iteration, driven as single-iteration library calls (K / V^T re-projected
+    # by every layer, as the reference does); module API included
+    gold = load_golden("unshared")
+    B, T, H, W, Nq, seed, layers = [int(x) for x in gold["shape"]]
+    sd = I.make_weights(seed, Nq, n_layers=layers)
+    tokens = I.make_tokens(B, T, H, W, seed=seed)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+    c = dict(tokens=tokens, camera=cam._data, T_cp=Tcp._data, T_wp=Twp._data, T_wl=Twl._data, H=H, W=W)
+    gold_outs = [{k: torch.from_numpy(gold[k][i]) for k in OUT_KEYS} for i in range(layers)]
+    refs = O.refs_from_outputs(gold_outs, sd)
+    eng = DecoderEngine(sd, dev, iters=layers)
+    assert eng.n_layers == layers
+    for graph in (False, True):
+        got = _engine_forward(eng, c, dev, forced_refs=refs.to(dev), graph=graph)
+        for i in range(layers):
+            assert bit_equal(got["coord_pos"][i], gold["coord_pos"][i])
+            for k in ("pred_logits", "center_unnormalized", "ortho6d", "sem_cls_prob"):
+                assert relerr(got[k][i].cpu(), gold[k][i]) <= TOL, (k, i, graph)
+    cfg = default_cfg(Nq, layers)
+    cfg.TRANSFORMER.SHARE_WEIGHTS = False
+    m = PARQDecoderB200(cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    out = m.to(dev)(tokens.to(dev), cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev))
+    torch.cuda.synchronize()
+    for k in OUT_KEYS:                                   # free running: iteration 0 is exact, iteration 1 starts from our own centres
+        assert relerr(out[0][k].cpu(), gold[k][0]) <= TOL, k
+    assert relerr(out[1]["center_unnormalized"].cpu(), gold["center_unnormalized"][1]) <= 5 * TOL
+
+
 def test_free_running_divergence_report(dev):
     """the free-running recurrence (no teacher forcing) is reported, not gated, next to the oracle's own
     sensitivity: the oracle re-run on tokens perturbed by a relative 1e-6 (fp32 rounding scale) and 2^-9 (bf16 operand

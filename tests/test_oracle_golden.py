@@ -127,3 +127,19 @@ def test_oracle_fpn_concat_matches_reference(name):
     assert bit_equal(af[:, :, ::16], gold["all_features"])
     cam = I.make_geometry(B, T, H * 4, W * 4, seed=seed)[0]
     assert bit_equal(camera_feature(cam)._data, gold["camera_feature"])
+
+
+def test_oracle_unshared_decoder_layers():
+    # SHARE_WEIGHTS False (transformer_parq.py:168-171, 311-314): fixture from the unmodified reference with 3 distinct layers
+    from parq_b200 import inputs as I
+    gold = load_golden("unshared")
+    B, T, H, W, Nq, seed, layers = [int(x) for x in gold["shape"]]
+    sd = I.make_weights(seed, Nq, n_layers=layers)
+    assert I.tensor_checksum(*[sd[k] for k in sorted(sd)]) == str(gold["weights_sum"])
+    tokens = I.make_tokens(B, T, H, W, seed=seed)
+    cam, Tcp, Twp, Twl = I.make_geometry(B, T, H, W, seed=seed)
+    gold_outs = [{k: torch.from_numpy(gold[k][i]) for k in OUT_KEYS} for i in range(layers)]
+    outs = O.decoder_forward(tokens, cam._data, Tcp._data, Twp._data, Twl._data, sd, iters=layers, forced_refs=O.refs_from_outputs(gold_outs, sd))
+    for i in range(layers):
+        for k in OUT_KEYS:
+            assert relerr(outs[i][k], gold[k][i]) <= 2e-5, (k, i)
