@@ -489,6 +489,7 @@ def run_ours(args):
     from parq_b200 import shard
     model.use_cuda_graph = True
     out = model(tokens, *geo)
+    shard.gather_detections({k: model.parse_pred(out)[k] for k in shard.DETECTION_KEYS + ("pred_mask",)}, world * B)   # untimed: NCCL channel set-up
     barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
