@@ -534,10 +534,13 @@ def run_ours(args):
         samp_bytes = n_inb * Cc * 2 + B * Nq * Cc * 4 + B * T * Nq * 9.0 + B * Nq * 12.0 + B * T * 72.0
         samp_moved = n_inb * Cc * 2 + B * Nq * Cc * 4 + B * Nq * 12.0 + B * T * 72.0
         kv_ms, kv_n = prof["kv_proj"]
-        traffic = None
+        traffic, traffic_src, samp_traffic = None, None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("cross_attn_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("cross_attn_dram_bytes_per_launch")
+            samp_traffic = tj.get("project_sample_dram_bytes_per_launch")
+            traffic_src = "ncu --set full capture summarised in profiles/r2_ncu_full_iter.md, taken at commit %s" % tj.get("captured_at_commit")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -553,11 +556,12 @@ def run_ours(args):
             "roofline": {"kernel": "attn3_tc_kernel<bf16> (CTA-pair flash cross-attention, stream-K schedule, over %d image tokens)" % Nk, "bound": "tensor",
                          "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sustained"]) if ach else None,
                          "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
-                         "flops_per_launch": flops, "ms_per_launch": ca_ms / max(ca_n, 1), "launches_timed": ca_n, "traffic": traffic},
+                         "flops_per_launch": flops, "ms_per_launch": ca_ms / max(ca_n, 1), "launches_timed": ca_n, "traffic": traffic,
+                         "traffic_source": traffic_src},
             "roofline_sampling": {"kernel": "project_sample_kernel", "bound": "hbm",
                                   "achieved": samp_bytes / (ps_ms / max(ps_n, 1) * 1e-3) / 1e9 if ps_n else None, "peak": pk["hbm"], "unit": "GB/s",
                                   "frac": samp_bytes / (ps_ms / max(ps_n, 1) * 1e-3) / 1e9 / pk["hbm"] if ps_n else None,
-                                  "algorithmic_bytes": samp_bytes, "moved_bytes": samp_moved, "bytes_per_launch": samp_bytes,
+                                  "algorithmic_bytes": samp_bytes, "moved_bytes": samp_moved, "traffic": samp_traffic, "bytes_per_launch": samp_bytes,
                                   "in_bounds_corners_per_launch": n_inb, "valid_view_fraction": valid_frac,
                                   "ms_per_launch": ps_ms / max(ps_n, 1), "launches_timed": ps_n,
                                   "timing": "CUDA events around each launch inside the timed steps (includes the event/launch gaps)",
