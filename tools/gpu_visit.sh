@@ -16,7 +16,7 @@ import json
 try:
     d = json.loads(open("gpurun_out/bench_${TAG}.json").read().strip().splitlines()[-1])
     print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "attn frac", d["roofline"]["frac"])
-    print("sampling", {k: d["roofline_sampling"][k] for k in ("frac", "ms_per_launch", "back_to_back")})
+    print("sampling", {k: d["roofline_sampling"][k] for k in ("frac", "ms_per_launch", "in_step")})
     print(d["breakdown_ms_per_step"]); print(d["breakdown_launches"]); print(d["clocks"]); print(d.get("cpu_baseline")); print(d.get("gpu_torch_baseline"))
 except Exception as e:
     print("bench line unreadable:", e)
