@@ -451,7 +451,7 @@ def run_ours(args):
                 copied[s].record(copy_stream)
             main.wait_event(copied[s])
             cam_s, Tcp_s, Twp_s, Twl_s = Camera(pgeo_dev[s][0]), Pose(pgeo_dev[s][1]), Pose(pgeo_dev[s][2]), Pose(pgeo_dev[s][3])
-            feats = fpn_concat(pyr_dev[s]).view(B, T, Cc, H, W)
+            feats = fpn_concat(pyr_dev[s], out_dtype=torch.bfloat16).view(B, T, Cc, H, W)
             toks = rpe.tokens(feats, cam_s, Tcp_s, Twp_s, Twl_s, out=tok_buf)
             o = model(toks, cam_s, Tcp_s, Twp_s, Twl_s)
             parsed_s = model.parse_pred(o)
@@ -550,7 +550,7 @@ def run_ours(args):
                     "note": "PARQDecoderB200.forward on pinned host tokens (bf16) + poses, double-buffered H2D on a copy stream, D2H of the last-iteration detections"},
             "e2e_pipeline": {"value": world * B / (ms_pipe / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_pipe, "d2h_bytes_per_step": d2h_pipe,
                              "ms_per_step": ms_pipe / args.steps,
-                             "note": "pinned host FPN pyramid (4 bf16 levels) + cameras / poses -> fpn_concat (f-3) -> AddRayPEB200.tokens (f-1) -> "
+                             "note": "pinned host FPN pyramid (4 bf16 levels) + cameras / poses -> fpn_concat (f-3, bf16 all_features) -> AddRayPEB200.tokens (f-1) -> "
                                      "PARQDecoderB200.forward -> parse_pred + NMS (f-2) -> D2H of the detections and pred_mask; double-buffered H2D"},
             "gpu_launches": launches,
             "roofline": {"kernel": "attn3_tc_kernel<bf16> (CTA-pair flash cross-attention, stream-K schedule, over %d image tokens)" % Nk, "bound": "tensor",

@@ -147,6 +147,11 @@ int parq_fpn_concat(const float *l0, const float *l1, const float *l2, const flo
 /* Same with bf16 pyramid levels (what an evaluation host ships over PCIe: 3.3 MB per view instead of 9.8 MB of tokens). */
 int parq_fpn_concat_bf16(const void *l0, const void *l1, const void *l2, const void *l3, const int32_t *level_hw, int BT,
                          int channels_per_level, int target_level, float *out_nchw, void *stream);
+/* General form: fp32 or bf16 levels, fp32 or bf16 output.  A bf16 `all_features` (half the bytes of this memory-bound pass
+ * and of the read-back in the AddRayPE producer, which takes it with PARQ_RAYPE_FEAT_BF16) is rounded once more when the
+ * encoding is added: the tokens then carry up to 1.5 bf16 ulp instead of 0.5. */
+int parq_fpn_concat_ex(const void *l0, const void *l1, const void *l2, const void *l3, int levels_bf16, const int32_t *level_hw,
+                       int BT, int channels_per_level, int target_level, void *out_nchw, int out_bf16, void *stream);
 
 /* "Next" row f-1: AddRayPE.forward (model/ray_positional_encoding.py:61-139; utils/encoding_utils.py:15-100) fused with
  * the tokeniser of PARQ.forward (model/parq_lightning.py:75-85).  feat_nchw (B,T,C,H,W) fp32 backbone features (may be
@@ -158,6 +163,7 @@ int parq_fpn_concat_bf16(const void *l0, const void *l1, const void *l2, const v
  * exact [hi|lo] bf16 split (fp32-grade encoding, 2x the second GEMM); without it the hidden layer is plain bf16, which is
  * below the bf16 rounding of the tokens themselves. */
 #define PARQ_RAYPE_SPLIT_HIDDEN 8u
+#define PARQ_RAYPE_FEAT_BF16 256u /* feat_nchw points at bf16 features (parq_fpn_concat_ex with out_bf16) */
 size_t parq_raype_packed_bytes(int C, int num_samples);
 size_t parq_raype_workspace_bytes(int B, int T, int H, int W, int C, int num_samples);
 int parq_raype_pack_weights(int C, int num_samples, const float *w0, const float *b0, const float *w2, const float *b2,

@@ -17,6 +17,7 @@ PARQ_FLAG_KV_HI_ONLY = 16
 PARQ_FLAG_NO_CHAIN = 64
 PARQ_FLAG_FORCE_CHAIN = 128
 PARQ_RAYPE_SPLIT_HIDDEN = 8
+PARQ_RAYPE_FEAT_BF16 = 256
 PARQ_NMS_SAME_CLASS = 1
 PARQ_NMS_NO_TRACK_SCALE = 2
 
@@ -24,7 +25,7 @@ EXPORTS = [
     "parq_version", "parq_last_error", "parq_packed_bytes", "parq_workspace_bytes", "parq_pack_weights",
     "parq_pose_chain", "parq_split_tokens", "parq_project_sample", "parq_kv_project", "parq_kv_project_views", "parq_chain_debug", "parq_decoder_forward",
     "parq_gemm_bf16", "parq_attention_scratch_bytes", "parq_attention",
-    "parq_parse_pred", "parq_fpn_concat", "parq_fpn_concat_bf16", "parq_raype_packed_bytes", "parq_raype_workspace_bytes", "parq_raype_pack_weights",
+    "parq_parse_pred", "parq_fpn_concat", "parq_fpn_concat_bf16", "parq_fpn_concat_ex", "parq_raype_packed_bytes", "parq_raype_workspace_bytes", "parq_raype_pack_weights",
     "parq_raype_forward", "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect", "parq_workspace_offset",
 ]
 PROFILE_TAGS = ("kv_proj", "project_sample", "gemm", "self_attn", "cross_attn", "combine", "rowwise")
@@ -115,6 +116,8 @@ def load():
     lib.parq_fpn_concat.argtypes = [f32p, f32p, f32p, f32p, C.POINTER(C.c_int32), i32, i32, i32, f32p, vp]
     lib.parq_fpn_concat_bf16.restype = C.c_int
     lib.parq_fpn_concat_bf16.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int32), i32, i32, i32, f32p, vp]
+    lib.parq_fpn_concat_ex.restype = C.c_int
+    lib.parq_fpn_concat_ex.argtypes = [vp, vp, vp, vp, i32, C.POINTER(C.c_int32), i32, i32, i32, vp, i32, vp]
     lib.parq_raype_packed_bytes.restype = sz
     lib.parq_raype_packed_bytes.argtypes = [i32, i32]
     lib.parq_raype_workspace_bytes.restype = sz

@@ -15,7 +15,7 @@ struct FpnParams {
   int h[4], w[4];
   int BT, Cl, H, W;        // output (BT, 4*Cl, H, W)
   int plane0;              // first output plane (bt * 4*Cl + c) of this launch
-  float* out;
+  void* out;               // fp32, or bf16 (TOut): the channels-first addend of the AddRayPE producer at half the bytes
 };
 
 // grid = (pixel tiles, BT * 4 * Cl planes): a block works inside ONE output plane, so the level / channel / image
@@ -27,7 +27,10 @@ __device__ __forceinline__ float fpn_ld<float>(const float* p) { return __ldg(p)
 template <>
 __device__ __forceinline__ float fpn_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
-template <typename TIn>
+__device__ __forceinline__ void fpn_st(float* p, float v) { *p = v; }
+__device__ __forceinline__ void fpn_st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 fpn_concat_kernel(const FpnParams p) {
   const int plane = p.plane0 + blockIdx.y;            // bt * 4*Cl + c
@@ -37,7 +40,7 @@ fpn_concat_kernel(const FpnParams p) {
   const int w = l == 0 ? p.w[0] : (l == 1 ? p.w[1] : (l == 2 ? p.w[2] : p.w[3]));
   const TIn* __restrict__ src = static_cast<const TIn*>(l == 0 ? p.level[0] : (l == 1 ? p.level[1] : (l == 2 ? p.level[2] : p.level[3]))) +
                                 (static_cast<long long>(bt) * p.Cl + cl) * h * w;
-  float* __restrict__ dst = p.out + static_cast<long long>(plane) * p.H * p.W;
+  TOut* __restrict__ dst = static_cast<TOut*>(p.out) + static_cast<long long>(plane) * p.H * p.W;
   const int HW = p.H * p.W;
   const bool copy = (h == p.H && w == p.W);
   const float sy = static_cast<float>(h) / static_cast<float>(p.H), sx = static_cast<float>(w) / static_cast<float>(p.W);
@@ -58,7 +61,7 @@ fpn_concat_kernel(const FpnParams p) {
       v = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01))),
                     __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11))));
     }
-    dst[pix] = v;
+    fpn_st(dst + pix, v);
   }
 }
 

@@ -322,7 +322,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int c = 0; c < BN / 32 && n0 + c * 32 < p.N; ++c, ++cc) {
           const int buf = cc % 3;
           mbar_wait(&add_empty[buf], ((cc / 3) & 1) ^ 1);
-          mbar_expect_tx(&add_full[buf], 32 * 128 * 4);
+          mbar_expect_tx(&add_full[buf], p.ep.nchw_add_bf16 ? 32 * 128 * 2 : 32 * 128 * 4);
           tma_load_2d(add_buf(buf), &tmC, &add_full[buf], pix0, bt * p.N + n0 + c * 32);
         }
       }

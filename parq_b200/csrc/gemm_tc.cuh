@@ -50,6 +50,7 @@ struct GemmEpilogue {
   //   nchw_out[(bt*N + col)*HW + pixel] = value                    (fp32; AddRayPE's (B,T,C,H,W) encoding)
   //   value += nchw_add[(bt*N + col)*HW + pixel]                    (fp32 backbone features, before out_f32 / out_lp)
   const float* nchw_add;
+  int nchw_add_bf16;   // the addend is bf16 (channels-first features written by parq_fpn_concat_ex), not fp32
   float* nchw_out;
   int nchw_HW;
   int add_tma;         // the addend is staged through shared memory by TMA (third tensor map; needs HW % 4 == 0)
@@ -155,16 +156,29 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpilogue& ep, const u
         if (full || col0 + i < N) ep.nchw_out[off + static_cast<long long>(i) * ep.nchw_HW] = v[i];
     }
     if (sadd != nullptr) {
-      // addend chunk staged by TMA as [32 channels][128 tile rows] fp32: conflict-free column reads
+      // addend chunk staged by TMA as [32 channels][128 tile rows] (fp32 or bf16): conflict-free column reads
+      if (ep.nchw_add_bf16) {
+        const __nv_bfloat16* s16 = reinterpret_cast<const __nv_bfloat16*>(sadd);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += sadd[i * 128 + rowin];
+        for (int i = 0; i < 32; ++i) v[i] += __bfloat162float(s16[i * 128 + rowin]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += sadd[i * 128 + rowin];
+      }
     } else if (ep.nchw_add != nullptr) {
       // tiles that straddle two images: straight from global memory (a loop of its own, so the 32 loads are
       // independent of the stores above)
-      const float* __restrict__ add = ep.nchw_add + off;
+      if (ep.nchw_add_bf16) {
+        const __nv_bfloat16* __restrict__ add = reinterpret_cast<const __nv_bfloat16*>(ep.nchw_add) + off;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (full || col0 + i < N) v[i] += __ldg(add + static_cast<long long>(i) * ep.nchw_HW);
+        for (int i = 0; i < 32; ++i)
+          if (full || col0 + i < N) v[i] += __bfloat162float(add[static_cast<long long>(i) * ep.nchw_HW]);
+      } else {
+        const float* __restrict__ add = ep.nchw_add + off;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (full || col0 + i < N) v[i] += __ldg(add + static_cast<long long>(i) * ep.nchw_HW);
+      }
     }
    }
     if (ep.out_lp != nullptr) {      // plain bf16 rows (the channels-last tokens)
@@ -523,7 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = 0; c < BN / 32 && n0 + c * 32 < p.N; ++c, ++cc) {
           const int buf = cc % 3;
           mbar_wait(&add_empty[buf], ((cc / 3) & 1) ^ 1);
-          mbar_expect_tx(&add_full[buf], 32 * 128 * 4);
+          mbar_expect_tx(&add_full[buf], p.ep.nchw_add_bf16 ? 32 * 128 * 2 : 32 * 128 * 4);
           tma_load_2d(add_buf(buf), &tmC, &add_full[buf], pix0, bt * p.N + n0 + c * 32);
         }
       }

@@ -220,14 +220,14 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
 }
 
 // 2-D map over a row-major fp32 matrix without swizzle: box = box_cols x box_rows (the channels-first addend of gemm_tc.cuh)
-static int make_map_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+static int make_map_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows, bool bf16 = false) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(PARQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 4};
+  cuuint64_t strides[1] = {cols * (bf16 ? 2 : 4)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PARQ_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", static_cast<int>(r));
   return PARQ_OK;
@@ -253,8 +253,9 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
   GemmParams gpl = gp;
   CUtensorMap tmC = tmA;                    // placeholder unless the channels-first addend goes through TMA
   gpl.ep.add_tma = 0;
-  if (gp.ep.nchw_add != nullptr && gp.ep.nchw_HW % 4 == 0 && (reinterpret_cast<uintptr_t>(gp.ep.nchw_add) & 15) == 0 && gp.M % gp.ep.nchw_HW == 0) {
-    TRY(make_map_f32(&tmC, gp.ep.nchw_add, static_cast<uint64_t>(gp.M / gp.ep.nchw_HW) * gp.N, gp.ep.nchw_HW, 128, 32));
+  if (gp.ep.nchw_add != nullptr && gp.ep.nchw_HW % (gp.ep.nchw_add_bf16 ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(gp.ep.nchw_add) & 15) == 0 &&
+      gp.M % gp.ep.nchw_HW == 0) {
+    TRY(make_map_f32(&tmC, gp.ep.nchw_add, static_cast<uint64_t>(gp.M / gp.ep.nchw_HW) * gp.N, gp.ep.nchw_HW, 128, 32, gp.ep.nchw_add_bf16 != 0));
     gpl.ep.add_tma = 1;
   }
   gpl.dual_a = (gp.nterms == 2 && gp.b_koff[0] == gp.b_koff[1] && gp.a_koff[0] != gp.a_koff[1] && !g_no_dual) ? 1 : 0;
@@ -896,19 +897,23 @@ int parq_split_tokens(const float* tokens_f32, void* hi_bf16, void* lo_bf16, lon
 
 // ---- f-3: FPN upsample + concat ---------------------------------------------------------------------------------
 static int fpn_concat_impl(const void* l0, const void* l1, const void* l2, const void* l3, int in_bf16, const int32_t* level_hw, int BT,
-                           int channels_per_level, int target_level, float* out_nchw, void* stream);
+                           int channels_per_level, int target_level, void* out_nchw, int out_bf16, void* stream);
 
 int parq_fpn_concat(const float* l0, const float* l1, const float* l2, const float* l3, const int32_t* level_hw, int BT, int channels_per_level,
                     int target_level, float* out_nchw, void* stream) {
-  return fpn_concat_impl(l0, l1, l2, l3, 0, level_hw, BT, channels_per_level, target_level, out_nchw, stream);
+  return fpn_concat_impl(l0, l1, l2, l3, 0, level_hw, BT, channels_per_level, target_level, out_nchw, 0, stream);
 }
 int parq_fpn_concat_bf16(const void* l0, const void* l1, const void* l2, const void* l3, const int32_t* level_hw, int BT, int channels_per_level,
                          int target_level, float* out_nchw, void* stream) {
-  return fpn_concat_impl(l0, l1, l2, l3, 1, level_hw, BT, channels_per_level, target_level, out_nchw, stream);
+  return fpn_concat_impl(l0, l1, l2, l3, 1, level_hw, BT, channels_per_level, target_level, out_nchw, 0, stream);
+}
+int parq_fpn_concat_ex(const void* l0, const void* l1, const void* l2, const void* l3, int levels_bf16, const int32_t* level_hw, int BT,
+                       int channels_per_level, int target_level, void* out_nchw, int out_bf16, void* stream) {
+  return fpn_concat_impl(l0, l1, l2, l3, levels_bf16 ? 1 : 0, level_hw, BT, channels_per_level, target_level, out_nchw, out_bf16 ? 1 : 0, stream);
 }
 
 static int fpn_concat_impl(const void* l0, const void* l1, const void* l2, const void* l3, int in_bf16, const int32_t* level_hw, int BT,
-                           int channels_per_level, int target_level, float* out_nchw, void* stream) {
+                           int channels_per_level, int target_level, void* out_nchw, int out_bf16, void* stream) {
   TRY(require_sm100());
   if (!l0 || !l1 || !l2 || !l3 || !level_hw || !out_nchw) return fail(PARQ_ERR_SHAPE, "null pointer");
   if (BT < 1 || channels_per_level < 1 || target_level < 0 || target_level > 3) return fail(PARQ_ERR_SHAPE, "bad fpn_concat arguments");
@@ -932,10 +937,12 @@ static int fpn_concat_impl(const void* l0, const void* l1, const void* l2, const
     // a launch covers planes [p0, p0+np): shift the output and let the kernel see plane indices from p0 via BT-relative pointers
     part.plane0 = static_cast<int>(p0);
     ProfScope ps(TAG_ROWWISE, static_cast<cudaStream_t>(stream));
-    if (in_bf16)
-      fpn_concat_kernel<__nv_bfloat16><<<dim3((fp.H * fp.W + 1023) / 1024, np), 256, 0, static_cast<cudaStream_t>(stream)>>>(part);
-    else
-      fpn_concat_kernel<float><<<dim3((fp.H * fp.W + 1023) / 1024, np), 256, 0, static_cast<cudaStream_t>(stream)>>>(part);
+    const dim3 grid((fp.H * fp.W + 1023) / 1024, np);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (in_bf16 && out_bf16) fpn_concat_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(part);
+    else if (in_bf16) fpn_concat_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(part);
+    else if (out_bf16) fpn_concat_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(part);
+    else fpn_concat_kernel<float, float><<<grid, 256, 0, st>>>(part);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
@@ -1069,6 +1076,7 @@ int parq_raype_forward(int B, int T, int H, int W, int C, int num_samples, const
   g.ep.nchw_out = encoding_nchw;
   if (tokens_bf16) {
     g.ep.nchw_add = feat_nchw;
+    g.ep.nchw_add_bf16 = (flags & PARQ_RAYPE_FEAT_BF16) ? 1 : 0;
     g.ep.out_lp = tokens_bf16; g.ep.ld_lp = C;
   }
   TRY(launch_gemm(st, ws + Wk.hidden, ntok, split_hidden ? 2 * C : C, pk + P.w2, C, 2 * C, g));

@@ -9,10 +9,12 @@ from .decoder import _ptr, _stream
 from .wrappers import Camera, raw
 
 
-def fpn_concat(features, layer=0):
+def fpn_concat(features, layer=0, out_dtype=torch.float32):
     """``features``: the backbone's dict {"0": (N,Cl,h0,w0), "1": ..., "2": ..., "3": ...} fp32 (or all-bf16) CUDA tensors
     (torchvision ``resnet_fpn_backbone`` output; "pool" is ignored).  Returns (N, 4*Cl, h_layer, w_layer) fp32 =
-    ``torch.cat([F.interpolate(features[str(l)], features[str(layer)].shape[-2:], mode="bilinear") for l in range(4)], 1)``."""
+    ``torch.cat([F.interpolate(features[str(l)], features[str(layer)].shape[-2:], mode="bilinear") for l in range(4)], 1)``.
+    ``out_dtype=torch.bfloat16`` writes the result in bf16 -- half the bytes of this memory-bound pass and of its read-back in
+    ``AddRayPEB200.tokens`` (which accepts it directly); the fp32 default is the reference's ``all_features``."""
     lv = [features[str(l)] for l in range(4)]
     if lv[0].device.type != "cuda":
         raise NotImplementedError("fpn_concat needs CUDA tensors on an sm_100 device (no CPU fallback)")
@@ -23,10 +25,12 @@ def fpn_concat(features, layer=0):
         raise ValueError("pyramid levels must be (N, Cl, h, w) with the same N and Cl")
     hw = (C.c_int32 * 8)(*[int(v) for t in lv for v in t.shape[-2:]])
     H, W = lv[int(layer)].shape[-2:]
-    out = torch.empty(N, 4 * Cl, H, W, dtype=torch.float32, device=lv[0].device)
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("out_dtype must be float32 or bfloat16")
+    out = torch.empty(N, 4 * Cl, H, W, dtype=out_dtype, device=lv[0].device)
     with torch.cuda.device(out.device):
-        fn = _lib.load().parq_fpn_concat_bf16 if bf16 else _lib.load().parq_fpn_concat
-        _lib.check(fn(_ptr(lv[0]), _ptr(lv[1]), _ptr(lv[2]), _ptr(lv[3]), hw, N, Cl, int(layer), _ptr(out), _stream()), "parq_fpn_concat")
+        _lib.check(_lib.load().parq_fpn_concat_ex(_ptr(lv[0]), _ptr(lv[1]), _ptr(lv[2]), _ptr(lv[3]), int(bf16), hw, N, Cl, int(layer), _ptr(out),
+                                                   int(out_dtype == torch.bfloat16), _stream()), "parq_fpn_concat_ex")
     return out
 
 

@@ -61,7 +61,10 @@ class AddRayPEB200(nn.Module):
         if Cc != self.dim_out:
             raise ValueError("images_feat has %d channels, module was built for %d" % (Cc, self.dim_out))
         f32 = lambda t: raw(t).detach().to(dev, torch.float32).contiguous()
-        feat, cam, Tcp, Twp, Twl = f32(images_feat), f32(camera), f32(T_camera_pseudoCam), f32(T_world_pseudoCam), f32(T_world_local)
+        # bf16 features (fpn_concat(..., out_dtype=torch.bfloat16)) are consumed as they are by the fused token producer
+        feat_bf16 = want_tokens and images_feat.dtype == torch.bfloat16
+        feat = images_feat.detach().contiguous() if feat_bf16 else f32(images_feat)
+        cam, Tcp, Twp, Twl = f32(camera), f32(T_camera_pseudoCam), f32(T_world_pseudoCam), f32(T_world_local)
         nws = lib.parq_raype_workspace_bytes(B, T, H, W, Cc, self.num_samples)
         if self._ws is None or self._ws.numel() < nws or self._ws.device != dev:
             self._ws = torch.empty(nws, dtype=torch.uint8, device=dev)
@@ -75,7 +78,8 @@ class AddRayPEB200(nn.Module):
         with torch.cuda.device(dev), torch.no_grad():
             _lib.check(lib.parq_raype_forward(B, T, H, W, Cc, self.num_samples, _ptr(feat), _ptr(cam), _ptr(Tcp), _ptr(Twp), _ptr(Twl),
                                               _ptr(self._depth), scale, _ptr(self._packed), _ptr(self._ws), self._ws.numel(),
-                                              _ptr(tokens), _ptr(enc), self._flags | (_lib.PARQ_RAYPE_SPLIT_HIDDEN if want_encoding else 0),
+                                              _ptr(tokens), _ptr(enc), self._flags | (_lib.PARQ_RAYPE_SPLIT_HIDDEN if want_encoding else 0) |
+                                              (_lib.PARQ_RAYPE_FEAT_BF16 if feat_bf16 else 0),
                                               _stream()), "parq_raype_forward")
         return tokens, enc
 

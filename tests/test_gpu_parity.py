@@ -507,18 +507,28 @@ def test_fpn_concat_against_reference_golden(dev, name):
     assert relerr(got, O.fpn_concat(pyr).view(B, T, 1024, H, W)) <= 1e-6
     other = fpn_concat({k: v.to(dev) for k, v in pyr.items()}, layer=1).cpu()                # a coarser target level (down- and up-sampling)
     assert relerr(other, O.fpn_concat(pyr, layer=1)) <= 1e-6
+    # bf16 output = the same arithmetic rounded once; bf16 levels in = the fp32 kernel on the rounded levels
+    half = fpn_concat({k: v.to(dev) for k, v in pyr.items()}, out_dtype=torch.bfloat16)
+    assert half.dtype == torch.bfloat16 and torch.equal(half.float().cpu(), got.reshape(B * T, 1024, H, W).bfloat16().float())
+    pyr16 = {k: v.bfloat16() for k, v in pyr.items()}
+    both = fpn_concat({k: v.to(dev) for k, v in pyr16.items()}, out_dtype=torch.bfloat16)
+    want = fpn_concat({k: v.float().to(dev) for k, v in pyr16.items()})
+    torch.cuda.synchronize()
+    assert torch.equal(both.float(), want.bfloat16().float())
 
 
-def test_pipeline_fpn_raype_decoder_nms_chain(dev):
+@pytest.mark.parametrize("feat_dtype", [torch.float32, torch.bfloat16], ids=["fp32-features", "bf16-features"])
+def test_pipeline_fpn_raype_decoder_nms_chain(dev, feat_dtype):
     # the hot path with its three "next" rows chained on the device, as PARQ.forward / update_metrics would run them:
-    # pyramid -> fpn_concat (f-3) -> AddRayPEB200.tokens (f-1) -> PARQDecoderB200 -> parse_pred (f-2)
+    # pyramid -> fpn_concat (f-3) -> AddRayPEB200.tokens (f-1) -> PARQDecoderB200 -> parse_pred (f-2).
+    # bf16-features: all_features written and read back in bf16 (half the bytes of f-3; one more rounding before the sum)
     from parq_b200.fpn import camera_feature, fpn_concat
     from parq_b200.raype import AddRayPEB200
     B, T, H, W, Nq, seed = 1, 2, 12, 16, 128, 71
     pyr = I.make_pyramid(B * T, H, W, seed=seed)
     cam_img, Tcp, Twp, Twl = I.make_geometry(B, T, 4 * H, 4 * W, seed=seed)
     cam = camera_feature(cam_img)                                      # image camera -> feature-map camera (1/4)
-    feats = fpn_concat({k: v.to(dev) for k, v in pyr.items()}).view(B, T, 1024, H, W)
+    feats = fpn_concat({k: v.to(dev) for k, v in pyr.items()}, out_dtype=feat_dtype).view(B, T, 1024, H, W)
     rpe = AddRayPEB200(1024, [-3, 3, -2, 0.5, 0.25, 5.25], 64, 0.25, 5.25).eval()
     rsd = I.make_raype_weights(seed)
     rpe.load_state_dict(rsd, strict=True)
@@ -530,9 +540,11 @@ def test_pipeline_fpn_raype_decoder_nms_chain(dev):
     parsed = dec.parse_pred(outs)
     torch.cuda.synchronize()
     # oracle chain up to the tokens, then the oracle decoder on OUR bf16 tokens (identical inputs) for iteration 0
-    enc_o, tok_o = O.add_ray_pe(O.fpn_concat(pyr).view(B, T, 1024, H, W), cam._data, Tcp._data, Twp._data, Twl._data, rsd)
+    feat_o = O.fpn_concat(pyr).view(B, T, 1024, H, W)
+    enc_o, tok_o = O.add_ray_pe(feat_o, cam._data, Tcp._data, Twp._data, Twl._data, rsd)
     d = (tokens.float().cpu() - tok_o).abs()
-    assert (d <= tok_o.abs() * 2.0 ** -8 + 3e-3 * enc_o.abs().max()).all()
+    pre = feat_o.permute(0, 1, 3, 4, 2).reshape(B, T * H * W, 1024).abs() * (2.0 ** -9 if feat_dtype == torch.bfloat16 else 0.0)
+    assert (d <= tok_o.abs() * 2.0 ** -8 + pre + 3e-3 * enc_o.abs().max()).all()
     ref = O.decoder_forward(tokens.float().cpu(), cam._data, Tcp._data, Twp._data, Twl._data, sd, iters=1)
     for k in ("pred_logits", "center_unnormalized", "ortho6d", "sem_cls_prob"):
         assert relerr(outs[0][k].cpu(), ref[0][k]) <= TOL, k

@@ -85,7 +85,7 @@ def main():
             marks[0].record()
             pyr = backbone(((rgb.view(n * T, 3, Himg, Wimg) - mean) / std))                 # model/resnet_fpn.py:64-71
             marks[1].record()
-            feats = fpn_concat(pyr).view(n, T, 1024, H, W)                                    # :73-85
+            feats = fpn_concat(pyr, out_dtype=torch.bfloat16).view(n, T, 1024, H, W)                                    # :73-85
             cam_feat._data.copy_(camera_feature(cam_img_in)._data)                             # :88-90 (into the static buffer)
             cam = cam_feat
             marks[2].record()
