@@ -80,6 +80,8 @@ struct GemmParams {
   int const_operand;   // 1: A holds constants (weights), 2: B does -- its first tiles are fetched before the PDL wait
   int a_split_n;       // > 0: output columns >= a_split_n read A at an extra K offset of a_split_off (two independent
   int a_split_off;     //      products that share M, e.g. the centre / rotation head layers, as ONE launch)
+  int bn;              // output-tile width of the single-CTA kernel: 0 / 256 (default) or 64 -- narrow tiles spread a GEMM with few
+                       // rows (one clip: 2 M-tiles) over 4x the SMs, each with a quarter of the MMA work (latency, not throughput)
   int dual_a;          // nterms == 2 with the SAME B segment (A_hi W + A_lo W): a ring stage holds both A tiles and one B
                        // tile, so W is fetched from L2 once per k-block instead of twice (3 stages of 64 KB)
   GemmEpilogue ep;
@@ -308,7 +310,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* add_empty = add_full + 3;      // [3]
   auto add_buf = [&](int i) { return reinterpret_cast<float*>(i == 0 ? smem + 3 * A_BYTES : smem + STAGES * A_BYTES + 3 * B_BYTES + (i - 1) * 16384); };
   auto tile_fast = [&](int m0) { return add_tma && (m0 % p.ep.nchw_HW) + BM <= p.ep.nchw_HW; };
-  const uint32_t stage_tx = dual ? 2 * A_BYTES + B_BYTES : A_BYTES + B_BYTES;
+  const int bn = p.bn > 0 ? p.bn : BN;                       // tile width (columns of B rows per stage: bn x 64)
+  const uint32_t b_bytes = static_cast<uint32_t>(bn) * BK * 2;
+  const uint32_t stage_tx = dual ? 2 * A_BYTES + b_bytes : A_BYTES + b_bytes;
   auto a_ptr = [&](int st, int which) { return dual ? smem + st * (2 * A_BYTES + B_BYTES) + which * A_BYTES : smem + st * A_BYTES; };
   auto b_ptr = [&](int st) { return dual ? smem + st * (2 * A_BYTES + B_BYTES) + 2 * A_BYTES : smem + STAGES * A_BYTES + st * B_BYTES; };
   uint64_t* empty_bar = full_bar + STAGES;
@@ -346,15 +350,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_n = (p.N + bn - 1) / bn;
   const int tiles_m = (p.M + BM - 1) / BM;
   const int num_tiles = tiles_m * tiles_n;
   // Tile order: the dimension with FEWER tiles varies fastest, so that the CTAs running at the same
   // time share the tile of the large (streamed) operand through L2 and it is read from HBM once.
   const bool m_fastest = tiles_m <= tiles_n;
   auto tile_origin = [&](int tile, int& m0, int& n0) {
-    if (m_fastest) { m0 = (tile % tiles_m) * BM; n0 = (tile / tiles_m) * BN; }
-    else           { m0 = (tile / tiles_n) * BM; n0 = (tile % tiles_n) * BN; }
+    if (m_fastest) { m0 = (tile % tiles_m) * BM; n0 = (tile / tiles_m) * bn; }
+    else           { m0 = (tile / tiles_n) * BM; n0 = (tile % tiles_n) * bn; }
   };
   const int kb_per_term = p.K / BK;
   const int nterm_loops = dual ? 1 : p.nterms;
@@ -419,7 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pdl_wait();
     pdl_launch_dependents();
     if (lane == 0) {                       // ---------------- MMA issuer
-      constexpr uint32_t idesc = umma_idesc(BM, BN, 1);
+      const uint32_t idesc = umma_idesc(BM, static_cast<uint32_t>(bn), 1);
       int stage = 0;
       uint32_t phase = 0;
       int lt = 0;
@@ -467,8 +471,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float row_bias = 0.f;
       if (col_bias) {
         float* sb = sbias + acc * BN;
-        sb[et] = (n0 + et < p.N) ? __ldg(p.ep.bias + n0 + et) : 0.f;
-        sb[et + 128] = (n0 + et + 128 < p.N) ? __ldg(p.ep.bias + n0 + et + 128) : 0.f;
+        sb[et] = (et < bn && n0 + et < p.N) ? __ldg(p.ep.bias + n0 + et) : 0.f;
+        sb[et + 128] = (et + 128 < bn && n0 + et + 128 < p.N) ? __ldg(p.ep.bias + n0 + et + 128) : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
       } else if (p.ep.bias != nullptr && row < p.M) {
         row_bias = __ldg(p.ep.bias + row);
@@ -481,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool fast = tile_fast(m0);
       tmem_ld32(taddr, r0);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; c += 2) {
+      for (int c = 0; c < bn / 32; c += 2) {
         tmem_wait_ld();
         tmem_ld32(taddr + (c + 1) * 32, r1);                 // next chunk in flight while this one is stored
         int col0 = n0 + c * 32;
@@ -492,7 +496,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (fast) { mbar_arrive(&add_empty[add_cc % 3]); ++add_cc; }
         }
         tmem_wait_ld();
-        if (c + 2 < BN / 32) tmem_ld32(taddr + (c + 2) * 32, r0);
+        if (c + 2 < bn / 32) tmem_ld32(taddr + (c + 2) * 32, r0);
         col0 += 32;
         if (col0 < p.N) {
           const float* sadd = nullptr;
@@ -534,7 +538,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tile_origin(tile, m0, n0);
         if (!tile_fast(m0)) continue;
         const int bt = m0 / p.ep.nchw_HW, pix0 = m0 - bt * p.ep.nchw_HW;
-        for (int c = 0; c < BN / 32 && n0 + c * 32 < p.N; ++c, ++cc) {
+        for (int c = 0; c < bn / 32 && n0 + c * 32 < p.N; ++c, ++cc) {
           const int buf = cc % 3;
           mbar_wait(&add_empty[buf], ((cc / 3) & 1) ^ 1);
           mbar_expect_tx(&add_full[buf], p.ep.nchw_add_bf16 ? 32 * 128 * 2 : 32 * 128 * 4);

@@ -143,6 +143,7 @@ static int require_sm100() {
 // The stand-alone entry points launch plainly (their inputs may come from the caller's previous kernel).
 static thread_local bool g_pdl = false;
 static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
+static const bool g_no_narrow = getenv("PARQ_NO_NARROW") != nullptr;         // A/B switch: 256-column tiles also for GEMMs of a few row tiles
 static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;
 static const int g_chain_min_rows = getenv("PARQ_CHAIN_MIN_ROWS") ? atoi(getenv("PARQ_CHAIN_MIN_ROWS")) : 2048;
 constexpr int HI_ONLY_DEFAULT = 0;
@@ -243,9 +244,14 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
   // shorter prologue (no cluster barriers) is worth more there (-6 % with the pair kernel)
   const long long tiles1 = static_cast<long long>((gp.M + gemm::BM - 1) / gemm::BM) * ((gp.N + gemm::BN - 1) / gemm::BN);
   const bool pairk = !g_no_pair && device_info().sms >= 2 && (tiles1 >= 2LL * device_info().sms || g_force_pair);
+  // narrow tiles for GEMMs of a few row tiles (one clip): 4x the CTAs, a quarter of the MMA latency each (not for the
+  // GroupNorm tile sums, whose slots are per 256 columns, nor for the channels-first epilogues)
+  const bool narrow = !pairk && !g_no_narrow && gp.ep.gn_out == nullptr && gp.ep.nchw_add == nullptr && gp.ep.nchw_out == nullptr && gp.N % 64 == 0 &&
+                      tiles1 * 4 <= device_info().sms;
+  const int bn = narrow ? 64 : gemm::BN;
   CUtensorMap tmA, tmB;
   TRY(make_map(&tmA, A, a_rows, a_cols, a_cols, gemm::BM));
-  TRY(make_map(&tmB, Bw, b_rows, b_cols, b_cols, pairk ? gemm2::BN / 2 : gemm::BN));
+  TRY(make_map(&tmB, Bw, b_rows, b_cols, b_cols, pairk ? gemm2::BN / 2 : bn));
   OPT_IN_SMEM(gemm_tc_kernel<false>, gemm::SMEM_BYTES);
   OPT_IN_SMEM(gemm_tc_kernel<true>, gemm::SMEM_BYTES);
   OPT_IN_SMEM(gemm2_tc_kernel<false>, gemm2::SMEM_BYTES);
@@ -258,8 +264,9 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
     TRY(make_map_f32(&tmC, gp.ep.nchw_add, static_cast<uint64_t>(gp.M / gp.ep.nchw_HW) * gp.N, gp.ep.nchw_HW, 128, 32, gp.ep.nchw_add_bf16 != 0));
     gpl.ep.add_tma = 1;
   }
+  gpl.bn = bn;
   gpl.dual_a = (gp.nterms == 2 && gp.b_koff[0] == gp.b_koff[1] && gp.a_koff[0] != gp.a_koff[1] && !g_no_dual) ? 1 : 0;
-  const int tiles = ((gp.M + gemm::BM - 1) / gemm::BM) * ((gp.N + gemm::BN - 1) / gemm::BN);
+  const int tiles = ((gp.M + gemm::BM - 1) / gemm::BM) * ((gp.N + bn - 1) / bn);
   const int grid = tiles < device_info().sms ? tiles : device_info().sms;
   {
     ProfScope ps(tag, st);
