@@ -359,7 +359,8 @@ static SplitPlan plan_split(int items, int ntiles, int sms, int force) {
     const int ns = (ntiles + tps - 1) / tps;
     const long long ctas = static_cast<long long>(items) * ns;
     const long long waves = (ctas + sms - 1) / sms;
-    const double cost = static_cast<double>(waves) * (tps + 3.0) + 0.02 * ns;   // small penalty per extra partial
+    // small penalty per extra partial; any split at all costs the combine launch (about three key tiles of latency)
+    const double cost = static_cast<double>(waves) * (tps + 3.0) + 0.02 * ns + (ns > 1 ? 3.0 : 0.0);
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = SplitPlan{ns, tps};

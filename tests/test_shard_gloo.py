@@ -33,11 +33,12 @@ def _worker(rank, world, port, n_clips, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = torch.Generator().manual_seed(7)
     full = {k: torch.randn(n_clips, 4, n, generator=g) for k, n in zip(DETECTION_KEYS, (3, 3, 6, 10))}
+    full["pred_mask"] = torch.rand(n_clips, 4, generator=g) > 0.5           # parse_pred's mask travels with the boxes (as bytes)
     local = shard_batch(full, rank, world)
     lo, hi = clip_range(n_clips, rank, world)
     assert local["ortho6d"].shape[0] == hi - lo
     got = gather_detections(local, n_clips)
-    ok = all(torch.equal(got[k], full[k]) for k in DETECTION_KEYS)
+    ok = all(torch.equal(got[k], full[k]) for k in DETECTION_KEYS + ("pred_mask",)) and got["pred_mask"].dtype == torch.bool
     ret[rank] = ok
     dist.barrier()
     dist.destroy_process_group()
