@@ -83,6 +83,7 @@ struct SampleParams {
   uint8_t* valid;                // (B, T, Nq)    or nullptr
   float* coord_pos;              // (B, Nq, 3)    or nullptr
   int B, T, H, W, C, Nq;
+  int ref_is_fresh;              // the reference points were written by the IMMEDIATELY preceding kernel: no projection before the PDL wait
   float span[3], lo[3];          // denormalisation: p*span + lo
 };
 
@@ -134,7 +135,7 @@ project_sample_kernel(const SampleParams p) {
   const float Wm1 = static_cast<float>(p.W - 1), Hm1 = static_cast<float>(p.H - 1);
   const float sx = Wm1 / 2.f, sy = Hm1 / 2.f;          // ATen CPU grid_sampler: scaling = (size-1)/2
   const int npairs = SAMPLE_QPB * p.T;
-  const bool early = npairs <= static_cast<int>(blockDim.x);   // one pair per thread: its outputs can wait in registers
+  const bool early = p.ref_is_fresh == 0 && npairs <= static_cast<int>(blockDim.x);   // one pair per thread: its outputs can wait in registers
   if (!early) {
     pdl_wait();
     pdl_launch_dependents();

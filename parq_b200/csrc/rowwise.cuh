@@ -34,6 +34,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 // pos2posemb3d (reference transformer_parq.py:45-64): 128 sin/cos features per axis, axes
 // concatenated in the order (y, x, z).  out: (R, 2*384) [hi|lo].
 // ---------------------------------------------------------------------------------------------
+// feature j (0..383) of a reference point (rx, ry, rz): axes in the order (y, x, z), sin on even / cos on odd indices
+__device__ __forceinline__ float posemb_value(float rx, float ry, float rz, int j, const float* __restrict__ dim_t) {
+  const int seg = j >> 7, i = j & 127;
+  const float r = (seg == 0) ? ry : (seg == 1 ? rx : rz);
+  const float a = __fdiv_rn(__fmul_rn(r, 6.283185307179586f), dim_t[i]);
+  return (i & 1) ? cosf(a) : sinf(a);
+}
+
 __global__ void posemb_kernel(const float* __restrict__ ref, const float* __restrict__ dim_t, __nv_bfloat16* __restrict__ out,
                               int R) {
   pdl_wait();
@@ -41,10 +49,7 @@ __global__ void posemb_kernel(const float* __restrict__ ref, const float* __rest
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * 384) return;
   const int row = idx / 384, j = idx % 384;
-  const int seg = j >> 7, i = j & 127;
-  const int axis = (seg == 0) ? 1 : (seg == 1 ? 0 : 2);
-  const float a = __fdiv_rn(__fmul_rn(ref[row * 3 + axis], 6.283185307179586f), dim_t[i]);
-  const float v = (i & 1) ? cosf(a) : sinf(a);
+  const float v = posemb_value(ref[row * 3 + 0], ref[row * 3 + 1], ref[row * 3 + 2], j, dim_t);
   store_split(out + static_cast<long long>(row) * 768 + j, 384, v);
 }
 
@@ -220,6 +225,8 @@ struct HeadsParams {
   const float* mean_size;  // (num_cls, 3)
   float *logits, *center, *size, *ortho6d, *prob, *coord_pos;   // outputs of this iteration
   float* ref_next;         // (R, 3)
+  __nv_bfloat16* posemb_next;   // optional (R, 768) [hi|lo]: pos2posemb3d of ref_next for the next iteration (saves its launch)
+  const float* dim_t;      // (128) with posemb_next
   float* rot;              // optional (R, 9): rotation matrix of ortho6d (utils/ortho6d_transforms.py:53-66)
   int R, Nq, C, num_cls;
   float span[3], lo[3];
@@ -237,6 +244,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // Epilogue of one row: lane j holds output slot j (bias not yet added).
 __device__ __forceinline__ void heads_row_epilogue(const HeadsParams& p, int row, int lane, float mine) {
   const bool is_cls = lane < p.num_cls;
+  float ref_n = 0.f;                         // next reference coordinate (centre lanes)
   const int k3 = lane >= HEADS_CLS_SLOTS + 3 ? lane - HEADS_CLS_SLOTS - 3 : lane - HEADS_CLS_SLOTS;   // axis for size / centre lanes
   if (is_cls) mine += p.b_cls[lane];
   else if (lane >= HEADS_CLS_SLOTS && lane < HEADS_CLS_SLOTS + 3) mine += p.b_size[lane - HEADS_CLS_SLOTS];
@@ -269,9 +277,21 @@ __device__ __forceinline__ void heads_row_epilogue(const HeadsParams& p, int row
     const float center = __fadd_rn(__fmul_rn(sg, p.span[k3]), p.lo[k3]);
     p.center[row * 3 + k3] = center;
     p.coord_pos[row * 3 + k3] = __fadd_rn(__fmul_rn(rr, p.span[k3]), p.lo[k3]);
-    p.ref_next[row * 3 + k3] = __fdiv_rn(__fadd_rn(center, -p.lo[k3]), p.span[k3]);
+    ref_n = __fdiv_rn(__fadd_rn(center, -p.lo[k3]), p.span[k3]);
+    p.ref_next[row * 3 + k3] = ref_n;
   } else if (lane >= HEADS_CLS_SLOTS + 6 && lane < HEADS_SLOTS) {
     p.ortho6d[row * 6 + lane - HEADS_CLS_SLOTS - 6] = mine;
+  }
+  if (p.posemb_next != nullptr) {
+    // sinusoidal embedding of the next reference point, the input of the next iteration's reference-point MLP
+    const float rx = __shfl_sync(0xffffffffu, ref_n, HEADS_CLS_SLOTS + 3), ry = __shfl_sync(0xffffffffu, ref_n, HEADS_CLS_SLOTS + 4),
+                rz = __shfl_sync(0xffffffffu, ref_n, HEADS_CLS_SLOTS + 5);
+    __nv_bfloat16* out = p.posemb_next + static_cast<long long>(row) * 768;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int j = k * 32 + lane;
+      store_split(out + j, 384, posemb_value(rx, ry, rz, j, p.dim_t));
+    }
   }
   if (p.rot != nullptr) {
     // Gram-Schmidt: x = a/|a|, z = (x X b)/|x X b|, y = z X x; columns [x y z]; norms clamped at 1e-8

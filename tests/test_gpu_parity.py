@@ -712,6 +712,22 @@ def test_unshared_decoder_layers_against_reference_golden(dev):
     assert relerr(out[1]["center_unnormalized"].cpu(), gold["center_unnormalized"][1]) <= 5 * TOL
 
 
+def test_free_running_equals_teacher_forcing_with_its_own_points(dev):
+    # The free-running forward takes shortcuts the teacher-forced one does not (the heads kernel writes the next iteration's
+    # sinusoidal embedding, the sampler projects after instead of before its dependency wait): feeding the free run's own
+    # reference points back as forced points must reproduce it bit for bit.
+    gold = load_golden("small")
+    c = regenerate_case(gold)
+    eng = DecoderEngine(c["sd"], dev)
+    for chain in (None, True):
+        free = {k: v.clone() for k, v in _engine_forward(eng, c, dev, chain=chain).items()}
+        outs = [{k: free[k][i].cpu() for k in OUT_KEYS} for i in range(8)]
+        refs = O.refs_from_outputs(outs, c["sd"])
+        forced = _engine_forward(eng, c, dev, forced_refs=refs.to(dev), chain=chain)
+        for k in OUT_KEYS:
+            assert torch.equal(forced[k], free[k]), (k, chain)
+
+
 def test_free_running_divergence_report(dev):
     """the free-running recurrence (no teacher forcing) is reported, not gated, next to the oracle's own
     sensitivity: the oracle re-run on tokens perturbed by a relative 1e-6 (fp32 rounding scale) and 2^-9 (bf16 operand
