@@ -249,7 +249,9 @@ class DecoderEngine:
     def _ref0(self, B):
         # sigmoid(refpoint.weight) repeated per clip (reference transformer_parq.py:121,309); cached per batch size
         if self._ref0_cache is None or self._ref0_cache.shape[0] != B:
-            self._ref0_cache = self.refpoint.sigmoid().unsqueeze(0).repeat(B, 1, 1).contiguous()
+            # evaluated on the CPU: the bit-exactness bar names the CPU reference as oracle device, and CUDA's sigmoid differs
+            # from it in the last place on some inputs (which would move coord_pos / center_im of iteration 0 by an ulp)
+            self._ref0_cache = self.refpoint.cpu().sigmoid().to(self.device).unsqueeze(0).repeat(B, 1, 1).contiguous()
         return self._ref0_cache
 
     def forward(self, tokens, camera, T_cp, T_wp, T_wl, H, W, forced_refs=None, ref0=None, debug=False, skip_kv=False,

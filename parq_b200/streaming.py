@@ -102,7 +102,7 @@ class StreamingWindow:
         T_al = _pose_mul(_pose_inv(Twa), Twl)                       # A <- L
         lo = torch.tensor(eng.scale[0::2], device=eng.device)
         span = torch.tensor(eng.scale[1::2], device=eng.device) - lo
-        p_l = eng.refpoint.sigmoid() * span + lo                    # (Nq, 3) metres in L
+        p_l = eng._ref0(1)[0] * span + lo                           # (Nq, 3) metres in L
         R_al = T_al[:, :9].reshape(self.B, 3, 3)
         p_a = p_l.unsqueeze(0) @ R_al.transpose(1, 2) + T_al[:, None, 9:]
         ref0 = ((p_a - lo) / span).contiguous()

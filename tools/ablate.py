@@ -18,6 +18,7 @@ ROWS = [
     ("hi-only: sa_v", {"PARQ_HI_ONLY": "2"}),
     ("hi-only: ca_q", {"PARQ_HI_ONLY": "4"}),
     ("hi-only: sa_qk + sa_v + ca_q", {"PARQ_HI_ONLY": "7"}),
+    ("no chain G (gn_apply kernel + GEMM for the second head layer)", {"PARQ_NO_CHAIN_G": "1"}),
     ("no chain (separate GEMM + LayerNorm launches)", {"PARQ_NO_CHAIN": "1"}),
 ]
 
@@ -60,8 +61,10 @@ def child():
 
 
 def main():
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]
+    rows = [r for r in ROWS if not only or any(o in r[0] for o in only)]
     print("| configuration | logits | centre | ortho6d | probabilities | ms / step (config 2) |\n|---|---|---|---|---|---|")
-    for name, env in ROWS:
+    for name, env in rows:
         e = dict(os.environ)
         e.update(env)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
