@@ -32,8 +32,6 @@ enum ChainEpilogue {
   CH_EP_SPLIT = 1,  // v = [relu](acc + bias) -> a_out = split(v)
   CH_EP_LP = 2,     // v = acc + bias -> out_lp (bf16 / fp16)
   CH_EP_F32 = 3,    // v = acc + bias -> out_f32 [, GroupNorm tile sums] [, out_sum_split = split(v + add_split)]
-  CH_EP_GNAPPLY = 4,  // no GEMM: a_out = split(relu(GroupNorm(1, C)(gn_in_f32))) with the per-clip statistics of gn_in_part
-                      //          (two groups of C columns side by side: centre | rotation head, generic_mlp.py:94-110)
 };
 
 struct ChainStage {
@@ -60,12 +58,6 @@ struct ChainStage {
   long long ld_lp;
   double2* gn_out;                     // CH_EP_F32: optional (sum, sum of squares) per 128 x 256 tile, slot m_tile * gn_stride + n0 / 256
   int gn_stride;
-  int a_split_n, a_split_off;          // GEMM stages: output columns >= a_split_n read A at an extra K offset (block-diagonal product)
-  const float* gn_in_f32;              // CH_EP_GNAPPLY: (M, N) pre-norm activations, N = 2 groups x C
-  const double2* gn_in_part;           //   tile sums written by the producing GEMM (slot m_tile * gn_stride + column tile)
-  const float* gamma2;                 //   gamma / beta = group 0, gamma2 / beta2 = group 1
-  const float* beta2;
-  int gn_nq;                           //   queries per clip (the statistics couple a clip's Nq x C block)
   const __nv_bfloat16* add_split;      // CH_EP_F32: optional (M, 2N) [hi|lo] addend ...
   __nv_bfloat16* out_sum_split;        // ... and the split of (v + addend)
 };
@@ -228,7 +220,6 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nstages; ++s) {
-      if (p.st[s].ep == CH_EP_GNAPPLY) continue;
       tma_prefetch_desc(&maps.a[s]);
       tma_prefetch_desc(&maps.b[s]);
     }
@@ -259,15 +250,6 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
       uint32_t phase = 0;
       for (int s = 0; s < p.nstages; ++s) {
         const ChainStage& S = p.st[s];
-        if (S.ep == CH_EP_GNAPPLY) {                       // no operands: only keep the dependency protocol in step
-          if (s == 0) {
-            pdl_wait();
-            pdl_launch_dependents();
-          } else {
-            mbar_wait_cluster(dbar, (s - 1) & 1);
-          }
-          continue;
-        }
         const int kb_per_term = S.K / BK;
         const int nterm_loops = dual ? 1 : S.nterms;
         const int num_kb = kb_per_term * nterm_loops;
@@ -303,7 +285,6 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
         int idx = 0;
         for (int j = 0; j < S.tiles; ++j) {
           const int n0 = n_base + j * S.tile_n;
-          const int asplit = (S.a_split_n > 0 && n0 >= S.a_split_n) ? S.a_split_off : 0;
           for (int t = 0; t < nterm_loops; ++t) {
             for (int kb = 0; kb < kb_per_term; ++kb, ++idx) {
               if (idx >= pre) {
@@ -311,8 +292,8 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                 mbar_expect_tx(&full_bar[slot], stage_tx);
                 tma_load_2d(b_ptr(slot), &maps.b[s], &full_bar[slot], b_off(t) + kb * BK, n0);
               }
-              tma_load_2d(a_ptr(slot, 0), &maps.a[s], &full_bar[slot], a_off(t) + asplit + kb * BK, m0);
-              if (lo_term) tma_load_2d(a_ptr(slot, 1), &maps.a[s], &full_bar[slot], a_off(1) + asplit + kb * BK, m0);
+              tma_load_2d(a_ptr(slot, 0), &maps.a[s], &full_bar[slot], a_off(t) + kb * BK, m0);
+              if (lo_term) tma_load_2d(a_ptr(slot, 1), &maps.a[s], &full_bar[slot], a_off(1) + kb * BK, m0);
               if (++slot == nst) { slot = 0; phase ^= 1; }
             }
           }
@@ -331,7 +312,6 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
       int cnt = 0;
       for (int s = 0; s < p.nstages; ++s) {
         const ChainStage& S = p.st[s];
-        if (S.ep == CH_EP_GNAPPLY) continue;
         const int num_kb = (S.K / BK) * (dual ? 1 : S.nterms);
         const uint32_t idesc = umma_idesc(BM, static_cast<uint32_t>(S.tile_n), 1);
         for (int j = 0; j < S.tiles; ++j, ++cnt) {
@@ -385,65 +365,6 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
       const int half = S.tile_n / 2, nchunks = half / 32;
       // stage the per-column vectors of this CTA's columns
       asm volatile("bar.sync 1, 256;" ::: "memory");        // the previous stage no longer reads s_vec
-      if (S.ep == CH_EP_GNAPPLY) {
-        // ---- GroupNorm(1, C) + ReLU + operand split of the first head layer: no accumulator, rows x this CTA's columns
-        const int Cg = S.N / 2;                              // columns per group; a CTA's columns lie in one group
-        const int g = n_base / Cg;
-        const float* gam = g == 0 ? S.gamma : S.gamma2;
-        const float* bet = g == 0 ? S.beta : S.beta2;
-        for (int i = et; i < ncta; i += 256) {              // gamma -> s_vec[0, ncta), beta -> s_vec[VEC_COLS, VEC_COLS + ncta)
-          s_vec[i] = __ldg(gam + (n_base - g * Cg) + i);
-          s_vec[VEC_COLS + i] = __ldg(bet + (n_base - g * Cg) + i);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        float mean = 0.f, rstd = 0.f;
-        if (lane == 0) {                                     // statistics of this row block's clip and this CTA's group
-          double sm = 0.0, sq = 0.0;
-          const int mt = S.gn_nq / BM, nt = Cg / 256, b = m0 / S.gn_nq;
-          for (int m = 0; m < mt; ++m)
-            for (int n = 0; n < nt; ++n) {
-              const double2 v = S.gn_in_part[static_cast<long long>(b * mt + m) * S.gn_stride + g * nt + n];
-              sm += v.x;
-              sq += v.y;
-            }
-          const double cnt_ = static_cast<double>(Cg) * S.gn_nq;
-          const double mu = sm / cnt_;
-          mean = static_cast<float>(mu);
-          rstd = static_cast<float>(1.0 / sqrt(fmax(sq / cnt_ - mu * mu, 0.0) + 1e-5));
-        }
-        mean = __shfl_sync(0xffffffffu, mean, 0);
-        rstd = __shfl_sync(0xffffffffu, rstd, 0);
-        const int cols_w = ncta / 2;                         // columns of this warp (column half h of the CTA's slice)
-        for (int c = 0; c < cols_w / 32; ++c) {
-          const int cl = h * cols_w + c * 32;                // inside the CTA's columns
-          const long long col = n_base + cl;
-          uint4 t0[4], t1[4];
-          const uint32_t* src = reinterpret_cast<const uint32_t*>(S.gn_in_f32 + wrow0 * S.N + col);
-          chain_issue16(t0, src, S.N, lane);
-          chain_issue16(t1, src + 16, S.N, lane);
-          uint32_t w0[16], w1[16];
-          chain_unstage16(stage, t0, w0, lane);
-          chain_unstage16(stage, t1, w1, lane);
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = fmaxf((__uint_as_float(w0[i]) - mean) * rstd * s_vec[cl + i] + s_vec[VEC_COLS + cl + i], 0.f);
-            v[16 + i] = fmaxf((__uint_as_float(w1[i]) - mean) * rstd * s_vec[cl + 16 + i] + s_vec[VEC_COLS + cl + 16 + i], 0.f);
-          }
-          // group g's [hi | lo] occupies columns [g*2*Cg, (g+1)*2*Cg) of a_out (row pitch 2N)
-          chain_store_split32(stage, S.a_out + wrow0 * 2 * S.N + g * 2 * Cg + (col - g * Cg), 2 * S.N, Cg, v, lane);
-        }
-        if (et == 0) CHAIN_STAMP(s * 8 + 6);
-        if (s + 1 < p.nstages) {
-          fence_proxy_async_all();
-          __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < CLUSTER; ++c) mbar_arrive_cluster(daddr[c]);
-          }
-        }
-        continue;
-      }
       for (int i = et; i < ncta; i += 256) {
         s_vec[i] = S.bias != nullptr ? __ldg(S.bias + n_base + i) : 0.f;
         if (S.ep == CH_EP_LN) {

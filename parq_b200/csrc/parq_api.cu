@@ -144,7 +144,6 @@ static int require_sm100() {
 static thread_local bool g_pdl = false;
 static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
 static const bool g_no_narrow = getenv("PARQ_NO_NARROW") != nullptr;         // A/B switch: 256-column tiles also for GEMMs of a few row tiles
-static const bool g_no_chain_g = getenv("PARQ_NO_CHAIN_G") != nullptr;       // A/B switch: gn_apply kernel + GEMM instead of the chained pair
 static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;
 static const int g_chain_min_rows = getenv("PARQ_CHAIN_MIN_ROWS") ? atoi(getenv("PARQ_CHAIN_MIN_ROWS")) : 2048;
 constexpr int HI_ONLY_DEFAULT = 0;
@@ -324,19 +323,6 @@ static int chain_add(ChainBuilder& cb, const void* A, uint64_t a_cols, const voi
 }
 static thread_local long long* g_chain_dbg = nullptr;     // parq_chain_debug: device buffer for clock stamps, 64 slots per chain launch
 static thread_local int g_chain_dbg_launch = 0;
-// a stage without a GEMM (CH_EP_GNAPPLY): no tensor maps, no accumulator tiles; N columns split over the cluster like any stage
-static int chain_add_elementwise(ChainBuilder& cb, bool w_lo, ChainStage S) {
-  if (cb.p.nstages >= chain::MAX_STAGES) return fail(PARQ_ERR_SHAPE, "too many chain stages");
-  if (S.N % chain::CLUSTER != 0 || S.N / chain::CLUSTER > chain::VEC_COLS || (S.N / chain::CLUSTER) % 64 != 0 || (S.N / 2) % (S.N / chain::CLUSTER) != 0 ||
-      S.gn_nq % chain::BM != 0)
-    return fail(PARQ_ERR_SHAPE, "chain GroupNorm stage N=%d Nq=%d not supported", S.N, S.gn_nq);
-  S.tile_n = 256; S.tiles = 0; S.K = 0;
-  S.dual_a = (!w_lo && !g_no_dual) ? 1 : 0;
-  if (cb.p.nstages > 0 && cb.p.st[0].dual_a != S.dual_a) return fail(PARQ_ERR_SHAPE, "chain stages must share the ring geometry");
-  cb.p.st[cb.p.nstages++] = S;
-  return PARQ_OK;
-}
-
 static int launch_chain(cudaStream_t st, ChainBuilder& cb) {
   if (g_chain_dbg != nullptr && g_chain_dbg_launch < 64) cb.p.dbg = g_chain_dbg + 64 * g_chain_dbg_launch++;
   if (cb.p.M % chain::BM != 0) return fail(PARQ_ERR_SHAPE, "chain kernel needs M %% 128 == 0 (M=%d)", cb.p.M);
@@ -1421,34 +1407,18 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     // K7: heads (two hidden layers with per-clip GroupNorm) + box update
     {
       GemmParams g;
-      if (chained && !g_no_chain_g) {
-        // ---- chain G: GroupNorm + ReLU + operand split of the first head layer (no GEMM) -> second head layer of the centre and
-        // rotation heads as one block-diagonal GEMM (+ GroupNorm tile sums for the final kernel)
-        ChainBuilder cb(R);
-        ChainStage S = chain_stage(2 * C, 0, CH_EP_GNAPPLY, nullptr);
-        S.gn_in_f32 = F32(W.h1); S.gn_in_part = reinterpret_cast<const double2*>(ws + W.gn1); S.gn_stride = GN_SLOTS_PER_MTILE; S.gn_nq = s.Nq;
-        S.gamma = PF(P.ctr1_g); S.beta = PF(P.ctr1_b); S.gamma2 = PF(P.rot1_g); S.beta2 = PF(P.rot1_b);
-        S.a_out = BF(W.a_h1);
-        TRY(chain_add_elementwise(cb, w_lo, S));
-        S = chain_stage(2 * C, C, CH_EP_F32, nullptr);
-        S.a_split_n = C; S.a_split_off = 2 * C;
-        S.out_f32 = F32(W.h2); S.gn_out = reinterpret_cast<double2*>(ws + W.gn2); S.gn_stride = GN_SLOTS_PER_MTILE;
-        TRY(chain_add(cb, ws + W.a_h1, 4 * C, pk + P.ctr4, w_lo, S));
-        TRY(launch_chain(st, cb));
-      } else {
-        { ProfScope ps(TAG_ROWWISE, st); launch_k(gn_apply_kernel, dim3(R), dim3(256), 0, st, F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1),
-                                                 PF(P.ctr1_g), PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1)); }
-        CUDA_TRY(cudaGetLastError());
-        // second hidden layer of the centre and rotation heads as ONE launch: the two weight matrices are adjacent in the
-        // packed buffer (one B operand of 2C rows), output columns >= C read the rotation half of a_h1
-        memset(&g, 0, sizeof(g));
-        g.M = R; g.N = 2 * C; term_offsets(g, C, w_lo, 0);
-        g.a_split_n = C; g.a_split_off = 2 * C;
-        g.ep = epilogue_none();
-        g.ep.out_f32 = F32(W.h2); g.ep.ld_f32 = 2 * C;
-        g.ep.gn_out = reinterpret_cast<double2*>(ws + W.gn2); g.ep.gn_stride = GN_SLOTS_PER_MTILE;
-        TRY(launch_gemm(st, ws + W.a_h1, R, 4 * C, pk + P.ctr4, 2 * C, 2 * C, g));
-      }
+      { ProfScope ps(TAG_ROWWISE, st); launch_k(gn_apply_kernel, dim3(R), dim3(256), 0, st, F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1),
+                                               PF(P.ctr1_g), PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1)); }
+      CUDA_TRY(cudaGetLastError());
+      // second hidden layer of the centre and rotation heads as ONE launch: the two weight matrices are adjacent in the
+      // packed buffer (one B operand of 2C rows), output columns >= C read the rotation half of a_h1
+      memset(&g, 0, sizeof(g));
+      g.M = R; g.N = 2 * C; term_offsets(g, C, w_lo, 0);
+      g.a_split_n = C; g.a_split_off = 2 * C;
+      g.ep = epilogue_none();
+      g.ep.out_f32 = F32(W.h2); g.ep.ld_f32 = 2 * C;
+      g.ep.gn_out = reinterpret_cast<double2*>(ws + W.gn2); g.ep.gn_stride = GN_SLOTS_PER_MTILE;
+      TRY(launch_gemm(st, ws + W.a_h1, R, 4 * C, pk + P.ctr4, 2 * C, 2 * C, g));
       hp.x = x3; hp.h2 = F32(W.h2); hp.partial = reinterpret_cast<const double2*>(ws + W.gn2);
       hp.gamma_c = PF(P.ctr5_g); hp.beta_c = PF(P.ctr5_b); hp.gamma_r = PF(P.rot5_g); hp.beta_r = PF(P.rot5_b);
       hp.w_cls = PF(P.cls_w); hp.b_cls = PF(P.cls_b); hp.w_size = PF(P.size_w); hp.b_size = PF(P.size_b);

@@ -18,7 +18,6 @@ ROWS = [
     ("hi-only: sa_v", {"PARQ_HI_ONLY": "2"}),
     ("hi-only: ca_q", {"PARQ_HI_ONLY": "4"}),
     ("hi-only: sa_qk + sa_v + ca_q", {"PARQ_HI_ONLY": "7"}),
-    ("no chain G (gn_apply kernel + GEMM for the second head layer)", {"PARQ_NO_CHAIN_G": "1"}),
     ("no chain (separate GEMM + LayerNorm launches)", {"PARQ_NO_CHAIN": "1"}),
 ]
 
