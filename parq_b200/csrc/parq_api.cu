@@ -1239,8 +1239,11 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     const int Nk = s.T * s.H * s.W;
     // sinusoidal embedding of the reference points (input of the reference-point MLP); launched BEFORE the sampling kernel so
     // that the reference points are two launches old when the sampler projects them in its pre-wait prologue
-    // (free-running iterations > 0: the heads kernel of the previous iteration already wrote it next to ref_next)
-    if (forced_refs != nullptr || it == 0) {
+    // (one clip, free-running iterations > 0: the heads kernel of the previous iteration already wrote it next to ref_next --
+    // one dependent launch less where launches are the cost; with thousands of rows the 12 sin / cos per lane and row make the
+    // heads kernel 19 us slower, more than this 9 us kernel and its launch)
+    const bool posemb_folded = forced_refs == nullptr && R < g_chain_min_rows;
+    if (!posemb_folded || it == 0) {
       ProfScope ps(TAG_ROWWISE, st);
       launch_k(posemb_kernel, dim3((R * 384 + 255) / 256), dim3(256), 0, st, ref, PF(P.dim_t), BF(W.a_pos), R);
     }
@@ -1249,7 +1252,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     sp.tokens = static_cast<const __nv_bfloat16*>(tokens_bf16);
     sp.tokens_lo = static_cast<const __nv_bfloat16*>(tokens_lo_bf16);
     sp.ref = ref; sp.T_cl = F32(W.T_cl); sp.camera = camera;
-    sp.ref_is_fresh = (forced_refs == nullptr && it > 0) ? 1 : 0;      // then the heads kernel is the direct predecessor (no posemb launch between)
+    sp.ref_is_fresh = (posemb_folded && it > 0) ? 1 : 0;      // then the heads kernel is the direct predecessor (no posemb launch between)
     sp.feat = out->features ? out->features + static_cast<size_t>(it) * R * C : nullptr;
     sp.a_x = BF(W.a_x);
     sp.center_im = out->center_im ? out->center_im + static_cast<size_t>(it) * s.B * s.T * s.Nq * 2 : nullptr;
@@ -1430,14 +1433,19 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       hp.ortho6d = out->ortho6d + o * 6; hp.coord_pos = out->coord_pos + o * 3;
       hp.rot = out->rotation ? out->rotation + o * 9 : nullptr;
       hp.ref_next = F32(W.ref_cur);
-      hp.posemb_next = (forced_refs == nullptr && it + 1 < s.iters) ? BF(W.a_pos) : nullptr;
+      hp.posemb_next = (posemb_folded && it + 1 < s.iters) ? BF(W.a_pos) : nullptr;
       hp.dim_t = PF(P.dim_t);
       hp.R = R; hp.Nq = s.Nq; hp.C = C; hp.num_cls = s.num_cls;
       { ProfScope ps(TAG_ROWWISE, st); {
         const int rpb = (R + device_info().sms - 1) / device_info().sms;     // rows per block: one block per SM
         const size_t hsm = static_cast<size_t>(HEADS_SLOTS + 4) * C * sizeof(float);
-        OPT_IN_SMEM(heads_final_kernel<1024>, hsm);
-        launch_k(heads_final_kernel<1024>, dim3((R + rpb - 1) / rpb), dim3(512), hsm, st, hp, rpb);
+        if (hp.posemb_next != nullptr) {
+          OPT_IN_SMEM((heads_final_kernel<1024, true>), hsm);
+          launch_k(heads_final_kernel<1024, true>, dim3((R + rpb - 1) / rpb), dim3(512), hsm, st, hp, rpb);
+        } else {
+          OPT_IN_SMEM((heads_final_kernel<1024, false>), hsm);
+          launch_k(heads_final_kernel<1024, false>, dim3((R + rpb - 1) / rpb), dim3(512), hsm, st, hp, rpb);
+        }
       } }
       CUDA_TRY(cudaGetLastError());
     }

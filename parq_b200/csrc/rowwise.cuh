@@ -242,6 +242,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // Epilogue of one row: lane j holds output slot j (bias not yet added).
+template <bool kPosemb>
 __device__ __forceinline__ void heads_row_epilogue(const HeadsParams& p, int row, int lane, float mine) {
   const bool is_cls = lane < p.num_cls;
   float ref_n = 0.f;                         // next reference coordinate (centre lanes)
@@ -282,7 +283,7 @@ __device__ __forceinline__ void heads_row_epilogue(const HeadsParams& p, int row
   } else if (lane >= HEADS_CLS_SLOTS + 6 && lane < HEADS_SLOTS) {
     p.ortho6d[row * 6 + lane - HEADS_CLS_SLOTS - 6] = mine;
   }
-  if (p.posemb_next != nullptr) {
+  if (kPosemb && p.posemb_next != nullptr) {
     // sinusoidal embedding of the next reference point, the input of the next iteration's reference-point MLP
     const float rx = __shfl_sync(0xffffffffu, ref_n, HEADS_CLS_SLOTS + 3), ry = __shfl_sync(0xffffffffu, ref_n, HEADS_CLS_SLOTS + 4),
                 rz = __shfl_sync(0xffffffffu, ref_n, HEADS_CLS_SLOTS + 5);
@@ -318,7 +319,9 @@ __device__ __forceinline__ void heads_row_epilogue(const HeadsParams& p, int row
 // constants); each warp then walks PAIRS of rows (queries) so that every weight read from shared memory
 // feeds two rows: 2 x 28 independent dot-product chains per lane, a butterfly reduction, and an epilogue
 // in which lane j owns output slot j (softmax/arg-max through warp shuffles).
-template <int C>
+// kPosemb: also write pos2posemb3d of the next reference point (HeadsParams::posemb_next); a separate instantiation so that
+// the common one keeps its register budget (the extra code spills under the 128-register cap of 512 threads).
+template <int C, bool kPosemb>
 __global__ void __launch_bounds__(512)
 heads_final_kernel(const HeadsParams p, int rows_per_block) {
   constexpr int NR = 2;
@@ -422,7 +425,7 @@ heads_final_kernel(const HeadsParams p, int rows_per_block) {
 #pragma unroll
       for (int j = 0; j < HEADS_SLOTS; ++j)
         if (lane == j) mine = acc[r][j];
-      if (row0 + r < row_end) heads_row_epilogue(p, row0 + r, lane, mine);
+      if (row0 + r < row_end) heads_row_epilogue<kPosemb>(p, row0 + r, lane, mine);
     }
   }
 }
