@@ -364,15 +364,15 @@ attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // directly and are skipped): out = sum_s 2^(m_s-M) O_s / sum_s 2^(m_s-M) l_s as the exact bf16 split [hi | lo].
 // One block per (item, 32 of its 256 query rows): the 64-bit range arithmetic that locates the item's pieces runs once
 // per block; 64 threads per row, a thread owns 4 consecutive channels.
-constexpr int SK_COMBINE_ROWS = 32;
+constexpr int SK_COMBINE_ROWS = 8;       // rows of an item per block (a thread walks rows / 4 of them): 8 -> 2 048 blocks at config 2
 constexpr int SK_MAX_PAIRS = 128;        // CTA pairs the schedule may use (74 on a B200)
 
 __global__ void __launch_bounds__(256)
-attn3_combine_kernel(const Attn3Params p) {
+attn3_combine_kernel(const Attn3Params p, const int rows) {
   pdl_wait();
   pdl_launch_dependents();
-  const int item = blockIdx.x / (256 / SK_COMBINE_ROWS);
-  const int r0 = (blockIdx.x % (256 / SK_COMBINE_ROWS)) * SK_COMBINE_ROWS;      // first row of this block inside the item
+  const int item = blockIdx.x / (256 / rows);
+  const int r0 = (blockIdx.x % (256 / rows)) * rows;      // first row of this block inside the item
   __shared__ int s_np;
   __shared__ long long s_slot[SK_MAX_PAIRS];                // first row of every piece of the item in o_part / ml_part (<= npairs pieces)
   if (threadIdx.x == 0) {
@@ -397,7 +397,7 @@ attn3_combine_kernel(const Attn3Params p) {
   const int b = bh / p.H, h = bh - b * p.H;
   const int C = p.H * 256;
   const int d = (threadIdx.x & 63) * 4;
-  for (int r = r0 + (threadIdx.x >> 6); r < r0 + SK_COMBINE_ROWS; r += 4) {
+  for (int r = r0 + (threadIdx.x >> 6); r < r0 + rows; r += 4) {
     float M = -INFINITY;
     for (int i = 0; i < np; ++i) M = fmaxf(M, __ldg(&p.ml_part[s_slot[i] + r].x));
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);

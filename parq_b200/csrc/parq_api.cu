@@ -143,6 +143,8 @@ static int require_sm100() {
 // The stand-alone entry points launch plainly (their inputs may come from the caller's previous kernel).
 static thread_local bool g_pdl = false;
 static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
+static const int g_combine_rows = (getenv("PARQ_COMBINE_ROWS") && (atoi(getenv("PARQ_COMBINE_ROWS")) == 4 || atoi(getenv("PARQ_COMBINE_ROWS")) == 16 ||
+                                                                   atoi(getenv("PARQ_COMBINE_ROWS")) == 32)) ? atoi(getenv("PARQ_COMBINE_ROWS")) : SK_COMBINE_ROWS;
 static const bool g_no_narrow = getenv("PARQ_NO_NARROW") != nullptr;         // A/B switch: 256-column tiles also for GEMMs of a few row tiles
 static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;
 static const int g_chain_min_rows = getenv("PARQ_CHAIN_MIN_ROWS") ? atoi(getenv("PARQ_CHAIN_MIN_ROWS")) : 2048;
@@ -445,7 +447,7 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
       CUDA_TRY(cudaGetLastError());
       {
         ProfScope ps(TAG_COMBINE, st);
-        launch_k(attn3_combine_kernel, dim3(B * H * sp.qpairs * (256 / SK_COMBINE_ROWS)), dim3(256), 0, st, sp);
+        launch_k(attn3_combine_kernel, dim3(B * H * sp.qpairs * (256 / g_combine_rows)), dim3(256), 0, st, sp, g_combine_rows);
       }
       CUDA_TRY(cudaGetLastError());
       return PARQ_OK;
