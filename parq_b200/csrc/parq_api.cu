@@ -940,19 +940,16 @@ static int fpn_concat_impl(const void* l0, const void* l1, const void* l2, const
   fp.out = out_nchw;
   const long long planes = static_cast<long long>(BT) * 4 * channels_per_level;
   if (planes > 0x7fffffffLL) return fail(PARQ_ERR_SHAPE, "too many feature planes");
-  // grid.y is limited to 65535 planes per launch
-  for (long long p0 = 0; p0 < planes; p0 += 65535) {
-    const int np = static_cast<int>(planes - p0 < 65535 ? planes - p0 : 65535);
-    FpnParams part = fp;
-    // a launch covers planes [p0, p0+np): shift the output and let the kernel see plane indices from p0 via BT-relative pointers
-    part.plane0 = static_cast<int>(p0);
-    ProfScope ps(TAG_ROWWISE, static_cast<cudaStream_t>(stream));
-    const dim3 grid((fp.H * fp.W + 1023) / 1024, np);
+  if (channels_per_level % FPN_CH != 0) return fail(PARQ_ERR_SHAPE, "channels_per_level=%d must be a multiple of %d", channels_per_level, FPN_CH);
+  {
+    fp.plane0 = 0;
+    const dim3 grid(static_cast<unsigned>(planes / FPN_CH));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (in_bf16 && out_bf16) fpn_concat_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(part);
-    else if (in_bf16) fpn_concat_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(part);
-    else if (out_bf16) fpn_concat_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(part);
-    else fpn_concat_kernel<float, float><<<grid, 256, 0, st>>>(part);
+    ProfScope ps(TAG_ROWWISE, st);
+    if (in_bf16 && out_bf16) fpn_concat_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(fp);
+    else if (in_bf16) fpn_concat_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(fp);
+    else if (out_bf16) fpn_concat_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(fp);
+    else fpn_concat_kernel<float, float><<<grid, 256, 0, st>>>(fp);
   }
   CUDA_TRY(cudaGetLastError());
   return PARQ_OK;
