@@ -32,6 +32,7 @@ enum ChainEpilogue {
   CH_EP_SPLIT = 1,  // v = [relu](acc + bias) -> a_out = split(v)
   CH_EP_LP = 2,     // v = acc + bias -> out_lp (bf16 / fp16)
   CH_EP_F32 = 3,    // v = acc + bias -> out_f32 [, GroupNorm tile sums] [, out_sum_split = split(v + add_split)]
+  CH_EP_LP_T = 4,   // v = acc + bias -> out_lp TRANSPOSED: out_lp[col * ld_lp + row] (V^T of the self-attention, K-major for P.V)
 };
 
 struct ChainStage {
@@ -518,6 +519,14 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
             const long long cc = col0 + c * 32;
             if (S.ep == CH_EP_SPLIT) {
               chain_store_split32(stage, S.a_out + wrow0 * 2 * S.N + cc, 2 * S.N, S.N, v, lane);
+            } else if (S.ep == CH_EP_LP_T) {
+              // lanes = 32 consecutive rows: every store instruction writes 64 contiguous bytes of one output row (= column here)
+              uint16_t* o = reinterpret_cast<uint16_t*>(S.out_lp) + cc * S.ld_lp + row;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const uint16_t hv = S.lp_fp16 ? __half_as_ushort(__float2half_rn(v[i])) : __bfloat16_as_ushort(__float2bfloat16_rn(v[i]));
+                o[static_cast<long long>(i) * S.ld_lp] = hv;
+              }
             } else if (S.ep == CH_EP_LP) {
               uint32_t w[16];
               if (S.lp_fp16) {

@@ -146,6 +146,7 @@ static const bool g_no_dual = getenv("PARQ_NO_DUAL_A") != nullptr;
 static const int g_combine_rows = (getenv("PARQ_COMBINE_ROWS") && (atoi(getenv("PARQ_COMBINE_ROWS")) == 4 || atoi(getenv("PARQ_COMBINE_ROWS")) == 16 ||
                                                                    atoi(getenv("PARQ_COMBINE_ROWS")) == 32)) ? atoi(getenv("PARQ_COMBINE_ROWS")) : SK_COMBINE_ROWS;
 static const bool g_no_narrow = getenv("PARQ_NO_NARROW") != nullptr;         // A/B switch: 256-column tiles also for GEMMs of a few row tiles
+static const bool g_no_chain_v = getenv("PARQ_NO_CHAIN_V") != nullptr;       // A/B switch: self-attention V^T as its own GEMM launch instead of stage 0 of chain P
 static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;
 static const int g_chain_min_rows = getenv("PARQ_CHAIN_MIN_ROWS") ? atoi(getenv("PARQ_CHAIN_MIN_ROWS")) : 2048;
 constexpr int HI_ONLY_DEFAULT = 0;
@@ -1262,7 +1263,14 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       // ---- chain P: pe = W2 relu(W1 posemb + b1) + b2 (+ x -> split(x + pe)) -> self-attention Q|K projection
       {
         ChainBuilder cb(R);
-        ChainStage S = chain_stage(C, 384, CH_EP_SPLIT, PF(P.pe0_b));
+        ChainStage S;
+        if (!g_no_chain_v) {
+          // V = x Wv^T + bv of the self-attention, stored transposed (V^T, K-major for P.V) in fp16: stage 0, it needs only x
+          S = chain_stage(C, C, CH_EP_LP_T, PF(P.sa_v_b));
+          S.out_lp = ws + W.vt_s; S.ld_lp = static_cast<long long>(W.ldvs); S.lp_fp16 = 1;
+          TRY(chain_add(cb, ws + W.a_x, 2 * C, pk + P.sa_v, w_lo, S));
+        }
+        S = chain_stage(C, 384, CH_EP_SPLIT, PF(P.pe0_b));
         S.relu = 1; S.a_out = BF(W.a_peh);
         TRY(chain_add(cb, ws + W.a_pos, 768, pk + P.pe0, w_lo, S));
         // (column-major private streams of the chained path: W.pe = pe, W.y = x, W.x1 = x1, W.x2 = x2 -- see chain_tc.cuh)
@@ -1274,8 +1282,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
         TRY(chain_add(cb, ws + W.a_xpe, 2 * C, pk + P.sa_qk, w_lo, S));
         TRY(launch_chain(st, cb));
       }
-      // V^T = Wv x^T + bv of the self-attention: weights are the A operand, activations the B operand
-      {
+      // (A/B switch PARQ_NO_CHAIN_V) V^T = Wv x^T + bv of the self-attention as its own GEMM: weights are the A operand, activations the B operand
+      if (g_no_chain_v) {
         GemmParams g; memset(&g, 0, sizeof(g));
         g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : ((hi_only & 2) ? 1 : 2); g.const_operand = 1;
         g.a_koff[0] = 0; g.b_koff[0] = 0; g.a_koff[1] = 0; g.b_koff[1] = C; g.a_koff[2] = C; g.b_koff[2] = 0;

@@ -18,6 +18,7 @@ ROWS = [
     ("hi-only: sa_v", {"PARQ_HI_ONLY": "2"}),
     ("hi-only: ca_q", {"PARQ_HI_ONLY": "4"}),
     ("hi-only: sa_qk + sa_v + ca_q", {"PARQ_HI_ONLY": "7"}),
+    ("self-attention V^T as its own GEMM (not stage 0 of chain P)", {"PARQ_NO_CHAIN_V": "1"}),
     ("no chain (separate GEMM + LayerNorm launches)", {"PARQ_NO_CHAIN": "1"}),
 ]
 
