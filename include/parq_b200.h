@@ -196,6 +196,15 @@ int parq_gemm_bf16(const void *A, int64_t a_rows, int64_t a_cols, const void *Bw
                    int bias_per_row, int relu, float *out_f32, int64_t ld_f32, void *out_lp, int64_t ld_lp, int lp_fp16,
                    int64_t lp_lo_off, void *stream);
 
+/* The chained cluster kernel (csrc/chain_tc.cuh) on a two-stage chain, for unit tests:
+ *   y = LayerNorm_1024(A W1^T + b1 + resid) * gamma + beta     (eps 1e-5; resid_cm is COLUMN-major fp32 [1024][M])
+ *   z = relu(y W2^T + b2)
+ * a_split (M, 2*K1), w1_split (1024, 2*K1), w2_split (N2, 2048): bf16 [hi|lo] along K; w_lo != 0 adds the A_hi x W_lo term.
+ * Outputs: y_f32 (M, 1024) row-major, y_split (M, 2048) and z_split (M, 2*N2) bf16 [hi|lo].  M % 128 == 0, N2 in {768, 1024, 2048}. */
+int parq_chain_ln_linear(const void *a_split, const void *w1_split, const float *b1, const float *resid_cm, const float *gamma,
+                         const float *beta, const void *w2_split, const float *b2, int M, int K1, int N2, int w_lo, float *y_f32,
+                         void *y_split, void *z_split, void *stream);
+
 /* softmax(Q K^T) V for head_dim 256: Q (B*Nq, H*256) pre-scaled, K (B*Nk, H*256), Vt (H*256, ldv) 16-bit
  * (bf16, or fp16 when fp16 != 0); out_split (B*Nq, 2*H*256) bf16 [hi|lo]; scratch >= parq_attention_scratch_bytes.
  * force_nsplit: > 0 fixes the number of key splits, 0 lets the library choose (stream-K schedule for long key

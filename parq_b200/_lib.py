@@ -24,7 +24,7 @@ PARQ_NMS_NO_TRACK_SCALE = 2
 EXPORTS = [
     "parq_version", "parq_last_error", "parq_packed_bytes", "parq_workspace_bytes", "parq_pack_weights",
     "parq_pose_chain", "parq_split_tokens", "parq_project_sample", "parq_kv_project", "parq_kv_project_views", "parq_chain_debug", "parq_decoder_forward",
-    "parq_gemm_bf16", "parq_attention_scratch_bytes", "parq_attention",
+    "parq_gemm_bf16", "parq_chain_ln_linear", "parq_attention_scratch_bytes", "parq_attention",
     "parq_parse_pred", "parq_fpn_concat", "parq_fpn_concat_bf16", "parq_fpn_concat_ex", "parq_raype_packed_bytes", "parq_raype_workspace_bytes", "parq_raype_pack_weights",
     "parq_raype_forward", "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect", "parq_workspace_offset",
 ]
@@ -105,6 +105,8 @@ def load():
     lib.parq_gemm_bf16.restype = C.c_int
     lib.parq_gemm_bf16.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                    f32p, i32, i32, f32p, i64, vp, i64, i32, i64, vp]
+    lib.parq_chain_ln_linear.restype = C.c_int
+    lib.parq_chain_ln_linear.argtypes = [vp, vp, f32p, f32p, f32p, f32p, vp, f32p, i32, i32, i32, i32, f32p, vp, vp, vp]
     lib.parq_attention_scratch_bytes.restype = sz
     lib.parq_attention_scratch_bytes.argtypes = [i32, i32, i32, i32]
     lib.parq_attention.restype = C.c_int

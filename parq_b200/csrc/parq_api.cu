@@ -1135,6 +1135,26 @@ int parq_gemm_bf16(const void* A, int64_t a_rows, int64_t a_cols, const void* Bw
   return launch_gemm(static_cast<cudaStream_t>(stream), A, a_rows, a_cols, Bw, b_rows, b_cols, gp);
 }
 
+/* Unit-test entry of the chained kernel: y = LayerNorm(x_split W1^T + b1 + resid) * gamma + beta, then z = relu(y W2^T + b2),
+ * as ONE launch of two chained stages (N1 = 1024 columns for the LayerNorm stage). */
+int parq_chain_ln_linear(const void* a_split, const void* w1_split, const float* b1, const float* resid_cm, const float* gamma, const float* beta,
+                         const void* w2_split, const float* b2, int M, int K1, int N2, int w_lo, float* y_f32, void* y_split, void* z_split,
+                         void* stream) {
+  TRY(require_sm100());
+  if (!a_split || !w1_split || !resid_cm || !gamma || !beta || !w2_split || !y_f32 || !y_split || !z_split)
+    return fail(PARQ_ERR_SHAPE, "null pointer");
+  const int N1 = 1024;
+  ChainBuilder cb(M);
+  ChainStage S = chain_stage(N1, K1, CH_EP_LN, b1);
+  S.resid_cm = resid_cm; S.gamma = gamma; S.beta = beta;
+  S.out_f32 = y_f32; S.a_out = static_cast<__nv_bfloat16*>(y_split);
+  TRY(chain_add(cb, a_split, 2 * static_cast<uint64_t>(K1), w1_split, w_lo != 0, S));
+  S = chain_stage(N2, N1, CH_EP_SPLIT, b2);
+  S.relu = 1; S.a_out = static_cast<__nv_bfloat16*>(z_split);
+  TRY(chain_add(cb, y_split, 2 * N1, w2_split, w_lo != 0, S));
+  return launch_chain(static_cast<cudaStream_t>(stream), cb);
+}
+
 size_t parq_attention_scratch_bytes(int B, int H, int Nq, int Nk) {
   const int ntiles = (Nk + attn::BKEY - 1) / attn::BKEY;
   const size_t a = attn_scratch_bytes(B, H, Nq, ntiles < 32 ? ntiles : 32), b = streamk_scratch_bytes(B, H, Nq, Nk, device_info().sms);

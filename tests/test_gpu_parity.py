@@ -170,6 +170,39 @@ def test_gemm_three_term_split_recovers_fp32_product(dev):
     assert relerr(out, ref) <= 3e-5
 
 
+@pytest.mark.parametrize("M,K1,N2,w_lo", [(128, 1024, 1024, 0), (512, 768, 768, 0), (256, 1024, 2048, 1)])
+def test_chained_kernel_linear_layernorm_linear(dev, M, K1, N2, w_lo):
+    # chain_tc.cuh in isolation: cluster of 4 CTAs per 128 rows, LayerNorm statistics exchanged over DSMEM, the second stage
+    # streams the first stage's output back as its A operand; against float64 torch on the same (split-representable) inputs
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + K1 + N2)
+    sp = lambda t: torch.cat([t.bfloat16(), (t - t.bfloat16().float()).bfloat16()], 1).contiguous()
+    rec = lambda s_: s_[:, : s_.shape[1] // 2].double() + s_[:, s_.shape[1] // 2:].double()
+    x = torch.randn(M, K1, generator=g).to(dev)
+    W1 = (torch.randn(1024, K1, generator=g) * 0.04).to(dev)
+    W2 = (torch.randn(N2, 1024, generator=g) * 0.04).to(dev)
+    if not w_lo:
+        W1, W2 = W1.bfloat16().float(), W2.bfloat16().float()
+    b1, b2 = torch.randn(1024, generator=g).to(dev), torch.randn(N2, generator=g).to(dev)
+    gamma, beta = (1 + 0.1 * torch.randn(1024, generator=g)).to(dev), (0.1 * torch.randn(1024, generator=g)).to(dev)
+    resid = torch.randn(M, 1024, generator=g).to(dev)
+    xs, w1s, w2s = sp(x), sp(W1), sp(W2)
+    y = torch.full((M, 1024), float("nan"), device=dev)
+    ys = torch.zeros(M, 2048, dtype=torch.bfloat16, device=dev)
+    zs = torch.zeros(M, 2 * N2, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.parq_chain_ln_linear(_ptr(xs), _ptr(w1s), _ptr(b1), _ptr(resid.t().contiguous()), _ptr(gamma), _ptr(beta), _ptr(w2s), _ptr(b2),
+                                        M, K1, N2, w_lo, _ptr(y), _ptr(ys), _ptr(zs), _stream()), "parq_chain_ln_linear")
+    torch.cuda.synchronize()
+    w1 = rec(w1s) if w_lo else W1.double()
+    z64 = rec(xs) @ w1.t() + b1.double() + resid.double()
+    y64 = torch.nn.functional.layer_norm(z64, (1024,), gamma.double(), beta.double(), 1e-5)
+    assert relerr(y, y64) <= 3e-5
+    assert relerr(rec(ys), y64) <= 3e-5                        # the operand split carries 16 mantissa bits
+    w2 = rec(w2s) if w_lo else W2.double()
+    out64 = torch.relu(rec(ys) @ w2.t() + b2.double())         # second stage on the operand it actually consumed
+    assert relerr(rec(zs), out64) <= 3e-5
+
+
 def _attention(dev, B, H, Nq, Nk, fp16, nsplit, seed, scale=1.0, spike=False):
     lib = _lib.load()
     g = torch.Generator().manual_seed(seed)
