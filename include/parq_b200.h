@@ -85,6 +85,12 @@ typedef struct ParqOutputs {
 #define PARQ_FLAG_KV_HI_ONLY 16u /* with WEIGHT_LO: project K / V^T with the high weight part only (they are stored in bf16 anyway) */
 #define PARQ_FLAG_NO_CHAIN 64u   /* per-iteration linears as separate GEMM + LayerNorm launches instead of the chained cluster kernel (A/B timing, tests) */
 #define PARQ_FLAG_FORCE_CHAIN 128u /* use the chained kernel also below its break-even batch (B*Nq < 2048 rows): tests */
+/* PARQ_FLAG_HI_ONLY_SET + bits 16..26: explicit per-GEMM mask "use only the high-order activation term" for the chained path with
+ * bf16-exact weights (precision / energy trade-off, measured in profiles/): bit 16 sa_qk, 17 sa_v, 18 ca_q, 19 pe0, 20 pe2,
+ * 21 sa_out, 22 ca_out, 23 lin1, 24 lin2, 25 hd1, 26 hd2.  Without PARQ_FLAG_HI_ONLY_SET the library default applies. */
+#define PARQ_FLAG_HI_ONLY_SHIFT 16
+#define PARQ_FLAG_HI_ONLY_MASK 0x07FF0000u
+#define PARQ_FLAG_HI_ONLY_SET 0x08000000u
 #define PARQ_FLAG_NO_PDL 4u      /* launch without programmatic dependent launch (plain stream order; for A/B timing) */
 
 int parq_version(void);
@@ -129,6 +135,11 @@ int parq_kv_project_views(const ParqShape *shape, const void *view_tokens_bf16, 
 /* Instrumentation of the chained GEMM kernel: clock64 stamps of its CTA 0 for the next <= 64 launches go to `buf`
  * (device memory, 64 x 64 int64); NULL switches it off.  Read by tools/chain_timeline.py. */
 int parq_chain_debug(void *buf);
+
+/* Instrumentation of the dependent launch chain: while a buffer is set, thread 0 of block 0 of every kernel of this library
+ * appends the global timer (ns) at the moment its stream dependency resolved (griddepcontrol.wait returned).  buf = device memory
+ * of `capacity` uint64, slot 0 counts the stamps; NULL switches it off.  Read by tools/launch_trace.py. */
+int parq_trace(void *buf, int capacity);
 
 /* The whole recurrent decoder.  tokens_lo_bf16: optional low-order token plane (parq_split_tokens) or NULL.
  * ref0 (B,Nq,3): normalised initial reference points (sigmoid(refpoint.weight) repeated per clip).

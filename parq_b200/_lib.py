@@ -16,6 +16,8 @@ PARQ_FLAG_NO_PDL = 4
 PARQ_FLAG_KV_HI_ONLY = 16
 PARQ_FLAG_NO_CHAIN = 64
 PARQ_FLAG_FORCE_CHAIN = 128
+PARQ_FLAG_HI_ONLY_SHIFT = 16
+PARQ_FLAG_HI_ONLY_SET = 0x08000000
 PARQ_RAYPE_SPLIT_HIDDEN = 8
 PARQ_RAYPE_FEAT_BF16 = 256
 PARQ_NMS_SAME_CLASS = 1
@@ -23,7 +25,7 @@ PARQ_NMS_NO_TRACK_SCALE = 2
 
 EXPORTS = [
     "parq_version", "parq_last_error", "parq_packed_bytes", "parq_workspace_bytes", "parq_pack_weights",
-    "parq_pose_chain", "parq_split_tokens", "parq_project_sample", "parq_kv_project", "parq_kv_project_views", "parq_chain_debug", "parq_decoder_forward",
+    "parq_pose_chain", "parq_split_tokens", "parq_project_sample", "parq_kv_project", "parq_kv_project_views", "parq_chain_debug", "parq_trace", "parq_decoder_forward",
     "parq_gemm_bf16", "parq_chain_ln_linear", "parq_attention_scratch_bytes", "parq_attention",
     "parq_parse_pred", "parq_fpn_concat", "parq_fpn_concat_bf16", "parq_fpn_concat_ex", "parq_raype_packed_bytes", "parq_raype_workspace_bytes", "parq_raype_pack_weights",
     "parq_raype_forward", "parq_kernel_launches", "parq_profile_enable", "parq_profile_collect", "parq_workspace_offset",
@@ -99,6 +101,8 @@ def load():
     lib.parq_kv_project_views.argtypes = [C.POINTER(ParqShape), vp, i32, i32, vp, vp, sz, u32, vp]
     lib.parq_chain_debug.restype = C.c_int
     lib.parq_chain_debug.argtypes = [vp]
+    lib.parq_trace.restype = C.c_int
+    lib.parq_trace.argtypes = [vp, i32]
     lib.parq_decoder_forward.restype = C.c_int
     lib.parq_decoder_forward.argtypes = [C.POINTER(ParqShape), vp, vp, f32p, f32p, f32p, f32p, f32p, f32p, vp, vp, sz,
                                          C.POINTER(ParqOutputs), u32, vp]

@@ -367,6 +367,9 @@ attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 constexpr int SK_COMBINE_ROWS = 8;       // rows of an item per block (a thread walks rows / 4 of them): 8 -> 2 048 blocks at config 2
 constexpr int SK_MAX_PAIRS = 128;        // CTA pairs the schedule may use (74 on a B200)
 
+// kWide (few items cut into many pieces each: one clip on the whole machine): the four 64-thread groups of a block share ONE row
+// and take every fourth piece of it, their partial merges meet in shared memory -- a quarter of the dependent loads per thread.
+template <bool kWide>
 __global__ void __launch_bounds__(256)
 attn3_combine_kernel(const Attn3Params p, const int rows) {
   pdl_wait();
@@ -375,6 +378,7 @@ attn3_combine_kernel(const Attn3Params p, const int rows) {
   const int r0 = (blockIdx.x % (256 / rows)) * rows;      // first row of this block inside the item
   __shared__ int s_np;
   __shared__ long long s_slot[SK_MAX_PAIRS];                // first row of every piece of the item in o_part / ml_part (<= npairs pieces)
+  __shared__ float s_merge[kWide ? 3 * 64 * 6 : 1];         // groups 1..3: (M, L, acc[4]) per thread of the group
   if (threadIdx.x == 0) {
     const long long ua = static_cast<long long>(item) * p.ntiles, ub = ua + p.ntiles - 1;      // first / last unit of the item
     auto pair_of = [&](long long u) {
@@ -397,18 +401,43 @@ attn3_combine_kernel(const Attn3Params p, const int rows) {
   const int b = bh / p.H, h = bh - b * p.H;
   const int C = p.H * 256;
   const int d = (threadIdx.x & 63) * 4;
-  for (int r = r0 + (threadIdx.x >> 6); r < r0 + rows; r += 4) {
+  const int grp = threadIdx.x >> 6;
+  const int r_first = kWide ? r0 : r0 + grp, r_step = kWide ? 1 : 4;
+  const int i_first = kWide ? grp : 0, i_step = kWide ? 4 : 1;
+  for (int r = r_first; r < r0 + rows; r += r_step) {
     float M = -INFINITY;
-    for (int i = 0; i < np; ++i) M = fmaxf(M, __ldg(&p.ml_part[s_slot[i] + r].x));
+    for (int i = i_first; i < np; i += i_step) M = fmaxf(M, __ldg(&p.ml_part[s_slot[i] + r].x));
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float L = 0.f;
-    for (int i = 0; i < np; ++i) {
+    for (int i = i_first; i < np; i += i_step) {
       const long long idx = s_slot[i] + r;
       const float2 ml = __ldg(&p.ml_part[idx]);
       const float4 o = __ldg(reinterpret_cast<const float4*>(p.o_part + idx * 256 + d));
       const float w = exp2f(ml.x - M);
       L += w * ml.y;
       acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
+    }
+    if (kWide) {
+      // merge the four groups' (M, L, acc) of this row in group 0 (a group without pieces carries M = -inf, L = 0)
+      float* mine = s_merge + ((grp - 1) * 64 + (threadIdx.x & 63)) * 6;
+      if (grp > 0) { mine[0] = M; mine[1] = L; mine[2] = acc.x; mine[3] = acc.y; mine[4] = acc.z; mine[5] = acc.w; }
+      __syncthreads();
+      if (grp == 0) {
+        float Mt = M;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) Mt = fmaxf(Mt, s_merge[(g * 64 + threadIdx.x) * 6]);
+        const float w0 = exp2f(M - Mt);                    // group 0 always has a piece (np >= 2 > 0)
+        L *= w0; acc.x *= w0; acc.y *= w0; acc.z *= w0; acc.w *= w0;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const float* o = s_merge + (g * 64 + threadIdx.x) * 6;
+          const float w = o[0] == -INFINITY ? 0.f : exp2f(o[0] - Mt);
+          L += w * o[1];
+          acc.x += w * o[2]; acc.y += w * o[3]; acc.z += w * o[4]; acc.w += w * o[5];
+        }
+      }
+      __syncthreads();
+      if (grp != 0) continue;
     }
     const float inv = 1.f / L;
     const float v[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};

@@ -41,6 +41,8 @@ struct ChainStage {
   int nterms, a_koff[3], b_koff[3], dual_a;
   int hi_only;               // dual-A ring only: skip the low-order activation term (outputs that are rounded to 16 bits anyway)
   int ep, relu, lp_fp16;
+  int dep;                   // index of the earlier stage of this launch whose output is this stage's A operand, or -1: the stage
+                             // starts as soon as the tensor pipe is free (its MMAs overlap the previous stage's epilogue)
   const float* bias;                   // (N) or null
   // "cm" = COLUMN-MAJOR fp32 scratch [N][M]: streams that are written and later read by the SAME epilogue thread (the
   // residual stream x / x1 / x2 and the positional feature) -- a thread owns a row, so with rows contiguous every access
@@ -83,6 +85,8 @@ constexpr int SMEM_BYTES = 1024 + RING_BYTES + 512 /*barriers*/ + 2 * CLUSTER * 
 struct ChainParams {
   int M, nstages;
   long long* dbg;          // optional: clock64 stamps of CTA 0 (tools/chain_timeline.py), 64 slots per launch, or null
+  int trace_slot;          // >= 0 while parq_trace is on: every CTA stamps the global timer at entry / dependency resolved / exit into
+                           // the upper half of the trace buffer, [trace_slot][blockIdx.x (< 160)][4]
   ChainStage st[chain::MAX_STAGES];
 };
 struct ChainMaps {
@@ -203,8 +207,9 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + 4;                                   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                                  // [2]
   uint64_t* xbar = tempty_bar + 2;        // row statistics of all four CTAs have arrived
-  uint64_t* dbar = xbar + 1;              // the stage's outputs of all four CTAs are in global memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dbar + 1);
+  uint64_t* dbar = xbar + 1;              // [MAX_STAGES] stage s: its outputs of all four CTAs are in global memory (one barrier per
+                                          // stage, single phase: an independent stage may run ahead of the previous stage's epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dbar + MAX_STAGES);
   float2* s_part = reinterpret_cast<float2*>(smem + RING_BYTES + 512);   // [2 * CLUSTER][BM] (mean, M2) partials
   float* s_vec = reinterpret_cast<float*>(s_part + 2 * CLUSTER * BM);    // bias [VEC_COLS] | gamma [LN_COLS] | beta [LN_COLS]
   double* s_gn = reinterpret_cast<double*>(s_vec + VEC_COLS + 2 * LN_COLS);   // [EPI_WARPS][2]
@@ -213,6 +218,15 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int m0 = (blockIdx.x / CLUSTER) * BM;
+  unsigned long long* tr = nullptr;
+  const long long tr_c0 = clock64();
+  if (threadIdx.x == 0 && p.trace_slot >= 0 && g_trace_buf != nullptr && blockIdx.x < 160) {
+    const unsigned long long o = g_trace_cap / 2 + (static_cast<unsigned long long>(p.trace_slot) * 160 + blockIdx.x) * 4;
+    if (o + 4 <= g_trace_cap) {
+      tr = g_trace_buf + o;
+      tr[0] = globaltimer_ns();
+    }
+  }
   // every stage of a chain uses the same ring geometry: dual-A (3 slots of [A_hi | A_lo | B]) or plain (4 slots of A + B)
   const bool dual = p.st[0].dual_a != 0;
   const int nst = dual ? 3 : 4;
@@ -235,7 +249,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
       mbar_init(&tempty_bar[i], EPI_WARPS);
     }
     mbar_init(xbar, CLUSTER * EPI_WARPS);
-    mbar_init(dbar, CLUSTER * EPI_WARPS);
+    for (int i = 0; i < MAX_STAGES; ++i) mbar_init(&dbar[i], CLUSTER * EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -278,8 +292,9 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
         if (s == 0) {
           pdl_wait();
           pdl_launch_dependents();
-        } else {
-          mbar_wait_cluster(dbar, (s - 1) & 1);
+          if (tr != nullptr) tr[1] = globaltimer_ns();
+        } else if (S.dep >= 0) {
+          mbar_wait_cluster(&dbar[S.dep], 0);
           fence_proxy_async_all();
         }
         CHAIN_STAMP(s * 8 + 0);              // the A operand of this stage may be loaded
@@ -357,7 +372,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
 #pragma unroll
     for (int c = 0; c < CLUSTER; ++c) {
       xaddr[c] = mapa_u32(smem_u32(xbar), c);
-      daddr[c] = mapa_u32(smem_u32(dbar), c);
+      daddr[c] = mapa_u32(smem_u32(dbar), c);          // + 8 * stage
     }
     for (int s = 0; s < p.nstages; ++s) {
       const ChainStage& S = p.st[s];
@@ -598,7 +613,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
-          for (int c = 0; c < CLUSTER; ++c) mbar_arrive_cluster(daddr[c]);
+          for (int c = 0; c < CLUSTER; ++c) mbar_arrive_cluster(daddr[c] + 8u * s);
         }
       }
     }
@@ -610,6 +625,10 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                      // no CTA leaves while a peer may still signal its barriers or write its statistics
+  if (tr != nullptr) {
+    tr[2] = globaltimer_ns();
+    tr[3] = static_cast<unsigned long long>(clock64() - tr_c0);      // SM cycles between the two stamps: the clock under load
+  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

@@ -310,7 +310,9 @@ static int chain_add(ChainBuilder& cb, const void* A, uint64_t a_cols, const voi
   if (cb.p.nstages >= chain::MAX_STAGES) return fail(PARQ_ERR_SHAPE, "too many chain stages");
   if (S.K <= 0 || S.K % chain::BK != 0 || !chain_cols_ok(S.N)) return fail(PARQ_ERR_SHAPE, "chain stage N=%d K=%d not supported", S.N, S.K);
   const int ncta = S.N / chain::CLUSTER;
-  S.tile_n = ncta <= 256 ? ncta : 256;
+  static const int tile_cap = getenv("PARQ_CHAIN_TILE") ? atoi(getenv("PARQ_CHAIN_TILE")) : 256;   // experiment: timing only (GN slots assume 256)
+  S.tile_n = ncta <= tile_cap ? ncta : (ncta % tile_cap == 0 ? tile_cap : ncta);
+  if (S.tile_n > 256) S.tile_n = 256;
   S.tiles = ncta / S.tile_n;
   S.nterms = w_lo ? 3 : 2;
   S.a_koff[0] = 0;   S.b_koff[0] = 0;
@@ -319,6 +321,8 @@ static int chain_add(ChainBuilder& cb, const void* A, uint64_t a_cols, const voi
   S.dual_a = (!w_lo && !g_no_dual) ? 1 : 0;
   if (cb.p.nstages > 0 && cb.p.st[0].dual_a != S.dual_a) return fail(PARQ_ERR_SHAPE, "chain stages must share the ring geometry");
   const int i = cb.p.nstages++;
+  if (S.dep == -2) S.dep = i - 1;
+  if (S.dep >= i) return fail(PARQ_ERR_SHAPE, "chain stage %d cannot depend on stage %d", i, S.dep);
   TRY(make_map(&cb.m.a[i], A, cb.p.M, a_cols, a_cols, chain::BM));
   TRY(make_map(&cb.m.b[i], W, S.N, 2 * static_cast<uint64_t>(S.K), 2 * static_cast<uint64_t>(S.K), S.tile_n));
   cb.p.st[i] = S;
@@ -326,7 +330,9 @@ static int chain_add(ChainBuilder& cb, const void* A, uint64_t a_cols, const voi
 }
 static thread_local long long* g_chain_dbg = nullptr;     // parq_chain_debug: device buffer for clock stamps, 64 slots per chain launch
 static thread_local int g_chain_dbg_launch = 0;
+static int g_trace_chain_slot = -1;                        // parq_trace: next per-CTA stamp block of a chain launch, -1 = trace off
 static int launch_chain(cudaStream_t st, ChainBuilder& cb) {
+  cb.p.trace_slot = g_trace_chain_slot >= 0 ? g_trace_chain_slot++ : -1;
   if (g_chain_dbg != nullptr && g_chain_dbg_launch < 64) cb.p.dbg = g_chain_dbg + 64 * g_chain_dbg_launch++;
   if (cb.p.M % chain::BM != 0) return fail(PARQ_ERR_SHAPE, "chain kernel needs M %% 128 == 0 (M=%d)", cb.p.M);
   OPT_IN_SMEM(chain_tc_kernel, chain::SMEM_BYTES);
@@ -342,6 +348,7 @@ static ChainStage chain_stage(int N, int K, int ep, const float* bias) {
   ChainStage S;
   memset(&S, 0, sizeof(S));
   S.N = N; S.K = K; S.ep = ep; S.bias = bias;
+  S.dep = -2;                // chain_add: the previous stage (set -1 for a stage that reads no earlier stage of the launch)
   return S;
 }
 
@@ -448,7 +455,11 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
       CUDA_TRY(cudaGetLastError());
       {
         ProfScope ps(TAG_COMBINE, st);
-        launch_k(attn3_combine_kernel, dim3(B * H * sp.qpairs * (256 / g_combine_rows)), dim3(256), 0, st, sp, g_combine_rows);
+        const int items = B * H * sp.qpairs;
+        if (2 * items <= sp.npairs)      // every item is cut into >= 3 pieces: 2 rows per block, the block's thread groups share a row
+          launch_k(attn3_combine_kernel<true>, dim3(items * (256 / 2)), dim3(256), 0, st, sp, 2);
+        else
+          launch_k(attn3_combine_kernel<false>, dim3(items * (256 / g_combine_rows)), dim3(256), 0, st, sp, g_combine_rows);
       }
       CUDA_TRY(cudaGetLastError());
       return PARQ_OK;
@@ -1181,6 +1192,20 @@ int parq_kv_project(const ParqShape* shape, const void* tokens_bf16, const void*
                     (flags & PARQ_FLAG_WEIGHT_LO) != 0 && !(flags & PARQ_FLAG_KV_HI_ONLY), static_cast<uint8_t*>(workspace), W);
 }
 
+/* instrumentation: global-timer stamp of every following kernel launch at the moment its stream dependency resolved (see ptx.cuh);
+ * buf = device memory of `capacity` uint64 (slot 0 = number of stamps so far, zeroed here), NULL switches it off */
+int parq_trace(void* buf, int capacity) {
+  unsigned long long* b = static_cast<unsigned long long*>(buf);
+  unsigned int cap = buf != nullptr && capacity > 1 ? static_cast<unsigned int>(capacity) : 0u;
+  if (cap == 0) b = nullptr;
+  if (b != nullptr) CUDA_TRY(cudaMemset(b, 0, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)));
+  CUDA_TRY(cudaMemcpyToSymbol(g_trace_buf, &b, sizeof(b)));
+  CUDA_TRY(cudaDeviceSynchronize());
+  g_trace_chain_slot = b != nullptr ? 0 : -1;
+  return PARQ_OK;
+}
+
 /* instrumentation: clock64 stamps of CTA 0 of the next <= 64 chain launches into buf (64 slots each); NULL switches it off */
 int parq_chain_debug(void* buf) {
   g_chain_dbg = static_cast<long long*>(buf);
@@ -1232,7 +1257,11 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   // the row-local linears of an iteration as three chained launches (chain_tc.cuh) instead of ten GEMMs + three LayerNorms
   // Low-order activation term of the three GEMMs whose output is rounded to 16 bits (self-attention Q|K and V^T in fp16,
   // cross-attention Q in bf16): PARQ_HI_ONLY (environment) overrides the default for the ablation of DESIGN.md
-  const int hi_only = getenv("PARQ_HI_ONLY") ? g_hi_only : HI_ONLY_DEFAULT;
+  // bits: 0 sa_qk, 1 sa_v, 2 ca_q, 3 pe0, 4 pe2, 5 sa_out, 6 ca_out, 7 lin1, 8 lin2, 9 hd1, 10 hd2 (chained path, bf16-exact weights)
+  const int hi_only = getenv("PARQ_HI_ONLY") ? g_hi_only
+                      : ((flags & PARQ_FLAG_HI_ONLY_SET) ? static_cast<int>((flags & PARQ_FLAG_HI_ONLY_MASK) >> PARQ_FLAG_HI_ONLY_SHIFT) & 0x7FF
+                                                         : HI_ONLY_DEFAULT);
+  auto hio = [&](int bit) { return (!w_lo && ((hi_only >> bit) & 1)) ? 1 : 0; };
   // It pays when the one-wave GEMMs it replaces fill the machine (R = 4096 rows at config 2: -0.46 ms per step); with a few
   // hundred rows (one clip: 2-4 clusters) the separate launches are faster (measured at config 5: 2.7 vs 3.5 ms per window).
   const bool chained = !(flags & PARQ_FLAG_NO_CHAIN) && !g_no_chain && chain_cols_ok(C) && chain_cols_ok(2 * C) && chain_cols_ok(F) && R % chain::BM == 0 &&
@@ -1283,22 +1312,25 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       // ---- chain P: pe = W2 relu(W1 posemb + b1) + b2 (+ x -> split(x + pe)) -> self-attention Q|K projection
       {
         ChainBuilder cb(R);
-        ChainStage S;
+        // stage order: pe0 first (short, K = 384), then V (independent of it: its MMAs run while pe0's epilogue drains), then
+        // pe2 (reads stage 0, long since complete: its MMAs cover V's epilogue), then Q|K
+        ChainStage S = chain_stage(C, 384, CH_EP_SPLIT, PF(P.pe0_b));
+        S.relu = 1; S.a_out = BF(W.a_peh); S.hi_only = hio(3);
+        TRY(chain_add(cb, ws + W.a_pos, 768, pk + P.pe0, w_lo, S));
         if (!g_no_chain_v) {
-          // V = x Wv^T + bv of the self-attention, stored transposed (V^T, K-major for P.V) in fp16: stage 0, it needs only x
+          // V = x Wv^T + bv of the self-attention, stored transposed (V^T, K-major for P.V) in fp16: it needs only x
           S = chain_stage(C, C, CH_EP_LP_T, PF(P.sa_v_b));
-          S.out_lp = ws + W.vt_s; S.ld_lp = static_cast<long long>(W.ldvs); S.lp_fp16 = 1;
+          S.out_lp = ws + W.vt_s; S.ld_lp = static_cast<long long>(W.ldvs); S.lp_fp16 = 1; S.dep = -1;
+          S.hi_only = hio(1);
           TRY(chain_add(cb, ws + W.a_x, 2 * C, pk + P.sa_v, w_lo, S));
         }
-        S = chain_stage(C, 384, CH_EP_SPLIT, PF(P.pe0_b));
-        S.relu = 1; S.a_out = BF(W.a_peh);
-        TRY(chain_add(cb, ws + W.a_pos, 768, pk + P.pe0, w_lo, S));
         // (column-major private streams of the chained path: W.pe = pe, W.y = x, W.x1 = x1, W.x2 = x2 -- see chain_tc.cuh)
         S = chain_stage(C, C, CH_EP_F32, PF(P.pe2_b));
-        S.out_cm = F32(W.pe); S.add_split = BF(W.a_x); S.out_sum_split = BF(W.a_xpe); S.add_cm_out = F32(W.y);
+        S.out_cm = F32(W.pe); S.add_split = BF(W.a_x); S.out_sum_split = BF(W.a_xpe); S.add_cm_out = F32(W.y); S.dep = 0;
+        S.hi_only = hio(4);
         TRY(chain_add(cb, ws + W.a_peh, 2 * C, pk + P.pe2, w_lo, S));
         S = chain_stage(2 * C, C, CH_EP_LP, PF(P.sa_qk_b));
-        S.out_lp = ws + W.qk_s; S.ld_lp = 2 * C; S.lp_fp16 = 1; S.hi_only = (!w_lo && (hi_only & 1)) ? 1 : 0;
+        S.out_lp = ws + W.qk_s; S.ld_lp = 2 * C; S.lp_fp16 = 1; S.hi_only = hio(0);
         TRY(chain_add(cb, ws + W.a_xpe, 2 * C, pk + P.sa_qk, w_lo, S));
         TRY(launch_chain(st, cb));
       }
@@ -1318,10 +1350,10 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
         ChainBuilder cb(R);
         ChainStage S = chain_stage(C, C, CH_EP_LN, PF(P.sa_out_b));
         S.resid_cm = F32(W.y); S.gamma = PF(P.ln1_g); S.beta = PF(P.ln1_b); S.pe_cm = F32(W.pe);
-        S.out_cm = F32(W.x1); S.a_out_pe = BF(W.a_x1pe);
+        S.out_cm = F32(W.x1); S.a_out_pe = BF(W.a_x1pe); S.hi_only = hio(5);
         TRY(chain_add(cb, ws + W.a_attn, 2 * C, pk + P.sa_out, w_lo, S));
         S = chain_stage(C, C, CH_EP_LP, PF(P.ca_q_b));
-        S.out_lp = ws + W.q_c; S.ld_lp = C; S.hi_only = (!w_lo && (hi_only & 4)) ? 1 : 0;
+        S.out_lp = ws + W.q_c; S.ld_lp = C; S.hi_only = hio(2);
         TRY(chain_add(cb, ws + W.a_x1pe, 2 * C, pk + P.ca_q, w_lo, S));
         TRY(launch_chain(st, cb));
       }
@@ -1333,17 +1365,17 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
         ChainBuilder cb(R);
         ChainStage S = chain_stage(C, C, CH_EP_LN, PF(P.ca_out_b));
         S.resid_cm = F32(W.x1); S.gamma = PF(P.ln2_g); S.beta = PF(P.ln2_b);
-        S.out_cm = F32(W.x2); S.a_out = BF(W.a_x2);
+        S.out_cm = F32(W.x2); S.a_out = BF(W.a_x2); S.hi_only = hio(6);
         TRY(chain_add(cb, ws + W.a_attn, 2 * C, pk + P.ca_out, w_lo, S));
         S = chain_stage(F, C, CH_EP_SPLIT, PF(P.lin1_b));
-        S.relu = 1; S.a_out = BF(W.a_ffn);
+        S.relu = 1; S.a_out = BF(W.a_ffn); S.hi_only = hio(7);
         TRY(chain_add(cb, ws + W.a_x2, 2 * C, pk + P.lin1, w_lo, S));
         S = chain_stage(C, F, CH_EP_LN, PF(P.lin2_b));
         S.resid_cm = F32(W.x2); S.gamma = PF(P.ln3_g); S.beta = PF(P.ln3_b);
-        S.out_f32 = x3; S.a_out = BF(W.a_x3);
+        S.out_f32 = x3; S.a_out = BF(W.a_x3); S.hi_only = hio(8);
         TRY(chain_add(cb, ws + W.a_ffn, 2 * F, pk + P.lin2, w_lo, S));
         S = chain_stage(2 * C, C, CH_EP_F32, nullptr);
-        S.out_f32 = F32(W.h1); S.gn_out = reinterpret_cast<double2*>(ws + W.gn1); S.gn_stride = GN_SLOTS_PER_MTILE;
+        S.out_f32 = F32(W.h1); S.gn_out = reinterpret_cast<double2*>(ws + W.gn1); S.gn_stride = GN_SLOTS_PER_MTILE; S.hi_only = hio(9);
         TRY(chain_add(cb, ws + W.a_x3, 2 * C, pk + P.hd1, w_lo, S));
         TRY(launch_chain(st, cb));
       }
@@ -1437,13 +1469,21 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     // K7: heads (two hidden layers with per-clip GroupNorm) + box update
     {
       GemmParams g;
-      { ProfScope ps(TAG_ROWWISE, st); launch_k(gn_apply_kernel, dim3(R), dim3(256), 0, st, F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1),
-                                               PF(P.ctr1_g), PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1)); }
+      { ProfScope ps(TAG_ROWWISE, st);
+        // 8 rows per block from a few thousand rows on (the statistics prologue once per block), one row per block below
+        if (R >= 2048)
+          launch_k(gn_apply_kernel<8>, dim3((R + 7) / 8), dim3(256), 0, st, F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1),
+                   PF(P.ctr1_g), PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1), R);
+        else
+          launch_k(gn_apply_kernel<1>, dim3(R), dim3(256), 0, st, F32(W.h1), 2 * C, C, s.Nq, 2, reinterpret_cast<const double2*>(ws + W.gn1),
+                   PF(P.ctr1_g), PF(P.ctr1_b), PF(P.rot1_g), PF(P.rot1_b), BF(W.a_h1), R);
+      }
       CUDA_TRY(cudaGetLastError());
       // second hidden layer of the centre and rotation heads as ONE launch: the two weight matrices are adjacent in the
       // packed buffer (one B operand of 2C rows), output columns >= C read the rotation half of a_h1
       memset(&g, 0, sizeof(g));
       g.M = R; g.N = 2 * C; term_offsets(g, C, w_lo, 0);
+      if (chained && hio(10)) g.nterms = 1;
       g.a_split_n = C; g.a_split_off = 2 * C;
       g.ep = epilogue_none();
       g.ep.out_f32 = F32(W.h2); g.ep.ld_f32 = 2 * C;
@@ -1465,13 +1505,13 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       hp.R = R; hp.Nq = s.Nq; hp.C = C; hp.num_cls = s.num_cls;
       { ProfScope ps(TAG_ROWWISE, st); {
         const int rpb = (R + device_info().sms - 1) / device_info().sms;     // rows per block: one block per SM
-        const size_t hsm = static_cast<size_t>(HEADS_SLOTS + 4) * C * sizeof(float);
+        const size_t hsm = heads_smem_bytes<1024>();
         if (hp.posemb_next != nullptr) {
           OPT_IN_SMEM((heads_final_kernel<1024, true>), hsm);
-          launch_k(heads_final_kernel<1024, true>, dim3((R + rpb - 1) / rpb), dim3(512), hsm, st, hp, rpb);
+          launch_k(heads_final_kernel<1024, true>, dim3((R + rpb - 1) / rpb), dim3(HEADS_THREADS), hsm, st, hp, rpb);
         } else {
           OPT_IN_SMEM((heads_final_kernel<1024, false>), hsm);
-          launch_k(heads_final_kernel<1024, false>, dim3((R + rpb - 1) / rpb), dim3(512), hsm, st, hp, rpb);
+          launch_k(heads_final_kernel<1024, false>, dim3((R + rpb - 1) / rpb), dim3(HEADS_THREADS), hsm, st, hp, rpb);
         }
       } }
       CUDA_TRY(cudaGetLastError());

@@ -33,7 +33,26 @@ __device__ __forceinline__ bool elect_one() {
 //   pdl_launch_dependents()  -- only now may the NEXT kernel start its own prologue
 // Because a kernel releases its dependents only after its own wait, at most one successor overlaps it, so
 // "produced >= 2 launches earlier" is complete by the time any prologue runs.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Instrumentation (parq_trace): when a trace buffer is set, thread 0 of block 0 of every kernel appends the global timer at the
+// moment its dependency wait returns (= the previous kernel of the stream has completed and flushed).  The difference of
+// consecutive stamps is the time each launch costs on the dependent chain of a forward, gaps included.  Slot 0 holds the count.
+__device__ unsigned long long* g_trace_buf = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if ((threadIdx.x | blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+    unsigned long long* b = g_trace_buf;
+    if (b != nullptr) {
+      const unsigned long long i = atomicAdd(b, 1ull) + 1;
+      if (i < g_trace_cap / 2) b[i] = globaltimer_ns();      // (upper half: per-CTA stamps of the chain kernel)
+    }
+  }
+}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------- mbarrier --

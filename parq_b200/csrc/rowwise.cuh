@@ -35,7 +35,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // concatenated in the order (y, x, z).  out: (R, 2*384) [hi|lo].
 // ---------------------------------------------------------------------------------------------
 // feature j (0..383) of a reference point (rx, ry, rz): axes in the order (y, x, z), sin on even / cos on odd indices
-__device__ __forceinline__ float posemb_value(float rx, float ry, float rz, int j, const float* __restrict__ dim_t) {
+// (not inlined: sinf / cosf carry a large slow path for big arguments; one copy instead of one per call site keeps the heads
+// kernel, which calls this 12 times per row, inside the instruction cache)
+__device__ __noinline__ float posemb_value(float rx, float ry, float rz, int j, const float* __restrict__ dim_t) {
   const int seg = j >> 7, i = j & 127;
   const float r = (seg == 0) ? ry : (seg == 1 ? rx : rz);
   const float a = __fdiv_rn(__fmul_rn(r, 6.283185307179586f), dim_t[i]);
@@ -174,16 +176,18 @@ __device__ __forceinline__ void gn_mean_rstd(const double2* partial, int b, int 
   rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
 }
 
-// out: (B*Nq, groups * 2C): group g's [hi | lo] at columns [g*2C, (g+1)*2C).  One block per row;
-// a thread owns 8 consecutive channels (C/8 threads per group).
+// out: (B*Nq, groups * 2C): group g's [hi | lo] at columns [g*2C, (g+1)*2C).  One block per GN_ROWS consecutive rows (they
+// belong to one clip: Nq % GN_ROWS == 0), so the double-precision reduction of the tile sums runs once per block instead of once
+// per row (it is a serial prologue of ~2-3 k cycles); a thread owns 8 consecutive channels of every row of the block.
+template <int GN_ROWS>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ h, int ldh, int C, int Nq, int groups, const double2* __restrict__ partial,
                 const float* __restrict__ gamma0, const float* __restrict__ beta0, const float* __restrict__ gamma1,
-                const float* __restrict__ beta1, __nv_bfloat16* __restrict__ out) {
+                const float* __restrict__ beta1, __nv_bfloat16* __restrict__ out, int R) {
   pdl_wait();
   pdl_launch_dependents();
-  const int row = blockIdx.x;           // b*Nq + q
-  const int b = row / Nq;
+  const int row0 = blockIdx.x * GN_ROWS;
+  const int b = row0 / Nq;
   const int per_group = C / 8;
   __shared__ float s_stat[2][2];
   if (threadIdx.x < groups) gn_mean_rstd(partial, b, threadIdx.x, C, Nq, s_stat[threadIdx.x][0], s_stat[threadIdx.x][1]);
@@ -193,17 +197,26 @@ gn_apply_kernel(const float* __restrict__ h, int ldh, int C, int Nq, int groups,
     const float mean = s_stat[g][0], rstd = s_stat[g][1];
     const float* gamma = g == 0 ? gamma0 : gamma1;
     const float* beta = g == 0 ? beta0 : beta1;
-    const float* src = h + static_cast<long long>(row) * ldh + g * C + c;
-    const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
     const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
     const float4 e0 = *reinterpret_cast<const float4*>(beta + c), e1 = *reinterpret_cast<const float4*>(beta + c + 4);
-    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     const float be[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-    float o[8];
+    float4 v0[GN_ROWS], v1[GN_ROWS];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = fmaxf((v[k] - mean) * rstd * gg[k] + be[k], 0.f);
-    store_split8(out + static_cast<long long>(row) * (groups * 2 * C) + g * 2 * C + c, C, o);
+    for (int r = 0; r < GN_ROWS; ++r) {                    // all loads of the block's rows in flight together
+      const float* src = h + static_cast<long long>(min(row0 + r, R - 1)) * ldh + g * C + c;
+      v0[r] = *reinterpret_cast<const float4*>(src);
+      v1[r] = *reinterpret_cast<const float4*>(src + 4);
+    }
+#pragma unroll
+    for (int r = 0; r < GN_ROWS; ++r) {
+      if (row0 + r >= R) break;
+      const float v[8] = {v0[r].x, v0[r].y, v0[r].z, v0[r].w, v1[r].x, v1[r].y, v1[r].z, v1[r].w};
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaxf((v[k] - mean) * rstd * gg[k] + be[k], 0.f);
+      store_split8(out + static_cast<long long>(row0 + r) * (groups * 2 * C) + g * 2 * C + c, C, o);
+    }
   }
 }
 
@@ -314,118 +327,167 @@ __device__ __forceinline__ void heads_row_epilogue(const HeadsParams& p, int row
   }
 }
 
-// Block = 16 warps.  The 28 x C final-layer weights (zero rows for unused class slots) and the GroupNorm
-// affine parameters are staged once per block in shared memory (before the dependency wait: they are
-// constants); each warp then walks PAIRS of rows (queries) so that every weight read from shared memory
-// feeds two rows: 2 x 28 independent dot-product chains per lane, a butterfly reduction, and an epilogue
-// in which lane j owns output slot j (softmax/arg-max through warp shuffles).
-// kPosemb: also write pos2posemb3d of the next reference point (HeadsParams::posemb_next); a separate instantiation so that
-// the common one keeps its register budget (the extra code spills under the 128-register cap of 512 threads).
+// 1-D bulk copy global -> shared (TMA engine, no tensor map), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Sum over the 32 lanes of 32 per-lane values so that lane j ends up with the total of slot j: a halving exchange
+// (16 + 8 + 4 + 2 + 1 = 31 shuffles) instead of 32 full butterflies (160).
+__device__ __forceinline__ float reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float keep = up ? v[w + k] : v[k];
+      const float send = up ? v[k] : v[w + k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
+
+// Block = 8 warps.  The 28 x C final-layer weights (zero rows for unused class slots) and the GroupNorm affine parameters
+// are staged once per block in shared memory by bulk copies issued before the dependency wait (they are constants); the
+// GroupNorm statistics of the (at most two) clips the block's rows belong to are reduced once per block.  A warp then takes
+// FOUR rows (queries) at a time: every 16-byte weight read from shared memory feeds four rows (with two, the kernel was
+// bound by the shared-memory bandwidth: 28 rows x 112 KB of weights per SM), 4 x 28 independent dot-product chains per
+// lane, a halving reduction that leaves output slot j in lane j, and an epilogue with softmax / arg-max through shuffles.
+// kPosemb: also write pos2posemb3d of the next reference point (HeadsParams::posemb_next).
+constexpr int HEADS_THREADS = 256;
+constexpr int HEADS_NR = 4;
+template <int C>
+constexpr size_t heads_smem_bytes() { return static_cast<size_t>(HEADS_SLOTS + 4) * C * sizeof(float) + 64; }
+
 template <int C, bool kPosemb>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(HEADS_THREADS)
 heads_final_kernel(const HeadsParams p, int rows_per_block) {
-  constexpr int NR = 2;
-  extern __shared__ float sw[];           // [HEADS_SLOTS][C] weights, then gamma_c | beta_c | gamma_r | beta_r
+  constexpr int NR = HEADS_NR;
+  extern __shared__ __align__(128) float sw[];           // [HEADS_SLOTS][C] weights, then gamma_c | beta_c | gamma_r | beta_r
   float* s_aff = sw + HEADS_SLOTS * C;
-  for (int i = threadIdx.x * 4; i < HEADS_SLOTS * C; i += blockDim.x * 4) {
-    const int j = i / C, c = i % C;
-    const float* src = nullptr;
-    if (j < HEADS_CLS_SLOTS) src = j < p.num_cls ? p.w_cls + j * C : nullptr;
-    else if (j < HEADS_CLS_SLOTS + 3) src = p.w_size + (j - HEADS_CLS_SLOTS) * C;
-    else if (j < HEADS_CLS_SLOTS + 6) src = p.w_c3 + (j - HEADS_CLS_SLOTS - 3) * C;
-    else src = p.w_r3 + (j - HEADS_CLS_SLOTS - 6) * C;
-    *reinterpret_cast<float4*>(sw + i) = src ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_aff + 4 * C);
+  float* s_stat = reinterpret_cast<float*>(bar + 1);      // [2 clips][2 groups][mean, rstd]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    const uint32_t row_b = C * sizeof(float);
+    mbar_expect_tx(bar, static_cast<uint32_t>(p.num_cls + 3 + 3 + 6 + 4) * row_b);
+    bulk_g2s(sw, p.w_cls, p.num_cls * row_b, bar);
+    bulk_g2s(sw + HEADS_CLS_SLOTS * C, p.w_size, 3 * row_b, bar);
+    bulk_g2s(sw + (HEADS_CLS_SLOTS + 3) * C, p.w_c3, 3 * row_b, bar);
+    bulk_g2s(sw + (HEADS_CLS_SLOTS + 6) * C, p.w_r3, 6 * row_b, bar);
+    bulk_g2s(s_aff, p.gamma_c, row_b, bar);
+    bulk_g2s(s_aff + C, p.beta_c, row_b, bar);
+    bulk_g2s(s_aff + 2 * C, p.gamma_r, row_b, bar);
+    bulk_g2s(s_aff + 3 * C, p.beta_r, row_b, bar);
   }
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    s_aff[i] = p.gamma_c[i]; s_aff[C + i] = p.beta_c[i]; s_aff[2 * C + i] = p.gamma_r[i]; s_aff[3 * C + i] = p.beta_r[i];
-  }
+  for (int i = p.num_cls * C + threadIdx.x * 4; i < HEADS_CLS_SLOTS * C; i += HEADS_THREADS * 4)     // unused class slots
+    *reinterpret_cast<float4*>(sw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   // everything above is constant weights: staged while the previous kernel drains
   pdl_wait();
   pdl_launch_dependents();
+  const int row_begin = blockIdx.x * rows_per_block;
+  const int row_end = min(p.R, row_begin + rows_per_block);
+  const int clip0 = row_begin / p.Nq;
+  if (threadIdx.x < 4) {
+    const int clip = min(clip0 + (threadIdx.x >> 1), (p.R - 1) / p.Nq);
+    gn_mean_rstd(p.partial, clip, threadIdx.x & 1, C, p.Nq, s_stat[threadIdx.x * 2], s_stat[threadIdx.x * 2 + 1]);
+  }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int row_end = min(p.R, (blockIdx.x + 1) * rows_per_block);
-  for (int row0 = blockIdx.x * rows_per_block + NR * (threadIdx.x >> 5); row0 < row_end; row0 += NR * (blockDim.x >> 5)) {
+  mbar_wait(bar, 0);
+  for (int row0 = row_begin + NR * warp; row0 < row_end; row0 += NR * (HEADS_THREADS >> 5)) {
     float mean_c[NR], rstd_c[NR], mean_r[NR], rstd_r[NR];
     long long xoff[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      const int row = min(row0 + r, row_end - 1);          // a missing second row repeats the first (result discarded)
+      const int row = min(row0 + r, row_end - 1);          // missing rows repeat the last one (results discarded)
       xoff[r] = static_cast<long long>(row) * C;
-      float mean_l = 0.f, rstd_l = 0.f;
-      if (lane < 2) gn_mean_rstd(p.partial, row / p.Nq, lane, C, p.Nq, mean_l, rstd_l);
-      mean_c[r] = __shfl_sync(0xffffffffu, mean_l, 0); rstd_c[r] = __shfl_sync(0xffffffffu, rstd_l, 0);
-      mean_r[r] = __shfl_sync(0xffffffffu, mean_l, 1); rstd_r[r] = __shfl_sync(0xffffffffu, rstd_l, 1);
+      const float* st = s_stat + (row / p.Nq - clip0) * 4;
+      mean_c[r] = st[0]; rstd_c[r] = st[1]; mean_r[r] = st[2]; rstd_r[r] = st[3];
     }
-    float acc[NR][HEADS_SLOTS];
+    float acc[NR][32];
 #pragma unroll
     for (int r = 0; r < NR; ++r)
 #pragma unroll
-      for (int j = 0; j < HEADS_SLOTS; ++j) acc[r][j] = 0.f;
-    // a lane owns 4 consecutive channels per step (16-byte global and shared loads); the loads of step i+1 are
-    // issued before the arithmetic of step i
+      for (int j = 0; j < 32; ++j) acc[r][j] = 0.f;
+    // a lane owns 4 consecutive channels per step (16-byte global and shared loads); the 12 loads of a step are issued
+    // together, the inputs are converted in place (x | relu(GN(h2 centre)) | relu(GN(h2 rotation)))
     constexpr int STEPS = C / 128;
-    float4 nx[NR], na[NR], nq[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      nx[r] = *reinterpret_cast<const float4*>(p.x + xoff[r] + lane * 4);
-      na[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xoff[r] + lane * 4);
-      nq[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xoff[r] + C + lane * 4);
-    }
 #pragma unroll 1
     for (int i = 0; i < STEPS; ++i) {
       const int c = i * 128 + lane * 4;
-      float4 cx[NR], ca[NR], cq[NR];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) { cx[r] = nx[r]; ca[r] = na[r]; cq[r] = nq[r]; }
-      if (i + 1 < STEPS) {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          nx[r] = *reinterpret_cast<const float4*>(p.x + xoff[r] + c + 128);
-          na[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xoff[r] + c + 128);
-          nq[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xoff[r] + C + c + 128);
-        }
-      }
-      const float4 gc = *reinterpret_cast<const float4*>(s_aff + c), bc = *reinterpret_cast<const float4*>(s_aff + C + c);
-      const float4 gr = *reinterpret_cast<const float4*>(s_aff + 2 * C + c), br = *reinterpret_cast<const float4*>(s_aff + 3 * C + c);
-      float xv[NR][4], hc[NR][4], hr[NR][4];
+      float4 vx[NR], vc[NR], vr[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        xv[r][0] = cx[r].x; xv[r][1] = cx[r].y; xv[r][2] = cx[r].z; xv[r][3] = cx[r].w;
-        hc[r][0] = fmaxf((ca[r].x - mean_c[r]) * rstd_c[r] * gc.x + bc.x, 0.f);
-        hc[r][1] = fmaxf((ca[r].y - mean_c[r]) * rstd_c[r] * gc.y + bc.y, 0.f);
-        hc[r][2] = fmaxf((ca[r].z - mean_c[r]) * rstd_c[r] * gc.z + bc.z, 0.f);
-        hc[r][3] = fmaxf((ca[r].w - mean_c[r]) * rstd_c[r] * gc.w + bc.w, 0.f);
-        hr[r][0] = fmaxf((cq[r].x - mean_r[r]) * rstd_r[r] * gr.x + br.x, 0.f);
-        hr[r][1] = fmaxf((cq[r].y - mean_r[r]) * rstd_r[r] * gr.y + br.y, 0.f);
-        hr[r][2] = fmaxf((cq[r].z - mean_r[r]) * rstd_r[r] * gr.z + br.z, 0.f);
-        hr[r][3] = fmaxf((cq[r].w - mean_r[r]) * rstd_r[r] * gr.w + br.w, 0.f);
+        vx[r] = *reinterpret_cast<const float4*>(p.x + xoff[r] + c);
+        vc[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xoff[r] + c);
+        vr[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xoff[r] + C + c);
       }
 #pragma unroll
-      for (int j = 0; j < HEADS_SLOTS; ++j) {
+      for (int j = 0; j < HEADS_CLS_SLOTS + 3; ++j) {
         const float4 w = *reinterpret_cast<const float4*>(sw + j * C + c);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          const float* v = j < HEADS_CLS_SLOTS + 3 ? xv[r] : (j < HEADS_CLS_SLOTS + 6 ? hc[r] : hr[r]);
-          acc[r][j] = fmaf(w.x, v[0], acc[r][j]);
-          acc[r][j] = fmaf(w.y, v[1], acc[r][j]);
-          acc[r][j] = fmaf(w.z, v[2], acc[r][j]);
-          acc[r][j] = fmaf(w.w, v[3], acc[r][j]);
+          acc[r][j] = fmaf(w.x, vx[r].x, acc[r][j]);
+          acc[r][j] = fmaf(w.y, vx[r].y, acc[r][j]);
+          acc[r][j] = fmaf(w.z, vx[r].z, acc[r][j]);
+          acc[r][j] = fmaf(w.w, vx[r].w, acc[r][j]);
+        }
+      }
+      {
+        const float4 g = *reinterpret_cast<const float4*>(s_aff + c), b = *reinterpret_cast<const float4*>(s_aff + C + c);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          vc[r].x = fmaxf((vc[r].x - mean_c[r]) * rstd_c[r] * g.x + b.x, 0.f);
+          vc[r].y = fmaxf((vc[r].y - mean_c[r]) * rstd_c[r] * g.y + b.y, 0.f);
+          vc[r].z = fmaxf((vc[r].z - mean_c[r]) * rstd_c[r] * g.z + b.z, 0.f);
+          vc[r].w = fmaxf((vc[r].w - mean_c[r]) * rstd_c[r] * g.w + b.w, 0.f);
+        }
+      }
+#pragma unroll
+      for (int j = HEADS_CLS_SLOTS + 3; j < HEADS_CLS_SLOTS + 6; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(sw + j * C + c);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          acc[r][j] = fmaf(w.x, vc[r].x, acc[r][j]);
+          acc[r][j] = fmaf(w.y, vc[r].y, acc[r][j]);
+          acc[r][j] = fmaf(w.z, vc[r].z, acc[r][j]);
+          acc[r][j] = fmaf(w.w, vc[r].w, acc[r][j]);
+        }
+      }
+      {
+        const float4 g = *reinterpret_cast<const float4*>(s_aff + 2 * C + c), b = *reinterpret_cast<const float4*>(s_aff + 3 * C + c);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          vr[r].x = fmaxf((vr[r].x - mean_r[r]) * rstd_r[r] * g.x + b.x, 0.f);
+          vr[r].y = fmaxf((vr[r].y - mean_r[r]) * rstd_r[r] * g.y + b.y, 0.f);
+          vr[r].z = fmaxf((vr[r].z - mean_r[r]) * rstd_r[r] * g.z + b.z, 0.f);
+          vr[r].w = fmaxf((vr[r].w - mean_r[r]) * rstd_r[r] * g.w + b.w, 0.f);
+        }
+      }
+#pragma unroll
+      for (int j = HEADS_CLS_SLOTS + 6; j < HEADS_SLOTS; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(sw + j * C + c);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          acc[r][j] = fmaf(w.x, vr[r].x, acc[r][j]);
+          acc[r][j] = fmaf(w.y, vr[r].y, acc[r][j]);
+          acc[r][j] = fmaf(w.z, vr[r].z, acc[r][j]);
+          acc[r][j] = fmaf(w.w, vr[r].w, acc[r][j]);
         }
       }
     }
+    float mine_r[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int j = 0; j < HEADS_SLOTS; ++j) acc[r][j] += __shfl_xor_sync(0xffffffffu, acc[r][j], o);
-      // lane j keeps output slot j
-      float mine = 0.f;
-#pragma unroll
-      for (int j = 0; j < HEADS_SLOTS; ++j)
-        if (lane == j) mine = acc[r][j];
-      if (row0 + r < row_end) heads_row_epilogue<kPosemb>(p, row0 + r, lane, mine);
+    for (int r = 0; r < NR; ++r) mine_r[r] = reduce_scatter32(acc[r], lane);     // lane j keeps output slot j
+#pragma unroll 1
+    for (int r = 0; r < NR && row0 + r < row_end; ++r) {      // one copy of the epilogue code
+      const float mine = r == 0 ? mine_r[0] : (r == 1 ? mine_r[1] : (r == 2 ? mine_r[2] : mine_r[3]));
+      heads_row_epilogue<kPosemb>(p, row0 + r, lane, mine);
     }
   }
 }
