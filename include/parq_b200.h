@@ -91,6 +91,8 @@ typedef struct ParqOutputs {
 #define PARQ_FLAG_HI_ONLY_SHIFT 16
 #define PARQ_FLAG_HI_ONLY_MASK 0x07FF0000u
 #define PARQ_FLAG_HI_ONLY_SET 0x08000000u
+#define PARQ_FLAG_FUSED_MERGE 512u /* merge the stream-K pieces of the cross-attention inside the attention kernel (flags + spin
+                                     * wait on an earlier-scheduled CTA pair) instead of the attn3_combine_kernel launch; off by default */
 #define PARQ_FLAG_NO_PDL 4u      /* launch without programmatic dependent launch (plain stream order; for A/B timing) */
 
 int parq_version(void);

@@ -29,7 +29,21 @@ struct Attn3Params {
   float2* ml_part;         // [(pair*slots + seg)*256 + row] = (m, l)
   __nv_bfloat16* out;      // (B*Nq, 2*H*256) [hi|lo]: direct output of whole-item segments
   int kv_const, kv_tiled;
+  uint32_t* flags;         // fused merge (items cut into <= 3 pieces), or null: [(pair*2 + rank)*4 + softmax warp], all zero before and
+                           // after a launch.  A piece that does not start its item is always the FIRST segment of its pair; its four
+                           // softmax warps publish their rows with flag = 1.  The pair that holds the item's first piece finishes it at
+                           // the very end of its range: it waits for those flags, folds the other pieces into its own O (still in
+                           // TMEM), writes the final operand and clears the flags -- no attn3_combine_kernel launch.
 };
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* ptr) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(uint32_t* ptr, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ long long sk_unit_begin(long long units, int npairs, int pair) {
   return units * pair / npairs;
@@ -58,7 +72,9 @@ attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();      // == blockIdx.x: which 128-query half of the item's 256 queries
   const bool leader = rank == 0;
-  const int pair = blockIdx.y;
+  // ranges are handed out in REVERSE block order: the pair that merges an item waits for pairs with higher range indices, i.e.
+  // for blocks with lower indices -- blocks that are scheduled first even if the grid were ever not fully resident
+  const int pair = p.npairs - 1 - static_cast<int>(blockIdx.y);
   const long long u0 = sk_unit_begin(p.units, p.npairs, pair), u1 = sk_unit_begin(p.units, p.npairs, pair + 1);
 
   if (warp == 0 && lane == 0) {
@@ -237,8 +253,21 @@ attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       int b, h, qt;
       item_bh(s.item, b, h, qt);
       float m_run = -INFINITY, l_run = 0.f;
+      const bool merger = p.flags != nullptr && s.ta == 0 && s.n < p.ntiles;
       for (int j = 0; j < s.n; ++j, ++g) {
         const int buf = g & 1;
+        if (merger && j == (s.n > 8 ? s.n - 8 : 0)) {
+          // a few tiles before the merge: pull this row of the other pieces (written long ago, evicted by the K / V^T stream) back
+          // into L2 -- the merge at the end of the kernel is a chain of dependent round trips on every SM at once
+          const long long ub = static_cast<long long>(s.item) * p.ntiles + p.ntiles - 1;
+          const int my_row = static_cast<int>(rank) * BQ + q * 32 + lane;
+          for (int k = 1; k <= 2; ++k) {
+            if (pair + k >= p.npairs || sk_unit_begin(p.units, p.npairs, pair + k) > ub) break;
+            const float* src = p.o_part + ((static_cast<long long>(pair + k) * p.slots) * 256 + my_row) * DH;
+#pragma unroll
+            for (int i = 0; i < DH * 4 / 128; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + i * 32));
+          }
+        }
         mbar_wait(&s_full[buf], (g >> 1) & 1);
         tc_fence_after();
         const uint32_t s_tmem = tmem_base + lane_base + buf * 128;
@@ -325,8 +354,78 @@ attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             reinterpret_cast<uint4*>(dst + C + c * 32)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
         }
+      } else if (p.flags != nullptr && s.ta == 0) {
+        // fused merge: this pair holds the FIRST piece of the item and finishes it last; the other pieces are the first
+        // segments of the following pairs (at most two of them)
+        const long long ub = static_cast<long long>(s.item) * p.ntiles + p.ntiles - 1;
+        const int my_row = static_cast<int>(rank) * BQ + q * 32 + lane;
+        // piece k lives in pair + 1 + k; the second one exists when that pair's range still starts inside the item
+        const bool two = pair + 2 < p.npairs && sk_unit_begin(p.units, p.npairs, pair + 2) <= ub;
+        const int nk = two ? 2 : 1;
+        if (lane == 0) {
+          for (int k = 0; k < nk; ++k)
+            while (ld_acquire_gpu_u32(p.flags + ((pair + 1 + k) * 2 + static_cast<int>(rank)) * 4 + q) == 0u) __nanosleep(100);
+        }
+        __syncwarp();
+        const long long part0 = (static_cast<long long>(pair + 1) * p.slots) * 256 + my_row;
+        const long long part1 = two ? (static_cast<long long>(pair + 2) * p.slots) * 256 + my_row : part0;
+        const float2 ml0 = __ldcg(&p.ml_part[part0]);
+        const float2 ml1 = two ? __ldcg(&p.ml_part[part1]) : make_float2(-INFINITY, 0.f);
+        const float* ok[2] = {p.o_part + part0 * DH, p.o_part + part1 * DH};
+        const float M = fmaxf(fmaxf(m_run, ml0.x), ml1.x);
+        const float w_me = fast_exp2(m_run - M);
+        const float wk[2] = {fast_exp2(ml0.x - M), two ? fast_exp2(ml1.x - M) : 0.f};
+        const float L = l_run * w_me + wk[0] * ml0.y + wk[1] * ml1.y;
+        const float inv = 1.f / L;
+        const float s_me = w_me * inv, s0 = wk[0] * inv, s1 = wk[1] * inv;
+        const int C = p.H * DH;
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.Nq + qt * BQ + q * 32 + lane) * (2 * C) + h * DH;
+        float4 a0[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a0[i] = __ldcg(reinterpret_cast<const float4*>(ok[0]) + i);
+#pragma unroll 1
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_base + c * 32, o);
+          tmem_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[4 * i] = __uint_as_float(o[4 * i]) * s_me + a0[i].x * s0;
+            v[4 * i + 1] = __uint_as_float(o[4 * i + 1]) * s_me + a0[i].y * s0;
+            v[4 * i + 2] = __uint_as_float(o[4 * i + 2]) * s_me + a0[i].z * s0;
+            v[4 * i + 3] = __uint_as_float(o[4 * i + 3]) * s_me + a0[i].w * s0;
+          }
+          if (c + 1 < DH / 32) {                              // the next chunk of the first piece, in flight during the stores below
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a0[i] = __ldcg(reinterpret_cast<const float4*>(ok[0] + (c + 1) * 32) + i);
+          }
+          if (two) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 a1 = __ldcg(reinterpret_cast<const float4*>(ok[1] + c * 32) + i);
+              v[4 * i] += a1.x * s1; v[4 * i + 1] += a1.y * s1; v[4 * i + 2] += a1.z * s1; v[4 * i + 3] += a1.w * s1;
+            }
+          }
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            lo[i] = pack_bf16x2(v[2 * i] - __uint_as_float(hi[i] << 16), v[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            reinterpret_cast<uint4*>(dst + c * 32)[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            reinterpret_cast<uint4*>(dst + C + c * 32)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          }
+        }
+        // the pieces are consumed: flags back to zero for the next launch
+        __syncwarp();
+        if (lane == 0) {
+          for (int k = 0; k < nk; ++k) p.flags[((pair + 1 + k) * 2 + static_cast<int>(rank)) * 4 + q] = 0u;
+        }
       } else {
-        // un-normalised O, m, l of this segment for attn3_combine_kernel
+        // un-normalised O, m, l of this segment for the merge (attn3_combine_kernel, or the pair that holds the item's first piece)
         const long long part = (static_cast<long long>(pair) * p.slots + segi) * 256 + static_cast<int>(rank) * BQ + q * 32 + lane;
         float* orow = p.o_part + part * DH;
 #pragma unroll 1
@@ -341,6 +440,11 @@ attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             __uint_as_float(o[4 * i + 3]));
         }
         p.ml_part[part] = make_float2(m_run, l_run);
+        if (p.flags != nullptr) {
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) st_release_gpu_u32(p.flags + (pair * 2 + static_cast<int>(rank)) * 4 + q, 1u);
+        }
       }
       tc_fence_before();
       mbar_arrive_leader(o_free);         // this CTA's O rows are read: the next segment may overwrite them
@@ -365,6 +469,7 @@ attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // One block per (item, 32 of its 256 query rows): the 64-bit range arithmetic that locates the item's pieces runs once
 // per block; 64 threads per row, a thread owns 4 consecutive channels.
 constexpr int SK_COMBINE_ROWS = 8;       // rows of an item per block (a thread walks rows / 4 of them): 8 -> 2 048 blocks at config 2
+constexpr int SK_FLAG_WORDS = 1024;       // Attn3Params::flags: (pair, rank, softmax warp) words, >= 2 * 4 * SK_MAX_PAIRS
 constexpr int SK_MAX_PAIRS = 128;        // CTA pairs the schedule may use (74 on a B200)
 
 // kWide (few items cut into many pieces each: one clip on the whole machine): the four 64-thread groups of a block share ONE row

@@ -148,7 +148,13 @@ static const int g_combine_rows = (getenv("PARQ_COMBINE_ROWS") && (atoi(getenv("
 static const bool g_no_narrow = getenv("PARQ_NO_NARROW") != nullptr;         // A/B switch: 256-column tiles also for GEMMs of a few row tiles
 static const bool g_no_chain_v = getenv("PARQ_NO_CHAIN_V") != nullptr;       // A/B switch: self-attention V^T as its own GEMM launch instead of stage 0 of chain P
 static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;
+static const bool g_fused_merge = getenv("PARQ_FUSED_MERGE") != nullptr;  // opt-in: merge the stream-K pieces inside the attention kernel instead of the attn3_combine_kernel launch
 static const int g_chain_min_rows = getenv("PARQ_CHAIN_MIN_ROWS") ? atoi(getenv("PARQ_CHAIN_MIN_ROWS")) : 2048;
+// Default: every GEMM keeps its low-order activation term.  Dropping it for the three GEMMs whose output is rounded to 16 bits
+// right away (mask 7: self-attention Q|K and V^T, cross-attention Q) buys -0.25 +- 0.06 ms per step at config 2 (in-process A/B,
+// tools/ab_step.py: the step is power-capped, removed tensor work is removed time) and stays inside the 1e-3 bar (1.0e-4 ->
+// 4-5e-4), but it flips the arg-max class of a near-tied query of the reference's own fixture (and 2 of 32 768 at config 2),
+// which changes size_unnormalized of that query visibly: parity first, so it stays an opt-in (PARQ_FLAG_HI_ONLY_SET, PARQ_HI_ONLY).
 constexpr int HI_ONLY_DEFAULT = 0;
 static const int g_hi_only = getenv("PARQ_HI_ONLY") ? atoi(getenv("PARQ_HI_ONLY")) : 0;   // ablation: bit0 sa_qk, bit1 sa_v, bit2 ca_q use the hi activation term only           // A/B switch: separate GEMM + LayerNorm launches instead of chain_tc.cuh
 static const bool g_force_pair = getenv("PARQ_FORCE_PAIR") != nullptr;   // every GEMM on the CTA-pair kernel (tests)
@@ -398,7 +404,8 @@ static size_t streamk_scratch_bytes(int B, int H, int Nq, int Nk, int sms) {
 
 static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const void* K, uint64_t ldk, const void* Vt,
                             uint64_t ldv, int B, int H, int Nq, int Nk, bool fp16, void* scratch, size_t scratch_bytes,
-                            __nv_bfloat16* out_split, int force_nsplit, bool kv_const = false, bool kv_tiled = false) {
+                            __nv_bfloat16* out_split, int force_nsplit, bool kv_const = false, bool kv_tiled = false,
+                            uint32_t* sk_flags = nullptr) {
   if (Nq % attn::BQ != 0) return fail(PARQ_ERR_SHAPE, "Nq=%d must be a multiple of 128", Nq);
   const int ntiles = (Nk + attn::BKEY - 1) / attn::BKEY;
   const SplitPlan plan = plan_split(B * H * (Nq / attn::BQ), ntiles, device_info().sms, force_nsplit < 0 ? 0 : force_nsplit);
@@ -445,6 +452,8 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
       sp.out = out_split;
       sp.kv_const = kv_const ? 1 : 0;
       sp.kv_tiled = kv_tiled ? 1 : 0;
+      // fused merge (attn3_tc.cuh) when no item is cut into more than three pieces: the shortest range covers half an item
+      sp.flags = (sk_flags != nullptr && 2 * (sp.units / sp.npairs) >= ntiles && 2 * sp.npairs * 4 <= SK_FLAG_WORDS) ? sk_flags : nullptr;
       {
         ProfScope ps(fp16 ? TAG_SELF_ATTN : TAG_CROSS_ATTN, st);
         if (fp16)
@@ -453,7 +462,7 @@ static int launch_attention(cudaStream_t st, const void* Q, uint64_t ldq, const 
           launch_kc(attn3_tc_kernel<false>, dim3(2, sp.npairs, 1), dim3(attn::THREADS), attn::SMEM_BYTES, st, dim3(2, 1, 1), tmQ, tmK, tmV, sp);
       }
       CUDA_TRY(cudaGetLastError());
-      {
+      if (sp.flags == nullptr) {
         ProfScope ps(TAG_COMBINE, st);
         const int items = B * H * sp.qpairs;
         if (2 * items <= sp.npairs)      // every item is cut into >= 3 pieces: 2 rows per block, the block's thread groups share a row
@@ -565,7 +574,7 @@ __global__ void copy_scale_kernel(const float* __restrict__ src, float* __restri
 // --------------------------------------------------------------------------- workspace layout --
 struct Workspace {
   size_t Kc, Vt, T_cl, ref_cur, a_pos, a_peh, pe, a_x, a_xpe, qk_s, vt_s, scratch, a_attn, y, x1, x2, x3, a_x1pe, q_c,
-      a_x2, a_ffn, a_x3, h1, a_h1, h2, gn1, gn2;
+      a_x2, a_ffn, a_x3, h1, a_h1, h2, gn1, gn2, sk_flags;
   size_t scratch_bytes, ldv, ldvs, total;
   int kv_tiled, ntile;      // tile-contiguous K / V^T caches (needs Nk % 32 == 0), key tiles per clip
   SplitPlan cross, self;
@@ -618,6 +627,7 @@ static Workspace workspace_layout(const ParqShape& s, int sms) {
   w.h2 = take(R * 2 * C * 4);
   w.gn1 = take(R / 128 * GN_SLOTS_PER_MTILE * sizeof(double2));
   w.gn2 = take(R / 128 * GN_SLOTS_PER_MTILE * sizeof(double2));
+  w.sk_flags = take(SK_FLAG_WORDS * sizeof(uint32_t));      // fused merge of the stream-K cross-attention: zero between launches
   w.total = off;
   return w;
 }
@@ -1257,7 +1267,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   // the row-local linears of an iteration as three chained launches (chain_tc.cuh) instead of ten GEMMs + three LayerNorms
   // Low-order activation term of the three GEMMs whose output is rounded to 16 bits (self-attention Q|K and V^T in fp16,
   // cross-attention Q in bf16): PARQ_HI_ONLY (environment) overrides the default for the ablation of DESIGN.md
-  // bits: 0 sa_qk, 1 sa_v, 2 ca_q, 3 pe0, 4 pe2, 5 sa_out, 6 ca_out, 7 lin1, 8 lin2, 9 hd1, 10 hd2 (chained path, bf16-exact weights)
+  // bits: 0 sa_qk, 1 sa_v, 2 ca_q (both launch paths), 3 pe0, 4 pe2, 5 sa_out, 6 ca_out, 7 lin1, 8 lin2, 9 hd1, 10 hd2 (chained
+  // path only); bf16-exact weights
   const int hi_only = getenv("PARQ_HI_ONLY") ? g_hi_only
                       : ((flags & PARQ_FLAG_HI_ONLY_SET) ? static_cast<int>((flags & PARQ_FLAG_HI_ONLY_MASK) >> PARQ_FLAG_HI_ONLY_SHIFT) & 0x7FF
                                                          : HI_ONLY_DEFAULT);
@@ -1270,6 +1281,10 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
   auto BF = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
   auto PF = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
 
+  // piece flags of the fused stream-K merge (attn3_tc.cuh): every launch leaves them zero, this covers the first use of a workspace
+  // (opt-in: in the power-capped steady state of config 2 the step time is the same with either merge)
+  const bool fused_merge = (flags & PARQ_FLAG_FUSED_MERGE) != 0 || g_fused_merge;
+  if (fused_merge) CUDA_TRY(cudaMemsetAsync(ws + W.sk_flags, 0, SK_FLAG_WORDS * sizeof(uint32_t), st));
   // K0: pose chain
   { ProfScope ps(TAG_ROWWISE, st); launch_k(pose_chain_kernel, dim3((s.B * s.T + 127) / 128), dim3(128), 0, st, T_cp, T_wp, T_wl, F32(W.T_cl), s.B, s.T); }
   CUDA_TRY(cudaGetLastError());
@@ -1337,7 +1352,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       // (A/B switch PARQ_NO_CHAIN_V) V^T = Wv x^T + bv of the self-attention as its own GEMM: weights are the A operand, activations the B operand
       if (g_no_chain_v) {
         GemmParams g; memset(&g, 0, sizeof(g));
-        g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : ((hi_only & 2) ? 1 : 2); g.const_operand = 1;
+        g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : (hio(1) ? 1 : 2); g.const_operand = 1;
         g.a_koff[0] = 0; g.b_koff[0] = 0; g.a_koff[1] = 0; g.b_koff[1] = C; g.a_koff[2] = C; g.b_koff[2] = 0;
         g.ep = epilogue_none(); g.ep.bias = PF(P.sa_v_b); g.ep.bias_per_row = 1;
         g.ep.out_lp = ws + W.vt_s; g.ep.ld_lp = static_cast<long long>(W.ldvs); g.ep.lp_fp16 = 1;
@@ -1359,7 +1374,7 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       }
       TRY(launch_attention(st, ws + W.q_c, C, ws + W.Kc, C, ws + W.Vt, W.ldv, s.B, s.heads, s.Nq, Nk, false, ws + W.scratch,
                            W.scratch_bytes, BF(W.a_attn), /*library's choice: stream-K or the planned split*/ 0, /*kv_const=*/true,
-                           W.kv_tiled != 0));
+                           W.kv_tiled != 0, fused_merge ? reinterpret_cast<uint32_t*>(ws + W.sk_flags) : nullptr));
       // ---- chain B: cross-attention out-projection + residual + LN2 -> FFN -> + residual + LN3 -> first head layer
       {
         ChainBuilder cb(R);
@@ -1400,12 +1415,13 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     {
       GemmParams g; memset(&g, 0, sizeof(g));
       g.M = R; g.N = 2 * C; term_offsets(g, C, w_lo, 0);
+      if (hio(0)) g.nterms = 1;
       g.ep = epilogue_none(); g.ep.bias = PF(P.sa_qk_b);
       g.ep.out_lp = ws + W.qk_s; g.ep.ld_lp = 2 * C; g.ep.lp_fp16 = 1;
       TRY(launch_gemm(st, ws + W.a_xpe, R, 2 * C, pk + P.sa_qk, 2 * C, 2 * C, g));
       // V^T = Wv x^T + bv : weights are the A operand, activations the B operand
       memset(&g, 0, sizeof(g));
-      g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : 2; g.const_operand = 1;
+      g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : (hio(1) ? 1 : 2); g.const_operand = 1;
       g.a_koff[0] = 0; g.b_koff[0] = 0; g.a_koff[1] = 0; g.b_koff[1] = C; g.a_koff[2] = C; g.b_koff[2] = 0;
       g.ep = epilogue_none(); g.ep.bias = PF(P.sa_v_b); g.ep.bias_per_row = 1;
       g.ep.out_lp = ws + W.vt_s; g.ep.ld_lp = static_cast<long long>(W.ldvs); g.ep.lp_fp16 = 1;
@@ -1426,12 +1442,13 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     {
       GemmParams g; memset(&g, 0, sizeof(g));
       g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
+      if (hio(2)) g.nterms = 1;
       g.ep = epilogue_none(); g.ep.bias = PF(P.ca_q_b);
       g.ep.out_lp = ws + W.q_c; g.ep.ld_lp = C;
       TRY(launch_gemm(st, ws + W.a_x1pe, R, 2 * C, pk + P.ca_q, C, 2 * C, g));
       TRY(launch_attention(st, ws + W.q_c, C, ws + W.Kc, C, ws + W.Vt, W.ldv, s.B, s.heads, s.Nq, Nk, false, ws + W.scratch,
                            W.scratch_bytes, BF(W.a_attn), /*library's choice: stream-K or the planned split*/ 0, /*kv_const=*/true,
-                           W.kv_tiled != 0));
+                           W.kv_tiled != 0, fused_merge ? reinterpret_cast<uint32_t*>(ws + W.sk_flags) : nullptr));
       memset(&g, 0, sizeof(g));
       g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
       g.ep = epilogue_none(); g.ep.bias = PF(P.ca_out_b);

@@ -111,6 +111,20 @@ def test_config2_full_size_all_clips_against_reference(dev):
     torch.cuda.synchronize()
     for k in OUT_KEYS:
         assert torch.equal(rep[k], got[k]), k
+    # the opt-in merge of the stream-K pieces inside the attention kernel (flags + spin wait) against the separate merge launch:
+    # same pieces, another summation order
+    fm = eng.forward(tokens.to(dev).bfloat16(), cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev), H, W, forced_refs=refs.to(dev), debug=True,
+                     fused_merge=True)
+    torch.cuda.synchronize()
+    for k in ("pred_logits", "center_unnormalized", "ortho6d", "sem_cls_prob", "decoder_out"):
+        assert relerr(fm[k].cpu(), got[k].cpu()) <= 1e-4, (k, "fused merge")
+    # ... and the opt-in that drops the low-order activation term of the three 16-bit-output GEMMs (hi_only=7): inside the bar, a few
+    # arg-max flips of near-tied queries (reported; the default keeps every term)
+    ho = eng.forward(tokens.to(dev).bfloat16(), cam.to(dev), Tcp.to(dev), Twp.to(dev), Twl.to(dev), H, W, forced_refs=refs.to(dev), debug=True,
+                     hi_only=7)
+    torch.cuda.synchronize()
+    worst7, flips7 = check_teacher_forced(ho, outs, 8, max_flips=B * 2)
+    print("config 2 with hi_only=7: worst %s, %d flips" % ({k: "%.1e" % v for k, v in worst7.items()}, flips7))
 
 
 def test_config4_full_size_against_reference(dev):

@@ -42,13 +42,15 @@ print("stamps %d = %d per step" % (n, per))
 d = (st[1:] - st[:-1]) / 1e3                      # us
 steps = [d[r * per:(r + 1) * per - 1] for r in range(reps) if (r + 1) * per - 1 <= len(d)]
 m = torch.stack(steps[1:]).mean(0) if len(steps) > 1 else steps[0]
-head = per - 11 * 8                                # launches before the first iteration (pose chain, K / V^T projection, ...)
 names = ["posemb", "sample", "chain P", "self-attn", "chain A", "cross-attn", "combine", "chain B", "gn_apply", "gemm hd2", "heads"]
+if (per - 3) % 8 == 0 and (per - 3) // 8 == 10:      # fused stream-K merge: no combine launch
+    names.remove("combine")
+NL = len(names)
+head = per - NL * 8                                # launches before the first iteration (pose chain, K / V^T projection, ...)
 print("prologue launches (us): " + " ".join("%.1f" % x for x in m[:head]))
 if (per - head) % 8 == 0 and (per - head) // 8 == len(names):
-    it = m[head - 1:head - 1 + 88].reshape(8, 11) if head >= 1 else None
     # stamp k marks the START (dependency resolved) of launch k: launch k costs stamp[k+1] - stamp[k]
-    it = torch.cat([m[head:], m.new_zeros(1)])[:88].reshape(8, 11)
+    it = torch.cat([m[head:], m.new_zeros(1)])[:8 * NL].reshape(8, NL)
     print("per launch, mean over iterations 1..6 (us):")
     for j, nm in enumerate(names):
         print("  %-10s %7.1f" % (nm, it[1:7, j].mean()))
@@ -66,10 +68,10 @@ ch = ch[order]
 last = st[(reps - 1) * per:(reps) * per]
 names_c = ["P", "A", "B"]
 for it in (2, 5):
-    for j, k in enumerate((2, 4, 7)):                 # chain P, A, B inside an iteration
+    for j, k in enumerate((names.index("chain P"), names.index("chain A"), names.index("chain B"))):
         slot = it * 3 + j
-        t_dep = float(last[head + it * 11 + k])
-        t_next = float(last[head + it * 11 + k + 1])
+        t_dep = float(last[head + it * NL + k])
+        t_next = float(last[head + it * NL + k + 1])
         c = ch[slot, :nct]
         e, w, x = (c[:, 0] - t_dep) / 1e3, (c[:, 1] - t_dep) / 1e3, (c[:, 2] - t_dep) / 1e3
         mhz = (c[:, 3] / (c[:, 2] - c[:, 0]) * 1e3).median()
