@@ -93,6 +93,7 @@ typedef struct ParqOutputs {
 #define PARQ_FLAG_HI_ONLY_SET 0x08000000u
 #define PARQ_FLAG_FUSED_MERGE 512u /* merge the stream-K pieces of the cross-attention inside the attention kernel (flags + spin
                                      * wait on an earlier-scheduled CTA pair) instead of the attn3_combine_kernel launch; off by default */
+#define PARQ_FLAG_NO_FORK 1024u  /* un-chained launch path: keep every launch on the caller's stream (no side-stream branches; A/B timing) */
 #define PARQ_FLAG_NO_PDL 4u      /* launch without programmatic dependent launch (plain stream order; for A/B timing) */
 
 int parq_version(void);

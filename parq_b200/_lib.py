@@ -17,6 +17,7 @@ PARQ_FLAG_KV_HI_ONLY = 16
 PARQ_FLAG_NO_CHAIN = 64
 PARQ_FLAG_FORCE_CHAIN = 128
 PARQ_FLAG_FUSED_MERGE = 512
+PARQ_FLAG_NO_FORK = 1024
 PARQ_FLAG_HI_ONLY_SHIFT = 16
 PARQ_FLAG_HI_ONLY_SET = 0x08000000
 PARQ_RAYPE_SPLIT_HIDDEN = 8

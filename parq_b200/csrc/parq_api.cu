@@ -148,6 +148,7 @@ static const int g_combine_rows = (getenv("PARQ_COMBINE_ROWS") && (atoi(getenv("
 static const bool g_no_narrow = getenv("PARQ_NO_NARROW") != nullptr;         // A/B switch: 256-column tiles also for GEMMs of a few row tiles
 static const bool g_no_chain_v = getenv("PARQ_NO_CHAIN_V") != nullptr;       // A/B switch: self-attention V^T as its own GEMM launch instead of stage 0 of chain P
 static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;
+static const bool g_no_fork = getenv("PARQ_NO_FORK") != nullptr;              // A/B switch: every launch of the un-chained path on the caller's stream
 static const bool g_fused_merge = getenv("PARQ_FUSED_MERGE") != nullptr;  // opt-in: merge the stream-K pieces inside the attention kernel instead of the attn3_combine_kernel launch
 static const int g_chain_min_rows = getenv("PARQ_CHAIN_MIN_ROWS") ? atoi(getenv("PARQ_CHAIN_MIN_ROWS")) : 2048;
 // Default: every GEMM keeps its low-order activation term.  Dropping it for the three GEMMs whose output is rounded to 16 bits
@@ -195,6 +196,47 @@ static void launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   launch_kc(kernel, grid, block, smem, st, dim3(1, 1, 1), static_cast<Args&&>(args)...);
+}
+
+// ------------------------------------------------------------------------------ side streams --
+// Independent launches of one iteration run on two side streams of the library (fork / join through events; inside a stream
+// capture they become parallel branches of the graph): with one clip an iteration is a chain of ~20 short dependent launches
+// and every launch taken off that chain is ~10 us of latency.  Created lazily outside a capture, per thread and device.
+struct SideStreams {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork_ev[2] = {nullptr, nullptr}, join_ev[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+static SideStreams* side_streams(cudaStream_t st) {
+  static thread_local SideStreams tab[MAX_DEVICES];
+  SideStreams& S = tab[current_device()];
+  if (!S.ok) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return nullptr;            // first use inside a capture: stay on one stream
+    }
+    for (int i = 0; i < 2; ++i) {
+      if (cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&S.fork_ev[i], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&S.join_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+    }
+    S.ok = true;
+  }
+  return &S;
+}
+static int side_fork(cudaStream_t st, SideStreams* S, int i) {       // work launched on S->s[i] from now on starts after what `st` holds
+  CUDA_TRY(cudaEventRecord(S->fork_ev[i], st));
+  CUDA_TRY(cudaStreamWaitEvent(S->s[i], S->fork_ev[i], 0));
+  return PARQ_OK;
+}
+static int side_join(cudaStream_t st, SideStreams* S, int i) {       // `st` continues after what S->s[i] holds
+  CUDA_TRY(cudaEventRecord(S->join_ev[i], S->s[i]));
+  CUDA_TRY(cudaStreamWaitEvent(st, S->join_ev[i], 0));
+  return PARQ_OK;
 }
 
 // ------------------------------------------------------------------------------ TMA tensor maps --
@@ -1245,6 +1287,32 @@ int parq_kv_project_views(const ParqShape* shape, const void* view_tokens_bf16, 
   return PARQ_OK;
 }
 
+// (un-chained launch path) pe = W2 relu(W1 posemb + b1) + b2 as two GEMM launches on `st`
+static int launch_pe_mlp(cudaStream_t st, const ParqShape& s, const Workspace& W, const Packed& P, uint8_t* ws, const uint8_t* pk, bool w_lo) {
+  const int C = s.C, R = s.B * s.Nq;
+  GemmParams g; memset(&g, 0, sizeof(g));
+  g.M = R; g.N = C; term_offsets(g, 384, w_lo, 0);
+  g.ep = epilogue_none(); g.ep.bias = reinterpret_cast<const float*>(pk + P.pe0_b); g.ep.relu = 1;
+  g.ep.out_lp = ws + W.a_peh; g.ep.ld_lp = 2 * C; g.ep.lp_lo_off = C;
+  TRY(launch_gemm(st, ws + W.a_pos, R, 768, pk + P.pe0, C, 768, g));
+  memset(&g, 0, sizeof(g));
+  g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
+  g.ep = epilogue_none(); g.ep.bias = reinterpret_cast<const float*>(pk + P.pe2_b);
+  g.ep.out_f32 = reinterpret_cast<float*>(ws + W.pe); g.ep.ld_f32 = C;
+  return launch_gemm(st, ws + W.a_peh, R, 2 * C, pk + P.pe2, C, 2 * C, g);
+}
+// (un-chained launch path) V^T = Wv x^T + bv of the self-attention: weights are the A operand, activations the B operand
+static int launch_sa_v(cudaStream_t st, const ParqShape& s, const Workspace& W, const Packed& P, uint8_t* ws, const uint8_t* pk, bool w_lo,
+                       bool hi_only) {
+  const int C = s.C, R = s.B * s.Nq;
+  GemmParams g; memset(&g, 0, sizeof(g));
+  g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : (hi_only ? 1 : 2); g.const_operand = 1;
+  g.a_koff[0] = 0; g.b_koff[0] = 0; g.a_koff[1] = 0; g.b_koff[1] = C; g.a_koff[2] = C; g.b_koff[2] = 0;
+  g.ep = epilogue_none(); g.ep.bias = reinterpret_cast<const float*>(pk + P.sa_v_b); g.ep.bias_per_row = 1;
+  g.ep.out_lp = ws + W.vt_s; g.ep.ld_lp = static_cast<long long>(W.ldvs); g.ep.lp_fp16 = 1;
+  return launch_gemm(st, pk + P.sa_v, C, 2 * C, ws + W.a_x, R, 2 * C, g);
+}
+
 int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const void* tokens_lo_bf16, const float* camera, const float* T_cp,
                          const float* T_wp, const float* T_wl, const float* ref0, const float* forced_refs, const void* packed, void* workspace,
                          size_t workspace_bytes, const ParqOutputs* out, uint32_t flags, void* stream) {
@@ -1322,6 +1390,13 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
     sp.center_im = out->center_im ? out->center_im + static_cast<size_t>(it) * s.B * s.T * s.Nq * 2 : nullptr;
     sp.valid = out->center_valid ? out->center_valid + static_cast<size_t>(it) * s.B * s.T * s.Nq : nullptr;
     sp.coord_pos = nullptr;
+    // un-chained launch path (one clip): the reference-point MLP needs only the sinusoidal embedding, not the sampled features --
+    // it runs on a side stream next to the sampling kernel; V^T of the self-attention (needs only x) next to the Q|K projection
+    SideStreams* sd = (!chained && !(flags & PARQ_FLAG_NO_FORK) && !g_no_fork) ? side_streams(st) : nullptr;
+    if (sd != nullptr) {
+      TRY(side_fork(st, sd, 0));
+      TRY(launch_pe_mlp(sd->s[0], s, W, P, ws, pk, w_lo));
+    }
     TRY(launch_sample(st, sp));
     if (chained) {
       // ---- chain P: pe = W2 relu(W1 posemb + b1) + b2 (+ x -> split(x + pe)) -> self-attention Q|K projection
@@ -1395,19 +1470,16 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
         TRY(launch_chain(st, cb));
       }
     } else {
-    // K2: reference-point positional feature  pe = W2 relu(W1 posemb + b1) + b2; the second GEMM also emits the split of
-    // x + pe, the query / key input of the self-attention (transformer_parq.py:372)
+    // K2: reference-point positional feature  pe = W2 relu(W1 posemb + b1) + b2, then the split of x + pe, the query / key input
+    // of the self-attention (transformer_parq.py:372)
     {
-      GemmParams g; memset(&g, 0, sizeof(g));
-      g.M = R; g.N = C; term_offsets(g, 384, w_lo, 0);
-      g.ep = epilogue_none(); g.ep.bias = PF(P.pe0_b); g.ep.relu = 1;
-      g.ep.out_lp = ws + W.a_peh; g.ep.ld_lp = 2 * C; g.ep.lp_lo_off = C;
-      TRY(launch_gemm(st, ws + W.a_pos, R, 768, pk + P.pe0, C, 768, g));
-      memset(&g, 0, sizeof(g));
-      g.M = R; g.N = C; term_offsets(g, C, w_lo, 0);
-      g.ep = epilogue_none(); g.ep.bias = PF(P.pe2_b);
-      g.ep.out_f32 = F32(W.pe); g.ep.ld_f32 = C;
-      TRY(launch_gemm(st, ws + W.a_peh, R, 2 * C, pk + P.pe2, C, 2 * C, g));
+      if (sd != nullptr) {
+        TRY(side_fork(st, sd, 1));                // after the sampler: V^T = Wv x^T + bv on side stream 1
+        TRY(launch_sa_v(sd->s[1], s, W, P, ws, pk, w_lo, hio(1) != 0));
+        TRY(side_join(st, sd, 0));                // pe is there
+      } else {
+        TRY(launch_pe_mlp(st, s, W, P, ws, pk, w_lo));
+      }
       { ProfScope ps(TAG_ROWWISE, st); launch_k(split_sum_kernel, dim3((R * (C / 8) + 255) / 256), dim3(256), 0, st, BF(W.a_x), F32(W.pe), BF(W.a_xpe), R, C); }
       CUDA_TRY(cudaGetLastError());
     }
@@ -1419,13 +1491,8 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       g.ep = epilogue_none(); g.ep.bias = PF(P.sa_qk_b);
       g.ep.out_lp = ws + W.qk_s; g.ep.ld_lp = 2 * C; g.ep.lp_fp16 = 1;
       TRY(launch_gemm(st, ws + W.a_xpe, R, 2 * C, pk + P.sa_qk, 2 * C, 2 * C, g));
-      // V^T = Wv x^T + bv : weights are the A operand, activations the B operand
-      memset(&g, 0, sizeof(g));
-      g.M = C; g.N = R; g.K = C; g.nterms = w_lo ? 3 : (hio(1) ? 1 : 2); g.const_operand = 1;
-      g.a_koff[0] = 0; g.b_koff[0] = 0; g.a_koff[1] = 0; g.b_koff[1] = C; g.a_koff[2] = C; g.b_koff[2] = 0;
-      g.ep = epilogue_none(); g.ep.bias = PF(P.sa_v_b); g.ep.bias_per_row = 1;
-      g.ep.out_lp = ws + W.vt_s; g.ep.ld_lp = static_cast<long long>(W.ldvs); g.ep.lp_fp16 = 1;
-      TRY(launch_gemm(st, pk + P.sa_v, C, 2 * C, ws + W.a_x, R, 2 * C, g));
+      if (sd != nullptr) TRY(side_join(st, sd, 1));
+      else TRY(launch_sa_v(st, s, W, P, ws, pk, w_lo, hio(1) != 0));
       TRY(launch_attention(st, ws + W.qk_s, 2 * C, ws + W.qk_s + static_cast<size_t>(C) * 2, 2 * C, ws + W.vt_s, W.ldvs, s.B, s.heads,
                            s.Nq, s.Nq, true, ws + W.scratch, W.scratch_bytes, BF(W.a_attn), W.self.nsplit));
       memset(&g, 0, sizeof(g));

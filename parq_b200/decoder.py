@@ -255,7 +255,7 @@ class DecoderEngine:
         return self._ref0_cache
 
     def forward(self, tokens, camera, T_cp, T_wp, T_wl, H, W, forced_refs=None, ref0=None, debug=False, skip_kv=False,
-                graph=False, pdl=True, chain=None, hi_only=None, fused_merge=False):
+                graph=False, pdl=True, chain=None, hi_only=None, fused_merge=False, fork=True):
         """tokens (B, T*H*W, C) bf16, or fp32 (split on the device into an exact bf16 pair, see ``_split_tokens``);
         camera (B,T,6); poses (B,T,12)/(B,1,12) fp32.
         Returns a dict of stacked per-iteration tensors (iters, B, Nq, n).
@@ -266,6 +266,7 @@ class DecoderEngine:
         ``hi_only``: per-GEMM bit mask "high-order activation term only" (include/parq_b200.h PARQ_FLAG_HI_ONLY_*), None = library default.
         ``fused_merge=True`` merges the stream-K pieces of the cross-attention inside the attention kernel instead of a
         separate launch (same step time in the power-capped steady state; off by default).
+        ``fork=False`` keeps every launch of the un-chained path (one clip) on one stream instead of side-stream branches.
         ``pdl=False`` launches the kernels in plain stream order instead of with programmatic dependent launch.
         ``graph=True`` replays the whole forward as ONE CUDA graph captured on first use per shape (see
         ``_forward_graph``); the returned tensors are then static buffers that the next replay overwrites."""
@@ -282,7 +283,7 @@ class DecoderEngine:
         ws = self._workspace(shape, (B, T, H, W))
         flags = self.flags | (_lib.PARQ_FLAG_SKIP_KV if skip_kv else 0) | (0 if pdl else _lib.PARQ_FLAG_NO_PDL) | \
             (0 if chain is None else (_lib.PARQ_FLAG_FORCE_CHAIN if chain else _lib.PARQ_FLAG_NO_CHAIN)) | \
-            (_lib.PARQ_FLAG_FUSED_MERGE if fused_merge else 0) | \
+            (_lib.PARQ_FLAG_FUSED_MERGE if fused_merge else 0) | (0 if fork else _lib.PARQ_FLAG_NO_FORK) | \
             (0 if hi_only is None else (_lib.PARQ_FLAG_HI_ONLY_SET | ((int(hi_only) & 0x7FF) << _lib.PARQ_FLAG_HI_ONLY_SHIFT)))
         if graph:
             return self._forward_graph(shape, ws, flags, tokens, camera, T_cp, T_wp, T_wl, forced_refs, ref0, debug)
