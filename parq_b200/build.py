@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libparq_b200.so")
 SOURCES = ["parq_api.cu"]
-HEADERS = ["ptx.cuh", "gemm_tc.cuh", "gemm2_tc.cuh", "chain_tc.cuh", "attn2_tc.cuh", "attn3_tc.cuh", "attn_tc.cuh", "project_sample.cuh", "rowwise.cuh",
+HEADERS = ["ptx.cuh", "gemm_tc.cuh", "gemm2_tc.cuh", "gemm_sk.cuh", "chain_tc.cuh", "attn2_tc.cuh", "attn3_tc.cuh", "attn_tc.cuh", "project_sample.cuh", "rowwise.cuh",
            "parse_pred.cuh", "raype.cuh", "fpn.cuh", os.path.join("..", "..", "include", "parq_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -59,7 +59,7 @@ struct ChainStage {
   __nv_bfloat16* a_out_pe;             // LN only, or null
   void* out_lp;                        // CH_EP_LP: (M, ld_lp) 16-bit
   long long ld_lp;
-  double2* gn_out;                     // CH_EP_F32: optional (sum, sum of squares) per 128 x 256 tile, slot m_tile * gn_stride + n0 / 256
+  double2* gn_out;                     // CH_EP_F32: optional (sum, sum of squares) per tile, slot m_tile * gn_stride + n0 / GN_SLOT_COLS (ptx.cuh)
   int gn_stride;
   const __nv_bfloat16* add_split;      // CH_EP_F32: optional (M, 2N) [hi|lo] addend ...
   __nv_bfloat16* out_sum_split;        // ... and the split of (v + addend)
@@ -597,7 +597,10 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
             if (et == 0) {
               double a = 0.0, b = 0.0;
               for (int k = 0; k < EPI_WARPS; ++k) { a += s_gn[2 * k]; b += s_gn[2 * k + 1]; }
-              S.gn_out[static_cast<long long>(m0 / BM) * S.gn_stride + (n_base + j * S.tile_n) / 256] = make_double2(a, b);
+              // slots of GN_SLOT_COLS columns (ptx.cuh): the tile's sums in its first slot, zeros in the others it covers
+              double2* slot = S.gn_out + static_cast<long long>(m0 / BM) * S.gn_stride + (n_base + j * S.tile_n) / GN_SLOT_COLS;
+              slot[0] = make_double2(a, b);
+              for (int i = 1; i < S.tile_n / GN_SLOT_COLS; ++i) slot[i] = make_double2(0.0, 0.0);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
           }

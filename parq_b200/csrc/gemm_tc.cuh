@@ -36,7 +36,7 @@ struct GemmEpilogue {
   long long ld_lp;
   int lp_fp16;
   long long lp_lo_off; // > 0: also store the bf16 residual (v - hi) at column offset lp_lo_off
-  double2* gn_out;     // optional: per-tile (sum, sum of squares) of the outputs, slot m_tile*gn_stride + n_tile
+  double2* gn_out;     // optional: per-tile (sum, sum of squares) of the outputs, slot m_tile*gn_stride + column/GN_SLOT_COLS (ptx.cuh)
   int gn_stride;
   // Tile-contiguous K / V^T cache for the cross-attention (16-bit output only; requires Nk % 32 == 0):
   //   1: rows are tokens (K = tokens Wk^T):   out[((tile*H + h)*128 + key%128)*256 + ch]
@@ -518,9 +518,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         double* sg = reinterpret_cast<double*>(sbias + 2 * BN);      // [4][2]
         if (lane == 0) { sg[2 * q] = ds; sg[2 * q + 1] = dq; }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0)
-          p.ep.gn_out[static_cast<long long>(m0 / BM) * p.ep.gn_stride + n0 / BN] =
-              make_double2((sg[0] + sg[2]) + (sg[4] + sg[6]), (sg[1] + sg[3]) + (sg[5] + sg[7]));
+        if (et == 0) {
+          // slots of GN_SLOT_COLS columns (ptx.cuh): the tile's sums in its first slot, zeros in the others it covers
+          double2* slot = p.ep.gn_out + static_cast<long long>(m0 / BM) * p.ep.gn_stride + n0 / GN_SLOT_COLS;
+          slot[0] = make_double2((sg[0] + sg[2]) + (sg[4] + sg[6]), (sg[1] + sg[3]) + (sg[5] + sg[7]));
+          for (int i = 1; i < bn / GN_SLOT_COLS; ++i) slot[i] = make_double2(0.0, 0.0);
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }

@@ -16,6 +16,7 @@
 #include "attn2_tc.cuh"
 #include "attn3_tc.cuh"
 #include "chain_tc.cuh"
+#include "gemm_sk.cuh"
 #include "fpn.cuh"
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
@@ -148,6 +149,7 @@ static const int g_combine_rows = (getenv("PARQ_COMBINE_ROWS") && (atoi(getenv("
 static const bool g_no_narrow = getenv("PARQ_NO_NARROW") != nullptr;         // A/B switch: 256-column tiles also for GEMMs of a few row tiles
 static const bool g_no_chain_v = getenv("PARQ_NO_CHAIN_V") != nullptr;       // A/B switch: self-attention V^T as its own GEMM launch instead of stage 0 of chain P
 static const bool g_no_chain = getenv("PARQ_NO_CHAIN") != nullptr;
+static const bool g_no_splitk = getenv("PARQ_NO_SPLITK") != nullptr;          // A/B switch: narrow single-CTA tiles instead of the cluster split-K GEMM (gemm_sk.cuh)
 static const bool g_no_fork = getenv("PARQ_NO_FORK") != nullptr;              // A/B switch: every launch of the un-chained path on the caller's stream
 static const bool g_fused_merge = getenv("PARQ_FUSED_MERGE") != nullptr;  // opt-in: merge the stream-K pieces inside the attention kernel instead of the attn3_combine_kernel launch
 static const int g_chain_min_rows = getenv("PARQ_CHAIN_MIN_ROWS") ? atoi(getenv("PARQ_CHAIN_MIN_ROWS")) : 2048;
@@ -296,9 +298,27 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
   const long long tiles1 = static_cast<long long>((gp.M + gemm::BM - 1) / gemm::BM) * ((gp.N + gemm::BN - 1) / gemm::BN);
   const bool pairk = !g_no_pair && device_info().sms >= 2 && (tiles1 >= 2LL * device_info().sms || g_force_pair);
   // narrow tiles for GEMMs of a few row tiles (one clip): 4x the CTAs, a quarter of the MMA latency each (not for the
-  // GroupNorm tile sums, whose slots are per 256 columns, nor for the channels-first epilogues)
-  const bool narrow = !pairk && !g_no_narrow && gp.ep.gn_out == nullptr && gp.ep.nchw_add == nullptr && gp.ep.nchw_out == nullptr && gp.N % 64 == 0 &&
+  // channels-first epilogues; the GroupNorm tile sums have one slot per 64 columns)
+  const bool narrow = !pairk && !g_no_narrow && gp.ep.nchw_add == nullptr && gp.ep.nchw_out == nullptr && gp.N % 64 == 0 &&
                       tiles1 * 4 <= device_info().sms;
+  // cluster split-K kernel (gemm_sk.cuh) for the same few-row GEMMs when the shape fits: activations [hi|lo] x bf16-exact weights
+  const int kblocks = gp.K / gemm::BK;
+  const bool splitk = narrow && !g_no_splitk && gp.nterms == 2 && gp.b_koff[0] == gp.b_koff[1] && gp.a_koff[0] != gp.a_koff[1] && gp.const_operand != 1 &&
+                      !gp.ep.bias_per_row && gp.ep.kv_tiled == 0 && gp.N % gemmsk::BN == 0 && kblocks % gemmsk::S == 0 &&
+                      kblocks / gemmsk::S <= gemmsk::MAX_STEPS && (gp.a_split_n == 0 || gp.a_split_n % gemmsk::BN == 0);
+  if (splitk) {
+    CUtensorMap tmA, tmB;
+    TRY(make_map(&tmA, A, a_rows, a_cols, a_cols, gemmsk::BM));
+    TRY(make_map(&tmB, Bw, b_rows, b_cols, b_cols, gemmsk::BN));
+    OPT_IN_SMEM(gemm_sk_kernel, gemmsk::SMEM_BYTES);
+    const int tiles = ((gp.M + gemmsk::BM - 1) / gemmsk::BM) * (gp.N / gemmsk::BN);
+    {
+      ProfScope ps(tag, st);
+      launch_kc(gemm_sk_kernel, dim3(gemmsk::S * tiles), dim3(gemmsk::THREADS), gemmsk::SMEM_BYTES, st, dim3(gemmsk::S, 1, 1), tmA, tmB, gp);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PARQ_OK;
+  }
   const int bn = narrow ? 64 : gemm::BN;
   CUtensorMap tmA, tmB;
   TRY(make_map(&tmA, A, a_rows, a_cols, a_cols, gemm::BM));
@@ -358,7 +378,7 @@ static int chain_add(ChainBuilder& cb, const void* A, uint64_t a_cols, const voi
   if (cb.p.nstages >= chain::MAX_STAGES) return fail(PARQ_ERR_SHAPE, "too many chain stages");
   if (S.K <= 0 || S.K % chain::BK != 0 || !chain_cols_ok(S.N)) return fail(PARQ_ERR_SHAPE, "chain stage N=%d K=%d not supported", S.N, S.K);
   const int ncta = S.N / chain::CLUSTER;
-  static const int tile_cap = getenv("PARQ_CHAIN_TILE") ? atoi(getenv("PARQ_CHAIN_TILE")) : 256;   // experiment: timing only (GN slots assume 256)
+  static const int tile_cap = getenv("PARQ_CHAIN_TILE") ? atoi(getenv("PARQ_CHAIN_TILE")) : 256;   // experiment switch (tools/chain_timeline.py)
   S.tile_n = ncta <= tile_cap ? ncta : (ncta % tile_cap == 0 ? tile_cap : ncta);
   if (S.tile_n > 256) S.tile_n = 256;
   S.tiles = ncta / S.tile_n;

@@ -55,6 +55,12 @@ __device__ __forceinline__ void pdl_wait() {
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// GroupNorm(1, C) tile sums of the head layers (rowwise.cuh): GEMM epilogues write (sum, sum of squares) double2 slots of
+// GN_SLOT_COLS output columns per 128-row tile, slot m_tile * GN_SLOTS_PER_MTILE + column / GN_SLOT_COLS.  A tile wider than one
+// slot puts its sums into its first slot and zeros into the others it covers.
+constexpr int GN_SLOT_COLS = 32;
+constexpr int GN_SLOTS_PER_MTILE = 64;         // 2 groups x 1024 columns / 32
+
 // ---------------------------------------------------------------- mbarrier --
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -156,19 +156,26 @@ add_ln_kernel(const float* __restrict__ x_in, const __nv_bfloat16* __restrict__ 
 //   gn_apply_kernel : reduces the partials in fixed order, applies affine + ReLU, emits bf16 split
 // h: (B*Nq, ldh) fp32, group g occupies columns [g*C, (g+1)*C).
 // ---------------------------------------------------------------------------------------------
-// Statistics come from the GEMM epilogue (gemm_tc.cuh): one (sum, sumsq) double2 per 128x256 output tile in
-// slot m_tile*8 + n_tile, where n_tile = g*(C/256) + tile-in-group.  A clip owns Nq/128 consecutive m-tiles.
-constexpr int GN_SLOTS_PER_MTILE = 8;
+// Statistics come from the GEMM epilogues (gemm_tc.cuh, gemm_sk.cuh, chain_tc.cuh) as (sum, sumsq) double2 slots of
+// GN_SLOT_COLS output columns per 128-row tile (ptx.cuh); group g (centre / rotation head) occupies the slots of columns
+// [g*C, (g+1)*C).  A clip owns Nq/128 consecutive m-tiles.
 
-__device__ __forceinline__ void gn_mean_rstd(const double2* partial, int b, int g, int C, int Nq, float& mean, float& rstd) {
+// One WARP reduces the slots of (clip b, group g): lanes stride over the slots, then a butterfly in double (fixed order:
+// deterministic); every lane returns the result.
+__device__ __forceinline__ void gn_mean_rstd(const double2* partial, int b, int g, int C, int Nq, int lane, float& mean, float& rstd) {
   double s = 0.0, ss = 0.0;
-  const int mt = Nq / 128, nt = C / 256;
-  for (int m = 0; m < mt; ++m)
-    for (int n = 0; n < nt; ++n) {
-      const double2 v = partial[static_cast<long long>(b * mt + m) * GN_SLOTS_PER_MTILE + g * nt + n];
-      s += v.x;
-      ss += v.y;
-    }
+  const int mt = Nq / 128, nt = C / GN_SLOT_COLS;
+  for (int i = lane; i < mt * nt; i += 32) {
+    const int m = i / nt, n = i - m * nt;
+    const double2 v = partial[static_cast<long long>(b * mt + m) * GN_SLOTS_PER_MTILE + g * nt + n];
+    s += v.x;
+    ss += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
   const double cnt = static_cast<double>(C) * Nq;
   const double m = s / cnt;
   const double var = fmax(ss / cnt - m * m, 0.0);
@@ -190,7 +197,11 @@ gn_apply_kernel(const float* __restrict__ h, int ldh, int C, int Nq, int groups,
   const int b = row0 / Nq;
   const int per_group = C / 8;
   __shared__ float s_stat[2][2];
-  if (threadIdx.x < groups) gn_mean_rstd(partial, b, threadIdx.x, C, Nq, s_stat[threadIdx.x][0], s_stat[threadIdx.x][1]);
+  if ((threadIdx.x >> 5) < groups) {
+    float mean, rstd;
+    gn_mean_rstd(partial, b, threadIdx.x >> 5, C, Nq, threadIdx.x & 31, mean, rstd);
+    if ((threadIdx.x & 31) == 0) { s_stat[threadIdx.x >> 5][0] = mean; s_stat[threadIdx.x >> 5][1] = rstd; }
+  }
   __syncthreads();
   for (int item = threadIdx.x; item < groups * per_group; item += blockDim.x) {
     const int g = item / per_group, c = (item % per_group) * 8;
@@ -393,9 +404,11 @@ heads_final_kernel(const HeadsParams p, int rows_per_block) {
   const int row_begin = blockIdx.x * rows_per_block;
   const int row_end = min(p.R, row_begin + rows_per_block);
   const int clip0 = row_begin / p.Nq;
-  if (threadIdx.x < 4) {
-    const int clip = min(clip0 + (threadIdx.x >> 1), (p.R - 1) / p.Nq);
-    gn_mean_rstd(p.partial, clip, threadIdx.x & 1, C, p.Nq, s_stat[threadIdx.x * 2], s_stat[threadIdx.x * 2 + 1]);
+  if (warp < 4) {                                           // (clip, group) = (warp >> 1, warp & 1)
+    const int clip = min(clip0 + (warp >> 1), (p.R - 1) / p.Nq);
+    float mean, rstd;
+    gn_mean_rstd(p.partial, clip, warp & 1, C, p.Nq, lane, mean, rstd);
+    if (lane == 0) { s_stat[warp * 2] = mean; s_stat[warp * 2 + 1] = rstd; }
   }
   __syncthreads();
   mbar_wait(bar, 0);

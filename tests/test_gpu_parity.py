@@ -170,6 +170,22 @@ def test_gemm_three_term_split_recovers_fp32_product(dev):
     assert relerr(out, ref) <= 3e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 1024, 1024), (256, 768, 1024), (256, 1024, 768), (200, 2048, 1024), (512, 1024, 256)])
+def test_gemm_cluster_split_k_against_float64(dev, M, N, K):
+    # gemm_sk.cuh: a GEMM of a few row tiles, activations [hi|lo] x bf16-exact weights -> a cluster of 4 CTAs per 128 x 128
+    # tile splits K and reduce-scatters the partial accumulators over distributed shared memory (bias + ReLU epilogue)
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(dev).bfloat16()
+    xs = torch.cat([x.bfloat16(), (x - x.bfloat16().float()).bfloat16()], 1).contiguous()
+    bias = torch.randn(N, generator=g).to(dev)
+    Ws = torch.cat([W, torch.zeros_like(W)], 1).contiguous()          # packed [hi|lo] weights with an empty low part
+    out = _gemm(dev, xs, Ws, M, N, K, nterms=2, a_koff=(0, K, 0), b_koff=(0, 0, 0), bias=bias, relu=1)
+    x16 = xs[:, :K].double() + xs[:, K:].double()
+    ref = torch.relu(x16 @ W.double().t() + bias.double()).float()
+    assert relerr(out, ref) <= 2e-6
+
+
 @pytest.mark.parametrize("M,K1,N2,w_lo", [(128, 1024, 1024, 0), (512, 768, 768, 0), (256, 1024, 2048, 1)])
 def test_chained_kernel_linear_layernorm_linear(dev, M, K1, N2, w_lo):
     # chain_tc.cuh in isolation: cluster of 4 CTAs per 128 rows, LayerNorm statistics exchanged over DSMEM, the second stage
