@@ -1610,7 +1610,12 @@ int parq_decoder_forward(const ParqShape* shape, const void* tokens_bf16, const 
       { ProfScope ps(TAG_ROWWISE, st); {
         const int rpb = (R + device_info().sms - 1) / device_info().sms;     // rows per block: one block per SM
         const size_t hsm = heads_smem_bytes<1024>();
-        if (hp.posemb_next != nullptr) {
+        if (R <= 1024) {
+          // a few rows (one clip): weights in registers, channels split over the warps of a block (rowwise.cuh)
+          const dim3 grid((R + HEADS_SMALL_ROWS - 1) / HEADS_SMALL_ROWS);
+          if (hp.posemb_next != nullptr) launch_k(heads_final_small_kernel<1024, true>, grid, dim3(256), 0, st, hp);
+          else launch_k(heads_final_small_kernel<1024, false>, grid, dim3(256), 0, st, hp);
+        } else if (hp.posemb_next != nullptr) {
           OPT_IN_SMEM((heads_final_kernel<1024, true>), hsm);
           launch_k(heads_final_kernel<1024, true>, dim3((R + rpb - 1) / rpb), dim3(HEADS_THREADS), hsm, st, hp, rpb);
         } else {

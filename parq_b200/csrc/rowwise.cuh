@@ -505,4 +505,80 @@ heads_final_kernel(const HeadsParams p, int rows_per_block) {
   }
 }
 
+// The same final layer for a FEW rows (one clip: 256 queries), where the kernel above would stage 128 KB of weights per block to
+// serve two rows.  Block = 8 warps for HEADS_SMALL_ROWS rows; warp w owns channels [128 w, 128 w + 128) and keeps ITS slice of
+// the 28 weight rows in registers (loaded before the dependency wait, every warp's 28 loads in flight at once, no shared-memory
+// round trip); per row a lane forms 28 four-channel partial dot products, the halving reduction leaves slot j in lane j, the
+// eight warps' partials meet in shared memory and warp r finishes row r with the common epilogue.
+constexpr int HEADS_SMALL_ROWS = 2;
+template <int C, bool kPosemb>
+__global__ void __launch_bounds__(256)
+heads_final_small_kernel(const HeadsParams p) {
+  static_assert(C == 1024, "8 warps x 32 lanes x 4 channels");
+  __shared__ float s_part[HEADS_SMALL_ROWS][8][32];
+  __shared__ float s_stat[4];                              // mean / rstd of the centre and rotation groups of the block's clip
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = warp * 128 + lane * 4;
+  float4 w[HEADS_SLOTS];
+#pragma unroll
+  for (int j = 0; j < HEADS_SLOTS; ++j) {
+    const float* src = nullptr;
+    if (j < HEADS_CLS_SLOTS) src = j < p.num_cls ? p.w_cls + j * C : nullptr;
+    else if (j < HEADS_CLS_SLOTS + 3) src = p.w_size + (j - HEADS_CLS_SLOTS) * C;
+    else if (j < HEADS_CLS_SLOTS + 6) src = p.w_c3 + (j - HEADS_CLS_SLOTS - 3) * C;
+    else src = p.w_r3 + (j - HEADS_CLS_SLOTS - 6) * C;
+    w[j] = src != nullptr ? __ldg(reinterpret_cast<const float4*>(src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4 gc = __ldg(reinterpret_cast<const float4*>(p.gamma_c + c)), bc = __ldg(reinterpret_cast<const float4*>(p.beta_c + c));
+  const float4 gr = __ldg(reinterpret_cast<const float4*>(p.gamma_r + c)), br = __ldg(reinterpret_cast<const float4*>(p.beta_r + c));
+  // everything above is constant weights: in flight while the previous kernel drains
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row_begin = blockIdx.x * HEADS_SMALL_ROWS;
+  float4 vx[HEADS_SMALL_ROWS], vc[HEADS_SMALL_ROWS], vr[HEADS_SMALL_ROWS];
+#pragma unroll
+  for (int r = 0; r < HEADS_SMALL_ROWS; ++r) {
+    const long long xo = static_cast<long long>(min(row_begin + r, p.R - 1)) * C;
+    vx[r] = *reinterpret_cast<const float4*>(p.x + xo + c);
+    vc[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xo + c);
+    vr[r] = *reinterpret_cast<const float4*>(p.h2 + 2 * xo + C + c);
+  }
+  if (warp < 2) {                                           // the rows of a block belong to one clip (Nq % HEADS_SMALL_ROWS == 0)
+    float mean, rstd;
+    gn_mean_rstd(p.partial, row_begin / p.Nq, warp, C, p.Nq, lane, mean, rstd);
+    if (lane == 0) { s_stat[warp * 2] = mean; s_stat[warp * 2 + 1] = rstd; }
+  }
+  __syncthreads();
+  const float mean_c = s_stat[0], rstd_c = s_stat[1], mean_r = s_stat[2], rstd_r = s_stat[3];
+#pragma unroll
+  for (int r = 0; r < HEADS_SMALL_ROWS; ++r) {
+    vc[r].x = fmaxf((vc[r].x - mean_c) * rstd_c * gc.x + bc.x, 0.f);
+    vc[r].y = fmaxf((vc[r].y - mean_c) * rstd_c * gc.y + bc.y, 0.f);
+    vc[r].z = fmaxf((vc[r].z - mean_c) * rstd_c * gc.z + bc.z, 0.f);
+    vc[r].w = fmaxf((vc[r].w - mean_c) * rstd_c * gc.w + bc.w, 0.f);
+    vr[r].x = fmaxf((vr[r].x - mean_r) * rstd_r * gr.x + br.x, 0.f);
+    vr[r].y = fmaxf((vr[r].y - mean_r) * rstd_r * gr.y + br.y, 0.f);
+    vr[r].z = fmaxf((vr[r].z - mean_r) * rstd_r * gr.z + br.z, 0.f);
+    vr[r].w = fmaxf((vr[r].w - mean_r) * rstd_r * gr.w + br.w, 0.f);
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < HEADS_SLOTS) {
+        const float4 v = j < HEADS_CLS_SLOTS + 3 ? vx[r] : (j < HEADS_CLS_SLOTS + 6 ? vc[r] : vr[r]);
+        acc[j] = fmaf(w[j].w, v.w, fmaf(w[j].z, v.z, fmaf(w[j].y, v.y, w[j].x * v.x)));
+      } else {
+        acc[j] = 0.f;
+      }
+    }
+    s_part[r][warp][lane] = reduce_scatter32(acc, lane);    // lane j: this warp's share of output slot j
+  }
+  __syncthreads();
+  if (warp < HEADS_SMALL_ROWS && row_begin + warp < p.R) {
+    float mine = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mine += s_part[warp][k][lane];          // fixed order: deterministic
+    heads_row_epilogue<kPosemb>(p, row_begin + warp, lane, mine);
+  }
+}
+
 }  // namespace parq
