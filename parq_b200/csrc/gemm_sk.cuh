@@ -31,7 +31,7 @@ constexpr int MAX_STEPS = 4;              // k-blocks per CTA
 constexpr int A_BYTES = BM * BK * 2;      // 16 KB
 constexpr int B_BYTES = BN * BK * 2;      // 16 KB
 constexpr int SLOT_BYTES = 2 * A_BYTES + B_BYTES;   // [A_hi | A_lo | W] of one k-block
-constexpr int THREADS = 192;              // warp 0 TMA, warp 1 MMA + TMEM allocation, warps 2-5 epilogue (TMEM quadrant = warp % 4)
+constexpr int THREADS = 192;              // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (TMEM quadrant = warp % 4; warp 2 allocates TMEM)
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + MAX_STEPS * SLOT_BYTES + 256 /*barriers*/ + 32 * 4 /*bias*/ + 64 /*GroupNorm sums*/ +
                            4 * 32 * 33 * 4 /*per-warp store staging*/;
 static_assert((S - 1) * 32 * BM * 4 <= SLOT_BYTES, "the received partials fit into the first operand stage");
@@ -64,21 +64,19 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb0 = static_cast<int>(rank) * steps;
   const int asplit = (p.a_split_n > 0 && n0 >= p.a_split_n) ? p.a_split_off : 0;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {                         // (every lane: no divergence in front of the block-wide barrier below)
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int i = 0; i < MAX_STEPS; ++i) mbar_init(&full_bar[i], 1);
-      mbar_init(tfull_bar, 1);
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc<128>(tmem_slot);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < MAX_STEPS; ++i) mbar_init(&full_bar[i], 1);
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
   }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  asm volatile("bar.sync 2, 192;" ::: "memory");      // == gemmsk::THREADS
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -188,9 +186,9 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 

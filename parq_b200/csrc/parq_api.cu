@@ -305,7 +305,9 @@ static int launch_gemm(cudaStream_t st, const void* A, uint64_t a_rows, uint64_t
   const int kblocks = gp.K / gemm::BK;
   const bool splitk = narrow && !g_no_splitk && gp.nterms == 2 && gp.b_koff[0] == gp.b_koff[1] && gp.a_koff[0] != gp.a_koff[1] && gp.const_operand != 1 &&
                       !gp.ep.bias_per_row && gp.ep.kv_tiled == 0 && gp.N % gemmsk::BN == 0 && kblocks % gemmsk::S == 0 &&
-                      kblocks / gemmsk::S <= gemmsk::MAX_STEPS && (gp.a_split_n == 0 || gp.a_split_n % gemmsk::BN == 0);
+                      kblocks / gemmsk::S <= gemmsk::MAX_STEPS && (gp.a_split_n == 0 || gp.a_split_n % gemmsk::BN == 0) &&
+                      // one wave of clusters: beyond that the output tiles alone fill the machine
+                      static_cast<long long>(gemmsk::S) * ((gp.M + gemmsk::BM - 1) / gemmsk::BM) * (gp.N / gemmsk::BN) <= device_info().sms;
   if (splitk) {
     CUtensorMap tmA, tmB;
     TRY(make_map(&tmA, A, a_rows, a_cols, a_cols, gemmsk::BM));
