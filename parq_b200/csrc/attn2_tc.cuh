@@ -200,105 +200,20 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_tmem = tmem_base + lane_base + buf * 128;
-      uint32_t su[128];                                // raw fp32 bits of this row of S
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&su[c * 32]));
-      tmem_wait_ld();
-      const int nvalid = p.Nk - (t0 + j) * BKEY;     // keys of this tile that belong to the clip
-      if (nvalid < BKEY) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= nvalid) su[i] = 0xff800000u;        // -inf
-      }
-      float tmax = __uint_as_float(su[0]);
-#pragma unroll
-      for (int i = 1; i < 128; ++i) tmax = fmaxf(tmax, __uint_as_float(su[i]));
-      tmax *= LOG2E;
-      // mbarrier waits are by phase parity, so every completion of pv_done has to be observed exactly
-      // once and in order (skipping one lets a later wait alias an older phase): tile j consumes the
-      // completion of P(j-1)V(j-1) either here, before touching O, or at the end of the iteration.
-      bool pv_seen = (j == 0);
-      if (j == 0) {
-        m_run = tmax;
-      } else if (__any_sync(0xffffffffu, tmax > m_run + RESCALE_THRESHOLD)) {
-        // O must be quiescent: wait for P(j-1) V(j-1) to retire, then rescale this warp's 32 rows.
-        mbar_wait(pv_done, (j - 1) & 1);
-        pv_seen = true;
-        tc_fence_after();
-        const float m_new = fmaxf(m_run, tmax);
-        const float alpha = fast_exp2(m_run - m_new);
-#pragma unroll 1
-        for (int c = 0; c < DH / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_base + c * 32, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tmem_O + lane_base + c * 32, o);
-        }
-        l_run *= alpha;
-        m_run = m_new;
-      }
-      float lsum = 0.f;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i]), LOG2E, -m_run));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i + 1]), LOG2E, -m_run));
-          lsum += p0 + p1;
-          pk[i] = kFp16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
-        }
-        tmem_st32(s_tmem + half * 32, pk);
-      }
-      l_run += lsum;
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive_leader(&p_full[buf]);
-      if (!pv_seen) mbar_wait(pv_done, (j - 1) & 1);
+      attn_softmax_tile<kFp16>(s_tmem, tmem_O + lane_base, p.Nk - (t0 + j) * BKEY, j == 0, pv_done, (j - 1) & 1, m_run, l_run,
+                               [&] { mbar_arrive_leader(&p_full[buf]); });
     }
     // epilogue
     mbar_wait(pv_done, (n - 1) & 1);
     tc_fence_after();
     if (p.out_direct != nullptr) {
       // single split: normalise here and emit the [hi|lo] operand of the out-projection directly
-      const float inv = 1.f / l_run;
       const int C = p.H * DH;
-      __nv_bfloat16* dst = p.out_direct + (static_cast<long long>(b) * p.Nq + qt * BQ + q * 32 + lane) * (2 * C) + h * DH;
-#pragma unroll 1
-      for (int c = 0; c < DH / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tmem_O + lane_base + c * 32, o);
-        tmem_wait_ld();
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float v0 = __uint_as_float(o[2 * i]) * inv, v1 = __uint_as_float(o[2 * i + 1]) * inv;
-          hi[i] = pack_bf16x2(v0, v1);
-          lo[i] = pack_bf16x2(v0 - __uint_as_float(hi[i] << 16), v1 - __uint_as_float(hi[i] & 0xFFFF0000u));
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          reinterpret_cast<uint4*>(dst + c * 32)[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-          reinterpret_cast<uint4*>(dst + C + c * 32)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-        }
-      }
+      attn_store_normalised(tmem_O + lane_base, 1.f / l_run, p.out_direct + (static_cast<long long>(b) * p.Nq + qt * BQ + q * 32 + lane) * (2 * C) + h * DH, C);
     } else {
       // un-normalised O, m, l of this split for attn_combine_kernel
       const long long part = (static_cast<long long>(bh) * p.nsplit + split) * p.Nq + qt * BQ + q * 32 + lane;
-      float* orow = p.o_part + part * DH;
-#pragma unroll 1
-      for (int c = 0; c < DH / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tmem_O + lane_base + c * 32, o);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          reinterpret_cast<float4*>(orow + c * 32)[i] =
-              make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
-                          __uint_as_float(o[4 * i + 3]));
-      }
+      attn_store_partial(tmem_O + lane_base, p.o_part + part * DH);
       p.ml_part[part] = make_float2(m_run, l_run);
     }
   }

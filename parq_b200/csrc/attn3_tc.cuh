@@ -271,89 +271,19 @@ attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&s_full[buf], (g >> 1) & 1);
         tc_fence_after();
         const uint32_t s_tmem = tmem_base + lane_base + buf * 128;
-        uint32_t su[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&su[c * 32]));
-        tmem_wait_ld();
-        const int nvalid = p.Nk - (s.ta + j) * BKEY;
-        if (nvalid < BKEY) {
-#pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (i >= nvalid) su[i] = 0xff800000u;
-        }
-        float tmax = __uint_as_float(su[0]);
-#pragma unroll
-        for (int i = 1; i < 128; ++i) tmax = fmaxf(tmax, __uint_as_float(su[i]));
-        tmax *= LOG2E;
-        // Every completion of pv_done is observed exactly once and in order (global tile counter g): tile g consumes
-        // the completion of P(g-1)V(g-1) here before touching O, or at the end of the iteration; for the first tile
-        // of a segment that completion was consumed by the previous segment's epilogue.
-        bool pv_seen = (j == 0);
-        if (j == 0) {
-          m_run = tmax;
-        } else if (__any_sync(0xffffffffu, tmax > m_run + RESCALE_THRESHOLD)) {
-          mbar_wait(pv_done, (g - 1) & 1);
-          pv_seen = true;
-          tc_fence_after();
-          const float m_new = fmaxf(m_run, tmax);
-          const float alpha = fast_exp2(m_run - m_new);
-#pragma unroll 1
-          for (int c = 0; c < DH / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tmem_O + lane_base + c * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem_O + lane_base + c * 32, o);
-          }
-          l_run *= alpha;
-          m_run = m_new;
-        }
-        float lsum = 0.f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i]), LOG2E, -m_run));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i + 1]), LOG2E, -m_run));
-            lsum += p0 + p1;
-            pk[i] = kFp16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
-          }
-          tmem_st32(s_tmem + half * 32, pk);
-        }
-        l_run += lsum;
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive_leader(&p_full[buf]);
-        if (!pv_seen) mbar_wait(pv_done, (g - 1) & 1);
+        // Every completion of pv_done is observed exactly once and in order (global tile counter g): tile g consumes the
+        // completion of P(g-1)V(g-1) before touching O or at its end; for the first tile of a segment that completion was
+        // consumed by the previous segment's epilogue.
+        attn_softmax_tile<kFp16>(s_tmem, tmem_O + lane_base, p.Nk - (s.ta + j) * BKEY, j == 0, pv_done, (g - 1) & 1, m_run, l_run,
+                                 [&] { mbar_arrive_leader(&p_full[buf]); });
       }
       // segment epilogue: g tiles issued so far, the last one is g-1
       mbar_wait(pv_done, (g - 1) & 1);
       tc_fence_after();
       if (s.ta == 0 && s.n == p.ntiles) {
         // the whole item was processed here: normalise and emit the [hi|lo] operand of the out-projection directly
-        const float inv = 1.f / l_run;
         const int C = p.H * DH;
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.Nq + qt * BQ + q * 32 + lane) * (2 * C) + h * DH;
-#pragma unroll 1
-        for (int c = 0; c < DH / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_base + c * 32, o);
-          tmem_wait_ld();
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float v0 = __uint_as_float(o[2 * i]) * inv, v1 = __uint_as_float(o[2 * i + 1]) * inv;
-            hi[i] = pack_bf16x2(v0, v1);
-            lo[i] = pack_bf16x2(v0 - __uint_as_float(hi[i] << 16), v1 - __uint_as_float(hi[i] & 0xFFFF0000u));
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            reinterpret_cast<uint4*>(dst + c * 32)[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            reinterpret_cast<uint4*>(dst + C + c * 32)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-          }
-        }
+        attn_store_normalised(tmem_O + lane_base, 1.f / l_run, p.out + (static_cast<long long>(b) * p.Nq + qt * BQ + q * 32 + lane) * (2 * C) + h * DH, C);
       } else if (p.flags != nullptr && s.ta == 0) {
         // fused merge: this pair holds the FIRST piece of the item and finishes it last; the other pieces are the first
         // segments of the following pairs (at most two of them)
@@ -427,18 +357,7 @@ attn3_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       } else {
         // un-normalised O, m, l of this segment for the merge (attn3_combine_kernel, or the pair that holds the item's first piece)
         const long long part = (static_cast<long long>(pair) * p.slots + segi) * 256 + static_cast<int>(rank) * BQ + q * 32 + lane;
-        float* orow = p.o_part + part * DH;
-#pragma unroll 1
-        for (int c = 0; c < DH / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_base + c * 32, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            reinterpret_cast<float4*>(orow + c * 32)[i] =
-                make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
-                            __uint_as_float(o[4 * i + 3]));
-        }
+        attn_store_partial(tmem_O + lane_base, p.o_part + part * DH);
         p.ml_part[part] = make_float2(m_run, l_run);
         if (p.flags != nullptr) {
           __threadfence();

@@ -67,6 +67,110 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// ---- pieces shared by the three flash-attention kernels (attn_tc / attn2_tc / attn3_tc); a softmax warp owns 32 query rows,
+// ---- thread = row (TMEM lane), s_tmem / o_tmem already carry the warp's lane offset ----------------------------------------
+// One key tile of the online softmax: S (128 fp32 columns of this row) -> masked row maximum -> lazy rescale of O -> P = 2^(S - m)
+// packed to 16 bits over S in TMEM -> arrive_p() tells the MMA issuer that P is there.
+// mbarrier waits are by phase parity, so every completion of pv_done has to be observed exactly once and in order (skipping one
+// lets a later wait alias an older phase): a tile consumes the completion of the previous P.V either before it touches O (the
+// rescale) or at its end; `first` = first tile of a (segment of an) item, whose predecessor was consumed by the epilogue before.
+template <bool kFp16, typename ArriveP>
+__device__ __forceinline__ void attn_softmax_tile(uint32_t s_tmem, uint32_t o_tmem, int nvalid, bool first, uint64_t* pv_done, uint32_t pv_parity,
+                                                  float& m_run, float& l_run, ArriveP arrive_p) {
+  using namespace attn;
+  uint32_t su[128];                                // raw fp32 bits of this row of S
+#pragma unroll
+  for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&su[c * 32]));
+  tmem_wait_ld();
+  if (nvalid < BKEY) {                             // keys of this tile that do not belong to the clip
+#pragma unroll
+    for (int i = 0; i < 128; ++i)
+      if (i >= nvalid) su[i] = 0xff800000u;        // -inf
+  }
+  float tmax = __uint_as_float(su[0]);
+#pragma unroll
+  for (int i = 1; i < 128; ++i) tmax = fmaxf(tmax, __uint_as_float(su[i]));
+  tmax *= LOG2E;
+  bool pv_seen = first;
+  if (first) {
+    m_run = tmax;
+  } else if (__any_sync(0xffffffffu, tmax > m_run + RESCALE_THRESHOLD)) {
+    // O must be quiescent: wait for the previous P.V to retire, then rescale this warp's 32 rows.
+    mbar_wait(pv_done, pv_parity);
+    pv_seen = true;
+    tc_fence_after();
+    const float m_new = fmaxf(m_run, tmax);
+    const float alpha = fast_exp2(m_run - m_new);
+#pragma unroll 1
+    for (int c = 0; c < DH / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(o_tmem + c * 32, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st32(o_tmem + c * 32, o);
+    }
+    l_run *= alpha;
+    m_run = m_new;
+  }
+  float lsum = 0.f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t pk[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float p0 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i]), LOG2E, -m_run));
+      const float p1 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i + 1]), LOG2E, -m_run));
+      lsum += p0 + p1;
+      pk[i] = kFp16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
+    }
+    tmem_st32(s_tmem + half * 32, pk);
+  }
+  l_run += lsum;
+  tmem_wait_st();
+  tc_fence_before();
+  arrive_p();
+  if (!pv_seen) mbar_wait(pv_done, pv_parity);
+}
+
+// O of this row, normalised, as the [hi|lo] operand of the out-projection: dst = &out[row][head * 256], C = channels of the layer
+__device__ __forceinline__ void attn_store_normalised(uint32_t o_tmem, float inv, __nv_bfloat16* dst, int C) {
+  using namespace attn;
+#pragma unroll 1
+  for (int c = 0; c < DH / 32; ++c) {
+    uint32_t o[32];
+    tmem_ld32(o_tmem + c * 32, o);
+    tmem_wait_ld();
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float v0 = __uint_as_float(o[2 * i]) * inv, v1 = __uint_as_float(o[2 * i + 1]) * inv;
+      hi[i] = pack_bf16x2(v0, v1);
+      lo[i] = pack_bf16x2(v0 - __uint_as_float(hi[i] << 16), v1 - __uint_as_float(hi[i] & 0xFFFF0000u));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      reinterpret_cast<uint4*>(dst + c * 32)[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+      reinterpret_cast<uint4*>(dst + C + c * 32)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+    }
+  }
+}
+
+// un-normalised O of this row for a merge kernel: orow = &o_part[partial row][0]
+__device__ __forceinline__ void attn_store_partial(uint32_t o_tmem, float* orow) {
+  using namespace attn;
+#pragma unroll 1
+  for (int c = 0; c < DH / 32; ++c) {
+    uint32_t o[32];
+    tmem_ld32(o_tmem + c * 32, o);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      reinterpret_cast<float4*>(orow + c * 32)[i] =
+          make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]), __uint_as_float(o[4 * i + 3]));
+  }
+}
+
 template <bool kFp16>
 __global__ void __launch_bounds__(attn::THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -237,105 +341,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_tmem = tmem_base + lane_base + buf * 128;
-      uint32_t su[128];                                // raw fp32 bits of this row of S
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&su[c * 32]));
-      tmem_wait_ld();
-      const int nvalid = p.Nk - (t0 + j) * BKEY;     // keys of this tile that belong to the clip
-      if (nvalid < BKEY) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= nvalid) su[i] = 0xff800000u;        // -inf
-      }
-      float tmax = __uint_as_float(su[0]);
-#pragma unroll
-      for (int i = 1; i < 128; ++i) tmax = fmaxf(tmax, __uint_as_float(su[i]));
-      tmax *= LOG2E;
-      // mbarrier waits are by phase parity, so every completion of pv_done has to be observed exactly
-      // once and in order (skipping one lets a later wait alias an older phase): tile j consumes the
-      // completion of P(j-1)V(j-1) either here, before touching O, or at the end of the iteration.
-      bool pv_seen = (j == 0);
-      if (j == 0) {
-        m_run = tmax;
-      } else if (__any_sync(0xffffffffu, tmax > m_run + RESCALE_THRESHOLD)) {
-        // O must be quiescent: wait for P(j-1) V(j-1) to retire, then rescale this warp's 32 rows.
-        mbar_wait(pv_done, (j - 1) & 1);
-        pv_seen = true;
-        tc_fence_after();
-        const float m_new = fmaxf(m_run, tmax);
-        const float alpha = fast_exp2(m_run - m_new);
-#pragma unroll 1
-        for (int c = 0; c < DH / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_base + c * 32, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tmem_O + lane_base + c * 32, o);
-        }
-        l_run *= alpha;
-        m_run = m_new;
-      }
-      float lsum = 0.f;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i]), LOG2E, -m_run));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(su[half * 64 + 2 * i + 1]), LOG2E, -m_run));
-          lsum += p0 + p1;
-          pk[i] = kFp16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
-        }
-        tmem_st32(s_tmem + half * 32, pk);
-      }
-      l_run += lsum;
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_full[buf]);
-      if (!pv_seen) mbar_wait(pv_done, (j - 1) & 1);
+      attn_softmax_tile<kFp16>(s_tmem, tmem_O + lane_base, p.Nk - (t0 + j) * BKEY, j == 0, pv_done, (j - 1) & 1, m_run, l_run,
+                               [&] { mbar_arrive(&p_full[buf]); });
     }
     // epilogue
     mbar_wait(pv_done, (n - 1) & 1);
     tc_fence_after();
     if (p.out_direct != nullptr) {
       // single split: normalise here and emit the [hi|lo] operand of the out-projection directly
-      const float inv = 1.f / l_run;
       const int C = p.H * DH;
-      __nv_bfloat16* dst = p.out_direct + (static_cast<long long>(b) * p.Nq + qt * BQ + q * 32 + lane) * (2 * C) + h * DH;
-#pragma unroll 1
-      for (int c = 0; c < DH / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tmem_O + lane_base + c * 32, o);
-        tmem_wait_ld();
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float v0 = __uint_as_float(o[2 * i]) * inv, v1 = __uint_as_float(o[2 * i + 1]) * inv;
-          hi[i] = pack_bf16x2(v0, v1);
-          lo[i] = pack_bf16x2(v0 - __uint_as_float(hi[i] << 16), v1 - __uint_as_float(hi[i] & 0xFFFF0000u));
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          reinterpret_cast<uint4*>(dst + c * 32)[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-          reinterpret_cast<uint4*>(dst + C + c * 32)[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-        }
-      }
+      attn_store_normalised(tmem_O + lane_base, 1.f / l_run, p.out_direct + (static_cast<long long>(b) * p.Nq + qt * BQ + q * 32 + lane) * (2 * C) + h * DH, C);
     } else {
       // un-normalised O, m, l of this split for attn_combine_kernel
       const long long part = (static_cast<long long>(bh) * p.nsplit + split) * p.Nq + qt * BQ + q * 32 + lane;
-      float* orow = p.o_part + part * DH;
-#pragma unroll 1
-      for (int c = 0; c < DH / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tmem_O + lane_base + c * 32, o);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          reinterpret_cast<float4*>(orow + c * 32)[i] =
-              make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
-                          __uint_as_float(o[4 * i + 3]));
-      }
+      attn_store_partial(tmem_O + lane_base, p.o_part + part * DH);
       p.ml_part[part] = make_float2(m_run, l_run);
     }
   }
