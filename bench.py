@@ -518,6 +518,22 @@ def run_ours(args):
                         "what": "parse_pred + NMS on the device for this rank's %d clips, then shard.gather_detections (one NCCL all_gather "
                                 "per tensor: centre, size, ortho6d, class probabilities, pred_mask) into global clip order" % B}
 
+    # ---- launch trace (N = 1): what every launch costs on the dependent chain of the replayed graph, and the SM clock inside
+    # the chained kernel (cycles / ns of its own CTAs) -- the evidence for "the step is power-capped" in DESIGN.md 4.0
+    trace = None
+    if world == 1 and rank == 0:
+        try:
+            from parq_b200.tracing import launch_trace
+            eng = model._engine
+            g4 = [g._data for g in geo]
+            tr = launch_trace(eng, lambda: eng.forward(tokens, *g4, H, W, graph=True), reps=8, iters=IT)
+            trace = {k: tr[k] for k in ("stamps_per_step", "step_us", "iteration_us", "iteration_launches_us", "prologue_us", "sm_mhz_in_chain_kernel") if k in tr}
+            trace["how"] = ("parq_trace: global-timer stamp of every kernel when its stream dependency resolves, 8 graph replays after the timed region; "
+                            "a launch costs the difference to the next stamp (execution + drain + hand-over); iterations 1..6; "
+                            "sm_mhz_in_chain_kernel = clock64 / globaltimer of the chained kernel's own CTAs")
+        except Exception as e:                       # instrumentation only: never fail the bench line
+            trace = {"error": repr(e)}
+
     gpu_torch = gpu_torch_baseline(dev, B) if (world == 1 and rank == 0) else None
 
     if rank == 0:
@@ -587,6 +603,7 @@ def run_ours(args):
                                               + ("the unmodified reference PARQDecoder.forward" if kind == "reference" else "oracle port, reference op order")
                                               + ", fp32 torch CPU"}
             line["gpu_torch_baseline"] = gpu_torch
+            line["launch_trace"] = trace
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
