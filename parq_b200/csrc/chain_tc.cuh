@@ -2,7 +2,7 @@
 //
 // Between the attention kernels an iteration is a chain of linear layers in which every output row depends only
 // on the same row of the input (reference transformer_parq.py:365-386, 176-180, 211-281):
-//     P:  pe0 -> ReLU -> pe2 (+x -> x+pe) -> self-attention Q|K projection
+//     P:  pe0 -> ReLU -> [self-attention V^T, independent] -> pe2 (+x -> x+pe) -> self-attention Q|K projection
 //     A:  self-attention out-projection + residual + LayerNorm1 (+pe) -> cross-attention Q projection
 //     B:  cross-attention out-projection + residual + LayerNorm2 -> FFN linear1 + ReLU -> linear2 + residual +
 //         LayerNorm3 -> first layer of the centre / rotation heads (+ GroupNorm tile sums)
@@ -11,8 +11,9 @@
 // Here a CLUSTER OF 4 CTAs owns a block of 128 rows for the whole chain: CTA r computes columns [r N/4, (r+1) N/4)
 // of every stage with the same TMA -> smem ring -> tcgen05.mma (TMEM accumulator) pipeline as gemm_tc.cuh, the
 // stage's output goes to global memory (it stays in L2), and the next stage streams it back as its A operand as
-// soon as all four CTAs have signalled "stage done" on a cluster-scope mbarrier.  Weight tiles of the next stage
-// are requested while the current stage's epilogue is still running.
+// soon as all four CTAs have signalled "stage done" on that stage's cluster-scope mbarrier.  Weight tiles of the next stage
+// are requested while the current stage's epilogue is still running, and a stage that does not read the previous one
+// (ChainStage::dep) starts its MMAs right away: they run under the previous stage's epilogue.
 //   LayerNorm inside a stage: the rows of z = acc + bias + residual are spread over the four CTAs (and two
 // epilogue warps per row); every thread reduces its 96-128 values to (mean, M2), writes that pair into all four
 // CTAs' shared memory (DSMEM), and after a cluster-scope mbarrier combines the 8 partials of its row in a fixed

@@ -15,7 +15,8 @@
 // Two cluster barriers per launch (all MMAs retired -> partials exchanged) replace three quarters of the k-loop.
 //
 // Used for every activation x weight GEMM of the un-chained launch path whose shape fits (K / 64 a multiple of 4 and at
-// most 16, N a multiple of 128): reference transformer_parq.py:176-180, 365-386, generic_mlp.py:94-110 at one clip.
+// most 16, N a multiple of 128, all clusters resident in one wave -- beyond that the output tiles alone fill the machine):
+// reference transformer_parq.py:176-180, 365-386, generic_mlp.py:94-110 at one clip.  launch_gemm (parq_api.cu) selects it.
 #pragma once
 #include "chain_tc.cuh"
 #include "gemm_tc.cuh"
