@@ -396,8 +396,6 @@ constexpr int SK_MAX_PAIRS = 128;        // CTA pairs the schedule may use (74 o
 template <bool kWide>
 __global__ void __launch_bounds__(256)
 attn3_combine_kernel(const Attn3Params p, const int rows) {
-  pdl_wait();
-  pdl_launch_dependents();
   const int item = blockIdx.x / (256 / rows);
   const int r0 = (blockIdx.x % (256 / rows)) * rows;      // first row of this block inside the item
   __shared__ int s_np;
@@ -418,6 +416,9 @@ attn3_combine_kernel(const Attn3Params p, const int rows) {
       s_slot[pr - pa] = (static_cast<long long>(pr) * p.slots + seg) * 256;
     }
   }
+  // the piece table above depends on the launch parameters only: it is built while the attention kernel drains
+  pdl_wait();
+  pdl_launch_dependents();
   __syncthreads();
   const int np = s_np;
   if (np == 1) return;                                       // whole item in one range: written directly
