@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit of round 2: parity tests, sampling micro-benchmark, both bench arms, one ncu capture.
-# usage (on the box): bash tools/gpu_visit.sh <tag> [stages...]   stages: proj test sample ref bench ncu_sample ncu_iter ncu_gemm launches trace configs ab sanit
+# usage (on the box): bash tools/gpu_visit.sh <tag> [stages...]   stages: proj test sample ref bench ncu_sample ncu_iter ncu_gemm ncu_one_clip launches trace configs ab sanit (one ncu capture per call: gpurun_out/ is capped at 64 MiB)
 TAG=${1:-r2x}; shift
 STAGES=${@:-proj test sample ref bench}
 mkdir -p gpurun_out
