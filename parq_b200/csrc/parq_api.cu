@@ -205,9 +205,12 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 // capture they become parallel branches of the graph): with one clip an iteration is a chain of ~20 short dependent launches
 // and every launch taken off that chain is ~10 us of latency.  Created lazily outside a capture, per thread and device.
 struct SideStreams {
+  static constexpr int NEV = 128;          // events are used round-robin: none is re-recorded within one forward (<= 4 per iteration)
   cudaStream_t s[2] = {nullptr, nullptr};
-  cudaEvent_t fork_ev[2] = {nullptr, nullptr}, join_ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev[NEV] = {};
+  int next = 0;
   bool ok = false;
+  cudaEvent_t take() { cudaEvent_t e = ev[next]; next = (next + 1) % NEV; return e; }
 };
 static SideStreams* side_streams(cudaStream_t st) {
   static thread_local SideStreams tab[MAX_DEVICES];
@@ -219,9 +222,13 @@ static SideStreams* side_streams(cudaStream_t st) {
       return nullptr;            // first use inside a capture: stay on one stream
     }
     for (int i = 0; i < 2; ++i) {
-      if (cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&S.fork_ev[i], cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&S.join_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+      if (cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+    }
+    for (int i = 0; i < SideStreams::NEV; ++i) {
+      if (cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
       }
@@ -231,13 +238,15 @@ static SideStreams* side_streams(cudaStream_t st) {
   return &S;
 }
 static int side_fork(cudaStream_t st, SideStreams* S, int i) {       // work launched on S->s[i] from now on starts after what `st` holds
-  CUDA_TRY(cudaEventRecord(S->fork_ev[i], st));
-  CUDA_TRY(cudaStreamWaitEvent(S->s[i], S->fork_ev[i], 0));
+  cudaEvent_t e = S->take();
+  CUDA_TRY(cudaEventRecord(e, st));
+  CUDA_TRY(cudaStreamWaitEvent(S->s[i], e, 0));
   return PARQ_OK;
 }
 static int side_join(cudaStream_t st, SideStreams* S, int i) {       // `st` continues after what S->s[i] holds
-  CUDA_TRY(cudaEventRecord(S->join_ev[i], S->s[i]));
-  CUDA_TRY(cudaStreamWaitEvent(st, S->join_ev[i], 0));
+  cudaEvent_t e = S->take();
+  CUDA_TRY(cudaEventRecord(e, S->s[i]));
+  CUDA_TRY(cudaStreamWaitEvent(st, e, 0));
   return PARQ_OK;
 }
 
